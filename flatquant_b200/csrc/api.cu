@@ -1,0 +1,401 @@
+// C-ABI entry points of libflatq_b200.so (see include/flatq_b200.h for the contract and the
+// reference interfaces each symbol replaces).  Host glue only: argument checks, TMA descriptors,
+// launch configuration.  No torch, no allocation.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <string>
+
+#include "../../include/flatq_b200.h"
+#include "elementwise.cuh"
+#include "gemm_w4a8.cuh"
+#include "kron_quant.cuh"
+
+using namespace flatq;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define FLATQ_CUDA(expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess) return fail(FLATQ_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define FLATQ_CHECK(cond, code, ...) \
+    do {                             \
+        if (!(cond)) return fail(code, __VA_ARGS__); \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+int grid_for(size_t n_items, int block, int max_waves = 8) {
+    size_t g = (n_items + block - 1) / block;
+    size_t cap = (size_t)num_sms() * max_waves;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ---- TMA descriptors through the runtime-resolved driver entry point (no link-time libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 2-D byte tensor [rows, cols_bytes] with row pitch `pitch`; box = [box_rows, box_cols] bytes.
+int make_map_u8(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols_bytes, uint64_t pitch,
+                uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = encode_fn();
+    FLATQ_CHECK(fn != nullptr, FLATQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    FLATQ_CHECK(aligned16(ptr) && pitch % 16 == 0, FLATQ_ERR_INVALID, "TMA operand must be 16-byte aligned (pitch %llu)",
+                (unsigned long long)pitch);
+    cuuint64_t dims[2] = {cols_bytes, rows};
+    cuuint64_t strides[1] = {pitch};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FLATQ_CHECK(r == CUDA_SUCCESS, FLATQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return FLATQ_OK;
+}
+
+// ---- GEMM launch
+template <int TN, int MODE>
+int launch_gemm_t(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, cudaStream_t st) {
+    auto kern = gemm_w4a8_kernel<TN, MODE>;
+    constexpr int smem = GemmSmem<TN>::kBytes;
+    static bool attr_set = false;  // benign race: idempotent
+    if (!attr_set) {
+        FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int tiles = ((p.N + kGemmBlockW - 1) / kGemmBlockW) * ((p.M + TN - 1) / TN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, kGemmThreads, smem, st>>>(tw, tx, p);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+template <int MODE>
+int launch_gemm_m(int tn, const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, cudaStream_t st) {
+    switch (tn) {
+        case 16: return launch_gemm_t<16, MODE>(tw, tx, p, st);
+        case 32: return launch_gemm_t<32, MODE>(tw, tx, p, st);
+        case 64: return launch_gemm_t<64, MODE>(tw, tx, p, st);
+        default: return launch_gemm_t<128, MODE>(tw, tx, p, st);
+    }
+}
+
+// w_packed [N, K/2]; x8 [M, K] int8 in the permuted operand format
+int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, int64_t K, int acc_shift, void* out,
+                int mode, const float* sx, const float* sw, const void* bias, cudaStream_t st) {
+    FLATQ_CHECK(M > 0 && N > 0 && K > 0, FLATQ_ERR_INVALID, "empty GEMM %lldx%lldx%lld", (long long)M, (long long)N,
+                (long long)K);
+    FLATQ_CHECK(K % 32 == 0, FLATQ_ERR_INVALID, "K=%lld must be a multiple of 32", (long long)K);
+    FLATQ_CHECK(K <= 65536 && M < (1ll << 31) && N < (1ll << 31), FLATQ_ERR_UNSUPPORTED, "GEMM too large");
+    const int tn = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128;
+    CUtensorMap tw, tx;
+    int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    rc = make_map_u8(&tx, x8, M, K, K, kGemmBlockK, tn, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    GemmParams p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = acc_shift;
+    p.out = out; p.s_x = sx; p.s_w = sw; p.bias = bias;
+    switch (mode) {
+        case kEpiI32: return launch_gemm_m<kEpiI32>(tn, tw, tx, p, st);
+        case kEpiF16: return launch_gemm_m<kEpiF16>(tn, tw, tx, p, st);
+        case kEpiBF16: return launch_gemm_m<kEpiBF16>(tn, tw, tx, p, st);
+    }
+    return fail(FLATQ_ERR_INVALID, "bad epilogue mode %d", mode);
+}
+
+// ---- Kronecker transform (+quant) launch
+template <int KT2>
+int launch_kron_t(const KronParams& p, int threads, size_t smem, int grid, cudaStream_t st) {
+    auto kern = kron_quant_mma_kernel<KT2>;
+    static size_t attr_smem = 0;
+    if (smem > 48 * 1024 && smem > attr_smem) {
+        FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    kern<<<grid, threads, smem, st>>>(p);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+int launch_kron(KronParams p, cudaStream_t st) {
+    FLATQ_CHECK(p.tokens > 0, FLATQ_ERR_INVALID, "no tokens");
+    FLATQ_CHECK(p.n1 >= 1 && p.n2 >= 16 && p.n1 <= 256 && p.n2 <= 256 && p.n2 % 16 == 0, FLATQ_ERR_UNSUPPORTED,
+                "unsupported Kronecker factor sizes (%d, %d): need n2 %% 16 == 0 and n1, n2 <= 256", p.n1, p.n2);
+    FLATQ_CHECK(aligned16(p.x), FLATQ_ERR_INVALID, "x must be 16-byte aligned");
+    p.p1 = (p.n1 + 15) / 16 * 16;
+    const int wpt = p.p1 / 16;
+    const int kt2 = p.n2 / 16;
+    const int max_threads = kt2 <= 8 ? 512 : 256;
+    FLATQ_CHECK(wpt * 32 <= max_threads, FLATQ_ERR_UNSUPPORTED, "Kronecker factors (%d, %d) need %d warps per token",
+                p.n1, p.n2, wpt);
+    int tpc = 8 / wpt;
+    if (tpc < 1) tpc = 1;
+    while (tpc > 1 && (tpc * wpt * 32 > max_threads ||
+                       kron_smem_bytes(p.n1, p.n2, p.p1, tpc, p.left != nullptr, p.right != nullptr) > 100 * 1024))
+        --tpc;
+    p.tokens_per_cta = tpc;
+    const size_t smem = kron_smem_bytes(p.n1, p.n2, p.p1, tpc, p.left != nullptr, p.right != nullptr);
+    FLATQ_CHECK(smem <= 227 * 1024, FLATQ_ERR_UNSUPPORTED, "Kronecker factors (%d, %d) exceed shared memory", p.n1, p.n2);
+    const int threads = tpc * wpt * 32;
+    int64_t ctas = (p.tokens + tpc - 1) / tpc;
+    const int64_t cap = (int64_t)num_sms() * (smem > 100 * 1024 ? 1 : 2);
+    const int grid = (int)(ctas < cap ? ctas : cap);
+    switch (kt2) {
+#define FLATQ_KRON_CASE(n) case n: return launch_kron_t<n>(p, threads, smem, grid, st);
+        FLATQ_KRON_CASE(1) FLATQ_KRON_CASE(2) FLATQ_KRON_CASE(3) FLATQ_KRON_CASE(4) FLATQ_KRON_CASE(5)
+        FLATQ_KRON_CASE(6) FLATQ_KRON_CASE(7) FLATQ_KRON_CASE(8) FLATQ_KRON_CASE(9) FLATQ_KRON_CASE(10)
+        FLATQ_KRON_CASE(11) FLATQ_KRON_CASE(12) FLATQ_KRON_CASE(13) FLATQ_KRON_CASE(14) FLATQ_KRON_CASE(15)
+        FLATQ_KRON_CASE(16)
+#undef FLATQ_KRON_CASE
+    }
+    return fail(FLATQ_ERR_UNSUPPORTED, "n2=%d", p.n2);
+}
+
+int launch_rowquant(const void* x, int64_t tokens, int64_t K, float cmax, float cmin, int half_math, uint8_t* xq4,
+                    int8_t* xq8, float* sx32, void* sx16, cudaStream_t st) {
+    FLATQ_CHECK(tokens > 0 && K > 0 && K % 8 == 0, FLATQ_ERR_INVALID, "quantize_rows: K=%lld must be a multiple of 8",
+                (long long)K);
+    FLATQ_CHECK(aligned16(x), FLATQ_ERR_INVALID, "x must be 16-byte aligned");
+    const int block = 256;
+    const int grid = grid_for((size_t)tokens * 32, block, 8);
+    rowquant_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __half*>(x), (int)tokens, (int)K, cmax, cmin,
+                                            half_math, xq4, xq8, sx32, reinterpret_cast<__half*>(sx16));
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int flatq_abi_version(void) { return FLATQ_ABI_VERSION; }
+const char* flatq_last_error(void) { return g_err.c_str(); }
+
+int flatq_device_supported(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10 ? 1 : 0;
+}
+
+int flatq_pack_i4(const int8_t* q, uint8_t* packed, int64_t rows, int64_t cols, flatq_stream_t stream) {
+    FLATQ_CHECK(q && packed, FLATQ_ERR_INVALID, "pack_i4: null pointer");
+    FLATQ_CHECK(rows >= 0 && cols >= 0 && cols % 16 == 0, FLATQ_ERR_INVALID, "pack_i4: cols=%lld must be a multiple of 16",
+                (long long)cols);
+    FLATQ_CHECK(aligned16(q) && (reinterpret_cast<uintptr_t>(packed) & 7) == 0, FLATQ_ERR_INVALID, "pack_i4: alignment");
+    const size_t n = (size_t)rows * cols / 16;
+    if (n == 0) return FLATQ_OK;
+    pack_i4_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(q, packed, n);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+int flatq_unpack_i4(const uint8_t* packed, int32_t* out, int64_t rows, int64_t cols_packed, flatq_stream_t stream) {
+    FLATQ_CHECK(packed && out, FLATQ_ERR_INVALID, "unpack_i4: null pointer");
+    FLATQ_CHECK(rows >= 0 && cols_packed >= 0 && cols_packed % 4 == 0, FLATQ_ERR_INVALID,
+                "unpack_i4: packed cols=%lld must be a multiple of 4", (long long)cols_packed);
+    FLATQ_CHECK((reinterpret_cast<uintptr_t>(packed) & 3) == 0 && aligned16(out), FLATQ_ERR_INVALID, "unpack_i4: alignment");
+    const size_t n = (size_t)rows * cols_packed / 4;
+    if (n == 0) return FLATQ_OK;
+    unpack_i4_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(packed, out, n);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+int flatq_sym_quant(const void* x, const void* scale, int64_t rows, int64_t cols, uint8_t* q, flatq_stream_t stream) {
+    FLATQ_CHECK(x && scale && q, FLATQ_ERR_INVALID, "sym_quant: null pointer");
+    FLATQ_CHECK(rows > 0 && cols > 0 && cols % 8 == 0, FLATQ_ERR_INVALID, "sym_quant: cols=%lld must be a multiple of 8",
+                (long long)cols);
+    FLATQ_CHECK(aligned16(x) && (reinterpret_cast<uintptr_t>(q) & 3) == 0, FLATQ_ERR_INVALID, "sym_quant: alignment");
+    const size_t n = (size_t)rows * cols / 8;
+    sym_quant_f16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(scale), q, (int)rows, (int)cols);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+int flatq_sym_dequant(const int32_t* acc, const void* s_row, const void* s_col, const void* bias, int64_t rows,
+                      int64_t cols, void* y, int out_dtype, int mode, flatq_stream_t stream) {
+    FLATQ_CHECK(acc && s_row && s_col && y, FLATQ_ERR_INVALID, "sym_dequant: null pointer");
+    FLATQ_CHECK(rows > 0 && cols > 0 && cols % 4 == 0, FLATQ_ERR_INVALID, "sym_dequant: cols=%lld must be a multiple of 4",
+                (long long)cols);
+    FLATQ_CHECK(aligned16(acc) && (reinterpret_cast<uintptr_t>(y) & 7) == 0, FLATQ_ERR_INVALID, "sym_dequant: alignment");
+    FLATQ_CHECK(mode == 0 || (mode == 1 && out_dtype == FLATQ_F16 && bias == nullptr), FLATQ_ERR_UNSUPPORTED,
+                "sym_dequant: mode %d needs fp16 output without bias", mode);
+    const size_t n = (size_t)rows * cols / 4;
+    const int g = grid_for(n, 256);
+    if (out_dtype == FLATQ_F16) {
+        sym_dequant_kernel<__half><<<g, 256, 0, (cudaStream_t)stream>>>(
+            acc, reinterpret_cast<const __half*>(s_row), reinterpret_cast<const __half*>(s_col),
+            reinterpret_cast<const __half*>(bias), reinterpret_cast<__half*>(y), (int)rows, (int)cols, mode);
+    } else if (out_dtype == FLATQ_BF16) {
+        sym_dequant_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(
+            acc, reinterpret_cast<const __half*>(s_row), reinterpret_cast<const __half*>(s_col),
+            reinterpret_cast<const __nv_bfloat16*>(bias), reinterpret_cast<__nv_bfloat16*>(y), (int)rows, (int)cols, mode);
+    } else {
+        return fail(FLATQ_ERR_INVALID, "sym_dequant: out_dtype %d", out_dtype);
+    }
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+size_t flatq_gemm_i4_workspace_bytes(int64_t M, int64_t K) { return align_up((size_t)M * K, 256); }
+
+int flatq_gemm_i4(const uint8_t* A, const uint8_t* B, int64_t M, int64_t N, int64_t K, int32_t* C, void* ws,
+                  size_t ws_bytes, flatq_stream_t stream) {
+    FLATQ_CHECK(A && B && C && ws, FLATQ_ERR_INVALID, "gemm_i4: null pointer");
+    // the reference asserts packed-K % 32 == 0 (deploy/__init__.py:38)
+    FLATQ_CHECK(K % 64 == 0, FLATQ_ERR_INVALID, "gemm_i4: K=%lld must be a multiple of 64", (long long)K);
+    FLATQ_CHECK(ws_bytes >= flatq_gemm_i4_workspace_bytes(M, K), FLATQ_ERR_WORKSPACE, "gemm_i4: workspace too small");
+    FLATQ_CHECK(aligned16(A) && aligned16(ws), FLATQ_ERR_INVALID, "gemm_i4: alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)M * (K / 2) / 16;
+    expand_i4_to_i8x16_kernel<<<grid_for(n, 256), 256, 0, st>>>(A, reinterpret_cast<uint8_t*>(ws), n);
+    FLATQ_CUDA(cudaGetLastError());
+    return launch_gemm(B, ws, M, N, K, 8, C, kEpiI32, nullptr, nullptr, nullptr, st);
+}
+
+size_t flatq_linear4bit_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    return align_up((size_t)M * K, 256) + align_up((size_t)M * 4, 256) + align_up((size_t)N * 4, 256);
+}
+
+int flatq_linear4bit(const uint8_t* A, const void* s_a, const uint8_t* B, const void* s_b, const void* bias, int64_t M,
+                     int64_t N, int64_t K, void* y, int out_dtype, void* ws, size_t ws_bytes, flatq_stream_t stream) {
+    FLATQ_CHECK(A && B && s_a && s_b && y && ws, FLATQ_ERR_INVALID, "linear4bit: null pointer");
+    FLATQ_CHECK(K % 64 == 0, FLATQ_ERR_INVALID, "linear4bit: K=%lld must be a multiple of 64", (long long)K);
+    FLATQ_CHECK(out_dtype == FLATQ_F16 || out_dtype == FLATQ_BF16, FLATQ_ERR_INVALID, "linear4bit: out_dtype");
+    FLATQ_CHECK(ws_bytes >= flatq_linear4bit_workspace_bytes(M, N, K), FLATQ_ERR_WORKSPACE, "linear4bit: workspace too small");
+    FLATQ_CHECK(aligned16(A) && aligned16(ws), FLATQ_ERR_INVALID, "linear4bit: alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* x8 = reinterpret_cast<uint8_t*>(ws);
+    float* sa32 = reinterpret_cast<float*>(x8 + align_up((size_t)M * K, 256));
+    float* sb32 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sa32) + align_up((size_t)M * 4, 256));
+    const size_t n = (size_t)M * (K / 2) / 16;
+    expand_i4_to_i8x16_kernel<<<grid_for(n, 256), 256, 0, st>>>(A, x8, n);
+    half_to_float_kernel<<<(int)((M + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half*>(s_a), sa32, (int)M);
+    half_to_float_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half*>(s_b), sb32, (int)N);
+    FLATQ_CUDA(cudaGetLastError());
+    return launch_gemm(B, x8, M, N, K, 8, y, out_dtype == FLATQ_F16 ? kEpiF16 : kEpiBF16, sa32, sb32, bias, st);
+}
+
+int flatq_kron_transform(const void* x, const void* left, const void* right, int64_t tokens, int n1, int n2, void* z,
+                         flatq_stream_t stream) {
+    FLATQ_CHECK(x && z, FLATQ_ERR_INVALID, "kron_transform: null pointer");
+    KronParams p = {};
+    p.x = reinterpret_cast<const __half*>(x);
+    p.left = reinterpret_cast<const __half*>(left);
+    p.right = reinterpret_cast<const __half*>(right);
+    p.tokens = (int)tokens; p.n1 = n1; p.n2 = n2;
+    p.do_quant = 0; p.c_max = p.c_min = 1.f;
+    p.z_out = reinterpret_cast<__half*>(z);
+    return launch_kron(p, (cudaStream_t)stream);
+}
+
+int flatq_transform_quant(const void* x, const void* left, const void* right, int64_t tokens, int n1, int n2,
+                          float clip_max, float clip_min, uint8_t* xq_packed, void* scales_f16, float* scales_f32,
+                          flatq_stream_t stream) {
+    FLATQ_CHECK(x, FLATQ_ERR_INVALID, "transform_quant: null pointer");
+    FLATQ_CHECK(!xq_packed || aligned16(xq_packed), FLATQ_ERR_INVALID, "transform_quant: output alignment");
+    if (!left && !right)
+        return launch_rowquant(x, tokens, (int64_t)n1 * n2, clip_max, clip_min, 0, xq_packed, nullptr, scales_f32,
+                               scales_f16, (cudaStream_t)stream);
+    KronParams p = {};
+    p.x = reinterpret_cast<const __half*>(x);
+    p.left = reinterpret_cast<const __half*>(left);
+    p.right = reinterpret_cast<const __half*>(right);
+    p.tokens = (int)tokens; p.n1 = n1; p.n2 = n2;
+    p.do_quant = 1; p.c_max = clip_max; p.c_min = clip_min;
+    p.xq4 = xq_packed;
+    p.sx_f16 = reinterpret_cast<__half*>(scales_f16);
+    p.sx_f32 = scales_f32;
+    return launch_kron(p, (cudaStream_t)stream);
+}
+
+int flatq_quantize_rows(const void* x, int64_t tokens, int64_t K, float clip_max, float clip_min, int half_math,
+                        uint8_t* xq_packed, void* scales_f16, float* scales_f32, flatq_stream_t stream) {
+    FLATQ_CHECK(x, FLATQ_ERR_INVALID, "quantize_rows: null pointer");
+    return launch_rowquant(x, tokens, K, clip_max, clip_min, half_math, xq_packed, nullptr, scales_f32, scales_f16,
+                           (cudaStream_t)stream);
+}
+
+size_t flatq_linear_fused_workspace_bytes(int64_t M, int64_t K) {
+    return align_up((size_t)M * K, 256) + align_up((size_t)M * 4, 256);
+}
+
+int flatq_linear_fused(const void* x, const void* left, const void* right, int n1, int n2, float clip_max,
+                       float clip_min, const uint8_t* w_packed, const float* s_w, const void* bias, int64_t M, int64_t N,
+                       void* y, int out_dtype, void* ws, size_t ws_bytes, flatq_stream_t stream) {
+    FLATQ_CHECK(x && w_packed && s_w && y && ws, FLATQ_ERR_INVALID, "linear_fused: null pointer");
+    FLATQ_CHECK(out_dtype == FLATQ_F16 || out_dtype == FLATQ_BF16, FLATQ_ERR_INVALID, "linear_fused: out_dtype");
+    const int64_t K = (int64_t)n1 * n2;
+    FLATQ_CHECK(K % 64 == 0, FLATQ_ERR_INVALID, "linear_fused: K=%lld must be a multiple of 64", (long long)K);
+    FLATQ_CHECK(ws_bytes >= flatq_linear_fused_workspace_bytes(M, K), FLATQ_ERR_WORKSPACE, "linear_fused: workspace too small");
+    FLATQ_CHECK(aligned16(ws), FLATQ_ERR_INVALID, "linear_fused: workspace alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    int8_t* x8 = reinterpret_cast<int8_t*>(ws);
+    float* sx = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + align_up((size_t)M * K, 256));
+    int rc;
+    if (!left && !right) {
+        rc = launch_rowquant(x, M, K, clip_max, clip_min, 0, nullptr, x8, sx, nullptr, st);
+    } else {
+        KronParams p = {};
+        p.x = reinterpret_cast<const __half*>(x);
+        p.left = reinterpret_cast<const __half*>(left);
+        p.right = reinterpret_cast<const __half*>(right);
+        p.tokens = (int)M; p.n1 = n1; p.n2 = n2;
+        p.do_quant = 1; p.c_max = clip_max; p.c_min = clip_min;
+        p.xq8 = x8; p.sx_f32 = sx;
+        rc = launch_kron(p, st);
+    }
+    if (rc) return rc;
+    return launch_gemm(w_packed, x8, M, N, K, 4, y, out_dtype == FLATQ_F16 ? kEpiF16 : kEpiBF16, sx, s_w, bias, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+// W4 x A8 -> INT32 GEMM on tcgen05 (UTCIMMA, kind::i8) for sm_100a.
+//
+// Replaces deploy/kernels/gemm.cu:7-46 (CUTLASS Sm80 s4 mma.sync GEMM) and, with the dequant
+// epilogue, deploy/kernels/quant.cu:66-101 + the bias add of deploy/nn/linear.py:48-54.
+//
+// B200 has no INT4 tensor-core instruction (tcgen05.mma.kind::i4 does not exist), so the 4-bit
+// weight stream is kept packed in HBM/L2/SMEM and expanded to int8 *in registers* on its way
+// into TENSOR MEMORY, where it is consumed as the A operand of tcgen05.mma (A may come from
+// TMEM, B must come from SMEM).  Roles are therefore swapped w.r.t. the reference GEMM:
+//
+//      D[n, m] (TMEM, int32)  =  sum_k  W[n, k] (TMEM, int8 = 16*w)  *  X[m, k] (SMEM, int8)
+//
+//   * UMMA M = 128 weight rows (TMEM lanes), UMMA N = TN tokens (16..128), UMMA K = 32.
+//   * Nibble expansion is two logic ops per 8 weights: (p<<4)&0xF0F0F0F0 and p&0xF0F0F0F0 give
+//     the even / odd nibbles as int8 values 16*w.  This permutes K inside every group of 8
+//     ([0,2,4,6,1,3,5,7]); the activation operand is stored with the same permutation, so the
+//     contraction is unchanged.  The factor 16 (or 256 when X is expanded the same way) is
+//     removed exactly by an arithmetic shift of the int32 accumulator.
+//   * Packed W tiles (128 rows x 64 B, SWIZZLE_64B) and int8 X tiles (TN rows x 128 B,
+//     SWIZZLE_128B) arrive by TMA into mbarrier-tracked rings.
+//
+// Warp roles (14 warps, persistent over output tiles):
+//   warp 0      TMA producer           warp 1       MMA issuer (+ TMEM alloc/dealloc)
+//   warps 2-9   nibble expanders (2 groups x 4 lane-quadrants)   warps 10-13  epilogue
+#pragma once
+#include "ptx.cuh"
+
+namespace flatq {
+
+constexpr int kGemmBlockW = 128;   // weight rows per tile
+constexpr int kGemmBlockK = 128;   // K elements per stage
+constexpr int kGemmThreads = 14 * 32;
+constexpr int kStagesX = 6;
+constexpr int kStagesW = 6;
+constexpr int kStagesA = 8;        // TMEM A-operand stages, 32 columns each
+constexpr int kTmemColsA0 = 256;   // accumulators at columns [0,128) and [128,256)
+constexpr int kWStageBytes = kGemmBlockW * (kGemmBlockK / 2);
+
+enum EpilogueMode : int { kEpiI32 = 0, kEpiF16 = 1, kEpiBF16 = 2 };
+
+struct GemmParams {
+    int M, N, K;          // tokens, out features, in features
+    int acc_shift;        // 4: X holds true int8 codes; 8: X holds 16*code
+    void* out;            // [M, N] int32 / f16 / bf16, row-major
+    const float* s_x;     // [M]  per-token scale   (dequant modes)
+    const float* s_w;     // [N]  per-channel scale (dequant modes)
+    const void* bias;     // [N] same dtype as out, or nullptr
+};
+
+template <int TN>
+struct GemmSmem {
+    static constexpr int kXStageBytes = TN * kGemmBlockK;
+    static constexpr int kBytes = kStagesX * kXStageBytes + kStagesW * kWStageBytes + 1024 /*align*/ + 512 /*bars*/;
+};
+
+template <int TN, int MODE>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                 const GemmParams p) {
+    static_assert(TN == 16 || TN == 32 || TN == 64 || TN == 128, "token tile");
+    constexpr int XB = GemmSmem<TN>::kXStageBytes;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* xs = smem;
+    uint8_t* ws = xs + kStagesX * XB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ws + kStagesW * kWStageBytes);
+    uint64_t* full_x = bars;                  // [kStagesX]
+    uint64_t* empty_x = full_x + kStagesX;    // [kStagesX]
+    uint64_t* full_w = empty_x + kStagesX;    // [kStagesW]
+    uint64_t* empty_w = full_w + kStagesW;    // [kStagesW]
+    uint64_t* full_a = empty_w + kStagesW;    // [kStagesA]
+    uint64_t* empty_a = full_a + kStagesA;    // [kStagesA]
+    uint64_t* full_acc = empty_a + kStagesA;  // [2]
+    uint64_t* empty_acc = full_acc + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_acc + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStagesX; ++i) { mbar_init(&full_x[i], 1); mbar_init(&empty_x[i], 1); }
+        for (int i = 0; i < kStagesW; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], 4); }
+        for (int i = 0; i < kStagesA; ++i) { mbar_init(&full_a[i], 4); mbar_init(&empty_a[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&full_acc[i], 1); mbar_init(&empty_acc[i], 128); }
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_x); }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int nb_w = (p.N + kGemmBlockW - 1) / kGemmBlockW;
+    const int nb_m = (p.M + TN - 1) / TN;
+    const int n_tiles = nb_w * nb_m;
+    const int KB = (p.K + kGemmBlockK - 1) / kGemmBlockK;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int n0 = (tile % nb_w) * kGemmBlockW;
+                const int m0 = (tile / nb_w) * TN;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const uint32_t sx = it % kStagesX, phx = (it / kStagesX) & 1;
+                    mbar_wait(&empty_x[sx], phx ^ 1);
+                    mbar_arrive_expect_tx(&full_x[sx], XB);
+                    tma_load_2d(xs + sx * XB, &tm_x, &full_x[sx], kb * kGemmBlockK, m0);
+                    const uint32_t sw = it % kStagesW, phw = (it / kStagesW) & 1;
+                    mbar_wait(&empty_w[sw], phw ^ 1);
+                    mbar_arrive_expect_tx(&full_w[sw], kWStageBytes);
+                    tma_load_2d(ws + sw * kWStageBytes, &tm_w, &full_w[sw], kb * (kGemmBlockK / 2), n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        constexpr uint32_t idesc = make_idesc(kDS32, kFmtS8, kFmtS8, 0, 0, kGemmBlockW, TN);
+        uint32_t it = 0, tile_iter = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+            const uint32_t b = tile_iter & 1, phb = (tile_iter >> 1) & 1;
+            mbar_wait(&empty_acc[b], phb ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + b * 128;
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const uint32_t sx = it % kStagesX, phx = (it / kStagesX) & 1;
+                const uint32_t sa = it % kStagesA, pha = (it / kStagesA) & 1;
+                mbar_wait(&full_x[sx], phx);
+                mbar_wait(&full_a[sa], pha);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t xaddr = smem_u32(xs + sx * XB);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t bdesc = make_smem_desc_kmajor(xaddr + kk * 32, 1024, kLayoutSw128);
+                        mma_i8_ts(d_tmem, tmem + kTmemColsA0 + sa * 32 + kk * 8, bdesc, idesc, (kb | kk) != 0);
+                    }
+                    tc_commit(&empty_x[sx]);
+                    tc_commit(&empty_a[sa]);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) tc_commit(&full_acc[b]);
+            __syncwarp();
+        }
+    } else if (warp < 10) {
+        // ================================ nibble expanders ================================
+        const int grp = (warp - 2) >> 2;  // handles k-block iterations with it % 2 == grp
+        const int q = warp & 3;           // TMEM lane quadrant this warp may touch
+        const uint32_t row = q * 32 + lane;
+        const uint32_t swz = (row >> 1) & 3;  // SWIZZLE_64B: 16-B chunk index ^= bits [7,9) of the address
+        const uint32_t ws_addr = smem_u32(ws) + row * 64;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                if ((it & 1) != (uint32_t)grp) continue;
+                const uint32_t sw = it % kStagesW, phw = (it / kStagesW) & 1;
+                const uint32_t sa = it % kStagesA, pha = (it / kStagesA) & 1;
+                mbar_wait(&full_w[sw], phw);
+                uint32_t a[32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 v = ld_shared_v4(ws_addr + sw * kWStageBytes + ((c ^ swz) << 4));
+                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        a[c * 8 + 2 * j] = (w4[j] << 4) & 0xF0F0F0F0u;   // nibbles 0,2,4,6 -> 16*w as int8
+                        a[c * 8 + 2 * j + 1] = w4[j] & 0xF0F0F0F0u;      // nibbles 1,3,5,7
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_w[sw]);
+                mbar_wait(&empty_a[sa], pha ^ 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + kTmemColsA0 + sa * 32;
+                tmem_st_x16(taddr, *reinterpret_cast<const uint32_t(*)[16]>(&a[0]));
+                tmem_st_x16(taddr + 16, *reinterpret_cast<const uint32_t(*)[16]>(&a[16]));
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_a[sa]);
+            }
+        }
+    } else {
+        // ================================ epilogue ================================
+        const int q = warp & 3;
+        uint32_t tile_iter = 0;
+        constexpr int CH = TN < 32 ? TN : 32;  // columns per TMEM load
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+            const int n0 = (tile % nb_w) * kGemmBlockW;
+            const int m0 = (tile / nb_w) * TN;
+            const uint32_t b = tile_iter & 1, phb = (tile_iter >> 1) & 1;
+            const int n = n0 + q * 32 + lane;
+            const bool n_ok = n < p.N;
+            float sw_n = 0.f, bias_n = 0.f;
+            if (MODE != kEpiI32 && n_ok) {
+                sw_n = p.s_w[n];
+                if (p.bias) {
+                    bias_n = MODE == kEpiF16 ? __half2float(reinterpret_cast<const __half*>(p.bias)[n])
+                                             : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
+                }
+            }
+            mbar_wait(&full_acc[b], phb);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < TN / CH; ++c) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + b * 128 + c * CH;
+                if (CH == 32) {
+                    tmem_ld_x32(taddr, r);
+                } else {
+                    tmem_ld_x16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int m = m0 + c * CH + j;
+                    if (m < p.M && n_ok) {
+                        const int32_t acc = static_cast<int32_t>(r[j]) >> p.acc_shift;  // exact: multiple of 2^shift
+                        const size_t o = (size_t)m * p.N + n;
+                        if (MODE == kEpiI32) {
+                            reinterpret_cast<int32_t*>(p.out)[o] = acc;
+                        } else {
+                            const float y = (float)acc * __ldg(&p.s_x[m]) * sw_n + bias_n;
+                            if (MODE == kEpiF16) reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(y);
+                            else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(y);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&empty_acc[b]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
+}  // namespace flatq

@@ -1,0 +1,194 @@
+"""Tensor-level wrappers over the C ABI: argument checks, output/workspace allocation, stream.
+
+Mirrors what the reference's pybind layer does (deploy/kernels/bindings.cpp:9-87: contiguity /
+device checks, outputs allocated with torch::empty) -- torch is used for device memory and the
+current stream only; all compute happens in libflatq_b200.so.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+F16, BF16 = 0, 1
+_DT = {torch.float16: F16, torch.bfloat16: BF16}
+_sm_checked = False
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    global _sm_checked
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("flatquant_b200 ops are CUDA-only (sm_100a); got a CPU tensor. There is no CPU fallback.")
+        if not t.is_contiguous():
+            raise RuntimeError("flatquant_b200 ops need contiguous tensors")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("flatquant_b200 ops need all tensors on the same GPU")
+    if not _sm_checked:
+        if not _lib.load().flatq_device_supported():
+            raise RuntimeError("flatquant_b200 needs an sm_100 (B200) device: tcgen05/TMA kernels only")
+        _sm_checked = True
+    return dev
+
+
+class _Workspace:
+    """Grow-only per-device scratch so steady-state calls do not allocate (CUDA-graph friendly)."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def get(self, dev, nbytes):
+        b = self.buf.get(dev)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+            self.buf[dev] = b
+        return b
+
+
+_ws = _Workspace()
+
+
+def pack_i4(q: torch.Tensor) -> torch.Tensor:
+    """int8 codes [..., cols] in [-8,7] -> uint8 [..., cols/2] (deploy.functional.pack_i4)."""
+    dev = _need_cuda(q)
+    if q.dtype != torch.int8:
+        q = q.to(torch.int8)
+    cols = q.shape[-1]
+    out = torch.empty(q.shape[:-1] + (cols // 2,), dtype=torch.uint8, device=dev)
+    _lib.check(_lib.load().flatq_pack_i4(_ptr(q), _ptr(out), q.numel() // max(cols, 1), cols, _stream()), "pack_i4")
+    return out
+
+
+def unpack_i4(p: torch.Tensor) -> torch.Tensor:
+    """uint8 [..., c] -> int32 [..., 2c] (deploy.functional.unpack_i4)."""
+    dev = _need_cuda(p)
+    assert p.dtype == torch.uint8, "The tensor to be unpacked should be stored in uint8"
+    c = p.shape[-1]
+    out = torch.empty(p.shape[:-1] + (2 * c,), dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().flatq_unpack_i4(_ptr(p), _ptr(out), p.numel() // max(c, 1), c, _stream()), "unpack_i4")
+    return out
+
+
+def sym_quant(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """deploy._CUDA.sym_quant: x f16 [rows, cols], scale f16 [rows] -> packed [rows, cols/2]."""
+    dev = _need_cuda(x, scale)
+    rows, cols = x.shape
+    if scale.numel() != rows:
+        raise RuntimeError(f"sym_quant: scale has {scale.numel()} elements, expected {rows}")
+    out = torch.empty((rows, cols // 2), dtype=torch.uint8, device=dev)
+    _lib.check(_lib.load().flatq_sym_quant(_ptr(x), _ptr(scale), rows, cols, _ptr(out), _stream()), "sym_quant")
+    return out
+
+
+def sym_dequant(q: torch.Tensor, scale_row: torch.Tensor, scale_col: torch.Tensor, bias=None, out_dtype=torch.float16,
+                ref_kernel_arith: bool = False) -> torch.Tensor:
+    dev = _need_cuda(q, scale_row, scale_col, bias)
+    rows, cols = q.shape
+    if scale_row.numel() != rows or scale_col.numel() != cols:
+        raise RuntimeError("sym_dequant: scale sizes do not match q")
+    y = torch.empty((rows, cols), dtype=out_dtype, device=dev)
+    _lib.check(_lib.load().flatq_sym_dequant(_ptr(q), _ptr(scale_row), _ptr(scale_col), _ptr(bias), rows, cols, _ptr(y),
+                                             _DT[out_dtype], 1 if ref_kernel_arith else 0, _stream()), "sym_dequant")
+    return y
+
+
+def gemm_i4(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """deploy._CUDA.matmul: packed A [M, K/2] x packed B [N, K/2]^T -> int32 [M, N]."""
+    dev = _need_cuda(a, b)
+    m, kp = a.shape
+    n = b.shape[0]
+    if b.shape[1] != kp:
+        raise RuntimeError("matmul: A and B disagree on K")
+    lib = _lib.load()
+    c = torch.empty((m, n), dtype=torch.int32, device=dev)
+    nb = lib.flatq_gemm_i4_workspace_bytes(m, kp * 2)
+    ws = _ws.get(dev, nb)
+    _lib.check(lib.flatq_gemm_i4(_ptr(a), _ptr(b), m, n, kp * 2, _ptr(c), _ptr(ws), ws.numel(), _stream()), "gemm_i4")
+    return c
+
+
+def linear4bit(a: torch.Tensor, s_a: torch.Tensor, b: torch.Tensor, s_b: torch.Tensor, bias=None,
+               out_dtype=torch.float16) -> torch.Tensor:
+    """Linear4bit.forward in one launch chain: (A.B^T) * s_a[m] * s_b[n] (+bias)."""
+    dev = _need_cuda(a, s_a, b, s_b, bias)
+    m, kp = a.shape
+    n = b.shape[0]
+    lib = _lib.load()
+    y = torch.empty((m, n), dtype=out_dtype, device=dev)
+    ws = _ws.get(dev, lib.flatq_linear4bit_workspace_bytes(m, n, kp * 2))
+    _lib.check(lib.flatq_linear4bit(_ptr(a), _ptr(s_a), _ptr(b), _ptr(s_b), _ptr(bias), m, n, kp * 2, _ptr(y),
+                                    _DT[out_dtype], _ptr(ws), ws.numel(), _stream()), "linear4bit")
+    return y
+
+
+def kron_transform(x: torch.Tensor, left, right, n1: int, n2: int) -> torch.Tensor:
+    """kronecker_matmul on fp16: x [..., n1*n2] -> same shape."""
+    dev = _need_cuda(x, left, right)
+    z = torch.empty_like(x)
+    tokens = x.numel() // (n1 * n2)
+    _lib.check(_lib.load().flatq_kron_transform(_ptr(x), _ptr(left), _ptr(right), tokens, n1, n2, _ptr(z), _stream()),
+               "kron_transform")
+    return z
+
+
+def transform_quant(x: torch.Tensor, left, right, n1: int, n2: int, clip_max: float = 1.0, clip_min: float = 1.0):
+    """OnlineTrans+Quantizer: returns (packed [tokens, K/2] u8, scales f16 [tokens], scales f32 [tokens])."""
+    dev = _need_cuda(x, left, right)
+    k = n1 * n2
+    tokens = x.numel() // k
+    xq = torch.empty((tokens, k // 2), dtype=torch.uint8, device=dev)
+    s16 = torch.empty((tokens,), dtype=torch.float16, device=dev)
+    s32 = torch.empty((tokens,), dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().flatq_transform_quant(_ptr(x), _ptr(left), _ptr(right), tokens, n1, n2, float(clip_max),
+                                                 float(clip_min), _ptr(xq), _ptr(s16), _ptr(s32), _stream()),
+               "transform_quant")
+    return xq, s16, s32
+
+
+def quantize_rows(x: torch.Tensor, clip_max: float = 1.0, clip_min: float = 1.0, half_math: bool = True):
+    dev = _need_cuda(x)
+    k = x.shape[-1]
+    tokens = x.numel() // k
+    xq = torch.empty((tokens, k // 2), dtype=torch.uint8, device=dev)
+    s16 = torch.empty((tokens,), dtype=torch.float16, device=dev)
+    s32 = torch.empty((tokens,), dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().flatq_quantize_rows(_ptr(x), tokens, k, float(clip_max), float(clip_min), int(half_math),
+                                               _ptr(xq), _ptr(s16), _ptr(s32), _stream()), "quantize_rows")
+    return xq, s16, s32
+
+
+def linear_fused(x: torch.Tensor, left, right, n1: int, n2: int, clip_max: float, clip_min: float,
+                 w_packed: torch.Tensor, s_w: torch.Tensor, bias=None, out_dtype=torch.float16) -> torch.Tensor:
+    """The whole FlatLinear: transform -> per-token INT4 quant -> W4A4 GEMM -> dequant(+bias).
+
+    x fp16 [..., K]; w_packed u8 [N, K/2]; s_w fp32 [N]; returns [..., N]."""
+    dev = _need_cuda(x, left, right, w_packed, s_w, bias)
+    k = n1 * n2
+    if x.shape[-1] != k or w_packed.shape[1] * 2 != k:
+        raise RuntimeError(f"linear_fused: K mismatch (x {x.shape[-1]}, factors {n1}x{n2}, W {w_packed.shape[1] * 2})")
+    if x.dtype != torch.float16:
+        raise RuntimeError("linear_fused: activations must be float16")
+    if s_w.dtype != torch.float32:
+        raise RuntimeError("linear_fused: s_w must be float32")
+    m = x.numel() // k
+    n = w_packed.shape[0]
+    lib = _lib.load()
+    y = torch.empty(x.shape[:-1] + (n,), dtype=out_dtype, device=dev)
+    ws = _ws.get(dev, lib.flatq_linear_fused_workspace_bytes(m, k))
+    _lib.check(lib.flatq_linear_fused(_ptr(x), _ptr(left), _ptr(right), n1, n2, float(clip_max), float(clip_min),
+                                      _ptr(w_packed), _ptr(s_w), _ptr(bias), m, n, _ptr(y), _DT[out_dtype], _ptr(ws),
+                                      ws.numel(), _stream()), "linear_fused")
+    return y

@@ -1,0 +1,118 @@
+/* flatq_b200 -- C ABI of the B200 (sm_100a) FlatQuant W4A4 FlatLinear hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point
+ * cites the reference interface it replaces (paths relative to the FlatQuant repository).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; tensors are dense row-major
+ *   - `stream` is a cudaStream_t (0 = legacy default stream, which is what the reference uses:
+ *     deploy/kernels/quant.cu:62,97 and gemm.cu:41 launch on it)
+ *   - return value 0 on success, negative flatq_status on failure; flatq_last_error() returns a
+ *     thread-local message (the reference throws std::runtime_error: deploy/kernels/include/common.h:16-23;
+ *     the Python shim turns a non-zero status into RuntimeError, so callers see the same behaviour)
+ *   - nothing is allocated inside; outputs and workspaces are caller-owned
+ *     (the reference allocates outputs in its pybind layer, bindings.cpp:20,39,74 -- the Python shim does that)
+ *   - 4-bit storage: two's-complement nibbles, element 2j in bits [3:0] and 2j+1 in bits [7:4] of byte j
+ *     (deploy/functional/quantization.py:49-56, deploy/kernels/include/int4.h:86-98)
+ *   - thread safe: no mutable global state except the lazily resolved driver entry point
+ */
+#ifndef FLATQ_B200_H_
+#define FLATQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLATQ_ABI_VERSION 1
+
+typedef void* flatq_stream_t; /* cudaStream_t */
+
+enum flatq_status {
+    FLATQ_OK = 0,
+    FLATQ_ERR_INVALID = -1,     /* bad shape / alignment / null pointer        */
+    FLATQ_ERR_UNSUPPORTED = -2, /* shape outside what the kernels implement    */
+    FLATQ_ERR_CUDA = -3,        /* a CUDA runtime / driver call failed         */
+    FLATQ_ERR_WORKSPACE = -4    /* workspace too small                         */
+};
+
+enum flatq_dtype { FLATQ_F16 = 0, FLATQ_BF16 = 1, FLATQ_I32 = 2 };
+
+int flatq_abi_version(void);
+const char* flatq_last_error(void);
+/* 1 when the current device is compute capability 10.x (tcgen05 present), else 0 */
+int flatq_device_supported(void);
+
+/* ---- a8: nibble pack / unpack (deploy/functional/quantization.py:49-82) -------------------- */
+/* q: int8 [rows, cols] in [-8,7], cols % 16 == 0  ->  packed uint8 [rows, cols/2] */
+int flatq_pack_i4(const int8_t* q, uint8_t* packed, int64_t rows, int64_t cols, flatq_stream_t stream);
+/* packed uint8 [rows, cols_packed], cols_packed % 4 == 0  ->  int32 [rows, 2*cols_packed] */
+int flatq_unpack_i4(const uint8_t* packed, int32_t* out, int64_t rows, int64_t cols_packed, flatq_stream_t stream);
+
+/* ---- a10: deploy._CUDA.sym_quant -> sym_quant_host (deploy/kernels/include/quant.h:6-13,
+ *      quant.cu:13-63).  x fp16 [rows, cols], scale fp16 [rows] -> packed [rows, cols/2];
+ *      q = clamp(rn(half(x/scale)), -8, 7).  cols % 8 == 0. */
+int flatq_sym_quant(const void* x_f16, const void* scale_f16, int64_t rows, int64_t cols, uint8_t* q_packed,
+                    flatq_stream_t stream);
+
+/* ---- a12: deploy._CUDA.sym_dequant -> sym_dequant_host (quant.h:16-23, quant.cu:66-101) plus the
+ *      bias add of deploy/nn/linear.py:51-54.  acc int32 [rows, cols], scale_row fp16 [rows],
+ *      scale_col fp16 [cols], bias (out dtype, may be NULL) -> y [rows, cols].
+ *      mode 0: y = acc*s_row*s_col (+bias) in fp32, one rounding (exact form; matches the fake-quant oracle)
+ *      mode 1: bit-level emulation of the reference kernel (half(int(acc/10))*10 in half arithmetic; fp16 only) */
+int flatq_sym_dequant(const int32_t* acc, const void* scale_row_f16, const void* scale_col_f16, const void* bias,
+                      int64_t rows, int64_t cols, void* y, int out_dtype, int mode, flatq_stream_t stream);
+
+/* ---- a11: deploy._CUDA.matmul -> matmul_host (deploy/kernels/include/gemm.h:6-13, gemm.cu:7-46)
+ *      C int32 [M, N] = A[M, K] . B[N, K]^T, both packed 4-bit ([M, K/2], [N, K/2]); K % 64 == 0.
+ *      workspace: flatq_gemm_i4_workspace_bytes(M, K) bytes (int8 expansion of A). */
+size_t flatq_gemm_i4_workspace_bytes(int64_t M, int64_t K);
+int flatq_gemm_i4(const uint8_t* A_packed, const uint8_t* B_packed, int64_t M, int64_t N, int64_t K, int32_t* C,
+                  void* workspace, size_t workspace_bytes, flatq_stream_t stream);
+
+/* ---- a11 + a12 fused: deploy.nn.Linear4bit.forward (deploy/nn/linear.py:40-54) in one kernel.
+ *      y[M, N] = (A . B^T) * s_a[m] * s_b[n] (+ bias[n]);  scales fp16, y/bias out_dtype. */
+int flatq_linear4bit(const uint8_t* A_packed, const void* s_a_f16, const uint8_t* B_packed, const void* s_b_f16,
+                     const void* bias, int64_t M, int64_t N, int64_t K, void* y, int out_dtype, void* workspace,
+                     size_t workspace_bytes, flatq_stream_t stream);
+size_t flatq_linear4bit_workspace_bytes(int64_t M, int64_t N, int64_t K);
+
+/* ---- a2/a3: kronecker_matmul (flatquant/flat_utils.py:6-17) / *TransMatrix eval forward
+ *      (flatquant/trans_utils.py:21-25,97-101).  z[t] = L^T . reshape(x[t], n1, n2) . R, fp16.
+ *      left [n1,n1] or NULL (identity), right [n2,n2] or NULL; n2 % 16 == 0, n1,n2 <= 256. */
+int flatq_kron_transform(const void* x_f16, const void* left_f16, const void* right_f16, int64_t tokens, int n1,
+                         int n2, void* z_f16, flatq_stream_t stream);
+
+/* ---- a9: deploy.nn.OnlineTrans + Quantizer -> kron_matmul / block_matmul
+ *      (deploy/functional/online_trans.py:113-141, deploy/kernels/kron_matmul.py:192-266).
+ *      transform, per-token scale (clip factors are the *multiplicative* factors, i.e. already
+ *      sigmoid(clip_factor_a_*) or the clip ratio), quantise, pack.
+ *      outputs (each may be NULL): xq_packed [tokens, K/2], scales_f16 [tokens], scales_f32 [tokens]. */
+int flatq_transform_quant(const void* x_f16, const void* left_f16, const void* right_f16, int64_t tokens, int n1,
+                          int n2, float clip_max, float clip_min, uint8_t* xq_packed, void* scales_f16,
+                          float* scales_f32, flatq_stream_t stream);
+
+/* ---- a10 (fused form): deploy.nn.Quantizer.forward (deploy/nn/quantization.py:13-36): per-token
+ *      absmax scale + quantise + pack in one pass.  half_math != 0 reproduces the fp16 arithmetic of the
+ *      deploy path (fp16 scale, __hdiv); 0 uses the fp32 arithmetic of the fake-quant LAC path. */
+int flatq_quantize_rows(const void* x_f16, int64_t tokens, int64_t K, float clip_max, float clip_min, int half_math,
+                        uint8_t* xq_packed, void* scales_f16, float* scales_f32, flatq_stream_t stream);
+
+/* ---- the whole FlatLinear: a2+a4+a11+a12 (FlatQuantizedLinear eval forward after the caller's
+ *      qa_trans: flatquant/flat_linear.py:75-80 + trans_utils.py:97-101;
+ *      == OnlineTrans -> Quantizer -> Linear4bit of benchmarks/qlinear_benchmark.py:70-74).
+ *      x fp16 [M, K=n1*n2]; left/right may be NULL (no transform / single-sided);
+ *      w_packed [N, K/2]; s_w fp32 [N]; bias out_dtype [N] or NULL; y [M, N] out_dtype.
+ *      workspace >= flatq_linear_fused_workspace_bytes(M, K). */
+size_t flatq_linear_fused_workspace_bytes(int64_t M, int64_t K);
+int flatq_linear_fused(const void* x_f16, const void* left_f16, const void* right_f16, int n1, int n2,
+                       float clip_max, float clip_min, const uint8_t* w_packed, const float* s_w, const void* bias,
+                       int64_t M, int64_t N, void* y, int out_dtype, void* workspace, size_t workspace_bytes,
+                       flatq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLATQ_B200_H_ */
