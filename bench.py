@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Benchmark of the FlatQuant W4A4 FlatLinear hot path on B200.
+
+Workload (BASELINE.json configs[1], "qlinear_benchmark.py: all Llama-3-8B linear shapes, W4A4, seq=2048"):
+one STEP = one prefill pass of a 2048-token batch through all 224 FlatLinears of Llama-3-8B
+(32 layers x {q,k,v,o,gate,up,down}); per layer that is 4 transform+quantise launches (q/k/v and
+gate/up share one quantised activation, as the fused design intends) and 4 tcgen05 GEMM launches
+(qkv N=6144, o N=4096, gate_up N=28672, down K=14336->4096).  Every layer has its own random packed
+weights (3.5 GB in total, so consecutive GEMMs never find their weights in the 126 MB L2).  Synthetic
+activations; attention / SiLU between the linears are outside the hot path and are not run.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for the definition of every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HIDDEN, INTER, KV = 4096, 14336, 1024
+N_LAYERS, SEQ = 32, 2048
+# (name, K, N, (n1, n2)) -- fused column groups of one decoder layer
+LINEARS = [("qkv", HIDDEN, HIDDEN + 2 * KV, (64, 64)), ("o", HIDDEN, HIDDEN, (64, 64)),
+           ("gate_up", HIDDEN, 2 * INTER, (64, 64)), ("down", INTER, HIDDEN, (112, 128))]
+OPS_PER_TOKEN_LAYER = sum(2 * k * n for _, k, n, _ in LINEARS)  # GEMM ops only
+METRIC = "Llama-3-8B W4A4 prefill tokens/sec/GPU (FlatLinear path: 224 linears, seq 2048)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        # "under load": the upper half of the samples (idle samples at the edges pull the median down)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_layers(dev, n_layers, gen):
+    """Random packed INT4 weights, per-channel scales and Kronecker factors for every layer."""
+    layers = []
+    for _ in range(n_layers):
+        layer = {}
+        for name, k, n, (n1, n2) in LINEARS:
+            layer[name] = dict(
+                w=torch.randint(0, 256, (n, k // 2), dtype=torch.uint8, device=dev, generator=gen),
+                s_w=(torch.rand(n, device=dev, generator=gen) * 0.01 + 0.005),
+                left=(torch.randn(n1, n1, device=dev, generator=gen) / n1 ** 0.5).half(),
+                right=(torch.randn(n2, n2, device=dev, generator=gen) / n2 ** 0.5).half())
+        layers.append(layer)
+    return layers
+
+
+class Runner:
+    """Holds device buffers so the timed region allocates nothing."""
+
+    def __init__(self, dev, layers):
+        from flatquant_b200 import ops
+        self.ops, self.dev, self.layers = ops, dev, layers
+        self.cm = float(torch.sigmoid(torch.tensor(4.0)))
+        self.x = {k: torch.empty(SEQ, k, dtype=torch.float16, device=dev) for k in (HIDDEN, INTER)}
+        self.xq = {k: (torch.empty(SEQ, k, dtype=torch.int8, device=dev), torch.empty(SEQ, dtype=torch.float32, device=dev))
+                   for k in (HIDDEN, INTER)}
+        self.y = {name: torch.empty(SEQ, n, dtype=torch.float16, device=dev) for name, _, n, _ in LINEARS}
+        self.launches = 0
+
+    def set_input(self, x_hidden, x_inter):
+        self.x[HIDDEN].copy_(x_hidden, non_blocking=True)
+        self.x[INTER].copy_(x_inter, non_blocking=True)
+
+    def step(self):
+        ops, cm = self.ops, self.cm
+        for layer in self.layers:
+            for name, k, n, (n1, n2) in LINEARS:
+                p = layer[name]
+                ops.act_quant(self.x[k], p["left"], p["right"], n1, n2, cm, cm, out=self.xq[k])
+                ops.gemm_w4a8(self.xq[k][0], self.xq[k][1], p["w"], p["s_w"], out=self.y[name])
+                self.launches += 2
+        return self.y["down"]
+
+    def gemm_only(self):
+        for layer in self.layers:
+            for name, k, n, _ in LINEARS:
+                p = layer[name]
+                self.ops.gemm_w4a8(self.xq[k][0], self.xq[k][1], p["w"], p["s_w"], out=self.y[name])
+
+
+def timed(fn, steps, dist_barrier):
+    dist_barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    dist_barrier()
+    return e0.elapsed_time(e1)  # ms on the launching (current) stream
+
+
+def cpu_reference_pass(n_layers_sample, threads, reps, warm):
+    """The oracle's fake-quant path (the reference's own CPU arithmetic: trans -> fake-quant -> F.linear),
+    fp32, on the host cores.  Sample = `n_layers_sample` full decoder layers at seq 2048."""
+    from oracle import flatq_oracle as O
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    lin = []
+    for name, k, n, (n1, n2) in LINEARS:
+        codes = torch.randint(-8, 8, (n, k), generator=g).float()
+        lin.append((torch.randn(SEQ, k, generator=g), torch.randn(n1, n1, generator=g) / n1 ** 0.5,
+                    torch.randn(n2, n2, generator=g) / n2 ** 0.5, codes * 0.01))
+    def one():
+        for x, L, R, w in lin:
+            O.flat_linear_fake(x, L, R, 4.0, 4.0, w)
+    for _ in range(warm):
+        one()
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for _ in range(n_layers_sample):
+            one()
+        times.append((time.perf_counter() - t0) / n_layers_sample)
+    t_layer = statistics.mean(times)
+    return SEQ / (t_layer * N_LAYERS), t_layer
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=N_LAYERS, help="debug only: fewer layers => INVALID as a bench value")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    threads = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        # Tier rule: the reference arm = the reference's own CPU implementation of the path (oracle port of the
+        # fake-quant code; /root/reference is not on the GPU box) on all host threads.  Rank 0 only.
+        if rank != 0:
+            return
+        tok_s, t_layer = cpu_reference_pass(1, threads, max(1, args.steps), max(1, min(args.warmup, 1)))
+        line = {"impl": "reference", "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_layer * N_LAYERS * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": "llama3-8b FlatLinear prefill, seq 2048, 224 linears",
+                                                "note": "each step times 1 of 32 identical-shape layers and scales by 32"},
+                "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": threads, "kind": "port",
+                                 "sample": "1 decoder layer (7 linears) at seq 2048 per step, x32"},
+                "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        barrier = lambda: dist.barrier()  # noqa: E731
+    else:
+        dist, barrier = None, (lambda: None)
+
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    layers = make_layers(dev, args.layers, gen)
+    run = Runner(dev, layers)
+    hx = torch.randn(SEQ, HIDDEN, generator=torch.Generator().manual_seed(rank)).half().pin_memory()
+    hi = torch.randn(SEQ, INTER, generator=torch.Generator().manual_seed(rank + 1)).half().pin_memory()
+    hy = torch.empty(SEQ, HIDDEN, dtype=torch.float16).pin_memory()
+    run.set_input(hx, hi)
+
+    for _ in range(max(3, args.warmup)):
+        run.step()
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing (value)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    run.launches = 0
+    ms = timed(run.step, args.steps, barrier)
+    launches = run.launches
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end through the public API with host buffers (e2e): H2D inputs + D2H result every step
+    def e2e_step():
+        run.set_input(hx, hi)
+        y = run.step()
+        hy.copy_(y, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps, barrier)
+
+    # ---- roofline pass: the dominant kernel (tcgen05 GEMM) alone, same weights / shapes
+    ms_gemm = timed(run.gemm_only, args.steps, barrier)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e, ms_gemm], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, ms_gemm = t.tolist()
+
+    if rank == 0:
+        scale = N_LAYERS / args.layers
+        tok_s = world * SEQ * args.steps / (ms * 1e-3) / scale
+        tok_s_e2e = world * SEQ * args.steps / (ms_e2e * 1e-3) / scale
+        hbm, bf16, src = peaks()
+        peak_i8 = 2 * bf16  # kind::i8 issues at twice the bf16 rate (same as fp8); no faster exact-integer path exists
+        n_gemm = args.steps * args.layers * len(LINEARS)
+        ops_total = OPS_PER_TOKEN_LAYER * SEQ * args.layers * args.steps
+        achieved = ops_total / (ms_gemm * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "s4 x s4 -> s32 (int8 tensor-core path), f16 in/out",
+            "data": "synthetic",
+            "config": {"workload": "llama3-8b FlatLinear prefill: 32 layers x (qkv, o, gate_up, down) W4A4, seq 2048, bsz 1",
+                       "l2": "inputs larger than L2: 3.5 GB of distinct per-layer packed weights per step",
+                       "parallelism": f"dp{world} (independent replicas, no collective on the path)",
+                       "layers": args.layers},
+            "tops_gemm": OPS_PER_TOKEN_LAYER * SEQ * args.layers * args.steps / (ms * 1e-3) / 1e12,
+            "clocks": clocks,
+            "e2e": {"value": tok_s_e2e, "unit": "tokens/s",
+                    "h2d_bytes_per_step": hx.numel() * 2 + hi.numel() * 2, "d2h_bytes_per_step": hy.numel() * 2},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "gemm_w4a8_kernel (tcgen05.mma kind::i8)",
+                         "achieved": achieved, "peak": peak_i8, "unit": "TOP/s", "frac": achieved / peak_i8,
+                         "peak_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({src})",
+                         "avg_launch_us": ms_gemm * 1e3 / n_gemm, "launches": n_gemm, "traffic": None},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, t_layer = cpu_reference_pass(1, threads, 2, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
+                                    "sample": "oracle fake-quant path, 1 of 32 decoder layers (7 linears) at seq 2048, x32; 1 warm-up + 2 timed"}
+        if args.layers != N_LAYERS:
+            line["INVALID"] = "debug run with fewer layers"
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

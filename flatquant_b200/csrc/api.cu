@@ -369,33 +369,45 @@ size_t flatq_linear_fused_workspace_bytes(int64_t M, int64_t K) {
     return align_up((size_t)M * K, 256) + align_up((size_t)M * 4, 256);
 }
 
+int flatq_act_quant(const void* x, const void* left, const void* right, int n1, int n2, float clip_max, float clip_min,
+                    int64_t M, int8_t* xq8, float* s_x, flatq_stream_t stream) {
+    FLATQ_CHECK(x && xq8 && s_x, FLATQ_ERR_INVALID, "act_quant: null pointer");
+    FLATQ_CHECK(aligned16(xq8), FLATQ_ERR_INVALID, "act_quant: xq8 alignment");
+    const int64_t K = (int64_t)n1 * n2;
+    FLATQ_CHECK(K % 32 == 0, FLATQ_ERR_INVALID, "act_quant: K=%lld must be a multiple of 32", (long long)K);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!left && !right) return launch_rowquant(x, M, K, clip_max, clip_min, 0, nullptr, xq8, s_x, nullptr, st);
+    KronParams p = {};
+    p.x = reinterpret_cast<const __half*>(x);
+    p.left = reinterpret_cast<const __half*>(left);
+    p.right = reinterpret_cast<const __half*>(right);
+    p.tokens = (int)M; p.n1 = n1; p.n2 = n2;
+    p.do_quant = 1; p.c_max = clip_max; p.c_min = clip_min;
+    p.xq8 = xq8; p.sx_f32 = s_x;
+    return launch_kron(p, st);
+}
+
+int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed, const float* s_w, const void* bias,
+                    int64_t M, int64_t N, int64_t K, void* y, int out_dtype, flatq_stream_t stream) {
+    FLATQ_CHECK(xq8 && s_x && w_packed && s_w && y, FLATQ_ERR_INVALID, "gemm_w4a8: null pointer");
+    FLATQ_CHECK(out_dtype == FLATQ_F16 || out_dtype == FLATQ_BF16, FLATQ_ERR_INVALID, "gemm_w4a8: out_dtype");
+    FLATQ_CHECK(K % 64 == 0, FLATQ_ERR_INVALID, "gemm_w4a8: K=%lld must be a multiple of 64", (long long)K);
+    return launch_gemm(w_packed, xq8, M, N, K, 4, y, out_dtype == FLATQ_F16 ? kEpiF16 : kEpiBF16, s_x, s_w, bias,
+                       (cudaStream_t)stream);
+}
+
 int flatq_linear_fused(const void* x, const void* left, const void* right, int n1, int n2, float clip_max,
                        float clip_min, const uint8_t* w_packed, const float* s_w, const void* bias, int64_t M, int64_t N,
                        void* y, int out_dtype, void* ws, size_t ws_bytes, flatq_stream_t stream) {
     FLATQ_CHECK(x && w_packed && s_w && y && ws, FLATQ_ERR_INVALID, "linear_fused: null pointer");
-    FLATQ_CHECK(out_dtype == FLATQ_F16 || out_dtype == FLATQ_BF16, FLATQ_ERR_INVALID, "linear_fused: out_dtype");
     const int64_t K = (int64_t)n1 * n2;
-    FLATQ_CHECK(K % 64 == 0, FLATQ_ERR_INVALID, "linear_fused: K=%lld must be a multiple of 64", (long long)K);
     FLATQ_CHECK(ws_bytes >= flatq_linear_fused_workspace_bytes(M, K), FLATQ_ERR_WORKSPACE, "linear_fused: workspace too small");
     FLATQ_CHECK(aligned16(ws), FLATQ_ERR_INVALID, "linear_fused: workspace alignment");
-    cudaStream_t st = (cudaStream_t)stream;
     int8_t* x8 = reinterpret_cast<int8_t*>(ws);
     float* sx = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + align_up((size_t)M * K, 256));
-    int rc;
-    if (!left && !right) {
-        rc = launch_rowquant(x, M, K, clip_max, clip_min, 0, nullptr, x8, sx, nullptr, st);
-    } else {
-        KronParams p = {};
-        p.x = reinterpret_cast<const __half*>(x);
-        p.left = reinterpret_cast<const __half*>(left);
-        p.right = reinterpret_cast<const __half*>(right);
-        p.tokens = (int)M; p.n1 = n1; p.n2 = n2;
-        p.do_quant = 1; p.c_max = clip_max; p.c_min = clip_min;
-        p.xq8 = x8; p.sx_f32 = sx;
-        rc = launch_kron(p, st);
-    }
+    int rc = flatq_act_quant(x, left, right, n1, n2, clip_max, clip_min, M, x8, sx, stream);
     if (rc) return rc;
-    return launch_gemm(w_packed, x8, M, N, K, 4, y, out_dtype == FLATQ_F16 ? kEpiF16 : kEpiBF16, sx, s_w, bias, st);
+    return flatq_gemm_w4a8(x8, sx, w_packed, s_w, bias, M, N, K, y, out_dtype, stream);
 }
 
 }  // extern "C"

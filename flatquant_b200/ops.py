@@ -192,3 +192,28 @@ def linear_fused(x: torch.Tensor, left, right, n1: int, n2: int, clip_max: float
                                       _ptr(w_packed), _ptr(s_w), _ptr(bias), m, n, _ptr(y), _DT[out_dtype], _ptr(ws),
                                       ws.numel(), _stream()), "linear_fused")
     return y
+
+
+def act_quant(x: torch.Tensor, left, right, n1: int, n2: int, clip_max: float = 1.0, clip_min: float = 1.0, out=None):
+    """Transform + per-token quantise into the GEMM operand format: (xq8 int8 [M, K] opaque, s_x f32 [M])."""
+    dev = _need_cuda(x, left, right)
+    k = n1 * n2
+    m = x.numel() // k
+    if out is None:
+        out = (torch.empty((m, k), dtype=torch.int8, device=dev), torch.empty((m,), dtype=torch.float32, device=dev))
+    xq8, sx = out
+    _lib.check(_lib.load().flatq_act_quant(_ptr(x), _ptr(left), _ptr(right), n1, n2, float(clip_max), float(clip_min), m,
+                                           _ptr(xq8), _ptr(sx), _stream()), "act_quant")
+    return xq8, sx
+
+
+def gemm_w4a8(xq8: torch.Tensor, s_x: torch.Tensor, w_packed: torch.Tensor, s_w: torch.Tensor, bias=None,
+              out_dtype=torch.float16, out=None) -> torch.Tensor:
+    """y[M, N] = (xq8 . W^T) * s_x[m] * s_w[n] (+bias) on the tcgen05 kernel."""
+    dev = _need_cuda(xq8, s_x, w_packed, s_w, bias)
+    m, k = xq8.shape
+    n = w_packed.shape[0]
+    y = out if out is not None else torch.empty((m, n), dtype=out_dtype, device=dev)
+    _lib.check(_lib.load().flatq_gemm_w4a8(_ptr(xq8), _ptr(s_x), _ptr(w_packed), _ptr(s_w), _ptr(bias), m, n, k, _ptr(y),
+                                           _DT[out_dtype], _stream()), "gemm_w4a8")
+    return y

@@ -1,0 +1,117 @@
+"""CPU-only: the C-ABI library loads and exports every symbol the header declares; host-side logic."""
+import os
+import re
+import types
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from flatquant_b200 import _lib
+    return _lib
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "flatq_b200.h")).read()
+    declared = set(re.findall(r"\b(flatq_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no symbols parsed from the header"
+    l = lib.load()
+    for name in declared:
+        assert hasattr(l, name), f"{name} declared in flatq_b200.h but not exported"
+    assert declared == set(lib.SIGNATURES), "ctypes signatures out of sync with the header"
+    assert l.flatq_abi_version() == 1
+
+
+def test_no_gpu_calls_fail_loudly(lib):
+    from flatquant_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.pack_i4(torch.zeros((2, 16), dtype=torch.int8))
+    assert lib.load().flatq_device_supported() in (0, 1)
+
+
+def test_workspace_queries(lib):
+    l = lib.load()
+    assert l.flatq_linear_fused_workspace_bytes(2048, 4096) >= 2048 * 4096 + 2048 * 4
+    assert l.flatq_gemm_i4_workspace_bytes(7, 128) >= 7 * 128
+
+
+def test_decompose_dim_matches_golden(golden):
+    from flatquant_b200.function_utils import get_decompose_dim
+    g = golden("decompose_dim")
+    for n, d in zip(g["n"], g["dims"]):
+        assert get_decompose_dim(int(n)) == (int(d[0]), int(d[1]))
+
+
+def test_state_dict_contract():
+    """Buffer / parameter names are part of the checkpoint format (flat_utils.py:65-78)."""
+    from flatquant_b200.flat_linear import FlatQuantizedLinear
+    from flatquant_b200.trans_utils import InvDecomposeTransMatrix, SVDDecomposeTransMatrix, SVDSingleTransMatrix
+    tr = SVDDecomposeTransMatrix(4, 8, add_diag=True)
+    keys = set(tr.state_dict())
+    assert {"linear_diag_left", "linear_diag_right", "diag_scale"} <= keys
+    assert any(k.startswith("linear_u_left.parametrizations.weight") for k in keys)
+    tr.to_eval_mode()
+    assert set(tr.state_dict()) == {"diag_scale", "matrix_left", "matrix_right", "matrix_left_inv", "matrix_right_inv"}
+    s = SVDSingleTransMatrix(8)
+    s.to_eval_mode()
+    assert set(s.state_dict()) == {"matrix", "matrix_inv_t"}
+    inv = InvDecomposeTransMatrix(4, 8)
+    inv.to_eval_mode()
+    assert {"matrix_left", "matrix_right", "matrix_left_inv", "matrix_right_inv"} <= set(inv.state_dict())
+    args = types.SimpleNamespace(w_bits=4, a_bits=4, w_asym=False, a_asym=False, lac=True, lwc=True, a_groupsize=-1)
+    fl = FlatQuantizedLinear(args, torch.nn.Linear(32, 16))
+    assert {"linear.weight", "linear.bias", "clip_factor_w_max", "clip_factor_w_min",
+            "act_quantizer.clip_factor_a_max", "act_quantizer.clip_factor_a_min",
+            "weight_quantizer.maxq", "weight_quantizer.scale", "weight_quantizer.zero"} <= set(fl.state_dict())
+
+
+def test_host_modules_match_oracle_on_cpu(golden):
+    """Train-mode / offline torch paths of the mirrored modules reproduce the reference numerics."""
+    from oracle import flatq_oracle as O
+    from flatquant_b200.flat_linear import FlatQuantizedLinear
+    from flatquant_b200.quant_utils import ActivationQuantizer, WeightQuantizer
+    g = golden("act_quant")
+    x = torch.from_numpy(g["x"])
+    aq = ActivationQuantizer(bits=4, sym=True, lac=True)
+    with torch.no_grad():
+        aq.clip_factor_a_max.fill_(4.0)
+        aq.clip_factor_a_min.fill_(2.0)
+        assert torch.equal(aq(x), torch.from_numpy(g["lac_fq"]))
+        assert torch.equal(aq(x.half()), torch.from_numpy(g["lac_fq_h"]))
+    assert torch.equal(ActivationQuantizer(bits=4, sym=True, clip_ratio=0.9)(x), torch.from_numpy(g["ratio_fq"]))
+    gw = golden("weight_rtn")
+    wq = WeightQuantizer()
+    wq.configure(4, perchannel=True, sym=True, mse=False)
+    wq.find_params(torch.from_numpy(gw["w"]))
+    assert torch.equal(wq.scale, torch.from_numpy(gw["scale"]))
+    assert torch.equal(wq.quantize(torch.from_numpy(gw["w"])), torch.from_numpy(gw["w_fq"]))
+    # reparameterize with the list form (o_proj) against the golden
+    go = golden("flatlinear_oproj")
+    lin = torch.nn.Linear(go["w0"].shape[1], go["w0"].shape[0], bias=False)
+    lin.weight.data = torch.from_numpy(go["w0"]).clone()
+    args = types.SimpleNamespace(w_bits=4, a_bits=4, w_asym=False, a_asym=False, lac=True, lwc=True, a_groupsize=-1)
+    fl = FlatQuantizedLinear(args, lin)
+    with torch.no_grad():
+        fl.clip_factor_w_max.copy_(torch.from_numpy(go["cw_max"]))
+        fl.clip_factor_w_min.copy_(torch.from_numpy(go["cw_min"]))
+        fl.reparameterize(qa_trans=[torch.from_numpy(go["o_inv_t"]), torch.from_numpy(go["v_inv_t"])])
+    assert torch.allclose(lin.weight.data, torch.from_numpy(go["w_rep"]), atol=1e-6)
+    assert fl._eval_mode
+    with pytest.raises(RuntimeError):
+        fl(torch.zeros(2, go["w0"].shape[1]))  # eval forward is CUDA-only
+    # train-mode forward is plain torch and must equal the oracle's fake path
+    g2 = golden("flatlinear_256_svd")
+    lin2 = torch.nn.Linear(256, 64, bias=False)
+    lin2.weight.data = torch.from_numpy(g2["w_rep"]).clone()
+    args2 = types.SimpleNamespace(w_bits=4, a_bits=4, w_asym=False, a_asym=False, lac=True, lwc=False, a_groupsize=-1)
+    fl2 = FlatQuantizedLinear(args2, lin2)
+    with torch.no_grad():
+        y = fl2(torch.from_numpy(g2["z"]))
+    assert torch.allclose(y, torch.from_numpy(g2["y"]), atol=2e-5)
+    assert O.get_decompose_dim(256) == (16, 16)

@@ -1,0 +1,282 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures
+generated from the reference.  Bit-exact for pack/unpack indexing, codes given identical inputs, and
+int32 accumulators; fp16 tolerances are stated where used."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import flatq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from flatquant_b200 import ops as _ops
+    return _ops
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+# ------------------------------------------------------------------ a8: storage format, bit exact
+def test_pack_unpack_golden(ops, dev, golden):
+    g = golden("pack_i4")
+    assert np.array_equal(ops.pack_i4(T(g["q"]).to(dev)).cpu().numpy(), g["packed"])
+    assert np.array_equal(ops.unpack_i4(T(g["packed"]).to(dev)).cpu().numpy(), g["unpacked"])
+
+
+def test_pack_unpack_roundtrip_large(ops, dev):
+    q = torch.randint(-8, 8, (2048, 4096), dtype=torch.int8, device=dev)
+    p = ops.pack_i4(q)
+    assert torch.equal(ops.unpack_i4(p), q.int())
+    assert np.array_equal(p[:64].cpu().numpy(), O.pack_i4(q[:64].cpu().numpy()))
+
+
+# ------------------------------------------------------------------ a10 / a12
+def test_sym_quant_golden_and_oracle(ops, dev, golden):
+    g = golden("sym_quant_half")
+    got = ops.unpack_i4(ops.sym_quant(T(g["x"]).to(dev), T(g["scale"]).reshape(-1).to(dev))).cpu().numpy()
+    assert np.array_equal(got, g["q"].astype(np.int32))
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((257, 1024)) * 5).astype(np.float16)
+    s = (np.abs(x).max(1) / 7).astype(np.float16)
+    got = ops.sym_quant(T(x).to(dev), T(s).to(dev)).cpu().numpy()
+    assert np.array_equal(got, O.pack_i4(O.sym_quant_half(x, s)))
+
+
+def test_sym_dequant_modes(ops, dev):
+    rng = np.random.default_rng(1)
+    acc = rng.integers(-900000, 900000, (96, 256)).astype(np.int32)
+    sr = rng.random(96).astype(np.float16)
+    sc = (rng.random(256) * 0.01).astype(np.float16)
+    y = ops.sym_dequant(T(acc).to(dev), T(sr).to(dev), T(sc).to(dev)).cpu().numpy()
+    assert np.array_equal(y, O.sym_dequant(acc, sr, sc).astype(np.float16))
+    yk = ops.sym_dequant(T(acc).to(dev), T(sr).to(dev), T(sc).to(dev), ref_kernel_arith=True).cpu().numpy()
+    assert np.array_equal(yk, O.sym_dequant_ref_kernel(acc, sr, sc))
+
+
+# ------------------------------------------------------------------ a11: INT4 x INT4 -> INT32, bit exact
+@pytest.mark.parametrize("m,n,k", [(1, 128, 64), (16, 128, 128), (100, 200, 192), (128, 256, 4096),
+                                   (33, 1024, 14336), (2048, 4096, 4096), (300, 6144, 4096)])
+def test_gemm_i4_exact(ops, dev, m, n, k):
+    rng = np.random.default_rng(m * 7 + n)
+    a = rng.integers(-8, 8, (m, k)).astype(np.int8)
+    b = rng.integers(-8, 8, (n, k)).astype(np.int8)
+    a[0, :] = -8
+    b[0, :] = -8  # extreme accumulator: 64*K
+    c = ops.gemm_i4(T(O.pack_i4(a)).to(dev), T(O.pack_i4(b)).to(dev)).cpu().numpy()
+    assert np.array_equal(c, O.gemm_i4(a, b))
+
+
+def test_linear4bit_matches_exact_dequant(ops, dev):
+    rng = np.random.default_rng(5)
+    m, n, k = 77, 384, 512
+    a = rng.integers(-8, 8, (m, k)).astype(np.int8)
+    b = rng.integers(-8, 8, (n, k)).astype(np.int8)
+    sa = rng.random(m).astype(np.float16)
+    sb = (rng.random(n) * 0.02).astype(np.float16)
+    bias = rng.standard_normal(n).astype(np.float16)
+    y = ops.linear4bit(T(O.pack_i4(a)).to(dev), T(sa).to(dev), T(O.pack_i4(b)).to(dev), T(sb).to(dev), T(bias).to(dev))
+    ref = O.sym_dequant(O.gemm_i4(a, b), sa, sb, bias).astype(np.float16)
+    assert np.array_equal(y.cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------ a2 / a3: online transform
+@pytest.mark.parametrize("dims", ["16x16", "14x16", "64x64"])
+def test_kron_transform_golden(ops, dev, golden, dims):
+    g = golden(f"kron_{dims}")
+    n1, n2 = g["left"].shape[0], g["right"].shape[0]
+    x = T(g["x"]).half()
+    L, R = T(g["left"]).half(), T(g["right"]).half()
+    z = ops.kron_transform(x.to(dev), L.to(dev), R.to(dev), n1, n2).float().cpu()
+    ref = O.kronecker_matmul(x.float(), L.float(), R.float())  # same fp16-rounded inputs, fp32 math
+    # tolerance: two fp16 roundings (intermediate + output) of values up to max|z|
+    tol = 3 * 2.0 ** -11 * float(ref.abs().max()) * (n1 ** 0.5)
+    assert (z - ref).abs().max() <= tol
+
+
+@pytest.mark.parametrize("n1,n2", [(64, 64), (112, 128), (86, 128), (56, 64), (32, 48), (128, 224), (8, 16)])
+def test_transform_quant_codes(ops, dev, n1, n2):
+    torch.manual_seed(n1 * 1000 + n2)
+    tokens, k = 37, n1 * n2
+    x = torch.randn(tokens, k).half()
+    x[3] = 0  # all-zero token: scale must be 1, codes 0
+    L = (torch.randn(n1, n1) / n1 ** 0.5).half()
+    R = (torch.randn(n2, n2) / n2 ** 0.5).half()
+    cmax, cmin = 0.982, 0.95
+    xq, s16, s32 = ops.transform_quant(x.to(dev), L.to(dev), R.to(dev), n1, n2, cmax, cmin)
+    codes = O.unpack_i4(xq.cpu().numpy())
+    # (1) quantiser is bit exact given the kernel's own fp16 transform output
+    zk = ops.kron_transform(x.to(dev), L.to(dev), R.to(dev), n1, n2).cpu().float()
+    hi = zk.amax(1).clamp(min=0) * torch.tensor(cmax)
+    lo = zk.amin(1).clamp(max=0) * torch.tensor(cmin)
+    m = torch.maximum(lo.abs(), hi)
+    s_ref = torch.where(m == 0, torch.ones_like(m), m / 7)
+    assert torch.equal(s32.cpu(), s_ref)
+    assert torch.equal(s16.cpu(), s_ref.half())
+    q_ref = torch.clamp(torch.round(zk / s_ref[:, None]), -8, 7).numpy().astype(np.int32)
+    assert np.array_equal(codes, q_ref)
+    assert s32[3].item() == 1.0 and not codes[3].any()
+    # (2) against the pure fp32 oracle: codes agree except for +-1 flips at rounding boundaries
+    z32 = O.kronecker_matmul(x.float(), L.float(), R.float())
+    hi, lo = z32.amax(1).clamp(min=0) * cmax, z32.amin(1).clamp(max=0) * cmin
+    m = torch.maximum(lo.abs(), hi)
+    so = torch.where(m == 0, torch.ones_like(m), m / 7)
+    qo = torch.clamp(torch.round(z32 / so[:, None]), -8, 7).numpy().astype(np.int32)
+    diff = np.abs(codes - qo)
+    assert diff.max() <= 1
+    assert (diff != 0).mean() < 0.02
+    assert torch.allclose(s32.cpu(), so, rtol=2e-3)
+
+
+def test_quantize_rows_deploy_semantics(ops, dev):
+    """deploy.nn.Quantizer: fp16 scale = max|x|/7, codes = sym_quant(x, scale)."""
+    torch.manual_seed(3)
+    x = (torch.randn(65, 4096) * 2).half()
+    xq, s16, _ = ops.quantize_rows(x.to(dev), 1.0, 1.0, half_math=True)
+    s_ref = (x.abs().amax(1).float() / 7).half()
+    assert torch.equal(s16.cpu(), s_ref)
+    assert np.array_equal(xq.cpu().numpy(), O.pack_i4(O.sym_quant_half(x.numpy(), s_ref.numpy())))
+
+
+# ------------------------------------------------------------------ the whole path vs the golden fixtures
+@pytest.mark.parametrize("case", ["flatlinear_256_svd", "flatlinear_224_inv_bias", "flatlinear_4096_svd"])
+def test_fused_linear_golden(ops, dev, golden, case):
+    g = golden(case)
+    n1, n2 = g["left"].shape[0], g["right"].shape[0]
+    x = T(g["x"]).half().reshape(-1, n1 * n2)
+    L, R = T(g["left"]).half(), T(g["right"]).half()
+    cmax = float(torch.sigmoid(torch.tensor(float(g["ca_max"]))))
+    cmin = float(torch.sigmoid(torch.tensor(float(g["ca_min"]))))
+    bias = T(g["bias"]).half().to(dev) if g["bias"].size else None
+    y = ops.linear_fused(x.to(dev), L.to(dev), R.to(dev), n1, n2, cmax, cmin, T(g["w_packed"]).to(dev),
+                         T(g["s_w"]).reshape(-1).float().to(dev), bias).float().cpu().numpy()
+    y_ref = g["y"].reshape(y.shape)  # the reference's fake-quant output (fp32 CPU)
+    # fp16 tolerance (north star): inputs/factors rounded to fp16 and an fp16 transform move a few codes by one
+    # step; each flip changes y by <= s_x*s_w*|w|.  Stated bound: 3% of max|y| worst case, 0.5% on average.
+    err = np.abs(y - y_ref)
+    assert err.max() <= 0.03 * np.abs(y_ref).max()
+    assert err.mean() <= 0.005 * np.abs(y_ref).max()
+    # tight check: oracle evaluated on the same fp16-rounded inputs with the kernel's own codes is exact to fp16
+    xq, _, s32 = ops.transform_quant(x.to(dev), L.to(dev), R.to(dev), n1, n2, cmax, cmin)
+    acc = O.gemm_i4(O.unpack_i4(xq.cpu().numpy()), g["w_codes"])
+    y2 = O.sym_dequant(acc, s32.cpu().numpy(), g["s_w"].reshape(-1), g["bias"] if g["bias"].size else None)
+    assert np.array_equal(y.astype(np.float16), y2.astype(np.float16))
+
+
+def test_fused_linear_full_size_consistency(ops, dev):
+    """BASELINE size (2048, 4096 -> 4096): fused output == oracle arithmetic on the kernel's own codes for
+    sampled rows, and linear in the weight scale."""
+    torch.manual_seed(11)
+    m, n, n1, n2 = 2048, 4096, 64, 64
+    k = n1 * n2
+    x = torch.randn(m, k, device=dev).half()
+    L = (torch.randn(n1, n1, device=dev) / 8).half()
+    R = (torch.randn(n2, n2, device=dev) / 8).half()
+    wq = torch.randint(-8, 8, (n, k), dtype=torch.int8, device=dev)
+    wp = ops.pack_i4(wq)
+    s_w = torch.rand(n, device=dev) * 0.02 + 0.01
+    y = ops.linear_fused(x, L, R, n1, n2, 0.98, 0.98, wp, s_w)
+    y2 = ops.linear_fused(x, L, R, n1, n2, 0.98, 0.98, wp, s_w * 2)
+    assert torch.equal((y.float() * 2).half(), y2)  # power-of-two scaling is exact
+    xq, _, s32 = ops.transform_quant(x, L, R, n1, n2, 0.98, 0.98)
+    rows = torch.tensor([0, 1, 127, 128, 1000, 2047])
+    codes = O.unpack_i4(xq[rows.to(dev)].cpu().numpy())
+    acc = O.gemm_i4(codes, wq.cpu().numpy())
+    ref = O.sym_dequant(acc, s32[rows.to(dev)].cpu().numpy(), s_w.cpu().numpy()).astype(np.float16)
+    assert np.array_equal(y[rows.to(dev)].cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------ reference operator API (drop-in)
+def _args():
+    import types
+    return types.SimpleNamespace(w_bits=4, a_bits=4, w_asym=False, a_asym=False, lac=True, lwc=True, a_groupsize=-1)
+
+
+def test_flat_quantized_linear_dropin(dev, golden):
+    """The reference call pattern: to_eval_mode -> reparameterize(qa_trans) -> RTN -> fl(trans(x))."""
+    from flatquant_b200.flat_linear import FlatQuantizedLinear
+    from flatquant_b200.quant_utils import WeightQuantizer
+    from flatquant_b200.trans_utils import SVDDecomposeTransMatrix
+    g = golden("flatlinear_256_svd")
+    n1, n2 = g["left"].shape[0], g["right"].shape[0]
+    n = g["w0"].shape[0]
+    lin = torch.nn.Linear(n1 * n2, n, bias=False)
+    lin.weight.data = T(g["w0"]).clone()
+    tr = SVDDecomposeTransMatrix(n1, n2, add_diag=True)
+    tr.to_eval_mode()
+    for name in ("left", "right", "left_inv", "right_inv"):
+        getattr(tr, f"matrix_{name}").data = T(g[name]).clone()
+    tr.use_diag = False
+    fl = FlatQuantizedLinear(_args(), lin)
+    with torch.no_grad():
+        fl.act_quantizer.clip_factor_a_max.fill_(float(g["ca_max"]))
+        fl.act_quantizer.clip_factor_a_min.fill_(float(g["ca_min"]))
+        fl.clip_factor_w_max.copy_(T(g["cw_max"]))
+        fl.clip_factor_w_min.copy_(T(g["cw_min"]))
+        fl.reparameterize(qa_trans=tr)
+        assert torch.allclose(lin.weight.data, T(g["w_rep"]), atol=1e-6)
+        wq = WeightQuantizer()
+        wq.configure(4, perchannel=True, sym=True, mse=False)
+        wq.find_params(lin.weight.data)
+        lin.weight.data = wq.quantize(lin.weight.data)
+        assert torch.equal(wq.scale.reshape(-1, 1), T(g["s_w"]))
+        fl, tr = fl.to(dev).half(), tr.to(dev)
+        x = T(g["x"]).half().to(dev)
+        y = fl(tr(x))  # transform kernel, then quant+GEMM+dequant kernel chain
+        y_f = fl.forward_fused(x, tr)  # one library call
+    y_ref = g["y"]
+    for out in (y, y_f):
+        err = np.abs(out.float().cpu().numpy() - y_ref)
+        assert err.max() <= 0.03 * np.abs(y_ref).max() and err.mean() <= 0.005 * np.abs(y_ref).max()
+    with pytest.raises(RuntimeError):
+        fl(T(g["x"]).half())  # CPU activations: no fallback
+
+
+def test_deploy_api_chain(dev):
+    """benchmarks/qlinear_benchmark.py:70-74: Sequential(OnlineTrans('matmul'), Quantizer, Linear4bit)."""
+    from flatquant_b200 import deploy
+    from flatquant_b200.deploy.nn import Linear4bit, OnlineTrans, Quantizer
+    torch.manual_seed(0)
+    k, n, bsz, seq = 4096, 512, 2, 24
+    base = torch.nn.Linear(k, n, bias=False).half()
+    base.weight.data = torch.randint(-8, 7, (n, k)).half()
+    s_w = torch.ones((n, 1), dtype=torch.float16)
+    mod = torch.nn.Sequential(OnlineTrans(k, trans="matmul"), Quantizer(input_clip_ratio=1.0),
+                              Linear4bit.from_float(base, weight_scales=s_w)).to(dev)
+    ot = mod[0]
+    ot.left_matrix.data = (torch.randn(64, 64) / 8).half().to(dev)
+    ot.right_matrix.data = (torch.randn(64, 64) / 8).half().to(dev)
+    x = torch.rand(bsz, seq, k).half()
+    y = mod(x.to(dev))
+    assert y.shape == (bsz * seq, n) and y.dtype == torch.float16
+    packed = ot(x.to(dev))
+    assert isinstance(packed, deploy.PackedQuantizedTensor) and packed.quantized_x.shape == (bsz * seq, k // 2)
+    codes = O.unpack_i4(packed.quantized_x.cpu().numpy())
+    acc = O.gemm_i4(codes, base.weight.data.float().numpy())
+    ref = O.sym_dequant(acc, packed.scales_x.float().cpu().numpy().reshape(-1), np.ones(n, np.float32)).astype(np.float16)
+    assert np.array_equal(y.cpu().numpy(), ref)
+    # int-only chain of the reference API
+    acc_gpu = deploy.matmul(packed.quantized_x, mod[2].weight)
+    assert np.array_equal(acc_gpu.cpu().numpy(), acc)
+    y2 = deploy.sym_dequant(acc_gpu, packed.scales_x, mod[2].weight_scales)
+    assert np.array_equal(y2.cpu().numpy(), ref)
+
+
+def test_error_behaviour(ops, dev):
+    a = torch.zeros((4, 24), dtype=torch.uint8, device=dev)  # K = 48: not a multiple of 64
+    with pytest.raises(RuntimeError):
+        ops.gemm_i4(a, a)
+    with pytest.raises(RuntimeError):
+        ops.pack_i4(torch.zeros((2, 16), dtype=torch.int8))  # CPU tensor
+    with pytest.raises(RuntimeError):
+        ops.kron_transform(torch.zeros((2, 15 * 24), dtype=torch.float16, device=dev),
+                           torch.zeros((15, 15), dtype=torch.float16, device=dev),
+                           torch.zeros((24, 24), dtype=torch.float16, device=dev), 15, 24)  # n2 % 16 != 0
