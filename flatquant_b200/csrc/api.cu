@@ -140,7 +140,7 @@ int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, i
     if (rc) return rc;
     GemmParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = acc_shift;
-    p.out = out; p.s_x = sx; p.s_w = sw; p.bias = bias;
+    p.out = out; p.s_x = sx; p.s_w = sw; p.bias = bias; p.prof = nullptr; p.dbg = 0;
     switch (mode) {
         case kEpiI32: return launch_gemm_m<kEpiI32>(tn, tw, tx, p, st);
         case kEpiF16: return launch_gemm_m<kEpiF16>(tn, tw, tx, p, st);
@@ -184,7 +184,8 @@ int launch_kron(KronParams p, cudaStream_t st) {
     FLATQ_CHECK(smem <= 227 * 1024, FLATQ_ERR_UNSUPPORTED, "Kronecker factors (%d, %d) exceed shared memory", p.n1, p.n2);
     const int threads = tpc * wpt * 32;
     int64_t ctas = (p.tokens + tpc - 1) / tpc;
-    const int64_t cap = (int64_t)num_sms() * (smem > 100 * 1024 ? 1 : 2);
+    const int64_t per_sm = (int64_t)(220 * 1024 / (smem + 1024));
+    const int64_t cap = (int64_t)num_sms() * (per_sm < 1 ? 1 : per_sm > 4 ? 4 : per_sm);
     const int grid = (int)(ctas < cap ? ctas : cap);
     switch (kt2) {
 #define FLATQ_KRON_CASE(n) case n: return launch_kron_t<n>(p, threads, smem, grid, st);
@@ -408,6 +409,29 @@ int flatq_linear_fused(const void* x, const void* left, const void* right, int n
     int rc = flatq_act_quant(x, left, right, n1, n2, clip_max, clip_min, M, x8, sx, stream);
     if (rc) return rc;
     return flatq_gemm_w4a8(x8, sx, w_packed, s_w, bias, M, N, K, y, out_dtype, stream);
+}
+
+
+// Debug only (not part of the public header): role-level cycle counters of the GEMM, TN=128 fp16 epilogue.
+// prof: int64 [grid, 14 warps, 5]
+int flatq_debug_gemm_profile(const int8_t* xq8, const float* s_x, const uint8_t* w_packed, const float* s_w, int64_t M,
+                             int64_t N, int64_t K, void* y, long long* prof, int dbg, flatq_stream_t stream) {
+    CUtensorMap tw, tx;
+    int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    rc = make_map_u8(&tx, xq8, M, K, K, kGemmBlockK, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    GemmParams p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = 4;
+    p.out = y; p.s_x = s_x; p.s_w = s_w; p.bias = nullptr; p.prof = prof; p.dbg = dbg;
+    auto kern = gemm_w4a8_kernel<128, kEpiF16, true>;
+    constexpr int smem = GemmSmem<128>::kBytes;
+    FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int tiles = (int)(((N + 127) / 128) * ((M + 127) / 128));
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(tw, tx, p);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
 }
 
 }  // extern "C"

@@ -107,8 +107,8 @@ __global__ void sym_dequant_kernel(const int32_t* __restrict__ acc, const __half
                 const __half y = __hmul(__hmul(__hmul(s_row[row], s_col[col + j]), xe), __float2half(10.0f));
                 o[j] = static_cast<OutT>(__half2float(y));
             } else {
-                float y = (float)av[j] * __half2float(s_row[row]) * __half2float(s_col[col + j]);
-                if (bias) y += static_cast<float>(bias[col + j]);
+                float y = __fmul_rn(__fmul_rn((float)av[j], __half2float(s_row[row])), __half2float(s_col[col + j]));
+                if (bias) y = __fadd_rn(y, static_cast<float>(bias[col + j]));
                 o[j] = static_cast<OutT>(y);
             }
         }

@@ -27,6 +27,17 @@
 
 namespace flatq {
 
+#define FLATQ_TWAIT(slot, stmt)                          \
+    do {                                                \
+        if (PROF) {                                     \
+            const long long t0_ = clock64();            \
+            stmt;                                       \
+            tacc[slot] += clock64() - t0_;              \
+        } else {                                        \
+            stmt;                                       \
+        }                                               \
+    } while (0)
+
 constexpr int kGemmBlockW = 128;   // weight rows per tile
 constexpr int kGemmBlockK = 128;   // K elements per stage
 constexpr int kGemmThreads = 14 * 32;
@@ -45,6 +56,8 @@ struct GemmParams {
     const float* s_x;     // [M]  per-token scale   (dequant modes)
     const float* s_w;     // [N]  per-channel scale (dequant modes)
     const void* bias;     // [N] same dtype as out, or nullptr
+    long long* prof;      // debug: per-CTA role timers (PROF instantiation only)
+    int dbg;              // debug (PROF only): 1 skip TMEM stores, 2 skip MMA issue, 4 skip epilogue math/stores
 };
 
 template <int TN>
@@ -53,7 +66,7 @@ struct GemmSmem {
     static constexpr int kBytes = kStagesX * kXStageBytes + kStagesW * kWStageBytes + 1024 /*align*/ + 512 /*bars*/;
 };
 
-template <int TN, int MODE>
+template <int TN, int MODE, bool PROF = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                  const GemmParams p) {
@@ -76,6 +89,8 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    long long tacc[4] = {0, 0, 0, 0};
+    const long long t_begin = PROF ? clock64() : 0;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStagesX; ++i) { mbar_init(&full_x[i], 1); mbar_init(&empty_x[i], 1); }
@@ -105,11 +120,11 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 const int m0 = (tile / nb_w) * TN;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t sx = it % kStagesX, phx = (it / kStagesX) & 1;
-                    mbar_wait(&empty_x[sx], phx ^ 1);
+                    FLATQ_TWAIT(0, mbar_wait(&empty_x[sx], phx ^ 1));
                     mbar_arrive_expect_tx(&full_x[sx], XB);
                     tma_load_2d(xs + sx * XB, &tm_x, &full_x[sx], kb * kGemmBlockK, m0);
                     const uint32_t sw = it % kStagesW, phw = (it / kStagesW) & 1;
-                    mbar_wait(&empty_w[sw], phw ^ 1);
+                    FLATQ_TWAIT(1, mbar_wait(&empty_w[sw], phw ^ 1));
                     mbar_arrive_expect_tx(&full_w[sw], kWStageBytes);
                     tma_load_2d(ws + sw * kWStageBytes, &tm_w, &full_w[sw], kb * (kGemmBlockK / 2), n0);
                 }
@@ -121,19 +136,20 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         uint32_t it = 0, tile_iter = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
             const uint32_t b = tile_iter & 1, phb = (tile_iter >> 1) & 1;
-            mbar_wait(&empty_acc[b], phb ^ 1);
+            FLATQ_TWAIT(2, mbar_wait(&empty_acc[b], phb ^ 1));
             tc_fence_after();
             const uint32_t d_tmem = tmem + b * 128;
             for (int kb = 0; kb < KB; ++kb, ++it) {
                 const uint32_t sx = it % kStagesX, phx = (it / kStagesX) & 1;
                 const uint32_t sa = it % kStagesA, pha = (it / kStagesA) & 1;
-                mbar_wait(&full_x[sx], phx);
-                mbar_wait(&full_a[sa], pha);
+                FLATQ_TWAIT(0, mbar_wait(&full_x[sx], phx));
+                FLATQ_TWAIT(1, mbar_wait(&full_a[sa], pha));
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t xaddr = smem_u32(xs + sx * XB);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
+                        if (PROF && (p.dbg & 2)) break;
                         const uint64_t bdesc = make_smem_desc_kmajor(xaddr + kk * 32, 1024, kLayoutSw128);
                         mma_i8_ts(d_tmem, tmem + kTmemColsA0 + sa * 32 + kk * 8, bdesc, idesc, (kb | kk) != 0);
                     }
@@ -158,7 +174,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 if ((it & 1) != (uint32_t)grp) continue;
                 const uint32_t sw = it % kStagesW, phw = (it / kStagesW) & 1;
                 const uint32_t sa = it % kStagesA, pha = (it / kStagesA) & 1;
-                mbar_wait(&full_w[sw], phw);
+                FLATQ_TWAIT(0, mbar_wait(&full_w[sw], phw));
                 uint32_t a[32];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -172,12 +188,14 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_w[sw]);
-                mbar_wait(&empty_a[sa], pha ^ 1);
+                FLATQ_TWAIT(1, mbar_wait(&empty_a[sa], pha ^ 1));
                 tc_fence_after();
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + kTmemColsA0 + sa * 32;
-                tmem_st_x16(taddr, *reinterpret_cast<const uint32_t(*)[16]>(&a[0]));
-                tmem_st_x16(taddr + 16, *reinterpret_cast<const uint32_t(*)[16]>(&a[16]));
-                tmem_st_wait();
+                if (!(PROF && (p.dbg & 1))) FLATQ_TWAIT(2, {
+                    tmem_st_x16(taddr, *reinterpret_cast<const uint32_t(*)[16]>(&a[0]));
+                    tmem_st_x16(taddr + 16, *reinterpret_cast<const uint32_t(*)[16]>(&a[16]));
+                    tmem_st_wait();
+                });
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_a[sa]);
@@ -202,10 +220,12 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                                              : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
                 }
             }
-            mbar_wait(&full_acc[b], phb);
+            FLATQ_TWAIT(0, mbar_wait(&full_acc[b], phb));
             tc_fence_after();
+            const long long t_epi0 = PROF ? clock64() : 0;
 #pragma unroll 1
             for (int c = 0; c < TN / CH; ++c) {
+                if (PROF && (p.dbg & 4)) break;
                 uint32_t r[32];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + b * 128 + c * CH;
                 if (CH == 32) {
@@ -223,7 +243,8 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                         if (MODE == kEpiI32) {
                             reinterpret_cast<int32_t*>(p.out)[o] = acc;
                         } else {
-                            const float y = (float)acc * __ldg(&p.s_x[m]) * sw_n + bias_n;
+                            // explicit _rn ops: no FMA contraction, so the result equals the oracle's fp32 arithmetic bit for bit
+                            const float y = __fadd_rn(__fmul_rn(__fmul_rn((float)acc, __ldg(&p.s_x[m])), sw_n), bias_n);
                             if (MODE == kEpiF16) reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(y);
                             else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(y);
                         }
@@ -232,9 +253,14 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             }
             tc_fence_before();
             mbar_arrive(&empty_acc[b]);
+            if (PROF) tacc[1] += clock64() - t_epi0;
         }
     }
 
+    if (PROF && lane == 0 && p.prof) {
+        long long* o = p.prof + ((size_t)blockIdx.x * 14 + warp) * 5;
+        o[0] = tacc[0]; o[1] = tacc[1]; o[2] = tacc[2]; o[3] = tacc[3]; o[4] = clock64() - t_begin;
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
