@@ -16,12 +16,19 @@
 //     ([0,2,4,6,1,3,5,7]); the activation operand is stored with the same permutation, so the
 //     contraction is unchanged.  The factor 16 (or 256 when X is expanded the same way) is
 //     removed exactly by an arithmetic shift of the int32 accumulator.
-//   * Packed W tiles (128 rows x 64 B, SWIZZLE_64B) and int8 X tiles (TN rows x 128 B,
-//     SWIZZLE_128B) arrive by TMA into mbarrier-tracked rings.
+//   * One pipeline stage = 256 K-elements: packed W tile 128 rows x 128 B (SWIZZLE_128B), int8 X
+//     tile = two TMA boxes of TN rows x 128 B (SWIZZLE_128B), A operand = 64 TMEM columns.
+//     Eight MMAs (512 tensor-pipe cycles at TN=128) are issued per stage behind ONE mbarrier wait
+//     and ONE tcgen05.commit: the issuing thread's loop overhead was the limiter with 128-wide
+//     stages and separate X / A barriers (profiles/r01_gemm_role_timers_v1.log).
 //
-// Warp roles (14 warps, persistent over output tiles):
-//   warp 0      TMA producer           warp 1       MMA issuer (+ TMEM alloc/dealloc)
-//   warps 2-9   nibble expanders (2 groups x 4 lane-quadrants)   warps 10-13  epilogue
+// Warp roles (19 warps, persistent over output tiles):
+//   warp 0  X TMA producer     warp 1  MMA issuer (+ TMEM alloc)     warp 2  W TMA producer
+//   warps 3-10  nibble expanders (2 groups x 4 lane-quadrants; a group takes every other stage)
+//   warps 11-18 epilogue (2 per lane-quadrant, each half of the token columns)
+//
+// Barriers per stage s:  full[s]  <- X bytes (expect_tx) + 4 expander warps;   empty[s] <- tcgen05.commit
+//                        wfull[s] <- W bytes;                                  wempty[s] <- 4 expander warps
 #pragma once
 #include "ptx.cuh"
 
@@ -39,13 +46,13 @@ namespace flatq {
     } while (0)
 
 constexpr int kGemmBlockW = 128;   // weight rows per tile
-constexpr int kGemmBlockK = 128;   // K elements per stage
-constexpr int kGemmThreads = 14 * 32;
-constexpr int kStagesX = 6;
-constexpr int kStagesW = 6;
-constexpr int kStagesA = 8;        // TMEM A-operand stages, 32 columns each
+constexpr int kGemmBlockK = 256;   // K elements per stage
+constexpr int kGemmWarps = 19;
+constexpr int kGemmThreads = kGemmWarps * 32;
+constexpr int kStages = 4;         // X smem ring == TMEM A ring (64 columns per stage)
+constexpr int kStagesW = 4;        // packed-W smem ring
 constexpr int kTmemColsA0 = 256;   // accumulators at columns [0,128) and [128,256)
-constexpr int kWStageBytes = kGemmBlockW * (kGemmBlockK / 2);
+constexpr int kWStageBytes = kGemmBlockW * (kGemmBlockK / 2);  // 16 KB
 
 enum EpilogueMode : int { kEpiI32 = 0, kEpiF16 = 1, kEpiBF16 = 2 };
 
@@ -62,8 +69,10 @@ struct GemmParams {
 
 template <int TN>
 struct GemmSmem {
-    static constexpr int kXStageBytes = TN * kGemmBlockK;
-    static constexpr int kBytes = kStagesX * kXStageBytes + kStagesW * kWStageBytes + 1024 /*align*/ + 512 /*bars*/;
+    static constexpr int kXHalfBytes = TN * 128;            // one TMA box: TN rows x 128 B
+    static constexpr int kXStageBytes = 2 * kXHalfBytes;    // 256 K-bytes per row, as two swizzle atoms
+    static constexpr int kBytes = kStages * kXStageBytes + kStagesW * kWStageBytes + 8 * 128 * 4 /*s_x per epi warp*/ +
+                                  1024 /*align*/ + 512 /*bars*/;
 };
 
 template <int TN, int MODE, bool PROF = false>
@@ -71,20 +80,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                  const GemmParams p) {
     static_assert(TN == 16 || TN == 32 || TN == 64 || TN == 128, "token tile");
+    constexpr int XH = GemmSmem<TN>::kXHalfBytes;
     constexpr int XB = GemmSmem<TN>::kXStageBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* xs = smem;
-    uint8_t* ws = xs + kStagesX * XB;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ws + kStagesW * kWStageBytes);
-    uint64_t* full_x = bars;                  // [kStagesX]
-    uint64_t* empty_x = full_x + kStagesX;    // [kStagesX]
-    uint64_t* full_w = empty_x + kStagesX;    // [kStagesW]
-    uint64_t* empty_w = full_w + kStagesW;    // [kStagesW]
-    uint64_t* full_a = empty_w + kStagesW;    // [kStagesA]
-    uint64_t* empty_a = full_a + kStagesA;    // [kStagesA]
-    uint64_t* full_acc = empty_a + kStagesA;  // [2]
-    uint64_t* empty_acc = full_acc + 2;       // [2]
+    uint8_t* ws = xs + kStages * XB;
+    float* sx_s = reinterpret_cast<float*>(ws + kStagesW * kWStageBytes);  // [8 warps][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sx_s + 8 * 128);
+    uint64_t* full = bars;                     // [kStages]
+    uint64_t* empty = full + kStages;          // [kStages]
+    uint64_t* wfull = empty + kStages;         // [kStagesW]
+    uint64_t* wempty = wfull + kStagesW;       // [kStagesW]
+    uint64_t* full_acc = wempty + kStagesW;    // [2]
+    uint64_t* empty_acc = full_acc + 2;        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_acc + 2);
 
     const int warp = threadIdx.x >> 5;
@@ -93,13 +102,13 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     const long long t_begin = PROF ? clock64() : 0;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStagesX; ++i) { mbar_init(&full_x[i], 1); mbar_init(&empty_x[i], 1); }
-        for (int i = 0; i < kStagesW; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], 4); }
-        for (int i = 0; i < kStagesA; ++i) { mbar_init(&full_a[i], 4); mbar_init(&empty_a[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&full_acc[i], 1); mbar_init(&empty_acc[i], 128); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 5); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kStagesW; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&full_acc[i], 1); mbar_init(&empty_acc[i], 256); }
         fence_mbar_init();
     }
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_x); }
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_x);
+    if (warp == 2 && lane == 0) tma_prefetch_desc(&tm_w);
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
@@ -112,21 +121,31 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     const int KB = (p.K + kGemmBlockK - 1) / kGemmBlockK;
 
     if (warp == 0) {
-        // ================================ TMA producer ================================
+        // ================================ X producer ================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile / nb_w) * TN;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                    FLATQ_TWAIT(0, mbar_wait(&empty[s], ph ^ 1));
+                    mbar_arrive_expect_tx(&full[s], XB);
+                    tma_load_2d(xs + s * XB, &tm_x, &full[s], kb * kGemmBlockK, m0);
+                    tma_load_2d(xs + s * XB + XH, &tm_x, &full[s], kb * kGemmBlockK + 128, m0);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ================================ W producer ================================
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int n0 = (tile % nb_w) * kGemmBlockW;
-                const int m0 = (tile / nb_w) * TN;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const uint32_t sx = it % kStagesX, phx = (it / kStagesX) & 1;
-                    FLATQ_TWAIT(0, mbar_wait(&empty_x[sx], phx ^ 1));
-                    mbar_arrive_expect_tx(&full_x[sx], XB);
-                    tma_load_2d(xs + sx * XB, &tm_x, &full_x[sx], kb * kGemmBlockK, m0);
-                    const uint32_t sw = it % kStagesW, phw = (it / kStagesW) & 1;
-                    FLATQ_TWAIT(1, mbar_wait(&empty_w[sw], phw ^ 1));
-                    mbar_arrive_expect_tx(&full_w[sw], kWStageBytes);
-                    tma_load_2d(ws + sw * kWStageBytes, &tm_w, &full_w[sw], kb * (kGemmBlockK / 2), n0);
+                    const uint32_t s = it % kStagesW, ph = (it / kStagesW) & 1;
+                    FLATQ_TWAIT(0, mbar_wait(&wempty[s], ph ^ 1));
+                    mbar_arrive_expect_tx(&wfull[s], kWStageBytes);
+                    tma_load_2d(ws + s * kWStageBytes, &tm_w, &wfull[s], kb * (kGemmBlockK / 2), n0);
                 }
             }
         }
@@ -140,113 +159,125 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             tc_fence_after();
             const uint32_t d_tmem = tmem + b * 128;
             for (int kb = 0; kb < KB; ++kb, ++it) {
-                const uint32_t sx = it % kStagesX, phx = (it / kStagesX) & 1;
-                const uint32_t sa = it % kStagesA, pha = (it / kStagesA) & 1;
-                FLATQ_TWAIT(0, mbar_wait(&full_x[sx], phx));
-                FLATQ_TWAIT(1, mbar_wait(&full_a[sa], pha));
+                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                FLATQ_TWAIT(0, mbar_wait(&full[s], ph));
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t xaddr = smem_u32(xs + sx * XB);
+                    const uint32_t xaddr = smem_u32(xs + s * XB);
+                    const uint32_t a_tmem = tmem + kTmemColsA0 + s * 64;
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
+                    for (int kk = 0; kk < 8; ++kk) {
                         if (PROF && (p.dbg & 2)) break;
-                        const uint64_t bdesc = make_smem_desc_kmajor(xaddr + kk * 32, 1024, kLayoutSw128);
-                        mma_i8_ts(d_tmem, tmem + kTmemColsA0 + sa * 32 + kk * 8, bdesc, idesc, (kb | kk) != 0);
+                        // K sub-block kk: 32 bytes inside swizzle atom (kk / 4)
+                        const uint64_t bdesc =
+                            make_smem_desc_kmajor(xaddr + (kk >> 2) * XH + (kk & 3) * 32, 1024, kLayoutSw128);
+                        mma_i8_ts(d_tmem, a_tmem + kk * 8, bdesc, idesc, (kb | kk) != 0);
                     }
-                    tc_commit(&empty_x[sx]);
-                    tc_commit(&empty_a[sa]);
+                    tc_commit(&empty[s]);
+                    if (kb == KB - 1) tc_commit(&full_acc[b]);
                 }
                 __syncwarp();
             }
-            if (lane == 0) tc_commit(&full_acc[b]);
-            __syncwarp();
         }
-    } else if (warp < 10) {
+    } else if (warp < 11) {
         // ================================ nibble expanders ================================
-        const int grp = (warp - 2) >> 2;  // handles k-block iterations with it % 2 == grp
+        const int grp = (warp - 3) >> 2;  // handles stage iterations with it % 2 == grp
         const int q = warp & 3;           // TMEM lane quadrant this warp may touch
         const uint32_t row = q * 32 + lane;
-        const uint32_t swz = (row >> 1) & 3;  // SWIZZLE_64B: 16-B chunk index ^= bits [7,9) of the address
-        const uint32_t ws_addr = smem_u32(ws) + row * 64;
+        const uint32_t swz = row & 7;     // SWIZZLE_128B: 16-B chunk index ^= (row % 8)
+        const uint32_t ws_addr = smem_u32(ws) + row * 128;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < KB; ++kb, ++it) {
                 if ((it & 1) != (uint32_t)grp) continue;
                 const uint32_t sw = it % kStagesW, phw = (it / kStagesW) & 1;
-                const uint32_t sa = it % kStagesA, pha = (it / kStagesA) & 1;
-                FLATQ_TWAIT(0, mbar_wait(&full_w[sw], phw));
-                uint32_t a[32];
+                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                FLATQ_TWAIT(0, mbar_wait(&wfull[sw], phw));
+                uint4 v[8];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint4 v = ld_shared_v4(ws_addr + sw * kWStageBytes + ((c ^ swz) << 4));
-                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        a[c * 8 + 2 * j] = (w4[j] << 4) & 0xF0F0F0F0u;   // nibbles 0,2,4,6 -> 16*w as int8
-                        a[c * 8 + 2 * j + 1] = w4[j] & 0xF0F0F0F0u;      // nibbles 1,3,5,7
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_w[sw]);
-                FLATQ_TWAIT(1, mbar_wait(&empty_a[sa], pha ^ 1));
+                for (int c = 0; c < 8; ++c) v[c] = ld_shared_v4(ws_addr + sw * kWStageBytes + ((c ^ swz) << 4));
+                FLATQ_TWAIT(1, mbar_wait(&empty[s], ph ^ 1));
                 tc_fence_after();
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + kTmemColsA0 + sa * 32;
-                if (!(PROF && (p.dbg & 1))) FLATQ_TWAIT(2, {
-                    tmem_st_x16(taddr, *reinterpret_cast<const uint32_t(*)[16]>(&a[0]));
-                    tmem_st_x16(taddr + 16, *reinterpret_cast<const uint32_t(*)[16]>(&a[16]));
-                    tmem_st_wait();
-                });
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + kTmemColsA0 + s * 64;
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {  // 16 TMEM columns (64 weights) per store
+                    uint32_t a[16];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const uint4 u = v[2 * h + c];
+                        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            a[c * 8 + 2 * j] = (w4[j] << 4) & 0xF0F0F0F0u;  // nibbles 0,2,4,6 -> 16*w as int8
+                            a[c * 8 + 2 * j + 1] = w4[j] & 0xF0F0F0F0u;     // nibbles 1,3,5,7
+                        }
+                    }
+                    if (!(PROF && (p.dbg & 1))) tmem_st_x16(taddr + h * 16, a);
+                }
+                // every packed byte of this row has been consumed by the ALU ops above: release the W slot
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&wempty[sw]);
+                FLATQ_TWAIT(2, tmem_st_wait());
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full_a[sa]);
+                if (lane == 0) mbar_arrive(&full[s]);
             }
         }
     } else {
         // ================================ epilogue ================================
-        const int q = warp & 3;
+        const int ew = warp - 11;          // 0..7
+        const int q = warp & 3;            // TMEM lane quadrant (warps 11..18 -> 3,0,1,2,3,0,1,2)
+        const int half = ew >> 2;          // which half of the token columns
+        float* sx_w = sx_s + ew * 128;
         uint32_t tile_iter = 0;
-        constexpr int CH = TN < 32 ? TN : 32;  // columns per TMEM load
+        constexpr int COLS = TN / 2 < 16 ? 16 : TN / 2;   // token columns per epilogue warp (TN=16: half 1 idles)
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
             const int n0 = (tile % nb_w) * kGemmBlockW;
             const int m0 = (tile / nb_w) * TN;
             const uint32_t b = tile_iter & 1, phb = (tile_iter >> 1) & 1;
             const int n = n0 + q * 32 + lane;
             const bool n_ok = n < p.N;
+            const int c0 = half * COLS;
             float sw_n = 0.f, bias_n = 0.f;
-            if (MODE != kEpiI32 && n_ok) {
-                sw_n = p.s_w[n];
-                if (p.bias) {
-                    bias_n = MODE == kEpiF16 ? __half2float(reinterpret_cast<const __half*>(p.bias)[n])
-                                             : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
+            if (MODE != kEpiI32) {
+                if (n_ok) {
+                    sw_n = p.s_w[n];
+                    if (p.bias) {
+                        bias_n = MODE == kEpiF16 ? __half2float(reinterpret_cast<const __half*>(p.bias)[n])
+                                                 : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
+                    }
                 }
+                // this warp's slice of the per-token scales -> its private smem strip (read back as broadcasts)
+                for (int j = lane; j < COLS; j += 32) {
+                    const int m = m0 + c0 + j;
+                    sx_w[j] = m < p.M ? p.s_x[m] : 0.f;
+                }
+                __syncwarp();
             }
             FLATQ_TWAIT(0, mbar_wait(&full_acc[b], phb));
             tc_fence_after();
             const long long t_epi0 = PROF ? clock64() : 0;
+            if (c0 < TN) {
 #pragma unroll 1
-            for (int c = 0; c < TN / CH; ++c) {
-                if (PROF && (p.dbg & 4)) break;
-                uint32_t r[32];
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + b * 128 + c * CH;
-                if (CH == 32) {
-                    tmem_ld_x32(taddr, r);
-                } else {
-                    tmem_ld_x16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-                }
-                tmem_ld_wait();
+                for (int c = 0; c < COLS / 16; ++c) {
+                    if (PROF && (p.dbg & 4)) break;
+                    uint32_t r[16];
+                    tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + b * 128 + c0 + c * 16, r);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < CH; ++j) {
-                    const int m = m0 + c * CH + j;
-                    if (m < p.M && n_ok) {
-                        const int32_t acc = static_cast<int32_t>(r[j]) >> p.acc_shift;  // exact: multiple of 2^shift
-                        const size_t o = (size_t)m * p.N + n;
-                        if (MODE == kEpiI32) {
-                            reinterpret_cast<int32_t*>(p.out)[o] = acc;
-                        } else {
-                            // explicit _rn ops: no FMA contraction, so the result equals the oracle's fp32 arithmetic bit for bit
-                            const float y = __fadd_rn(__fmul_rn(__fmul_rn((float)acc, __ldg(&p.s_x[m])), sw_n), bias_n);
-                            if (MODE == kEpiF16) reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(y);
-                            else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(y);
+                    for (int j = 0; j < 16; ++j) {
+                        const int m = m0 + c0 + c * 16 + j;
+                        if (m < p.M && n_ok) {
+                            const int32_t acc = static_cast<int32_t>(r[j]) >> p.acc_shift;  // exact: multiple of 2^shift
+                            const size_t o = (size_t)m * p.N + n;
+                            if (MODE == kEpiI32) {
+                                reinterpret_cast<int32_t*>(p.out)[o] = acc;
+                            } else {
+                                // explicit _rn ops: no FMA contraction, so the result equals the oracle's fp32 arithmetic
+                                const float y = __fadd_rn(__fmul_rn(__fmul_rn((float)acc, sx_w[c * 16 + j]), sw_n), bias_n);
+                                if (MODE == kEpiF16) reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(y);
+                                else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(y);
+                            }
                         }
                     }
                 }
@@ -254,11 +285,12 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             tc_fence_before();
             mbar_arrive(&empty_acc[b]);
             if (PROF) tacc[1] += clock64() - t_epi0;
+            __syncwarp();
         }
     }
 
     if (PROF && lane == 0 && p.prof) {
-        long long* o = p.prof + ((size_t)blockIdx.x * 14 + warp) * 5;
+        long long* o = p.prof + ((size_t)blockIdx.x * kGemmWarps + warp) * 5;
         o[0] = tacc[0]; o[1] = tacc[1]; o[2] = tacc[2]; o[3] = tacc[3]; o[4] = clock64() - t_begin;
     }
     tc_fence_before();

@@ -57,9 +57,7 @@ __host__ __device__ inline size_t kron_smem_bytes(int n1, int n2, int p1, int tp
     size_t b = 0;
     if (has_l) b += (size_t)p1 * (p1 + 8) * 2;
     if (has_r) b += (size_t)n2 * (n2 + 8) * 2;
-    b += (size_t)tpc * p1 * (n2 + 8) * 2;         // X tiles
-    b += (size_t)tpc * p1 * n2;                   // int8 staging
-    b += (size_t)tpc * p1 * (n2 / 2);             // nibble staging
+    b += (size_t)tpc * p1 * (n2 + 8) * 2;         // X tiles; the int8 + nibble staging (1.5 B/elem) aliases them
     b += (size_t)tpc * 16 * 2 * sizeof(float);    // max/min partials (<=16 warps per token)
     return b + 16;
 }
@@ -76,10 +74,11 @@ kron_quant_mma_kernel(const KronParams p) {
     __half* Rs = Ls + (has_l ? (size_t)P1 * LDL : 0);
     __half* Xs = Rs + (has_r ? (size_t)P2 * LDX : 0);
     const int tpc = p.tokens_per_cta;
-    int8_t* q8s = reinterpret_cast<int8_t*>(Xs + (size_t)tpc * P1 * LDX);
+    // staging for the quantised rows reuses the X tiles: every warp is past its last ldmatrix of X when the
+    // block-wide barrier after the max/min exchange has been crossed
+    int8_t* q8s = reinterpret_cast<int8_t*>(Xs);
     uint8_t* q4s = reinterpret_cast<uint8_t*>(q8s + (size_t)tpc * P1 * P2);
-    float* red = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(q4s + (size_t)tpc * P1 * (P2 / 2)) + 15) &
-                                          ~uintptr_t(15));
+    float* red = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(Xs + (size_t)tpc * P1 * LDX) + 15) & ~uintptr_t(15));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
     const int wpt = P1 >> 4;

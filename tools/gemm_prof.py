@@ -22,7 +22,7 @@ for (m, n, k) in shapes:
     y = torch.empty(m, n, dtype=torch.float16, device=dev)
     grid = min(148, ((n + 127) // 128) * ((m + 127) // 128))
     for dbg in (0, 1, 2, 4, 3, 7):
-        prof = torch.zeros(grid, 14, 5, dtype=torch.int64, device=dev)
+        prof = torch.zeros(grid, 19, 5, dtype=torch.int64, device=dev)
         st = torch.cuda.current_stream().cuda_stream
         for _ in range(2):
             rc = fn(x8.data_ptr(), sx.data_ptr(), w.data_ptr(), sw.data_ptr(), m, n, k, y.data_ptr(), prof.data_ptr(), dbg, st)
@@ -36,11 +36,11 @@ for (m, n, k) in shapes:
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 5 * 1e3
         p = prof.double().mean(0).cpu()  # [14, 5] averaged over CTAs
-        kb_total = (k // 128) * ((n + 127) // 128) * ((m + 127) // 128) / grid  # k-blocks per CTA
+        kb_total = (k // 256) * ((n + 127) // 128) * ((m + 127) // 128) / grid  # k-blocks per CTA
         print(f"== M={m} N={n} K={k} dbg={dbg}: {us:.1f} us, {2*m*n*k/us/1e6:.0f} TOPS; kernel cycles {p[0,4]:.0f}; k-blocks/CTA {kb_total:.0f} -> {p[0,4]/kb_total:.0f} cyc/k-block")
-        print(f"   producer: wait empty_x {p[0,0]:.0f}  wait empty_w {p[0,1]:.0f}")
-        print(f"   mma     : wait full_x {p[1,0]:.0f}  wait full_a {p[1,1]:.0f}  wait empty_acc {p[1,2]:.0f}")
-        ex = p[2:10]
-        print(f"   expander: wait full_w {ex[:,0].mean():.0f}  wait empty_a {ex[:,1].mean():.0f}  tmem st+wait {ex[:,2].mean():.0f}  (per warp; each does half the k-blocks)")
-        ep = p[10:14]
+        print(f"   producers: X wait empty {p[0,0]:.0f}   W wait wempty {p[2,0]:.0f}")
+        print(f"   mma     : wait full {p[1,0]:.0f}  wait empty_acc {p[1,2]:.0f}")
+        ex = p[3:11]
+        print(f"   expander: wait wfull {ex[:,0].mean():.0f}  wait empty {ex[:,1].mean():.0f}  tmem st wait {ex[:,2].mean():.0f}  (per warp; each does half the stages)")
+        ep = p[11:19]
         print(f"   epilogue: wait full_acc {ep[:,0].mean():.0f}  busy {ep[:,1].mean():.0f}")
