@@ -121,7 +121,8 @@ int launch_gemm_m(int tn, const CUtensorMap& tw, const CUtensorMap& tx, const Ge
         case 16: return launch_gemm_t<16, MODE>(tw, tx, p, st);
         case 32: return launch_gemm_t<32, MODE>(tw, tx, p, st);
         case 64: return launch_gemm_t<64, MODE>(tw, tx, p, st);
-        default: return launch_gemm_t<128, MODE>(tw, tx, p, st);
+        case 128: return launch_gemm_t<128, MODE>(tw, tx, p, st);
+        default: return launch_gemm_t<256, MODE>(tw, tx, p, st);
     }
 }
 
@@ -132,9 +133,9 @@ int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, i
                 (long long)K);
     FLATQ_CHECK(K % 32 == 0, FLATQ_ERR_INVALID, "K=%lld must be a multiple of 32", (long long)K);
     FLATQ_CHECK(K <= 65536 && M < (1ll << 31) && N < (1ll << 31), FLATQ_ERR_UNSUPPORTED, "GEMM too large");
-    const int tn = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128;
+    const int tn = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
     CUtensorMap tw, tx;
-    int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
     rc = make_map_u8(&tx, x8, M, K, K, 128, tn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -392,7 +393,7 @@ int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed
                     int64_t M, int64_t N, int64_t K, void* y, int out_dtype, flatq_stream_t stream) {
     FLATQ_CHECK(xq8 && s_x && w_packed && s_w && y, FLATQ_ERR_INVALID, "gemm_w4a8: null pointer");
     FLATQ_CHECK(out_dtype == FLATQ_F16 || out_dtype == FLATQ_BF16, FLATQ_ERR_INVALID, "gemm_w4a8: out_dtype");
-    FLATQ_CHECK(K % 64 == 0, FLATQ_ERR_INVALID, "gemm_w4a8: K=%lld must be a multiple of 64", (long long)K);
+    FLATQ_CHECK(K % 32 == 0, FLATQ_ERR_INVALID, "gemm_w4a8: K=%lld must be a multiple of 32", (long long)K);
     return launch_gemm(w_packed, xq8, M, N, K, 4, y, out_dtype == FLATQ_F16 ? kEpiF16 : kEpiBF16, s_x, s_w, bias,
                        (cudaStream_t)stream);
 }
@@ -417,17 +418,17 @@ int flatq_linear_fused(const void* x, const void* left, const void* right, int n
 int flatq_debug_gemm_profile(const int8_t* xq8, const float* s_x, const uint8_t* w_packed, const float* s_w, int64_t M,
                              int64_t N, int64_t K, void* y, long long* prof, int dbg, flatq_stream_t stream) {
     CUtensorMap tw, tx;
-    int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
-    rc = make_map_u8(&tx, xq8, M, K, K, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_map_u8(&tx, xq8, M, K, K, 128, 256, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     GemmParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = 4;
     p.out = y; p.s_x = s_x; p.s_w = s_w; p.bias = nullptr; p.prof = prof; p.dbg = dbg;
-    auto kern = gemm_w4a8_kernel<128, kEpiF16, true>;
-    constexpr int smem = GemmSmem<128>::kBytes;
+    auto kern = gemm_w4a8_kernel<256, kEpiF16, true>;
+    constexpr int smem = GemmSmem<256>::kBytes;
     FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int tiles = (int)(((N + 127) / 128) * ((M + 127) / 128));
+    const int tiles = (int)(((N + 127) / 128) * ((M + 255) / 256));
     const int grid = tiles < num_sms() ? tiles : num_sms();
     kern<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(tw, tx, p);
     FLATQ_CUDA(cudaGetLastError());

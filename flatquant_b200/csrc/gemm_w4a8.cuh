@@ -16,11 +16,12 @@
 //     ([0,2,4,6,1,3,5,7]); the activation operand is stored with the same permutation, so the
 //     contraction is unchanged.  The factor 16 (or 256 when X is expanded the same way) is
 //     removed exactly by an arithmetic shift of the int32 accumulator.
-//   * One pipeline stage = 256 K-elements: packed W tile 128 rows x 128 B (SWIZZLE_128B), int8 X
-//     tile = two TMA boxes of TN rows x 128 B (SWIZZLE_128B), A operand = 64 TMEM columns.
-//     Eight MMAs (512 tensor-pipe cycles at TN=128) are issued per stage behind ONE mbarrier wait
-//     and ONE tcgen05.commit: the issuing thread's loop overhead was the limiter with 128-wide
-//     stages and separate X / A barriers (profiles/r01_gemm_role_timers_v1.log).
+//   * tcgen05.mma issue cost on B200 is >= 128 cycles per instruction whatever N is
+//     (profiles/r01_mma_rate_microbench.log: i8 M128 K32 takes 127 / 127 / 128 cycles at N = 64 / 128 / 256),
+//     so only N = 256 reaches the 8192 MAC/cycle/SM peak.  Prefill tiles are therefore 128 weight rows x
+//     256 tokens: 256 TMEM columns of int32 accumulator (single-buffered) + a 5-stage A ring of 32 columns.
+//   * One pipeline stage = 128 K-elements: packed W tile 128 rows x 64 B (SWIZZLE_64B), int8 X tile
+//     TN rows x 128 B (SWIZZLE_128B), four MMAs behind ONE mbarrier wait and ONE tcgen05.commit.
 //
 // Warp roles (19 warps, persistent over output tiles):
 //   warp 0  X TMA producer     warp 1  MMA issuer (+ TMEM alloc)     warp 2  W TMA producer
@@ -46,13 +47,13 @@ namespace flatq {
     } while (0)
 
 constexpr int kGemmBlockW = 128;   // weight rows per tile
-constexpr int kGemmBlockK = 256;   // K elements per stage
+constexpr int kGemmBlockK = 128;   // K elements per stage
 constexpr int kGemmWarps = 19;
 constexpr int kGemmThreads = kGemmWarps * 32;
-constexpr int kStages = 4;         // X smem ring == TMEM A ring (64 columns per stage)
+constexpr int kStages = 5;         // X smem ring == TMEM A ring (32 columns per stage)
 constexpr int kStagesW = 4;        // packed-W smem ring
-constexpr int kTmemColsA0 = 256;   // accumulators at columns [0,128) and [128,256)
-constexpr int kWStageBytes = kGemmBlockW * (kGemmBlockK / 2);  // 16 KB
+constexpr int kTmemColsA0 = 256;   // accumulator(s) in columns [0,256): one 256-wide or two 128-wide buffers
+constexpr int kWStageBytes = kGemmBlockW * (kGemmBlockK / 2);  // 8 KB
 
 enum EpilogueMode : int { kEpiI32 = 0, kEpiF16 = 1, kEpiBF16 = 2 };
 
@@ -64,13 +65,13 @@ struct GemmParams {
     const float* s_w;     // [N]  per-channel scale (dequant modes)
     const void* bias;     // [N] same dtype as out, or nullptr
     long long* prof;      // debug: per-CTA role timers (PROF instantiation only)
-    int dbg;              // debug (PROF only): 1 skip TMEM stores, 2 skip MMA issue, 4 skip epilogue math/stores
+    int dbg;              // debug (PROF only): 1 skip TMEM stores, 2 skip MMA issue, 4 skip epilogue, 8 no X TMA, 16 no W TMA/LDS
 };
 
 template <int TN>
 struct GemmSmem {
-    static constexpr int kXHalfBytes = TN * 128;            // one TMA box: TN rows x 128 B
-    static constexpr int kXStageBytes = 2 * kXHalfBytes;    // 256 K-bytes per row, as two swizzle atoms
+    static constexpr int kXStageBytes = TN * 128;           // one TMA box: TN rows x 128 B
+    static constexpr int kAccBufs = TN > 128 ? 1 : 2;       // TMEM accumulator buffers
     static constexpr int kBytes = kStages * kXStageBytes + kStagesW * kWStageBytes + 8 * 128 * 4 /*s_x per epi warp*/ +
                                   1024 /*align*/ + 512 /*bars*/;
 };
@@ -79,8 +80,8 @@ template <int TN, int MODE, bool PROF = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                  const GemmParams p) {
-    static_assert(TN == 16 || TN == 32 || TN == 64 || TN == 128, "token tile");
-    constexpr int XH = GemmSmem<TN>::kXHalfBytes;
+    static_assert(TN == 16 || TN == 32 || TN == 64 || TN == 128 || TN == 256, "token tile");
+    constexpr int NBUF = GemmSmem<TN>::kAccBufs;
     constexpr int XB = GemmSmem<TN>::kXStageBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -129,9 +130,9 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                     FLATQ_TWAIT(0, mbar_wait(&empty[s], ph ^ 1));
+                    if (PROF && (p.dbg & 8)) { mbar_arrive(&full[s]); continue; }
                     mbar_arrive_expect_tx(&full[s], XB);
                     tma_load_2d(xs + s * XB, &tm_x, &full[s], kb * kGemmBlockK, m0);
-                    tma_load_2d(xs + s * XB + XH, &tm_x, &full[s], kb * kGemmBlockK + 128, m0);
                 }
             }
         }
@@ -144,6 +145,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t s = it % kStagesW, ph = (it / kStagesW) & 1;
                     FLATQ_TWAIT(0, mbar_wait(&wempty[s], ph ^ 1));
+                    if (PROF && (p.dbg & 16)) { mbar_arrive(&wfull[s]); continue; }
                     mbar_arrive_expect_tx(&wfull[s], kWStageBytes);
                     tma_load_2d(ws + s * kWStageBytes, &tm_w, &wfull[s], kb * (kGemmBlockK / 2), n0);
                 }
@@ -154,7 +156,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         constexpr uint32_t idesc = make_idesc(kDS32, kFmtS8, kFmtS8, 0, 0, kGemmBlockW, TN);
         uint32_t it = 0, tile_iter = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
-            const uint32_t b = tile_iter & 1, phb = (tile_iter >> 1) & 1;
+            const uint32_t b = tile_iter % NBUF, phb = (tile_iter / NBUF) & 1;
             FLATQ_TWAIT(2, mbar_wait(&empty_acc[b], phb ^ 1));
             tc_fence_after();
             const uint32_t d_tmem = tmem + b * 128;
@@ -164,13 +166,11 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t xaddr = smem_u32(xs + s * XB);
-                    const uint32_t a_tmem = tmem + kTmemColsA0 + s * 64;
+                    const uint32_t a_tmem = tmem + kTmemColsA0 + s * 32;
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
+                    for (int kk = 0; kk < 4; ++kk) {
                         if (PROF && (p.dbg & 2)) break;
-                        // K sub-block kk: 32 bytes inside swizzle atom (kk / 4)
-                        const uint64_t bdesc =
-                            make_smem_desc_kmajor(xaddr + (kk >> 2) * XH + (kk & 3) * 32, 1024, kLayoutSw128);
+                        const uint64_t bdesc = make_smem_desc_kmajor(xaddr + kk * 32, 1024, kLayoutSw128);
                         mma_i8_ts(d_tmem, a_tmem + kk * 8, bdesc, idesc, (kb | kk) != 0);
                     }
                     tc_commit(&empty[s]);
@@ -184,8 +184,8 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const int grp = (warp - 3) >> 2;  // handles stage iterations with it % 2 == grp
         const int q = warp & 3;           // TMEM lane quadrant this warp may touch
         const uint32_t row = q * 32 + lane;
-        const uint32_t swz = row & 7;     // SWIZZLE_128B: 16-B chunk index ^= (row % 8)
-        const uint32_t ws_addr = smem_u32(ws) + row * 128;
+        const uint32_t swz = (row >> 1) & 3;  // SWIZZLE_64B: 16-B chunk index ^= bits [7,9) of the address
+        const uint32_t ws_addr = smem_u32(ws) + row * 64;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -193,14 +193,17 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 const uint32_t sw = it % kStagesW, phw = (it / kStagesW) & 1;
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                 FLATQ_TWAIT(0, mbar_wait(&wfull[sw], phw));
-                uint4 v[8];
+                uint4 v[4];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = ld_shared_v4(ws_addr + sw * kWStageBytes + ((c ^ swz) << 4));
+                for (int c = 0; c < 4; ++c) {
+                    if (PROF && (p.dbg & 16)) v[c] = make_uint4(it, c, lane, 7);
+                    else v[c] = ld_shared_v4(ws_addr + sw * kWStageBytes + ((c ^ swz) << 4));
+                }
                 FLATQ_TWAIT(1, mbar_wait(&empty[s], ph ^ 1));
                 tc_fence_after();
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + kTmemColsA0 + s * 64;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + kTmemColsA0 + s * 32;
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {  // 16 TMEM columns (64 weights) per store
+                for (int h = 0; h < 2; ++h) {  // 16 TMEM columns (64 weights) per store
                     uint32_t a[16];
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
@@ -234,7 +237,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
             const int n0 = (tile % nb_w) * kGemmBlockW;
             const int m0 = (tile / nb_w) * TN;
-            const uint32_t b = tile_iter & 1, phb = (tile_iter >> 1) & 1;
+            const uint32_t b = tile_iter % NBUF, phb = (tile_iter / NBUF) & 1;
             const int n = n0 + q * 32 + lane;
             const bool n_ok = n < p.N;
             const int c0 = half * COLS;

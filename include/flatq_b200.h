@@ -118,7 +118,7 @@ int flatq_linear_fused(const void* x_f16, const void* left_f16, const void* righ
  *      flatq_act_quant: transform + per-token quantise into the GEMM's activation operand format
  *        xq8 int8 [M, K] (codes; K order permuted [0,2,4,6,1,3,5,7] inside each group of 8 -- opaque),
  *        s_x fp32 [M].
- *      flatq_gemm_w4a8: y[M,N] = (xq8 . W^T) * s_x[m] * s_w[n] (+bias), W packed [N, K/2]. */
+ *      flatq_gemm_w4a8: y[M,N] = (xq8 . W^T) * s_x[m] * s_w[n] (+bias), W packed [N, K/2]; K % 32 == 0. */
 int flatq_act_quant(const void* x_f16, const void* left_f16, const void* right_f16, int n1, int n2, float clip_max,
                     float clip_min, int64_t M, int8_t* xq8, float* s_x, flatq_stream_t stream);
 int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed, const float* s_w, const void* bias,

@@ -20,8 +20,8 @@ for (m, n, k) in shapes:
     w = torch.randint(0, 256, (n, k // 2), dtype=torch.uint8, device=dev)
     sw = torch.rand(n, device=dev)
     y = torch.empty(m, n, dtype=torch.float16, device=dev)
-    grid = min(148, ((n + 127) // 128) * ((m + 127) // 128))
-    for dbg in (0, 1, 2, 4, 3, 7):
+    grid = min(148, ((n + 127) // 128) * ((m + 255) // 256))
+    for dbg in (0, 4, 2):
         prof = torch.zeros(grid, 19, 5, dtype=torch.int64, device=dev)
         st = torch.cuda.current_stream().cuda_stream
         for _ in range(2):
@@ -36,7 +36,7 @@ for (m, n, k) in shapes:
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 5 * 1e3
         p = prof.double().mean(0).cpu()  # [14, 5] averaged over CTAs
-        kb_total = (k // 256) * ((n + 127) // 128) * ((m + 127) // 128) / grid  # k-blocks per CTA
+        kb_total = (k // 128) * ((n + 127) // 128) * ((m + 255) // 256) / grid  # k-blocks per CTA
         print(f"== M={m} N={n} K={k} dbg={dbg}: {us:.1f} us, {2*m*n*k/us/1e6:.0f} TOPS; kernel cycles {p[0,4]:.0f}; k-blocks/CTA {kb_total:.0f} -> {p[0,4]/kb_total:.0f} cyc/k-block")
         print(f"   producers: X wait empty {p[0,0]:.0f}   W wait wempty {p[2,0]:.0f}")
         print(f"   mma     : wait full {p[1,0]:.0f}  wait empty_acc {p[1,2]:.0f}")
