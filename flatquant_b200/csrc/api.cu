@@ -135,7 +135,7 @@ int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, i
     FLATQ_CHECK(K <= 65536 && M < (1ll << 31) && N < (1ll << 31), FLATQ_ERR_UNSUPPORTED, "GEMM too large");
     const int tn = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
     CUtensorMap tw, tx;
-    int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_64B);
+    int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = make_map_u8(&tx, x8, M, K, K, 128, tn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -418,7 +418,7 @@ int flatq_linear_fused(const void* x, const void* left, const void* right, int n
 int flatq_debug_gemm_profile(const int8_t* xq8, const float* s_x, const uint8_t* w_packed, const float* s_w, int64_t M,
                              int64_t N, int64_t K, void* y, long long* prof, int dbg, flatq_stream_t stream) {
     CUtensorMap tw, tx;
-    int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_64B);
+    int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = make_map_u8(&tx, xq8, M, K, K, 128, 256, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;

@@ -16,17 +16,20 @@
 //     ([0,2,4,6,1,3,5,7]); the activation operand is stored with the same permutation, so the
 //     contraction is unchanged.  The factor 16 (or 256 when X is expanded the same way) is
 //     removed exactly by an arithmetic shift of the int32 accumulator.
-//   * tcgen05.mma issue cost on B200 is >= 128 cycles per instruction whatever N is
-//     (profiles/r01_mma_rate_microbench.log: i8 M128 K32 takes 127 / 127 / 128 cycles at N = 64 / 128 / 256),
-//     so only N = 256 reaches the 8192 MAC/cycle/SM peak.  Prefill tiles are therefore 128 weight rows x
-//     256 tokens: 256 TMEM columns of int32 accumulator (single-buffered) + a 5-stage A ring of 32 columns.
-//   * One pipeline stage = 128 K-elements: packed W tile 128 rows x 64 B (SWIZZLE_64B), int8 X tile
-//     TN rows x 128 B (SWIZZLE_128B), four MMAs behind ONE mbarrier wait and ONE tcgen05.commit.
+//   * Measured on B200 (profiles/r01_mma_rate_microbench.log): one tcgen05.mma costs >= 128 cycles whatever N
+//     is (i8 M128 K32: 127 / 127 / 128 cycles at N = 64 / 128 / 256), so only N = 256 reaches the
+//     8192 MAC/cycle/SM peak; and a tcgen05.commit after every 4 MMAs costs 144-173 cycles/MMA while
+//     >= 8 MMAs per commit run at a flat 128.1.  Prefill tiles are therefore 128 weight rows x 256 tokens
+//     (256 TMEM columns of int32 accumulator, single-buffered, + a 3-stage A ring of 64 columns) and
+//     one pipeline stage is 256 K-elements = 8 MMAs behind ONE mbarrier wait and ONE commit.
+//   * Stage contents: packed W tile 128 rows x 128 B (SWIZZLE_128B), int8 X tile = two TMA boxes of
+//     TN rows x 128 B (SWIZZLE_128B).
 //
-// Warp roles (19 warps, persistent over output tiles):
+// Warp roles (27 warps, persistent over output tiles):
 //   warp 0  X TMA producer     warp 1  MMA issuer (+ TMEM alloc)     warp 2  W TMA producer
 //   warps 3-10  nibble expanders (2 groups x 4 lane-quadrants; a group takes every other stage)
-//   warps 11-18 epilogue (2 per lane-quadrant, each half of the token columns)
+//   warps 11-26 epilogue (4 per lane-quadrant, each a quarter of the token columns): dequantise the
+//               accumulator into registers, release the TMEM buffer, then store.
 //
 // Barriers per stage s:  full[s]  <- X bytes (expect_tx) + 4 expander warps;   empty[s] <- tcgen05.commit
 //                        wfull[s] <- W bytes;                                  wempty[s] <- 4 expander warps
@@ -34,6 +37,11 @@
 #include "ptx.cuh"
 
 namespace flatq {
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 
 #define FLATQ_TWAIT(slot, stmt)                          \
     do {                                                \
@@ -47,13 +55,12 @@ namespace flatq {
     } while (0)
 
 constexpr int kGemmBlockW = 128;   // weight rows per tile
-constexpr int kGemmBlockK = 128;   // K elements per stage
-constexpr int kGemmWarps = 19;
+constexpr int kGemmBlockK = 256;   // K elements per stage
+constexpr int kGemmWarps = 27;
 constexpr int kGemmThreads = kGemmWarps * 32;
-constexpr int kStages = 5;         // X smem ring == TMEM A ring (32 columns per stage)
-constexpr int kStagesW = 4;        // packed-W smem ring
+constexpr int kStagesW = 2;        // packed-W smem ring
 constexpr int kTmemColsA0 = 256;   // accumulator(s) in columns [0,256): one 256-wide or two 128-wide buffers
-constexpr int kWStageBytes = kGemmBlockW * (kGemmBlockK / 2);  // 8 KB
+constexpr int kWStageBytes = kGemmBlockW * (kGemmBlockK / 2);  // 16 KB
 
 enum EpilogueMode : int { kEpiI32 = 0, kEpiF16 = 1, kEpiBF16 = 2 };
 
@@ -70,10 +77,11 @@ struct GemmParams {
 
 template <int TN>
 struct GemmSmem {
-    static constexpr int kXStageBytes = TN * 128;           // one TMA box: TN rows x 128 B
+    static constexpr int kXHalfBytes = TN * 128;            // one TMA box: TN rows x 128 B
+    static constexpr int kXStageBytes = 2 * kXHalfBytes;    // 256 K-bytes per row, as two swizzle atoms
+    static constexpr int kStages = TN > 128 ? 3 : 4;        // X smem ring == TMEM A ring (64 columns per stage)
     static constexpr int kAccBufs = TN > 128 ? 1 : 2;       // TMEM accumulator buffers
-    static constexpr int kBytes = kStages * kXStageBytes + kStagesW * kWStageBytes + 8 * 128 * 4 /*s_x per epi warp*/ +
-                                  1024 /*align*/ + 512 /*bars*/;
+    static constexpr int kBytes = kStages * kXStageBytes + kStagesW * kWStageBytes + 1024 /*align*/ + 512 /*bars*/;
 };
 
 template <int TN, int MODE, bool PROF = false>
@@ -82,13 +90,14 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                  const GemmParams p) {
     static_assert(TN == 16 || TN == 32 || TN == 64 || TN == 128 || TN == 256, "token tile");
     constexpr int NBUF = GemmSmem<TN>::kAccBufs;
+    constexpr int kStages = GemmSmem<TN>::kStages;
+    constexpr int XH = GemmSmem<TN>::kXHalfBytes;
     constexpr int XB = GemmSmem<TN>::kXStageBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* xs = smem;
     uint8_t* ws = xs + kStages * XB;
-    float* sx_s = reinterpret_cast<float*>(ws + kStagesW * kWStageBytes);  // [8 warps][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sx_s + 8 * 128);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ws + kStagesW * kWStageBytes);
     uint64_t* full = bars;                     // [kStages]
     uint64_t* empty = full + kStages;          // [kStages]
     uint64_t* wfull = empty + kStages;         // [kStagesW]
@@ -105,7 +114,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 5); mbar_init(&empty[i], 1); }
         for (int i = 0; i < kStagesW; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 4); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&full_acc[i], 1); mbar_init(&empty_acc[i], 256); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&full_acc[i], 1); mbar_init(&empty_acc[i], 512); }
         fence_mbar_init();
     }
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_x);
@@ -133,6 +142,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                     if (PROF && (p.dbg & 8)) { mbar_arrive(&full[s]); continue; }
                     mbar_arrive_expect_tx(&full[s], XB);
                     tma_load_2d(xs + s * XB, &tm_x, &full[s], kb * kGemmBlockK, m0);
+                    tma_load_2d(xs + s * XB + XH, &tm_x, &full[s], kb * kGemmBlockK + 128, m0);
                 }
             }
         }
@@ -166,11 +176,13 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t xaddr = smem_u32(xs + s * XB);
-                    const uint32_t a_tmem = tmem + kTmemColsA0 + s * 32;
+                    const uint32_t a_tmem = tmem + kTmemColsA0 + s * 64;
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
+                    for (int kk = 0; kk < 8; ++kk) {
                         if (PROF && (p.dbg & 2)) break;
-                        const uint64_t bdesc = make_smem_desc_kmajor(xaddr + kk * 32, 1024, kLayoutSw128);
+                        // K sub-block kk: 32 bytes inside swizzle atom (kk / 4)
+                        const uint64_t bdesc =
+                            make_smem_desc_kmajor(xaddr + (kk >> 2) * XH + (kk & 3) * 32, 1024, kLayoutSw128);
                         mma_i8_ts(d_tmem, a_tmem + kk * 8, bdesc, idesc, (kb | kk) != 0);
                     }
                     tc_commit(&empty[s]);
@@ -184,8 +196,8 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const int grp = (warp - 3) >> 2;  // handles stage iterations with it % 2 == grp
         const int q = warp & 3;           // TMEM lane quadrant this warp may touch
         const uint32_t row = q * 32 + lane;
-        const uint32_t swz = (row >> 1) & 3;  // SWIZZLE_64B: 16-B chunk index ^= bits [7,9) of the address
-        const uint32_t ws_addr = smem_u32(ws) + row * 64;
+        const uint32_t swz = row & 7;     // SWIZZLE_128B: 16-B chunk index ^= (row % 8)
+        const uint32_t ws_addr = smem_u32(ws) + row * 128;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -193,17 +205,23 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 const uint32_t sw = it % kStagesW, phw = (it / kStagesW) & 1;
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                 FLATQ_TWAIT(0, mbar_wait(&wfull[sw], phw));
-                uint4 v[4];
+                uint4 v[8];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 8; ++c) {
                     if (PROF && (p.dbg & 16)) v[c] = make_uint4(it, c, lane, 7);
                     else v[c] = ld_shared_v4(ws_addr + sw * kWStageBytes + ((c ^ swz) << 4));
                 }
+                // Release the W slot as soon as the loads are issued (in order, ~30 cycles to land): a refill needs the
+                // producer to observe 4 arrivals, issue a TMA and get the bytes from L2 (>= 500 cycles) before it can
+                // overwrite the slot, so the loads above always win.  Holding the slot until the TMEM stage is free
+                // would stall the 2-deep W ring whenever the MMA pipe is the limiter (the intended regime).
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&wempty[sw]);
                 FLATQ_TWAIT(1, mbar_wait(&empty[s], ph ^ 1));
                 tc_fence_after();
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + kTmemColsA0 + s * 32;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + kTmemColsA0 + s * 64;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {  // 16 TMEM columns (64 weights) per store
+                for (int h = 0; h < 4; ++h) {  // 16 TMEM columns (64 weights) per store
                     uint32_t a[16];
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
@@ -217,9 +235,6 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                     }
                     if (!(PROF && (p.dbg & 1))) tmem_st_x16(taddr + h * 16, a);
                 }
-                // every packed byte of this row has been consumed by the ALU ops above: release the W slot
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&wempty[sw]);
                 FLATQ_TWAIT(2, tmem_st_wait());
                 tc_fence_before();
                 __syncwarp();
@@ -228,12 +243,11 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         }
     } else {
         // ================================ epilogue ================================
-        const int ew = warp - 11;          // 0..7
-        const int q = warp & 3;            // TMEM lane quadrant (warps 11..18 -> 3,0,1,2,3,0,1,2)
-        const int half = ew >> 2;          // which half of the token columns
-        float* sx_w = sx_s + ew * 128;
+        const int ew = warp - 11;          // 0..15
+        const int q = warp & 3;            // TMEM lane quadrant (warps 11.. -> 3,0,1,2,3,0,1,2,...)
+        const int half = ew >> 2;          // which quarter of the token columns
         uint32_t tile_iter = 0;
-        constexpr int COLS = TN / 2 < 16 ? 16 : TN / 2;   // token columns per epilogue warp (TN=16: half 1 idles)
+        constexpr int COLS = TN / 4 < 16 ? 16 : TN / 4;   // token columns per epilogue warp (small TN: some quarters idle)
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
             const int n0 = (tile % nb_w) * kGemmBlockW;
             const int m0 = (tile / nb_w) * TN;
@@ -250,43 +264,73 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                                                  : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
                     }
                 }
-                // this warp's slice of the per-token scales -> its private smem strip (read back as broadcasts)
-                for (int j = lane; j < COLS; j += 32) {
-                    const int m = m0 + c0 + j;
-                    sx_w[j] = m < p.M ? p.s_x[m] : 0.f;
-                }
-                __syncwarp();
             }
             FLATQ_TWAIT(0, mbar_wait(&full_acc[b], phb));
             tc_fence_after();
             const long long t_epi0 = PROF ? clock64() : 0;
-            if (c0 < TN) {
+            // Drain this warp's COLS accumulator columns into registers as dequantised fp16 pairs, hand the
+            // TMEM buffer back to the MMA issuer, and only then do the (slow) global stores.
+            uint32_t yh[COLS / 2];  // MODE != I32: half2 / bf16x2 of tokens (2i, 2i+1); I32 keeps raw values in two passes
+            if (MODE == kEpiI32) {
+                if (c0 < TN) {
 #pragma unroll 1
-                for (int c = 0; c < COLS / 16; ++c) {
-                    if (PROF && (p.dbg & 4)) break;
-                    uint32_t r[16];
-                    tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + b * 128 + c0 + c * 16, r);
-                    tmem_ld_wait();
+                    for (int c = 0; c < COLS / 16; ++c) {
+                        if (PROF && (p.dbg & 4)) break;
+                        uint32_t r[16];
+                        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + b * 128 + c0 + c * 16, r);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int m = m0 + c0 + c * 16 + j;
-                        if (m < p.M && n_ok) {
-                            const int32_t acc = static_cast<int32_t>(r[j]) >> p.acc_shift;  // exact: multiple of 2^shift
-                            const size_t o = (size_t)m * p.N + n;
-                            if (MODE == kEpiI32) {
-                                reinterpret_cast<int32_t*>(p.out)[o] = acc;
+                        for (int j = 0; j < 16; ++j) {
+                            const int m = m0 + c0 + c * 16 + j;
+                            if (m < p.M && n_ok)
+                                reinterpret_cast<int32_t*>(p.out)[(size_t)m * p.N + n] = static_cast<int32_t>(r[j]) >> p.acc_shift;
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&empty_acc[b]);
+            } else {
+                if (c0 < TN && !(PROF && (p.dbg & 4))) {
+#pragma unroll
+                    for (int c = 0; c < COLS / 16; ++c) {
+                        uint32_t r[16];
+                        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + b * 128 + c0 + c * 16, r);
+                        float sxv[16];  // warp-uniform addresses: one broadcast transaction per vector, L1-resident
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const int m = m0 + c0 + c * 16 + j;
+                            const float4 t4 = m + 3 < p.M ? __ldg(reinterpret_cast<const float4*>(p.s_x + m))
+                                                          : make_float4(m < p.M ? p.s_x[m] : 0.f, m + 1 < p.M ? p.s_x[m + 1] : 0.f,
+                                                                        m + 2 < p.M ? p.s_x[m + 2] : 0.f, 0.f);
+                            sxv[j] = t4.x; sxv[j + 1] = t4.y; sxv[j + 2] = t4.z; sxv[j + 3] = t4.w;
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            // explicit _rn ops: no FMA contraction, so the result equals the oracle's fp32 arithmetic
+                            const float y0 = __fadd_rn(__fmul_rn(__fmul_rn((float)(static_cast<int32_t>(r[j]) >> p.acc_shift), sxv[j]), sw_n), bias_n);
+                            const float y1 = __fadd_rn(__fmul_rn(__fmul_rn((float)(static_cast<int32_t>(r[j + 1]) >> p.acc_shift), sxv[j + 1]), sw_n), bias_n);
+                            if (MODE == kEpiF16) {
+                                yh[c * 8 + j / 2] = pack_half2(y0, y1);
                             } else {
-                                // explicit _rn ops: no FMA contraction, so the result equals the oracle's fp32 arithmetic
-                                const float y = __fadd_rn(__fmul_rn(__fmul_rn((float)acc, sx_w[c * 16 + j]), sw_n), bias_n);
-                                if (MODE == kEpiF16) reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(y);
-                                else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(y);
+                                __nv_bfloat162 v = __floats2bfloat162_rn(y0, y1);
+                                yh[c * 8 + j / 2] = *reinterpret_cast<uint32_t*>(&v);
                             }
                         }
                     }
                 }
+                tc_fence_before();
+                mbar_arrive(&empty_acc[b]);  // accumulator free: the next tile's MMAs overlap the stores below
+                if (c0 < TN && n_ok && !(PROF && (p.dbg & 4))) {
+                    uint16_t* out16 = reinterpret_cast<uint16_t*>(p.out);
+#pragma unroll
+                    for (int i = 0; i < COLS / 2; ++i) {
+                        const int m = m0 + c0 + 2 * i;
+                        if (m < p.M) out16[(size_t)m * p.N + n] = (uint16_t)(yh[i] & 0xFFFF);
+                        if (m + 1 < p.M) out16[(size_t)(m + 1) * p.N + n] = (uint16_t)(yh[i] >> 16);
+                    }
+                }
             }
-            tc_fence_before();
-            mbar_arrive(&empty_acc[b]);
             if (PROF) tacc[1] += clock64() - t_epi0;
             __syncwarp();
         }

@@ -57,6 +57,57 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int mode, int n, int reps,
     if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc<512>(tmem); }
 }
 
+
+// ---- issue-pattern probe: i8 TS M128 N256, `per` MMAs then commit (+ optional wait/fence), with `stw` warps
+// hammering tcgen05.st into the A region like the nibble expanders do.
+__global__ void __launch_bounds__(32 * 9, 1) pattern_kernel(int per, int do_wait, int stw, int reps, long long* out) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar[8];
+    __shared__ uint64_t done;
+    __shared__ uint32_t slot;
+    __shared__ volatile int stop;
+    for (int i = threadIdx.x; i < (49152) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u;
+    if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1); mbar_init(&done, 1); stop = 0; fence_mbar_init(); }
+    if (threadIdx.x < 32) tmem_alloc<512>(&slot);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        const uint64_t bdesc = make_smem_desc_kmajor(smem_u32(smem + 16384), 1024, kLayoutSw128);
+        const uint32_t idesc = make_idesc(kDS32, kFmtS8, kFmtS8, 0, 0, 128, 256);
+        const long long t0 = clock64();
+        int issued = 0;
+        for (int it = 0; issued < reps; ++it) {
+            const int s = it & 7;
+            if (do_wait && it >= 8) { mbar_wait(&bar[s], ((it >> 3) - 1) & 1); tc_fence_after(); }
+            for (int k = 0; k < per; ++k, ++issued)
+                mma_i8_ts(tmem, tmem + 256 + s * 32 + (k & 3) * 8, bdesc + (k & 3) * 2, idesc, issued != 0);
+            tc_commit(&bar[s]);
+        }
+        tc_commit(&done);
+        mbar_wait(&done, 0);
+        const long long t2 = clock64();
+        stop = 1;
+        if (blockIdx.x == 0) { out[0] = t2 - t0; out[1] = issued; }
+    } else if (warp >= 1 && warp <= stw) {
+        uint32_t a[16];
+        for (int i = 0; i < 16; ++i) a[i] = i * 0x01010101u;
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256 + 160;  // columns outside the MMA's A stages
+        while (!stop) {
+            tmem_st_x16(taddr, a);
+            tmem_st_x16(taddr + 16, a);
+            tmem_st_wait();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc<512>(tmem); }
+}
+
 // ---- exactness: D = sum over `reps` k-blocks of A(128x128 e4m3 ints) . B(128x128)^T, fp32 accumulate
 __host__ __device__ inline uint8_t e4m3_of_int(int v) {  // |v| <= 8 exactly representable
     if (v == 0) return 0;
@@ -131,6 +182,17 @@ int main() {
                        kper[mode], grid, (double)h[0] / reps, cyc, 128.0 * n * kper[mode] / cyc, e == cudaSuccess ? "" : cudaGetErrorString(e));
             }
         }
+    cudaFuncSetAttribute(pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024);
+    for (int per : {4, 8, 16, 4096})
+        for (int do_wait : {0, 1})
+            for (int stw : {0, 4, 8}) {
+                pattern_kernel<<<148, 32 * 9, 60 * 1024>>>(per, do_wait, stw, 4096, out);
+                cudaError_t e = cudaDeviceSynchronize();
+                long long h[2];
+                cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
+                printf("pattern i8 TS N256: %4d MMAs/commit wait=%d st_warps=%d: %.1f cyc/mma %s\n", per, do_wait, stw,
+                       (double)h[0] / (double)h[1], e == cudaSuccess ? "" : cudaGetErrorString(e));
+            }
     // exactness of integer-valued fp8 accumulation
     uint8_t *ha = (uint8_t*)malloc(16384), *hb = (uint8_t*)malloc(16384), *ha8 = (uint8_t*)malloc(16384), *hb8 = (uint8_t*)malloc(16384);
     int* ia = (int*)malloc(16384 * 4); int* ib = (int*)malloc(16384 * 4);
