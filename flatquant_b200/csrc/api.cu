@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <string>
@@ -13,6 +14,7 @@
 #include "elementwise.cuh"
 #include "gemm_w4a8.cuh"
 #include "kron_quant.cuh"
+#include "kron_quant_tc.cuh"
 
 using namespace flatq;
 
@@ -133,6 +135,7 @@ int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, i
                 (long long)K);
     FLATQ_CHECK(K % 32 == 0, FLATQ_ERR_INVALID, "K=%lld must be a multiple of 32", (long long)K);
     FLATQ_CHECK(K <= 65536 && M < (1ll << 31) && N < (1ll << 31), FLATQ_ERR_UNSUPPORTED, "GEMM too large");
+    FLATQ_CHECK(mode == kEpiI32 || N % 2 == 0, FLATQ_ERR_UNSUPPORTED, "N=%lld must be even for 16-bit outputs", (long long)N);
     const int tn = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
     CUtensorMap tw, tx;
     int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -164,8 +167,18 @@ int launch_kron_t(const KronParams& p, int threads, size_t smem, int grid, cudaS
     return FLATQ_OK;
 }
 
+int launch_kron_tc(const KronParams& p, cudaStream_t st);
+
 int launch_kron(KronParams p, cudaStream_t st) {
     FLATQ_CHECK(p.tokens > 0, FLATQ_ERR_INVALID, "no tokens");
+    FLATQ_CHECK(aligned16(p.x), FLATQ_ERR_INVALID, "x must be 16-byte aligned");
+    {
+        static const bool no_tc = getenv("FLATQ_KRON_HMMA") != nullptr;  // debugging aid: force the HMMA kernel
+        if (!no_tc) {
+            const int rc = launch_kron_tc(p, st);
+            if (rc != 1) return rc;
+        }
+    }
     FLATQ_CHECK(p.n1 >= 1 && p.n2 >= 16 && p.n1 <= 256 && p.n2 <= 256 && p.n2 % 16 == 0, FLATQ_ERR_UNSUPPORTED,
                 "unsupported Kronecker factor sizes (%d, %d): need n2 %% 16 == 0 and n1, n2 <= 256", p.n1, p.n2);
     FLATQ_CHECK(aligned16(p.x), FLATQ_ERR_INVALID, "x must be 16-byte aligned");
@@ -197,6 +210,44 @@ int launch_kron(KronParams p, cudaStream_t st) {
 #undef FLATQ_KRON_CASE
     }
     return fail(FLATQ_ERR_UNSUPPORTED, "n2=%d", p.n2);
+}
+
+
+// ---- tcgen05 Kronecker transform + quantise (the shapes of the Llama linears); other shapes use the HMMA kernel
+template <int N2, int N1P, int T>
+int launch_kron_tc_t(const KronParams& p, cudaStream_t st) {
+    using C = KronTc<N2, N1P, T>;
+    auto kern = kron_quant_tc_kernel<N2, N1P, T>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        attr_set = true;
+    }
+    CUtensorMap tx;  // x as a 2-D byte tensor [tokens * n1 rows][n2 * 2 bytes]
+    int rc = make_map_u8(&tx, p.x, (uint64_t)p.tokens * p.n1, (uint64_t)N2 * 2, (uint64_t)N2 * 2, 128, C::kXRows,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    const int groups = (p.tokens + T - 1) / T;
+    const int cap = 2 * num_sms();
+    kern<<<groups < cap ? groups : cap, C::kThreads, C::kSmemBytes, st>>>(tx, p);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+// returns 1 if no tcgen05 instantiation covers the shape (caller falls back to the HMMA kernel)
+int launch_kron_tc(const KronParams& p, cudaStream_t st) {
+    if (!p.do_quant || p.z_out || p.tokens <= 0 || (p.n1 * p.n2) % 32 != 0) return 1;
+    if (p.n2 == 64) {
+        if (p.n1 == 64) return launch_kron_tc_t<64, 64, 2>(p, st);
+        if (p.n1 > 48 && p.n1 < 64) return launch_kron_tc_t<64, 64, 1>(p, st);
+        if (p.n1 == 32) return launch_kron_tc_t<64, 32, 2>(p, st);
+    } else if (p.n2 == 128) {
+        if (p.n1 == 64) return launch_kron_tc_t<128, 64, 2>(p, st);
+        if (p.n1 > 64 && p.n1 <= 96) return launch_kron_tc_t<128, 96, 1>(p, st);
+        if (p.n1 > 96 && p.n1 <= 112) return launch_kron_tc_t<128, 112, 1>(p, st);
+        if (p.n1 > 112 && p.n1 <= 128) return launch_kron_tc_t<128, 128, 1>(p, st);
+    }
+    return 1;
 }
 
 int launch_rowquant(const void* x, int64_t tokens, int64_t K, float cmax, float cmin, int half_math, uint8_t* xq4,

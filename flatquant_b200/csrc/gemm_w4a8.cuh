@@ -43,6 +43,9 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+struct FoldTrue { static constexpr bool value = true; };
+struct FoldFalse { static constexpr bool value = false; };
+
 #define FLATQ_TWAIT(slot, stmt)                          \
     do {                                                \
         if (PROF) {                                     \
@@ -265,6 +268,13 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                     }
                 }
             }
+            // per-token scales of this warp's columns, one (two) per lane; fetched while the MMAs still run
+            float sx_lo = 0.f, sx_hi = 0.f;
+            if (MODE != kEpiI32) {
+                const int ma = m0 + c0 + lane, mb = m0 + c0 + 32 + lane;
+                if (lane < COLS && ma < p.M) sx_lo = p.s_x[ma];
+                if (COLS > 32 && mb < p.M) sx_hi = p.s_x[mb];
+            }
             FLATQ_TWAIT(0, mbar_wait(&full_acc[b], phb));
             tc_fence_after();
             const long long t_epi0 = PROF ? clock64() : 0;
@@ -290,26 +300,29 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 tc_fence_before();
                 mbar_arrive(&empty_acc[b]);
             } else {
-                if (c0 < TN && !(PROF && (p.dbg & 4))) {
+                // fast path: the raw accumulator (16x the true one) is exactly representable in fp32 (|raw| <= 2^10 K), so
+                // the power-of-two factor moves into the per-token scale instead of a per-element shift
+                const bool fold = p.acc_shift == 4 && p.K <= 16384;
+                const bool has_bias = p.bias != nullptr;
+                if (fold) { sx_lo *= 0.0625f; sx_hi *= 0.0625f; }
+                auto drain = [&](auto fold_c) {
+                    constexpr bool FOLD = decltype(fold_c)::value;
 #pragma unroll
                     for (int c = 0; c < COLS / 16; ++c) {
                         uint32_t r[16];
                         tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + b * 128 + c0 + c * 16, r);
-                        float sxv[16];  // warp-uniform addresses: one broadcast transaction per vector, L1-resident
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const int m = m0 + c0 + c * 16 + j;
-                            const float4 t4 = m + 3 < p.M ? __ldg(reinterpret_cast<const float4*>(p.s_x + m))
-                                                          : make_float4(m < p.M ? p.s_x[m] : 0.f, m + 1 < p.M ? p.s_x[m + 1] : 0.f,
-                                                                        m + 2 < p.M ? p.s_x[m + 2] : 0.f, 0.f);
-                            sxv[j] = t4.x; sxv[j + 1] = t4.y; sxv[j + 2] = t4.z; sxv[j + 3] = t4.w;
-                        }
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 16; j += 2) {
+                            // per-token scales live one per lane (loaded before the accumulator was ready)
+                            const float s0 = __shfl_sync(0xffffffffu, (c * 16 + j) >= 32 ? sx_hi : sx_lo, (c * 16 + j) & 31);
+                            const float s1 = __shfl_sync(0xffffffffu, (c * 16 + j + 1) >= 32 ? sx_hi : sx_lo, (c * 16 + j + 1) & 31);
+                            const int32_t a0 = FOLD ? static_cast<int32_t>(r[j]) : static_cast<int32_t>(r[j]) >> p.acc_shift;
+                            const int32_t a1 = FOLD ? static_cast<int32_t>(r[j + 1]) : static_cast<int32_t>(r[j + 1]) >> p.acc_shift;
                             // explicit _rn ops: no FMA contraction, so the result equals the oracle's fp32 arithmetic
-                            const float y0 = __fadd_rn(__fmul_rn(__fmul_rn((float)(static_cast<int32_t>(r[j]) >> p.acc_shift), sxv[j]), sw_n), bias_n);
-                            const float y1 = __fadd_rn(__fmul_rn(__fmul_rn((float)(static_cast<int32_t>(r[j + 1]) >> p.acc_shift), sxv[j + 1]), sw_n), bias_n);
+                            float y0 = __fmul_rn(__fmul_rn((float)a0, s0), sw_n);
+                            float y1 = __fmul_rn(__fmul_rn((float)a1, s1), sw_n);
+                            if (has_bias) { y0 = __fadd_rn(y0, bias_n); y1 = __fadd_rn(y1, bias_n); }
                             if (MODE == kEpiF16) {
                                 yh[c * 8 + j / 2] = pack_half2(y0, y1);
                             } else {
@@ -318,16 +331,25 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                             }
                         }
                     }
+                };
+                if (c0 < TN && !(PROF && (p.dbg & 4))) {
+                    if (fold) drain(FoldTrue{}); else drain(FoldFalse{});
                 }
                 tc_fence_before();
                 mbar_arrive(&empty_acc[b]);  // accumulator free: the next tile's MMAs overlap the stores below
-                if (c0 < TN && n_ok && !(PROF && (p.dbg & 4))) {
-                    uint16_t* out16 = reinterpret_cast<uint16_t*>(p.out);
+                if (c0 < TN && !(PROF && (p.dbg & 4))) {
+                    // lanes (2i, 2i+1) swap halves so that each stores 4 bytes: even lane -> (token m; n, n+1),
+                    // odd lane -> (token m+1; n-1, n).  N is even (checked on the host).
+                    const bool odd = lane & 1;
+                    uint32_t* out32 = reinterpret_cast<uint32_t*>(p.out);
 #pragma unroll
                     for (int i = 0; i < COLS / 2; ++i) {
-                        const int m = m0 + c0 + 2 * i;
-                        if (m < p.M) out16[(size_t)m * p.N + n] = (uint16_t)(yh[i] & 0xFFFF);
-                        if (m + 1 < p.M) out16[(size_t)(m + 1) * p.N + n] = (uint16_t)(yh[i] >> 16);
+                        const uint32_t mine = yh[i];
+                        const uint32_t send = odd ? (mine & 0xFFFFu) : (mine >> 16);
+                        const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                        const uint32_t outv = odd ? (recv | (mine & 0xFFFF0000u)) : ((mine & 0xFFFFu) | (recv << 16));
+                        const int m = m0 + c0 + 2 * i + (odd ? 1 : 0);
+                        if (m < p.M && n_ok) out32[((size_t)m * p.N + (n & ~1)) >> 1] = outv;  // n_ok is pair-uniform: N even
                     }
                 }
             }
