@@ -214,10 +214,10 @@ int launch_kron(KronParams p, cudaStream_t st) {
 
 
 // ---- tcgen05 Kronecker transform + quantise (the shapes of the Llama linears); other shapes use the HMMA kernel
-template <int N2, int N1P, int T>
+template <int N2, int N1P, int T, bool OUT8>
 int launch_kron_tc_t(const KronParams& p, cudaStream_t st) {
     using C = KronTc<N2, N1P, T>;
-    auto kern = kron_quant_tc_kernel<N2, N1P, T>;
+    auto kern = kron_quant_tc_kernel<N2, N1P, T, OUT8>;
     static bool attr_set = false;
     if (!attr_set) {
         FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -234,18 +234,24 @@ int launch_kron_tc_t(const KronParams& p, cudaStream_t st) {
     return FLATQ_OK;
 }
 
-// returns 1 if no tcgen05 instantiation covers the shape (caller falls back to the HMMA kernel)
+template <int N2, int N1P, int T>
+int launch_kron_tc_o(const KronParams& p, cudaStream_t st) {
+    return p.xq8 ? launch_kron_tc_t<N2, N1P, T, true>(p, st) : launch_kron_tc_t<N2, N1P, T, false>(p, st);
+}
+
+// returns 1 if no tcgen05 instantiation covers the request (caller falls back to the HMMA kernel)
 int launch_kron_tc(const KronParams& p, cudaStream_t st) {
     if (!p.do_quant || p.z_out || p.tokens <= 0 || (p.n1 * p.n2) % 32 != 0) return 1;
+    if ((p.xq8 != nullptr) == (p.xq4 != nullptr)) return 1;  // exactly one code format per launch
     if (p.n2 == 64) {
-        if (p.n1 == 64) return launch_kron_tc_t<64, 64, 2>(p, st);
-        if (p.n1 > 48 && p.n1 < 64) return launch_kron_tc_t<64, 64, 1>(p, st);
-        if (p.n1 == 32) return launch_kron_tc_t<64, 32, 2>(p, st);
+        if (p.n1 == 64) return launch_kron_tc_o<64, 64, 2>(p, st);
+        if (p.n1 > 32 && p.n1 < 64) return launch_kron_tc_o<64, 64, 1>(p, st);
+        if (p.n1 == 32) return launch_kron_tc_o<64, 32, 2>(p, st);
     } else if (p.n2 == 128) {
-        if (p.n1 == 64) return launch_kron_tc_t<128, 64, 2>(p, st);
-        if (p.n1 > 64 && p.n1 <= 96) return launch_kron_tc_t<128, 96, 1>(p, st);
-        if (p.n1 > 96 && p.n1 <= 112) return launch_kron_tc_t<128, 112, 1>(p, st);
-        if (p.n1 > 112 && p.n1 <= 128) return launch_kron_tc_t<128, 128, 1>(p, st);
+        if (p.n1 > 32 && p.n1 <= 64) return launch_kron_tc_o<128, 64, 1>(p, st);
+        if (p.n1 > 64 && p.n1 <= 96) return launch_kron_tc_o<128, 96, 1>(p, st);
+        if (p.n1 > 96 && p.n1 <= 112) return launch_kron_tc_o<128, 112, 1>(p, st);
+        if (p.n1 > 112 && p.n1 <= 128) return launch_kron_tc_o<128, 128, 1>(p, st);
     }
     return 1;
 }

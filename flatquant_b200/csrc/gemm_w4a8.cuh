@@ -214,12 +214,6 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                     if (PROF && (p.dbg & 16)) v[c] = make_uint4(it, c, lane, 7);
                     else v[c] = ld_shared_v4(ws_addr + sw * kWStageBytes + ((c ^ swz) << 4));
                 }
-                // Release the W slot as soon as the loads are issued (in order, ~30 cycles to land): a refill needs the
-                // producer to observe 4 arrivals, issue a TMA and get the bytes from L2 (>= 500 cycles) before it can
-                // overwrite the slot, so the loads above always win.  Holding the slot until the TMEM stage is free
-                // would stall the 2-deep W ring whenever the MMA pipe is the limiter (the intended regime).
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&wempty[sw]);
                 FLATQ_TWAIT(1, mbar_wait(&empty[s], ph ^ 1));
                 tc_fence_after();
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + kTmemColsA0 + s * 64;
@@ -238,6 +232,9 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                     }
                     if (!(PROF && (p.dbg & 1))) tmem_st_x16(taddr + h * 16, a);
                 }
+                // every packed byte of this row has been consumed by the ALU ops above: release the W slot
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&wempty[sw]);
                 FLATQ_TWAIT(2, tmem_st_wait());
                 tc_fence_before();
                 __syncwarp();

@@ -102,7 +102,29 @@ def test_kron_transform_golden(ops, dev, golden, dims):
     assert (z - ref).abs().max() <= tol
 
 
-@pytest.mark.parametrize("n1,n2", [(64, 64), (112, 128), (86, 128), (56, 64), (32, 48), (128, 224), (8, 16)])
+def _emulated_codes(x, L, R, cmax, cmin, order):
+    """CPU model of the kernels' arithmetic: fp32-accumulated products with the fp16 roundings the kernels apply
+    (order 'xr' = L^T.(X.R) of the tcgen05 kernel / reference; 'lx' = (L^T.X).R of the HMMA kernel)."""
+    n1, n2 = L.shape[0], R.shape[0]
+    xm = x.float().reshape(-1, n1, n2)
+    if order == "xr":
+        y = torch.matmul(xm, R.float()).half().float()
+        z = torch.matmul(L.float().t(), y).half().float()
+    else:
+        u = torch.matmul(L.float().t(), xm).half().float()
+        z = torch.matmul(u, R.float()).half().float()
+    z = z.reshape(x.shape[0], -1)
+    hi = z.amax(1).clamp(min=0) * torch.tensor(cmax)
+    lo = z.amin(1).clamp(max=0) * torch.tensor(cmin)
+    m = torch.maximum(lo.abs(), hi)
+    s = torch.where(m == 0, torch.ones_like(m), m / 7)
+    q = torch.clamp(torch.round(z / s[:, None]), -8, 7).numpy().astype(np.int32)
+    return q, s
+
+
+# tcgen05 kernel shapes: (64,64) (112,128) (86,128) (56,64) (32,64) (64,128);  HMMA kernel: the rest
+@pytest.mark.parametrize("n1,n2", [(64, 64), (112, 128), (86, 128), (56, 64), (32, 64), (64, 128), (32, 48), (128, 224),
+                                   (8, 16), (14, 16)])
 def test_transform_quant_codes(ops, dev, n1, n2):
     torch.manual_seed(n1 * 1000 + n2)
     tokens, k = 37, n1 * n2
@@ -113,17 +135,25 @@ def test_transform_quant_codes(ops, dev, n1, n2):
     cmax, cmin = 0.982, 0.95
     xq, s16, s32 = ops.transform_quant(x.to(dev), L.to(dev), R.to(dev), n1, n2, cmax, cmin)
     codes = O.unpack_i4(xq.cpu().numpy())
-    # (1) quantiser is bit exact given the kernel's own fp16 transform output
-    zk = ops.kron_transform(x.to(dev), L.to(dev), R.to(dev), n1, n2).cpu().float()
-    hi = zk.amax(1).clamp(min=0) * torch.tensor(cmax)
-    lo = zk.amin(1).clamp(max=0) * torch.tensor(cmin)
-    m = torch.maximum(lo.abs(), hi)
-    s_ref = torch.where(m == 0, torch.ones_like(m), m / 7)
-    assert torch.equal(s32.cpu(), s_ref)
-    assert torch.equal(s16.cpu(), s_ref.half())
-    q_ref = torch.clamp(torch.round(zk / s_ref[:, None]), -8, 7).numpy().astype(np.int32)
-    assert np.array_equal(codes, q_ref)
     assert s32[3].item() == 1.0 and not codes[3].any()
+    assert torch.equal(s16.cpu(), s32.cpu().half())
+    tc = n2 in (64, 128) and 32 <= n1 <= 128
+    # (1) against a CPU model with the kernel's own rounding points.  Only the fp32 summation order inside the tensor
+    #     core differs, which can move an fp16 rounding (and hence a code) in rare cases.
+    q_em, s_em = _emulated_codes(x, L, R, cmax, cmin, "xr" if tc else "lx")
+    d = np.abs(codes - q_em)
+    assert d.max() <= 1 and (d != 0).mean() < 2e-3
+    assert torch.allclose(s32.cpu(), s_em, rtol=1e-3)
+    if not tc:
+        # HMMA kernel: the quantiser is bit exact given the kernel's own fp16 transform output
+        zk = ops.kron_transform(x.to(dev), L.to(dev), R.to(dev), n1, n2).cpu().float()
+        hi = zk.amax(1).clamp(min=0) * torch.tensor(cmax)
+        lo = zk.amin(1).clamp(max=0) * torch.tensor(cmin)
+        m = torch.maximum(lo.abs(), hi)
+        s_ref = torch.where(m == 0, torch.ones_like(m), m / 7)
+        assert torch.equal(s32.cpu(), s_ref)
+        q_ref = torch.clamp(torch.round(zk / s_ref[:, None]), -8, 7).numpy().astype(np.int32)
+        assert np.array_equal(codes, q_ref)
     # (2) against the pure fp32 oracle: codes agree except for +-1 flips at rounding boundaries
     z32 = O.kronecker_matmul(x.float(), L.float(), R.float())
     hi, lo = z32.amax(1).clamp(min=0) * cmax, z32.amin(1).clamp(max=0) * cmin
@@ -134,6 +164,15 @@ def test_transform_quant_codes(ops, dev, n1, n2):
     assert diff.max() <= 1
     assert (diff != 0).mean() < 0.02
     assert torch.allclose(s32.cpu(), so, rtol=2e-3)
+    # (3) the GEMM operand format (int8, K-permuted) carries the same codes
+    xq8, sx = ops.act_quant(x.to(dev), L.to(dev), R.to(dev), n1, n2, cmax, cmin)
+    perm = np.array([0, 2, 4, 6, 1, 3, 5, 7])
+    unperm = xq8.cpu().numpy().reshape(tokens, k // 8, 8)
+    restored = np.empty_like(unperm)
+    restored[:, :, perm] = unperm
+    d8 = np.abs(restored.reshape(tokens, k).astype(np.int32) - codes)
+    assert d8.max() <= (1 if tc else 0) and (d8 != 0).mean() < 2e-3
+    assert torch.allclose(sx.cpu(), s32.cpu(), rtol=1e-3)
 
 
 def test_quantize_rows_deploy_semantics(ops, dev):
@@ -280,3 +319,15 @@ def test_error_behaviour(ops, dev):
         ops.kron_transform(torch.zeros((2, 15 * 24), dtype=torch.float16, device=dev),
                            torch.zeros((15, 15), dtype=torch.float16, device=dev),
                            torch.zeros((24, 24), dtype=torch.float16, device=dev), 15, 24)  # n2 % 16 != 0
+
+
+def test_gemm_i4_repeatable(ops, dev):
+    """Race detector: the same large GEMM 12 times must give the identical (exact) result every time."""
+    rng = np.random.default_rng(99)
+    m, n, k = 1024, 2048, 4096
+    a = rng.integers(-8, 8, (m, k)).astype(np.int8)
+    b = rng.integers(-8, 8, (n, k)).astype(np.int8)
+    ap, bp = T(O.pack_i4(a)).to(dev), T(O.pack_i4(b)).to(dev)
+    ref = torch.from_numpy(O.gemm_i4(a, b)).to(dev)
+    for _ in range(12):
+        assert torch.equal(ops.gemm_i4(ap, bp), ref)
