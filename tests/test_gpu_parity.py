@@ -206,7 +206,8 @@ def test_fused_linear_golden(ops, dev, golden, case):
     # tight check: oracle evaluated on the same fp16-rounded inputs with the kernel's own codes is exact to fp16
     xq, _, s32 = ops.transform_quant(x.to(dev), L.to(dev), R.to(dev), n1, n2, cmax, cmin)
     acc = O.gemm_i4(O.unpack_i4(xq.cpu().numpy()), g["w_codes"])
-    y2 = O.sym_dequant(acc, s32.cpu().numpy(), g["s_w"].reshape(-1), g["bias"] if g["bias"].size else None)
+    y2 = O.sym_dequant(acc, s32.cpu().numpy(), g["s_w"].reshape(-1),
+                       g["bias"].astype(np.float16).astype(np.float32) if g["bias"].size else None)
     assert np.array_equal(y.astype(np.float16), y2.astype(np.float16))
 
 
