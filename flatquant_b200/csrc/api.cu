@@ -214,10 +214,10 @@ int launch_kron(KronParams p, cudaStream_t st) {
 
 
 // ---- tcgen05 Kronecker transform + quantise (the shapes of the Llama linears); other shapes use the HMMA kernel
-template <int N2, int N1P, int T, bool OUT8>
+template <int N2, int N1P, int T, bool OUT8, bool EXACT>
 int launch_kron_tc_t(const KronParams& p, cudaStream_t st) {
     using C = KronTc<N2, N1P, T>;
-    auto kern = kron_quant_tc_kernel<N2, N1P, T, OUT8>;
+    auto kern = kron_quant_tc_kernel<N2, N1P, T, OUT8, EXACT>;
     static bool attr_set = false;
     if (!attr_set) {
         FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -236,7 +236,8 @@ int launch_kron_tc_t(const KronParams& p, cudaStream_t st) {
 
 template <int N2, int N1P, int T>
 int launch_kron_tc_o(const KronParams& p, cudaStream_t st) {
-    return p.xq8 ? launch_kron_tc_t<N2, N1P, T, true>(p, st) : launch_kron_tc_t<N2, N1P, T, false>(p, st);
+    if (p.n1 == N1P) return p.xq8 ? launch_kron_tc_t<N2, N1P, T, true, true>(p, st) : launch_kron_tc_t<N2, N1P, T, false, true>(p, st);
+    return p.xq8 ? launch_kron_tc_t<N2, N1P, T, true, false>(p, st) : launch_kron_tc_t<N2, N1P, T, false, false>(p, st);
 }
 
 // returns 1 if no tcgen05 instantiation covers the request (caller falls back to the HMMA kernel)
