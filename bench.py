@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -131,6 +131,77 @@ class Runner:
                 self.ops.gemm_w4a8(self.xq[k][0], self.xq[k][1], p["w"], p["s_w"], out=self.y[name])
 
 
+# ---------------------------------------------------------------- configs[3]: Llama-3-70B tensor parallel
+H70, I70, KV70, L70 = 8192, 28672, 1024, 80
+
+
+def run_tp70(args, rank, world, local):
+    """Llama-3-70B FlatLinears sharded row/column parallel over `world` GPUs (flatquant_b200/tp.py): per layer
+    qkv (column), o (row + all-reduce), gate_up (column), down (row + all-reduce); seq 2048.  Strong scaling."""
+    import torch.distributed as dist
+    from flatquant_b200 import ops, tp as TP
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+    gen = torch.Generator(device=dev).manual_seed(77 + rank)
+    n_layers = args.layers if args.layers != N_LAYERS else L70
+    cm = float(torch.sigmoid(torch.tensor(4.0)))
+    specs = [("qkv", "col", H70, H70 + 2 * KV70), ("o", "row", H70, H70), ("gate_up", "col", H70, 2 * I70), ("down", "row", I70, H70)]
+    layers = []
+    for _ in range(n_layers):
+        layer = []
+        for name, kind, K, N in specs:
+            sh = TP.column_shard(K, N, world, rank) if kind == "col" else TP.row_shard(K, N, world, rank)
+            kk, nn = sh.k1 - sh.k0, sh.n1 - sh.n0
+            n1, n2 = sh.factors
+            layer.append(dict(kind=kind, sh=sh, kk=kk, nn=nn, n1=n1, n2=n2,
+                              w=torch.randint(0, 256, (nn, kk // 2), dtype=torch.uint8, device=dev, generator=gen),
+                              s_w=torch.rand(nn, device=dev, generator=gen) * 0.01 + 0.005,
+                              left=(torch.randn(n1, n1, device=dev, generator=gen) / n1 ** 0.5).half(),
+                              right=(torch.randn(n2, n2, device=dev, generator=gen) / n2 ** 0.5).half()))
+        layers.append(layer)
+    xs = {kk: torch.randn(SEQ, kk, device=dev, generator=gen).half() for kk in {l["kk"] for l in layers[0]}}
+    xq = {kk: (torch.empty(SEQ, kk, dtype=torch.int8, device=dev), torch.empty(SEQ, dtype=torch.float32, device=dev)) for kk in xs}
+    ys = {i: torch.empty(SEQ, l["nn"], dtype=torch.float16, device=dev) for i, l in enumerate(layers[0])}
+    launches = [0]
+
+    def step():
+        for layer in layers:
+            for i, l in enumerate(layer):
+                ops.act_quant(xs[l["kk"]], l["left"], l["right"], l["n1"], l["n2"], cm, cm, out=xq[l["kk"]])
+                ops.gemm_w4a8(xq[l["kk"]][0], xq[l["kk"]][1], l["w"], l["s_w"], out=ys[i])
+                launches[0] += 2
+                if l["kind"] == "row" and world > 1:
+                    dist.all_reduce(ys[i])
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    launches[0] = 0
+    ms = timed(step, args.steps, barrier)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    if rank == 0:
+        scale = L70 / n_layers
+        ops_layer = sum(2 * K * N for _, _, K, N in specs) * SEQ
+        line = {"metric": "Llama-3-70B W4A4 tensor-parallel prefill tokens/sec (FlatLinear path, 80 layers, seq 2048)",
+                "value": SEQ * args.steps / (ms * 1e-3) / scale, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps * scale, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "s4 x s4 -> s32, f16 in/out", "data": "synthetic",
+                "config": {"workload": "llama3-70b FlatLinear prefill, row/column parallel, 2 NCCL all-reduces of [2048, 8192] f16 per layer",
+                           "parallelism": f"tp{world}", "layers": n_layers},
+                "tops_gemm_per_gpu": ops_layer * n_layers * args.steps / world / (ms * 1e-3) / 1e12,
+                "gpu_launches": launches[0]}
+        if n_layers != L70:
+            line["note"] = f"{n_layers} of 80 identical layers timed, scaled"
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def timed(fn, steps, dist_barrier):
     dist_barrier()
     torch.cuda.synchronize()
@@ -178,6 +249,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=N_LAYERS, help="debug only: fewer layers => INVALID as a bench value")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="llama8b", choices=["llama8b", "llama70b-tp"],
+                    help="llama8b = BASELINE configs[1] (default, data-parallel replicas); llama70b-tp = configs[3]")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -201,6 +274,9 @@ def main():
                 "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
+
+    if args.workload == "llama70b-tp":
+        return run_tp70(args, rank, world, local)
 
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
