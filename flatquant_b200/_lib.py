@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libflatq_b200.so")
@@ -36,6 +36,11 @@ SIGNATURES = {
                                 c_void_p]),
     "flatq_gemm_w4a8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                 c_int, c_void_p]),
+    "flatq_hadamard": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
+    "flatq_kv_quant": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                               c_int, c_int, c_int, c_void_p]),
+    "flatq_kv_decode_i4": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                   c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "flatq_linear_fused_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "flatq_linear_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
                                    c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),

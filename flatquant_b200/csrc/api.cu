@@ -15,6 +15,7 @@
 #include "gemm_w4a8.cuh"
 #include "kron_quant.cuh"
 #include "kron_quant_tc.cuh"
+#include "qattention.cuh"
 
 using namespace flatq;
 
@@ -470,6 +471,62 @@ int flatq_linear_fused(const void* x, const void* left, const void* right, int n
     return flatq_gemm_w4a8(x8, sx, w_packed, s_w, bias, M, N, K, y, out_dtype, stream);
 }
 
+
+int flatq_hadamard(const void* x, void* out, int64_t rows, int n, float scale, flatq_stream_t stream) {
+    FLATQ_CHECK(x && out, FLATQ_ERR_INVALID, "hadamard: null pointer");
+    FLATQ_CHECK(n >= 8 && n <= 32768 && (n & (n - 1)) == 0, FLATQ_ERR_UNSUPPORTED,
+                "hadamard: n=%d must be a power of two in [8, 32768]", n);
+    FLATQ_CHECK(rows > 0 && aligned16(x) && aligned16(out), FLATQ_ERR_INVALID, "hadamard: rows / alignment");
+    int log_n = 0;
+    while ((1 << log_n) < n) ++log_n;
+    int threads = n / 8 < 32 ? 32 : (n / 8 > 1024 ? 1024 : n / 8);
+    const size_t smem = (size_t)(n + n / 32 + 1) * sizeof(float);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        FLATQ_CUDA(cudaFuncSetAttribute(fht_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    const int64_t cap = (int64_t)num_sms() * (n <= 1024 ? 8 : 2);
+    fht_kernel<<<(int)(rows < cap ? rows : cap), threads, smem, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), (int)rows, n, log_n, scale);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+int flatq_kv_quant(const void* x, int64_t tokens, int heads, int head_dim, uint8_t* q_out, void* param_out, uint8_t* kv_data,
+                   void* kv_param, const int32_t* slot, int layer, int n_layers, int kv_select, int page_size,
+                   flatq_stream_t stream) {
+    FLATQ_CHECK(x && (q_out || kv_data), FLATQ_ERR_INVALID, "kv_quant: null pointer");
+    FLATQ_CHECK(head_dim == 128, FLATQ_ERR_UNSUPPORTED, "kv_quant: head_dim=%d (only 128, as in the reference bindings.cpp:148)", head_dim);
+    FLATQ_CHECK(!kv_data || (kv_param && slot && page_size > 0 && n_layers > 0 && layer >= 0 && layer < n_layers &&
+                             (kv_select == 0 || kv_select == 1)), FLATQ_ERR_INVALID, "kv_quant: paged-cache arguments");
+    FLATQ_CHECK(tokens > 0 && heads > 0, FLATQ_ERR_INVALID, "kv_quant: empty");
+    KvQuantParams p;
+    p.x = reinterpret_cast<const __half*>(x); p.tokens = (int)tokens; p.heads = heads; p.D = head_dim;
+    p.q_out = q_out; p.param_out = reinterpret_cast<__half*>(param_out);
+    p.kv_data = kv_data; p.kv_param = reinterpret_cast<__half*>(kv_param); p.slot = slot;
+    p.layer = layer; p.n_layers = n_layers; p.kv_select = kv_select; p.page_size = page_size;
+    kv_quant_kernel<<<grid_for((size_t)tokens * heads * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(p);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+int flatq_kv_decode_i4(const void* q, void* o, const uint8_t* kv_data, const void* kv_param, const int32_t* kv_indptr,
+                       const int32_t* kv_indices, const int32_t* last_page_len, int batch, int q_heads, int kv_heads,
+                       int head_dim, int page_size, int layer, int n_layers, float sm_scale, flatq_stream_t stream) {
+    FLATQ_CHECK(q && o && kv_data && kv_param && kv_indptr && kv_indices && last_page_len, FLATQ_ERR_INVALID, "kv_decode: null pointer");
+    FLATQ_CHECK(head_dim == 128, FLATQ_ERR_UNSUPPORTED, "kv_decode: head_dim=%d (only 128)", head_dim);
+    FLATQ_CHECK(batch > 0 && q_heads > 0 && kv_heads > 0 && q_heads % kv_heads == 0, FLATQ_ERR_INVALID, "kv_decode: heads");
+    DecodeParams p;
+    p.q = reinterpret_cast<const __half*>(q); p.o = reinterpret_cast<__half*>(o);
+    p.kv_data = kv_data; p.kv_param = reinterpret_cast<const __half*>(kv_param);
+    p.kv_indptr = kv_indptr; p.kv_indices = kv_indices; p.last_page_len = last_page_len;
+    p.batch = batch; p.q_heads = q_heads; p.kv_heads = kv_heads; p.D = head_dim; p.page_size = page_size;
+    p.layer = layer; p.n_layers = n_layers; p.sm_scale = sm_scale;
+    decode_attn_i4_kernel<<<dim3(batch, q_heads), 128, 0, (cudaStream_t)stream>>>(p);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
 
 // Debug only (not part of the public header): role-level cycle counters of the GEMM, TN=128 fp16 epilogue.
 // prof: int64 [grid, kGemmWarps, 5]

@@ -1,0 +1,211 @@
+// qattention side path: online Hadamard transform, 4-bit asymmetric KV-cache quantisation into a
+// paged cache, and single-query (decode) attention over the packed INT4 cache.  All HBM-bound SIMT kernels.
+//
+//   fht_kernel             replaces third-party/fast-hadamard-transform/csrc/fast_hadamard_transform_cuda.cu:153-229
+//                          (out = scale * x . H_n per row, n = 2^k): radix-8 butterflies in registers, shared-memory
+//                          exchanges between passes, fp32 arithmetic, 16-byte global accesses.
+//   kv_quant_kernel        replaces deploy/transformers/kv_cache.py:11-51 (`asym_quantize_and_pack_i4`, ~10 torch
+//                          kernels) + AppendPagedKVCache{Prefill,Decode}Kernel (deploy/kernels/include/flashinfer/
+//                          page.cuh:119-219): per (token, head): s = (max-min).clamp(1e-5)/15, zero = -min,
+//                          q = clamp(rint((x+zero)/s), 0, 15) with the reference's fp16 op-by-op rounding, packed
+//                          two per byte and scattered into the page table, params (s, zero) as half2.
+//   decode_attn_i4_kernel  replaces BatchDecodeWithPagedKVCacheKernel (decode.cuh:480-689; dequant quantization.cuh:
+//                          59-84: x_hat = nibble*s - zero): softmax(q.K^T/sqrt(d)).V, online softmax in fp32.
+// Cache layout (kv_cache.py:180-193): data  [pages, layers, 2 (K/V), heads, page_size, head_dim/2] u8
+//                                     param [pages, layers, 2, heads, page_size, 2] f16 (scale, zero)
+#pragma once
+#include "ptx.cuh"
+
+namespace flatq {
+
+// ------------------------------------------------------------------------------------------------ FHT
+// One CTA per row.  smem holds the row as fp32 with one pad word per 32 (bank-conflict-free strided access).
+__device__ __forceinline__ int fht_pad(int i) { return i + (i >> 5); }
+
+template <int RADIX_BITS>
+__device__ __forceinline__ void fht_pass(float* s, int n, int shift, int tid, int nthreads) {
+    constexpr int R = 1 << RADIX_BITS;
+    const int groups = n >> RADIX_BITS;
+    for (int t = tid; t < groups; t += nthreads) {
+        const int base = ((t >> shift) << (shift + RADIX_BITS)) | (t & ((1 << shift) - 1));
+        float v[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = s[fht_pad(base + (j << shift))];
+#pragma unroll
+        for (int h = 1; h < R; h <<= 1) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                if (!(j & h)) {
+                    const float a = v[j], b = v[j | h];
+                    v[j] = a + b;
+                    v[j | h] = a - b;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) s[fht_pad(base + (j << shift))] = v[j];
+    }
+}
+
+__global__ void __launch_bounds__(1024) fht_kernel(const __half* __restrict__ x, __half* __restrict__ out, int rows, int n,
+                                                  int log_n, float scale) {
+    extern __shared__ float fht_s[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)row * n);
+        for (int i = tid; i < n / 8; i += nt) {
+            const uint4 v = src[i];
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h[j]);
+                fht_s[fht_pad(i * 8 + 2 * j)] = f.x;
+                fht_s[fht_pad(i * 8 + 2 * j + 1)] = f.y;
+            }
+        }
+        __syncthreads();
+        int shift = 0;
+        for (; shift + 3 <= log_n; shift += 3) { fht_pass<3>(fht_s, n, shift, tid, nt); __syncthreads(); }
+        if (log_n - shift == 2) { fht_pass<2>(fht_s, n, shift, tid, nt); __syncthreads(); }
+        if (log_n - shift == 1) { fht_pass<1>(fht_s, n, shift, tid, nt); __syncthreads(); }
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * n);
+        for (int i = tid; i < n / 8; i += nt) {
+            uint4 v;
+            __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                h[j] = __floats2half2_rn(fht_s[fht_pad(i * 8 + 2 * j)] * scale, fht_s[fht_pad(i * 8 + 2 * j + 1)] * scale);
+            dst[i] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ KV quantise (+ append)
+// One warp per (token, head) row of D = 128 halves (4 per lane).  slot[token] = page * page_size + offset gives the
+// destination inside the paged cache (host/torch computes it from kv_indptr / kv_indices / last_page_offset).
+struct KvQuantParams {
+    const __half* x;       // [tokens, heads, D]
+    int tokens, heads, D;  // D == 128
+    // contiguous outputs (may be null)
+    uint8_t* q_out;        // [tokens, heads, D/2]
+    __half* param_out;     // [tokens, heads, 2]
+    // paged outputs (may be null)
+    uint8_t* kv_data;      // page layout, see file header
+    __half* kv_param;
+    const int* slot;       // [tokens]
+    int layer, n_layers, kv_select /*0 = K, 1 = V*/, page_size;
+};
+
+__global__ void __launch_bounds__(256) kv_quant_kernel(const KvQuantParams p) {
+    const int lane = threadIdx.x & 31;
+    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int rows = p.tokens * p.heads;
+    for (int r = wg; r < rows; r += nw) {
+        const uint2 raw = reinterpret_cast<const uint2*>(p.x + (size_t)r * p.D)[lane];
+        const __half2 h0 = *reinterpret_cast<const __half2*>(&raw.x), h1 = *reinterpret_cast<const __half2*>(&raw.y);
+        __half2 mx = __hmax2(h0, h1), mn = __hmin2(h0, h1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            uint32_t a = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(&mx), o);
+            uint32_t b = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(&mn), o);
+            mx = __hmax2(mx, *reinterpret_cast<__half2*>(&a));
+            mn = __hmin2(mn, *reinterpret_cast<__half2*>(&b));
+        }
+        const __half xmax = __hmax(__low2half(mx), __high2half(mx)), xmin = __hmin(__low2half(mn), __high2half(mn));
+        // the reference's fp16 tensor ops, one rounding each: (xmax - xmin).clamp(min=1e-5) / 15 ; zero = -xmin
+        __half range = __hsub(xmax, xmin);
+        const __half eps = __float2half_rn(1e-5f);
+        if (__hlt(range, eps)) range = eps;
+        const __half scale = __float2half_rn(__half2float(range) / 15.0f);
+        const __half zero = __hneg(xmin);
+        const float fs = __half2float(scale);
+        uint32_t q[4];
+        const __half xv[4] = {__low2half(h0), __high2half(h0), __low2half(h1), __high2half(h1)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __half t = __hadd(xv[j], zero);                                  // h(x + zero)
+            const __half u = __float2half_rn(__fdiv_rn(__half2float(t), fs));      // h(t / scale)
+            q[j] = (uint32_t)max(0, min(15, __half2int_rn(u)));                    // round half even, clamp
+        }
+        const uint16_t packed = (uint16_t)(q[0] | (q[1] << 4) | (q[2] << 8) | (q[3] << 12));  // elements 4l..4l+3
+        const int token = r / p.heads, head = r % p.heads;
+        if (p.q_out) reinterpret_cast<uint16_t*>(p.q_out + (size_t)r * (p.D / 2))[lane] = packed;
+        if (p.param_out && lane == 0) reinterpret_cast<__half2*>(p.param_out)[r] = __halves2half2(scale, zero);
+        if (p.kv_data) {
+            const int s = p.slot[token], page = s / p.page_size, off = s % p.page_size;
+            const size_t idx = ((((size_t)page * p.n_layers + p.layer) * 2 + p.kv_select) * p.heads + head) * p.page_size + off;
+            reinterpret_cast<uint16_t*>(p.kv_data + idx * (p.D / 2))[lane] = packed;
+            if (lane == 0) reinterpret_cast<__half2*>(p.kv_param)[idx] = __halves2half2(scale, zero);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ decode attention
+// grid (batch, q_heads); 128 threads = 4 warps, each warp takes every 4th token; lane owns 4 of the 128 dims.
+struct DecodeParams {
+    const __half* q;         // [batch, q_heads, D]
+    __half* o;               // [batch, q_heads, D]
+    const uint8_t* kv_data;  // paged, see header
+    const __half* kv_param;
+    const int* kv_indptr;    // [batch + 1] page ranges into kv_indices
+    const int* kv_indices;   // page ids
+    const int* last_page_len;  // [batch] valid entries in the last page (1..page_size)
+    int batch, q_heads, kv_heads, D, page_size, layer, n_layers;
+    float sm_scale;
+};
+
+__global__ void __launch_bounds__(128) decode_attn_i4_kernel(const DecodeParams p) {
+    const int b = blockIdx.x, hq = blockIdx.y, hk = hq / (p.q_heads / p.kv_heads);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ float s_m[4], s_l[4], s_acc[4][128];
+    const uint2 qraw = reinterpret_cast<const uint2*>(p.q + ((size_t)b * p.q_heads + hq) * p.D)[lane];
+    const float2 q01 = __half22float2(*reinterpret_cast<const __half2*>(&qraw.x));
+    const float2 q23 = __half22float2(*reinterpret_cast<const __half2*>(&qraw.y));
+    const float qv[4] = {q01.x * p.sm_scale, q01.y * p.sm_scale, q23.x * p.sm_scale, q23.y * p.sm_scale};
+    float m = -INFINITY, l = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int pg0 = p.kv_indptr[b], pg1 = p.kv_indptr[b + 1];
+    const int n_tok = (pg1 - pg0 - 1) * p.page_size + p.last_page_len[b];
+    for (int t = warp; t < n_tok; t += 4) {
+        const int page = p.kv_indices[pg0 + t / p.page_size], off = t % p.page_size;
+        const size_t kidx = ((((size_t)page * p.n_layers + p.layer) * 2 + 0) * p.kv_heads + hk) * p.page_size + off;
+        const size_t vidx = kidx + (size_t)p.kv_heads * p.page_size;
+        const uint16_t kp = reinterpret_cast<const uint16_t*>(p.kv_data + kidx * (p.D / 2))[lane];
+        const uint16_t vp = reinterpret_cast<const uint16_t*>(p.kv_data + vidx * (p.D / 2))[lane];
+        const float2 kpar = __half22float2(reinterpret_cast<const __half2*>(p.kv_param)[kidx]);
+        const float2 vpar = __half22float2(reinterpret_cast<const __half2*>(p.kv_param)[vidx]);
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dot += qv[j] * ((float)((kp >> (4 * j)) & 0xF) * kpar.x - kpar.y);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        const float m_new = fmaxf(m, dot);
+        const float corr = __expf(m - m_new), pexp = __expf(dot - m_new);
+        l = l * corr + pexp;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = acc[j] * corr + pexp * ((float)((vp >> (4 * j)) & 0xF) * vpar.x - vpar.y);
+        m = m_new;
+    }
+    if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s_acc[warp][lane * 4 + j] = acc[j];
+    __syncthreads();
+    if (warp == 0) {
+        float mm = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
+        float ll = 0.f, out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float c = s_m[w] == -INFINITY ? 0.f : __expf(s_m[w] - mm);
+            ll += s_l[w] * c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[j] += s_acc[w][lane * 4 + j] * c;
+        }
+        const float inv = ll > 0.f ? 1.f / ll : 0.f;
+        uint2 ov;
+        *reinterpret_cast<__half2*>(&ov.x) = __floats2half2_rn(out[0] * inv, out[1] * inv);
+        *reinterpret_cast<__half2*>(&ov.y) = __floats2half2_rn(out[2] * inv, out[3] * inv);
+        reinterpret_cast<uint2*>(p.o + ((size_t)b * p.q_heads + hq) * p.D)[lane] = ov;
+    }
+}
+
+}  // namespace flatq

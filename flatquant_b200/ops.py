@@ -217,3 +217,44 @@ def gemm_w4a8(xq8: torch.Tensor, s_x: torch.Tensor, w_packed: torch.Tensor, s_w:
     _lib.check(_lib.load().flatq_gemm_w4a8(_ptr(xq8), _ptr(s_x), _ptr(w_packed), _ptr(s_w), _ptr(bias), m, n, k, _ptr(y),
                                            _DT[out_dtype], _stream()), "gemm_w4a8")
     return y
+
+
+def hadamard(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """out = scale * x . H_n over the last axis (n a power of two), fp16."""
+    dev = _need_cuda(x)
+    n = x.shape[-1]
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().flatq_hadamard(_ptr(x), _ptr(out), x.numel() // n, n, float(scale), _stream()), "hadamard")
+    return out
+
+
+def kv_quant(x: torch.Tensor, kv_data=None, kv_param=None, slot=None, layer: int = 0, kv_select: int = 0):
+    """Asymmetric 4-bit quantise + pack of K or V rows x [tokens, heads, 128] (fp16).
+
+    Returns (packed u8 [tokens, heads, 64], param f16 [tokens, heads, 2] = (scale, zero)); with a paged cache
+    (kv_data [pages, layers, 2, heads, page_size, 64], kv_param [..., page_size, 2], slot int32 [tokens]) the rows
+    are also scattered into it."""
+    dev = _need_cuda(x, kv_data, kv_param, slot)
+    tokens, heads, d = x.shape
+    q = torch.empty((tokens, heads, d // 2), dtype=torch.uint8, device=dev)
+    par = torch.empty((tokens, heads, 2), dtype=torch.float16, device=dev)
+    n_layers = kv_data.shape[1] if kv_data is not None else 1
+    page_size = kv_data.shape[4] if kv_data is not None else 1
+    _lib.check(_lib.load().flatq_kv_quant(_ptr(x), tokens, heads, d, _ptr(q), _ptr(par), _ptr(kv_data), _ptr(kv_param),
+                                          _ptr(slot), layer, n_layers, kv_select, page_size, _stream()), "kv_quant")
+    return q, par
+
+
+def kv_decode_i4(q: torch.Tensor, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, layer: int = 0,
+                 sm_scale=None) -> torch.Tensor:
+    """Single-query attention over the paged INT4 cache: q [batch, q_heads, 128] fp16 -> o same shape."""
+    dev = _need_cuda(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len)
+    batch, q_heads, d = q.shape
+    o = torch.empty_like(q)
+    if sm_scale is None:
+        sm_scale = d ** -0.5
+    _lib.check(_lib.load().flatq_kv_decode_i4(_ptr(q), _ptr(o), _ptr(kv_data), _ptr(kv_param), _ptr(kv_indptr),
+                                              _ptr(kv_indices), _ptr(last_page_len), batch, q_heads, kv_data.shape[3], d,
+                                              kv_data.shape[4], layer, kv_data.shape[1], float(sm_scale), _stream()),
+               "kv_decode_i4")
+    return o

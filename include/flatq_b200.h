@@ -124,6 +124,27 @@ int flatq_act_quant(const void* x_f16, const void* left_f16, const void* right_f
 int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed, const float* s_w, const void* bias,
                     int64_t M, int64_t N, int64_t K, void* y, int out_dtype, flatq_stream_t stream);
 
+/* ---- a14: qattention side path ------------------------------------------------------------------
+ * flatq_hadamard: out = scale * x . H_n per row, n a power of two in [8, 32768], fp16 in/out, fp32 butterflies.
+ *   Replaces fast_hadamard_transform.hadamard_transform (third-party/fast-hadamard-transform/csrc/
+ *   fast_hadamard_transform.cpp:71-112), as used by deploy/functional/online_trans.py:144-151 and
+ *   deploy/transformers/kv_cache.py:64-67.
+ * flatq_kv_quant: per (token, head) asymmetric 4-bit quantise + pack of K or V (deploy/transformers/kv_cache.py:11-51,
+ *   non-LAC branch) and, when kv_data != NULL, the scatter into the paged cache (init_kv_i4 / append_kv_i4:
+ *   deploy/kernels/bindings.cpp:118-245, include/flashinfer/page.cuh:119-219).  head_dim == 128.
+ *   slot[token] = page_id * page_size + offset.  Cache layout: data [pages, layers, 2, heads, page_size, 64] u8,
+ *   param [pages, layers, 2, heads, page_size, 2] f16 (scale, zero)  (kv_cache.py:180-193).
+ * flatq_kv_decode_i4: single-query attention over the packed cache (batch_decode_i4: bindings.cpp:118-170,
+ *   include/flashinfer/decode.cuh:480-689): o = softmax(q.K^T * sm_scale) . V with x_hat = nibble*scale - zero. */
+int flatq_hadamard(const void* x_f16, void* out_f16, int64_t rows, int n, float scale, flatq_stream_t stream);
+int flatq_kv_quant(const void* x_f16, int64_t tokens, int heads, int head_dim, uint8_t* q_out, void* param_out_f16,
+                   uint8_t* kv_data, void* kv_param_f16, const int32_t* slot, int layer, int n_layers, int kv_select,
+                   int page_size, flatq_stream_t stream);
+int flatq_kv_decode_i4(const void* q_f16, void* o_f16, const uint8_t* kv_data, const void* kv_param_f16,
+                       const int32_t* kv_indptr, const int32_t* kv_indices, const int32_t* last_page_len, int batch,
+                       int q_heads, int kv_heads, int head_dim, int page_size, int layer, int n_layers, float sm_scale,
+                       flatq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -332,3 +332,85 @@ def test_gemm_i4_repeatable(ops, dev):
     ref = torch.from_numpy(O.gemm_i4(a, b)).to(dev)
     for _ in range(12):
         assert torch.equal(ops.gemm_i4(ap, bp), ref)
+
+
+# ------------------------------------------------------------------ a14: qattention side path
+@pytest.mark.parametrize("n", [32, 128, 1024, 4096])
+def test_hadamard_golden(ops, dev, golden, n):
+    g = golden("hadamard")
+    x = T(g[f"x_{n}"]).half()
+    y = ops.hadamard(x.to(dev), 1.0 / n ** 0.5).float().cpu().numpy()
+    ref = O.hadamard_transform(x.float().numpy(), 1.0 / n ** 0.5)
+    # FHT tolerance rule of third-party/fast-hadamard-transform/tests: a few fp16 ulps of the output magnitude
+    assert np.abs(y - ref).max() <= 2 ** -9 * max(1.0, np.abs(ref).max())
+    assert np.abs(y - g[f"y_{n}"]).max() <= 2e-2  # golden is from the fp32 input; x was rounded to fp16 here
+
+
+def test_hadamard_properties_large(ops, dev):
+    """n = 32768 (the FHT maximum): H.H = n.I (round trip) and Parseval, on 64 rows."""
+    torch.manual_seed(0)
+    x = torch.randn(64, 32768, device=dev).half()
+    y = ops.hadamard(x, 1.0 / 32768 ** 0.5)
+    z = ops.hadamard(y, 1.0 / 32768 ** 0.5)
+    assert (z.float() - x.float()).abs().max() < 2e-2
+    assert torch.allclose(y.float().pow(2).sum(1), x.float().pow(2).sum(1), rtol=1e-2)
+
+
+def test_kv_quant_golden_bit_exact(ops, dev, golden):
+    g = golden("kv_asym")
+    x = T(g["x"]).reshape(-1, g["x"].shape[-2], 128)  # [tokens, heads, 128]
+    q, par = ops.kv_quant(x.to(dev))
+    assert np.array_equal(q.cpu().numpy(), g["packed"].reshape(q.shape))
+    assert np.array_equal(par[..., 0].cpu().numpy(), g["scale"].reshape(par.shape[:2]))
+    assert np.array_equal(par[..., 1].cpu().numpy(), g["zero"].reshape(par.shape[:2]))
+    torch.manual_seed(1)
+    x2 = (torch.randn(300, 8, 128) * 2).half()
+    q2, par2 = ops.kv_quant(x2.to(dev))
+    pk, s, z = O.kv_asym_quant(x2)
+    assert torch.equal(q2.cpu(), pk) and torch.equal(par2[..., :1].cpu(), s) and torch.equal(par2[..., 1:].cpu(), z)
+
+
+def test_paged_kv_append_and_decode(ops, dev):
+    """init (prefill) + append (decode) into the paged INT4 cache, then single-query attention, vs the oracle."""
+    torch.manual_seed(2)
+    B, Hq, Hkv, D, PS, L, layer = 3, 8, 2, 128, 16, 2, 1
+    lens = [37, 16, 5]
+    pages_per = [(n + PS - 1) // PS for n in lens]
+    n_pages = sum(pages_per) + 2
+    kv_data = torch.zeros(n_pages, L, 2, Hkv, PS, D // 2, dtype=torch.uint8, device=dev)
+    kv_param = torch.zeros(n_pages, L, 2, Hkv, PS, 2, dtype=torch.float16, device=dev)
+    perm = torch.randperm(n_pages)[:sum(pages_per)].tolist()  # scattered page ids
+    indptr, indices, slots, last = [0], [], [], []
+    ks, vs = [], []
+    for b, n in enumerate(lens):
+        pg = perm[indptr[-1]:indptr[-1] + pages_per[b]]
+        indices += pg
+        indptr.append(indptr[-1] + pages_per[b])
+        last.append(n - (pages_per[b] - 1) * PS)
+        slots += [pg[t // PS] * PS + t % PS for t in range(n)]
+        ks.append((torch.randn(n, Hkv, D) * 1.5).half())
+        vs.append(torch.randn(n, Hkv, D).half())
+    k_all, v_all = torch.cat(ks).to(dev), torch.cat(vs).to(dev)
+    slot_t = torch.tensor(slots, dtype=torch.int32, device=dev)
+    # all but the last token of every sequence in one "init" call, the last one as a decode-time append
+    is_last = torch.zeros(len(slots), dtype=torch.bool)
+    pos = 0
+    for n in lens:
+        is_last[pos + n - 1] = True
+        pos += n
+    for sel, src in ((0, k_all), (1, v_all)):
+        ops.kv_quant(src[~is_last.to(dev)].contiguous(), kv_data, kv_param, slot_t[~is_last.to(dev)].contiguous(), layer, sel)
+        ops.kv_quant(src[is_last.to(dev)].contiguous(), kv_data, kv_param, slot_t[is_last.to(dev)].contiguous(), layer, sel)
+    q = torch.randn(B, Hq, D).half()
+    o = ops.kv_decode_i4(q.to(dev), kv_data, kv_param, torch.tensor(indptr, dtype=torch.int32, device=dev),
+                         torch.tensor(indices, dtype=torch.int32, device=dev), torch.tensor(last, dtype=torch.int32, device=dev),
+                         layer=layer).float().cpu()
+    assert not kv_data[:, 0].any()  # the other layer is untouched
+    for b, n in enumerate(lens):
+        kp, ksc, kz = O.kv_asym_quant(ks[b])
+        vp, vsc, vz = O.kv_asym_quant(vs[b])
+        rep = Hq // Hkv
+        ref = O.decode_attention_i4(q[b:b + 1], kp.repeat_interleave(rep, 1)[None], ksc.repeat_interleave(rep, 1)[None],
+                                    kz.repeat_interleave(rep, 1)[None], vp.repeat_interleave(rep, 1)[None],
+                                    vsc.repeat_interleave(rep, 1)[None], vz.repeat_interleave(rep, 1)[None])[0]
+        assert (o[b] - ref).abs().max() < 5e-3  # fp16 output + fp16-vs-fp32 dequant arithmetic
