@@ -1,0 +1,96 @@
+"""Paged 4-bit KV cache (mirror of deploy/transformers/kv_cache.py:170-359, without the HF `Cache` base class so that it
+does not depend on a transformers version).  Same constructor arguments, same storage layout
+
+    pages  [max_pages * batch, n_layers, 2, heads, page_size, head_dim/2] u8
+    scales [max_pages * batch, n_layers, 2, heads, page_size, 2] f16   (scale, zero)
+
+and the same `update(key_states, value_states, layer_idx, cache_kwargs)` protocol: the first call per layer (prefill)
+stores the quantised K/V and returns the (transformed) fp16 states for flash attention; later calls (one token) append
+and return a closure that runs single-query attention over the packed cache.
+
+Per call the reference launches ~15 torch kernels + FHT/matmul + an append kernel (kv_cache.py:263-353); here it is
+one transform launch (Hadamard or 128x128 matmul) + one fused quantise/pack/scatter launch per K and V, and one
+decode-attention launch."""
+import functools
+import math
+
+import torch
+
+from ... import ops
+
+
+class MultiLayerPagedKVCache4Bit:
+    def __init__(self, batch_size, page_size, max_seq_len, device, n_layers, num_heads, head_dim, disable_quant=False,
+                 trans_dtype=torch.float16, trans="had", group_size=1):
+        if disable_quant:
+            raise NotImplementedError("flatquant_b200 implements the INT4 cache only")
+        self.batch_size, self.page_size, self.max_seq_len = batch_size, page_size, max_seq_len
+        self.device, self.n_layers, self.num_heads, self.org_head_dim = device, n_layers, num_heads, head_dim
+        self.trans, self.trans_dtype, self.group_size = trans, trans_dtype, group_size
+        self.max_page_cnt = self.page_cnt_from_length(max_seq_len)
+        self.pages = torch.zeros((self.max_page_cnt * batch_size, n_layers, 2, num_heads, page_size, head_dim // 2),
+                                 dtype=torch.uint8, device=device)
+        self.scales = torch.zeros((self.max_page_cnt * batch_size, n_layers, 2, num_heads, page_size, 2),
+                                  dtype=torch.float16, device=device)
+        self._needs_init = [True] * n_layers
+        self.length = 0
+        # sequence b owns pages [b * max_page_cnt, (b + 1) * max_page_cnt)
+        self._page_base = torch.arange(batch_size, dtype=torch.int32, device=device) * self.max_page_cnt
+
+    def page_cnt_from_length(self, length):
+        return (length + self.page_size - 1) // self.page_size
+
+    def seen_tokens(self):
+        return self.length
+
+    def _transform(self, x, matrix):
+        """K (and Q at decode) <- x . T_k: 128x128 matmul ('matmul*') or H_128/sqrt(128) ('had')."""
+        if self.trans == "had":
+            return ops.hadamard(x.to(torch.float16).contiguous(), 1.0 / math.sqrt(x.shape[-1]))
+        if self.trans.startswith("matmul"):
+            flat = x.to(torch.float16).reshape(-1, x.shape[-1]).contiguous()
+            n = flat.shape[-1]
+            return ops.kron_transform(flat, None, matrix.to(flat).contiguous(), 1, n).view(x.shape)
+        return x
+
+    def _slots(self, start, count):
+        """slot = page * page_size + offset for tokens [start, start + count) of every sequence -> int32 [batch * count]"""
+        t = torch.arange(start, start + count, dtype=torch.int32, device=self.device)
+        page = self._page_base[:, None] + (t // self.page_size)[None, :]
+        return (page * self.page_size + (t % self.page_size)[None, :]).reshape(-1).contiguous()
+
+    def _attention_kwargs(self):
+        n_pages = self.page_cnt_from_length(self.length)
+        indptr = torch.arange(self.batch_size + 1, dtype=torch.int32, device=self.device) * n_pages
+        indices = (self._page_base[:, None] + torch.arange(n_pages, dtype=torch.int32, device=self.device)[None, :]).reshape(-1)
+        last = torch.full((self.batch_size,), self.length - (n_pages - 1) * self.page_size, dtype=torch.int32, device=self.device)
+        return dict(kv_indptr=indptr, kv_indices=indices.contiguous(), last_page_len=last)
+
+    def _decode(self, q, num_kv_heads, attention_kwargs, layer_idx, k_inv_t):
+        b, q_len, hq, d = q.shape
+        assert q_len == 1
+        qt = self._transform(q.view(b, hq, d), k_inv_t)
+        o = ops.kv_decode_i4(qt.contiguous(), self.pages, self.scales, layer=layer_idx, **attention_kwargs)
+        return o.unsqueeze(1)
+
+    def update(self, key_states, value_states, layer_idx, cache_kwargs=None):
+        cache_kwargs = cache_kwargs or {}
+        k_mat, k_inv_t = cache_kwargs.get("trans_matrix_k"), cache_kwargs.get("trans_matrix_k_inv_t")
+        b, added, heads, d = key_states.shape
+        assert b == self.batch_size
+        key_t = self._transform(key_states, k_mat)
+        if layer_idx == 0:
+            start = self.length
+            self.length += added
+            self._start = start
+        slots = self._slots(self._start, added)
+        kq = key_t.reshape(b * added, heads, d).to(torch.float16).contiguous()
+        vq = value_states.reshape(b * added, heads, d).to(torch.float16).contiguous()
+        ops.kv_quant(kq, self.pages, self.scales, slots, layer_idx, 0)
+        ops.kv_quant(vq, self.pages, self.scales, slots, layer_idx, 1)
+        if self._needs_init[layer_idx]:
+            self._needs_init[layer_idx] = False
+            return key_t, value_states  # prefill: attention runs on the (transformed) fp16 states
+        assert added == 1
+        return functools.partial(self._decode, num_kv_heads=heads, attention_kwargs=self._attention_kwargs(),
+                                 layer_idx=layer_idx, k_inv_t=k_inv_t if self.trans.startswith("matmul") else None)

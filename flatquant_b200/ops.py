@@ -138,6 +138,9 @@ def kron_transform(x: torch.Tensor, left, right, n1: int, n2: int) -> torch.Tens
     """kronecker_matmul on fp16: x [..., n1*n2] -> same shape."""
     dev = _need_cuda(x, left, right)
     z = torch.empty_like(x)
+    if left is None:  # rows are independent: group 16 of them per "token" so that no MMA row is padding
+        rows = x.numel() // n2
+        n1 = next(c for c in (16, 8, 4, 2, 1) if rows % c == 0)
     tokens = x.numel() // (n1 * n2)
     _lib.check(_lib.load().flatq_kron_transform(_ptr(x), _ptr(left), _ptr(right), tokens, n1, n2, _ptr(z), _stream()),
                "kron_transform")

@@ -414,3 +414,59 @@ def test_paged_kv_append_and_decode(ops, dev):
                                     kz.repeat_interleave(rep, 1)[None], vp.repeat_interleave(rep, 1)[None],
                                     vsc.repeat_interleave(rep, 1)[None], vz.repeat_interleave(rep, 1)[None])[0]
         assert (o[b] - ref).abs().max() < 5e-3  # fp16 output + fp16-vs-fp32 dequant arithmetic
+
+
+def test_kv_cache_module_prefill_then_decode(dev):
+    """deploy.transformers.MultiLayerPagedKVCache4Bit protocol (kv_cache.py:231-359): prefill update returns the
+    transformed fp16 states, decode update returns a closure running attention over the INT4 pages."""
+    from flatquant_b200.deploy.transformers import MultiLayerPagedKVCache4Bit
+    torch.manual_seed(5)
+    B, T, H, D, L = 2, 21, 4, 128, 2
+    cache = MultiLayerPagedKVCache4Bit(B, 16, 64, dev, L, H, D, trans="had")
+    k = torch.randn(B, T, H, D, device=dev).half()
+    v = torch.randn(B, T, H, D, device=dev).half()
+    for layer in range(L):
+        kt, vt = cache.update(k, v, layer)
+        assert kt.shape == k.shape and torch.equal(vt, v)
+    assert cache.seen_tokens() == T
+    k1 = torch.randn(B, 1, H, D, device=dev).half()
+    v1 = torch.randn(B, 1, H, D, device=dev).half()
+    q = torch.randn(B, 1, 2 * H, D, device=dev).half()  # GQA: 2 query heads per kv head
+    for layer in range(L):
+        attn = cache.update(k1, v1, layer)
+        o = attn(q)
+        assert o.shape == (B, 1, 2 * H, D)
+        if layer == L - 1:
+            had = lambda t: torch.from_numpy(O.hadamard_transform(t.float().cpu().numpy(), 1 / D ** 0.5)).half()  # noqa: E731
+            kk = torch.cat([had(k), had(k1)], 1)
+            vv = torch.cat([v.cpu(), v1.cpu()], 1)
+            kp, ks, kz = O.kv_asym_quant(kk)
+            vp, vs_, vz = O.kv_asym_quant(vv)
+            r = lambda t: t.repeat_interleave(2, 2)  # noqa: E731
+            ref = O.decode_attention_i4(had(q)[:, 0], r(kp), r(ks), r(kz), r(vp), r(vs_), r(vz))
+            assert (o[:, 0].float().cpu() - ref).abs().max() < 2e-2
+
+
+def test_kernel_level_api(dev):
+    """deploy.kernels.kron_matmul / block_matmul signatures (kron_matmul.py:192, block_matmul.py:231)."""
+    from flatquant_b200.deploy.kernels.block_matmul import block_matmul
+    from flatquant_b200.deploy.kernels.kron_matmul import kron_matmul
+    torch.manual_seed(6)
+    B, n1, n2 = 10, 64, 64
+    L = (torch.randn(n1, n1) / 8).half()
+    R = (torch.randn(n2, n2) / 8).half()
+    x = torch.randn(B, n1, n2).half()
+    pk = kron_matmul(L.t().contiguous().to(dev), x.to(dev), R.to(dev), 5, 4.0, 4.0)
+    q_em, _ = _emulated_codes(x.reshape(B, -1), L, R, float(torch.sigmoid(torch.tensor(4.0))), float(torch.sigmoid(torch.tensor(4.0))), "xr")
+    d = np.abs(O.unpack_i4(pk.quantized_x.cpu().numpy()) - q_em)
+    assert pk.scales_x.shape == (B, 1) and d.max() <= 1 and (d != 0).mean() < 2e-3
+    heads, hd = 32, 128
+    a = torch.randn(B, hd, heads).half()  # [B, M=head_dim, N=heads]
+    o_t = (torch.randn(heads, heads) / heads ** 0.5).half()
+    pb = block_matmul(a.to(dev), o_t.to(dev), 5, 4.0, 4.0)
+    z = torch.matmul(a.float(), o_t.float()).transpose(1, 2).reshape(B, -1)  # transposed packing order
+    c = float(torch.sigmoid(torch.tensor(4.0)))
+    s = torch.maximum((z.amin(1).clamp(max=0) * c).abs(), z.amax(1).clamp(min=0) * c) / 7
+    qz = torch.clamp(torch.round(z / s[:, None]), -8, 7).numpy().astype(np.int32)
+    d = np.abs(O.unpack_i4(pb.quantized_x.cpu().numpy()) - qz)
+    assert d.max() <= 1 and (d != 0).mean() < 0.02
