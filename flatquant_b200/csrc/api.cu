@@ -65,6 +65,20 @@ int grid_for(size_t n_items, int block, int max_waves = 8) {
     return (int)g;
 }
 
+// ---- launches with programmatic dependent launch (PDL): the kernel's prologue overlaps the previous kernel's tail
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    static const bool use_pdl = getenv("FLATQ_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- TMA descriptors through the runtime-resolved driver entry point (no link-time libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -113,8 +127,7 @@ int launch_gemm_t(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams
     }
     const int tiles = ((p.N + kGemmBlockW - 1) / kGemmBlockW) * ((p.M + TN - 1) / TN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, kGemmThreads, smem, st>>>(tw, tx, p);
-    FLATQ_CUDA(cudaGetLastError());
+    FLATQ_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, st, tw, tx, p));
     return FLATQ_OK;
 }
 
@@ -163,8 +176,7 @@ int launch_kron_t(const KronParams& p, int threads, size_t smem, int grid, cudaS
         FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
-    kern<<<grid, threads, smem, st>>>(p);
-    FLATQ_CUDA(cudaGetLastError());
+    FLATQ_CUDA(launch_pdl(kern, dim3(grid), dim3(threads), smem, st, p));
     return FLATQ_OK;
 }
 
@@ -230,8 +242,7 @@ int launch_kron_tc_t(const KronParams& p, cudaStream_t st) {
     if (rc) return rc;
     const int groups = (p.tokens + T - 1) / T;
     const int cap = 2 * num_sms();
-    kern<<<groups < cap ? groups : cap, C::kThreads, C::kSmemBytes, st>>>(tx, p);
-    FLATQ_CUDA(cudaGetLastError());
+    FLATQ_CUDA(launch_pdl(kern, dim3(groups < cap ? groups : cap), dim3(C::kThreads), (size_t)C::kSmemBytes, st, tx, p));
     return FLATQ_OK;
 }
 
@@ -265,9 +276,8 @@ int launch_rowquant(const void* x, int64_t tokens, int64_t K, float cmax, float 
     FLATQ_CHECK(aligned16(x), FLATQ_ERR_INVALID, "x must be 16-byte aligned");
     const int block = 256;
     const int grid = grid_for((size_t)tokens * 32, block, 8);
-    rowquant_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __half*>(x), (int)tokens, (int)K, cmax, cmin,
-                                            half_math, xq4, xq8, sx32, reinterpret_cast<__half*>(sx16));
-    FLATQ_CUDA(cudaGetLastError());
+    FLATQ_CUDA(launch_pdl(rowquant_kernel, dim3(grid), dim3(block), 0, st, reinterpret_cast<const __half*>(x), (int)tokens,
+                          (int)K, cmax, cmin, half_math, xq4, xq8, sx32, reinterpret_cast<__half*>(sx16)));
     return FLATQ_OK;
 }
 

@@ -127,6 +127,8 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    grid_dep_launch();  // PDL: the next kernel may begin its prologue as SMs free up
+    grid_dep_wait();    // everything above overlapped the previous kernel's tail; its outputs are visible from here
 
     const int nb_w = (p.N + kGemmBlockW - 1) / kGemmBlockW;
     const int nb_m = (p.M + TN - 1) / TN;

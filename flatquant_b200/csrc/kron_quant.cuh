@@ -99,6 +99,8 @@ kron_quant_mma_kernel(const KronParams p) {
         }
     }
 
+    grid_dep_launch();  // PDL: factors are static weights; activations are read after the wait
+    grid_dep_wait();
     const int mi = lane >> 3, r8 = lane & 7;
     for (int tb = blockIdx.x * tpc; tb < p.tokens; tb += gridDim.x * tpc) {
         __syncthreads();
@@ -258,6 +260,8 @@ __global__ void __launch_bounds__(256)
 rowquant_kernel(const __half* __restrict__ x, int tokens, int K, float c_max, float c_min, int half_math,
                 uint8_t* __restrict__ xq4, int8_t* __restrict__ xq8, float* __restrict__ sx_f32,
                 __half* __restrict__ sx_f16) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int t = warp_g; t < tokens; t += nwarps) {

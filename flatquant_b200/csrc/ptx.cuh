@@ -199,6 +199,13 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// wait: block until the grids this one depends on have completed and their writes are visible (no-op when the kernel
+// was not launched with the programmatic-serialisation attribute).  launch: let the next grid in the stream start
+// its prologue (barrier init, TMEM alloc, factor set-up) on SMs this grid no longer needs.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- misc
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
