@@ -132,6 +132,8 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
 
     const int nb_w = (p.N + kGemmBlockW - 1) / kGemmBlockW;
     const int nb_m = (p.M + TN - 1) / TN;
+    // tile order: token blocks fastest, so the CTAs running concurrently share few weight tiles (each packed W tile
+    // is fetched from HBM once and re-read from L2 by its other token blocks) while all of X stays L2-resident
     const int n_tiles = nb_w * nb_m;
     const int KB = (p.K + kGemmBlockK - 1) / kGemmBlockK;
 
@@ -140,7 +142,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m0 = (tile / nb_w) * TN;
+                const int m0 = (tile % nb_m) * TN;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                     FLATQ_TWAIT(0, mbar_wait(&empty[s], ph ^ 1));
@@ -156,7 +158,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int n0 = (tile % nb_w) * kGemmBlockW;
+                const int n0 = (tile / nb_m) * kGemmBlockW;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t s = it % kStagesW, ph = (it / kStagesW) & 1;
                     FLATQ_TWAIT(0, mbar_wait(&wempty[s], ph ^ 1));
@@ -251,8 +253,8 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         uint32_t tile_iter = 0;
         constexpr int COLS = TN / 4 < 16 ? 16 : TN / 4;   // token columns per epilogue warp (small TN: some quarters idle)
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
-            const int n0 = (tile % nb_w) * kGemmBlockW;
-            const int m0 = (tile / nb_w) * TN;
+            const int n0 = (tile / nb_m) * kGemmBlockW;
+            const int m0 = (tile % nb_m) * TN;
             const uint32_t b = tile_iter % NBUF, phb = (tile_iter / NBUF) & 1;
             const int n = n0 + q * 32 + lane;
             const bool n_ok = n < p.N;
