@@ -125,7 +125,7 @@ int launch_gemm_t(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams
         FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    const int tiles = ((p.N + kGemmBlockW - 1) / kGemmBlockW) * ((p.M + TN - 1) / TN);
+    const int tiles = ((p.N + kGemmBlockW - 1) / kGemmBlockW) * ((p.M + TN - 1) / TN) * (p.k_splits > 1 ? p.k_splits : 1);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     FLATQ_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, st, tw, tx, p));
     return FLATQ_OK;
@@ -144,7 +144,7 @@ int launch_gemm_m(int tn, const CUtensorMap& tw, const CUtensorMap& tx, const Ge
 
 // w_packed [N, K/2]; x8 [M, K] int8 in the permuted operand format
 int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, int64_t K, int acc_shift, void* out,
-                int mode, const float* sx, const float* sw, const void* bias, cudaStream_t st) {
+                int mode, const float* sx, const float* sw, const void* bias, cudaStream_t st, int k_splits = 1) {
     FLATQ_CHECK(M > 0 && N > 0 && K > 0, FLATQ_ERR_INVALID, "empty GEMM %lldx%lldx%lld", (long long)M, (long long)N,
                 (long long)K);
     FLATQ_CHECK(K % 32 == 0, FLATQ_ERR_INVALID, "K=%lld must be a multiple of 32", (long long)K);
@@ -158,7 +158,7 @@ int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, i
     if (rc) return rc;
     GemmParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = acc_shift;
-    p.out = out; p.s_x = sx; p.s_w = sw; p.bias = bias; p.prof = nullptr; p.dbg = 0;
+    p.out = out; p.s_x = sx; p.s_w = sw; p.bias = bias; p.prof = nullptr; p.dbg = 0; p.k_splits = k_splits;
     switch (mode) {
         case kEpiI32: return launch_gemm_m<kEpiI32>(tn, tw, tx, p, st);
         case kEpiF16: return launch_gemm_m<kEpiF16>(tn, tw, tx, p, st);
@@ -436,8 +436,24 @@ int flatq_quantize_rows(const void* x, int64_t tokens, int64_t K, float clip_max
                            (cudaStream_t)stream);
 }
 
-size_t flatq_linear_fused_workspace_bytes(int64_t M, int64_t K) {
-    return align_up((size_t)M * K, 256) + align_up((size_t)M * 4, 256);
+// decode shapes (M <= 64): too few 128-row tiles to occupy the chip -> split K over CTAs into an int32 workspace
+static int decode_splits(int64_t M, int64_t N, int64_t K) {
+    if (M > 64) return 1;
+    const int64_t tiles = (N + kGemmBlockW - 1) / kGemmBlockW;
+    const int64_t kb = (K + kGemmBlockK - 1) / kGemmBlockK;
+    int64_t s = num_sms() / tiles;
+    if (s > 8) s = 8;
+    if (s > kb) s = kb;
+    return s < 2 ? 1 : (int)s;
+}
+
+size_t flatq_linear_fused_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    return align_up((size_t)M * K, 256) + align_up((size_t)M * 4, 256) + (M <= 64 ? align_up((size_t)M * N * 4, 256) : 0);
+}
+
+size_t flatq_gemm_w4a8_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    (void)K;
+    return M <= 64 ? align_up((size_t)M * N * 4, 256) : 0;
 }
 
 int flatq_act_quant(const void* x, const void* left, const void* right, int n1, int n2, float clip_max, float clip_min,
@@ -459,12 +475,30 @@ int flatq_act_quant(const void* x, const void* left, const void* right, int n1, 
 }
 
 int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed, const float* s_w, const void* bias,
-                    int64_t M, int64_t N, int64_t K, void* y, int out_dtype, flatq_stream_t stream) {
+                    int64_t M, int64_t N, int64_t K, void* y, int out_dtype, void* ws, size_t ws_bytes,
+                    flatq_stream_t stream) {
     FLATQ_CHECK(xq8 && s_x && w_packed && s_w && y, FLATQ_ERR_INVALID, "gemm_w4a8: null pointer");
     FLATQ_CHECK(out_dtype == FLATQ_F16 || out_dtype == FLATQ_BF16, FLATQ_ERR_INVALID, "gemm_w4a8: out_dtype");
     FLATQ_CHECK(K % 32 == 0, FLATQ_ERR_INVALID, "gemm_w4a8: K=%lld must be a multiple of 32", (long long)K);
-    return launch_gemm(w_packed, xq8, M, N, K, 4, y, out_dtype == FLATQ_F16 ? kEpiF16 : kEpiBF16, s_x, s_w, bias,
-                       (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int splits = (ws && ws_bytes >= flatq_gemm_w4a8_workspace_bytes(M, N, K)) ? decode_splits(M, N, K) : 1;
+    if (splits == 1)
+        return launch_gemm(w_packed, xq8, M, N, K, 4, y, out_dtype == FLATQ_F16 ? kEpiF16 : kEpiBF16, s_x, s_w, bias, st);
+    // split-K: zero the int32 workspace, accumulate partial tiles with atomics, dequantise in a finalize pass
+    FLATQ_CHECK(aligned16(ws), FLATQ_ERR_INVALID, "gemm_w4a8: workspace alignment");
+    FLATQ_CUDA(cudaMemsetAsync(ws, 0, (size_t)M * N * 4, st));
+    int rc = launch_gemm(w_packed, xq8, M, N, K, 4, ws, kEpiI32, nullptr, nullptr, nullptr, st, splits);
+    if (rc) return rc;
+    const int g = grid_for((size_t)M * N, 256, 4);
+    if (out_dtype == FLATQ_F16)
+        splitk_finalize_kernel<__half><<<g, 256, 0, st>>>(reinterpret_cast<const int32_t*>(ws), s_x, s_w,
+                                                          reinterpret_cast<const __half*>(bias), reinterpret_cast<__half*>(y), (int)M, (int)N);
+    else
+        splitk_finalize_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(reinterpret_cast<const int32_t*>(ws), s_x, s_w,
+                                                                 reinterpret_cast<const __nv_bfloat16*>(bias),
+                                                                 reinterpret_cast<__nv_bfloat16*>(y), (int)M, (int)N);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
 }
 
 int flatq_linear_fused(const void* x, const void* left, const void* right, int n1, int n2, float clip_max,
@@ -472,15 +506,17 @@ int flatq_linear_fused(const void* x, const void* left, const void* right, int n
                        void* y, int out_dtype, void* ws, size_t ws_bytes, flatq_stream_t stream) {
     FLATQ_CHECK(x && w_packed && s_w && y && ws, FLATQ_ERR_INVALID, "linear_fused: null pointer");
     const int64_t K = (int64_t)n1 * n2;
-    FLATQ_CHECK(ws_bytes >= flatq_linear_fused_workspace_bytes(M, K), FLATQ_ERR_WORKSPACE, "linear_fused: workspace too small");
+    FLATQ_CHECK(ws_bytes >= flatq_linear_fused_workspace_bytes(M, N, K), FLATQ_ERR_WORKSPACE, "linear_fused: workspace too small");
     FLATQ_CHECK(aligned16(ws), FLATQ_ERR_INVALID, "linear_fused: workspace alignment");
     int8_t* x8 = reinterpret_cast<int8_t*>(ws);
-    float* sx = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + align_up((size_t)M * K, 256));
+    uint8_t* p = reinterpret_cast<uint8_t*>(ws) + align_up((size_t)M * K, 256);
+    float* sx = reinterpret_cast<float*>(p);
+    void* acc_ws = M <= 64 ? p + align_up((size_t)M * 4, 256) : nullptr;
     int rc = flatq_act_quant(x, left, right, n1, n2, clip_max, clip_min, M, x8, sx, stream);
     if (rc) return rc;
-    return flatq_gemm_w4a8(x8, sx, w_packed, s_w, bias, M, N, K, y, out_dtype, stream);
+    return flatq_gemm_w4a8(x8, sx, w_packed, s_w, bias, M, N, K, y, out_dtype, acc_ws, acc_ws ? align_up((size_t)M * N * 4, 256) : 0,
+                           stream);
 }
-
 
 int flatq_hadamard(const void* x, void* out, int64_t rows, int n, float scale, flatq_stream_t stream) {
     FLATQ_CHECK(x && out, FLATQ_ERR_INVALID, "hadamard: null pointer");
@@ -549,7 +585,7 @@ int flatq_debug_gemm_profile(const int8_t* xq8, const float* s_x, const uint8_t*
     if (rc) return rc;
     GemmParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = 4;
-    p.out = y; p.s_x = s_x; p.s_w = s_w; p.bias = nullptr; p.prof = prof; p.dbg = dbg;
+    p.out = y; p.s_x = s_x; p.s_w = s_w; p.bias = nullptr; p.prof = prof; p.dbg = dbg; p.k_splits = 1;
     auto kern = gemm_w4a8_kernel<256, kEpiF16, true>;
     constexpr int smem = GemmSmem<256>::kBytes;
     FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -116,6 +116,20 @@ __global__ void sym_dequant_kernel(const int32_t* __restrict__ acc, const __half
     }
 }
 
+// split-K finalize: y = acc * s_x[m] * s_w[n] (+bias) from the int32 workspace the GEMM CTAs accumulated into
+template <typename OutT>
+__global__ void splitk_finalize_kernel(const int32_t* __restrict__ acc, const float* __restrict__ s_x,
+                                       const float* __restrict__ s_w, const OutT* __restrict__ bias, OutT* __restrict__ out,
+                                       int rows, int cols) {
+    const size_t n = (size_t)rows * cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i % cols);
+        float y = __fmul_rn(__fmul_rn((float)acc[i], s_x[r]), s_w[c]);
+        if (bias) y = __fadd_rn(y, static_cast<float>(bias[c]));
+        out[i] = static_cast<OutT>(y);
+    }
+}
+
 // fp16 -> fp32 scale conversion for the fused-epilogue GEMM entry point
 __global__ void half_to_float_kernel(const __half* __restrict__ in, float* __restrict__ out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

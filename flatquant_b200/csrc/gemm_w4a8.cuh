@@ -74,6 +74,7 @@ struct GemmParams {
     const float* s_x;     // [M]  per-token scale   (dequant modes)
     const float* s_w;     // [N]  per-channel scale (dequant modes)
     const void* bias;     // [N] same dtype as out, or nullptr
+    int k_splits;         // > 1: split-K over CTAs, int32 atomics into `out` (MODE == kEpiI32 only; decode shapes)
     long long* prof;      // debug: per-CTA role timers (PROF instantiation only)
     int dbg;              // debug (PROF only): 1 skip TMEM stores, 2 skip MMA issue, 4 skip epilogue, 8 no X TMA, 16 no W TMA/LDS
 };
@@ -134,16 +135,24 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     const int nb_m = (p.M + TN - 1) / TN;
     // tile order: token blocks fastest, so the CTAs running concurrently share few weight tiles (each packed W tile
     // is fetched from HBM once and re-read from L2 by its other token blocks) while all of X stays L2-resident
-    const int n_tiles = nb_w * nb_m;
-    const int KB = (p.K + kGemmBlockK - 1) / kGemmBlockK;
+    const int KB_all = (p.K + kGemmBlockK - 1) / kGemmBlockK;
+    const int splits = p.k_splits > 1 ? p.k_splits : 1;
+    const int n_tiles = nb_w * nb_m * splits;  // work units: (output tile, K range)
+    // unit -> output tile and K-stage range [kb0, kb1)
+#define FLATQ_UNIT(unit)                                              \
+    const int tile = (unit) / splits, split_ = (unit) % splits;       \
+    const int kb0 = (int)((long long)KB_all * split_ / splits);       \
+    const int kb1 = (int)((long long)KB_all * (split_ + 1) / splits); \
+    (void)tile; (void)kb0; (void)kb1;
 
     if (warp == 0) {
         // ================================ X producer ================================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x) {
+                FLATQ_UNIT(unit)
                 const int m0 = (tile % nb_m) * TN;
-                for (int kb = 0; kb < KB; ++kb, ++it) {
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                     FLATQ_TWAIT(0, mbar_wait(&empty[s], ph ^ 1));
                     if (PROF && (p.dbg & 8)) { mbar_arrive(&full[s]); continue; }
@@ -157,9 +166,10 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         // ================================ W producer ================================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x) {
+                FLATQ_UNIT(unit)
                 const int n0 = (tile / nb_m) * kGemmBlockW;
-                for (int kb = 0; kb < KB; ++kb, ++it) {
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const uint32_t s = it % kStagesW, ph = (it / kStagesW) & 1;
                     FLATQ_TWAIT(0, mbar_wait(&wempty[s], ph ^ 1));
                     if (PROF && (p.dbg & 16)) { mbar_arrive(&wfull[s]); continue; }
@@ -172,12 +182,13 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         // ================================ MMA issuer ================================
         constexpr uint32_t idesc = make_idesc(kDS32, kFmtS8, kFmtS8, 0, 0, kGemmBlockW, TN);
         uint32_t it = 0, tile_iter = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+        for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x, ++tile_iter) {
+            FLATQ_UNIT(unit)
             const uint32_t b = tile_iter % NBUF, phb = (tile_iter / NBUF) & 1;
             FLATQ_TWAIT(2, mbar_wait(&empty_acc[b], phb ^ 1));
             tc_fence_after();
             const uint32_t d_tmem = tmem + b * 128;
-            for (int kb = 0; kb < KB; ++kb, ++it) {
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                 FLATQ_TWAIT(0, mbar_wait(&full[s], ph));
                 tc_fence_after();
@@ -190,10 +201,10 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                         // K sub-block kk: 32 bytes inside swizzle atom (kk / 4)
                         const uint64_t bdesc =
                             make_smem_desc_kmajor(xaddr + (kk >> 2) * XH + (kk & 3) * 32, 1024, kLayoutSw128);
-                        mma_i8_ts(d_tmem, a_tmem + kk * 8, bdesc, idesc, (kb | kk) != 0);
+                        mma_i8_ts(d_tmem, a_tmem + kk * 8, bdesc, idesc, ((kb - kb0) | kk) != 0);
                     }
                     tc_commit(&empty[s]);
-                    if (kb == KB - 1) tc_commit(&full_acc[b]);
+                    if (kb == kb1 - 1) tc_commit(&full_acc[b]);
                 }
                 __syncwarp();
             }
@@ -206,8 +217,9 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const uint32_t swz = row & 7;     // SWIZZLE_128B: 16-B chunk index ^= (row % 8)
         const uint32_t ws_addr = smem_u32(ws) + row * 128;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int kb = 0; kb < KB; ++kb, ++it) {
+        for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x) {
+            FLATQ_UNIT(unit)
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 if ((it & 1) != (uint32_t)grp) continue;
                 const uint32_t sw = it % kStagesW, phw = (it / kStagesW) & 1;
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
@@ -252,7 +264,8 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const int half = ew >> 2;          // which quarter of the token columns
         uint32_t tile_iter = 0;
         constexpr int COLS = TN / 4 < 16 ? 16 : TN / 4;   // token columns per epilogue warp (small TN: some quarters idle)
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+        for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x, ++tile_iter) {
+            FLATQ_UNIT(unit)
             const int n0 = (tile / nb_m) * kGemmBlockW;
             const int m0 = (tile % nb_m) * TN;
             const uint32_t b = tile_iter % NBUF, phb = (tile_iter / NBUF) & 1;
@@ -293,8 +306,11 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const int m = m0 + c0 + c * 16 + j;
-                            if (m < p.M && n_ok)
-                                reinterpret_cast<int32_t*>(p.out)[(size_t)m * p.N + n] = static_cast<int32_t>(r[j]) >> p.acc_shift;
+                            if (m < p.M && n_ok) {
+                                int32_t* dst = reinterpret_cast<int32_t*>(p.out) + (size_t)m * p.N + n;
+                                const int32_t val = static_cast<int32_t>(r[j]) >> p.acc_shift;  // exact per partial sum
+                                if (splits > 1) atomicAdd(dst, val); else *dst = val;
+                            }
                         }
                     }
                 }

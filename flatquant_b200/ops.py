@@ -59,6 +59,7 @@ class _Workspace:
 
 
 _ws = _Workspace()
+_ws2 = _Workspace()
 
 
 def pack_i4(q: torch.Tensor) -> torch.Tensor:
@@ -190,7 +191,7 @@ def linear_fused(x: torch.Tensor, left, right, n1: int, n2: int, clip_max: float
     n = w_packed.shape[0]
     lib = _lib.load()
     y = torch.empty(x.shape[:-1] + (n,), dtype=out_dtype, device=dev)
-    ws = _ws.get(dev, lib.flatq_linear_fused_workspace_bytes(m, k))
+    ws = _ws.get(dev, lib.flatq_linear_fused_workspace_bytes(m, n, k))
     _lib.check(lib.flatq_linear_fused(_ptr(x), _ptr(left), _ptr(right), n1, n2, float(clip_max), float(clip_min),
                                       _ptr(w_packed), _ptr(s_w), _ptr(bias), m, n, _ptr(y), _DT[out_dtype], _ptr(ws),
                                       ws.numel(), _stream()), "linear_fused")
@@ -217,8 +218,11 @@ def gemm_w4a8(xq8: torch.Tensor, s_x: torch.Tensor, w_packed: torch.Tensor, s_w:
     m, k = xq8.shape
     n = w_packed.shape[0]
     y = out if out is not None else torch.empty((m, n), dtype=out_dtype, device=dev)
-    _lib.check(_lib.load().flatq_gemm_w4a8(_ptr(xq8), _ptr(s_x), _ptr(w_packed), _ptr(s_w), _ptr(bias), m, n, k, _ptr(y),
-                                           _DT[out_dtype], _stream()), "gemm_w4a8")
+    lib = _lib.load()
+    nb = lib.flatq_gemm_w4a8_workspace_bytes(m, n, k)
+    ws = _ws2.get(dev, nb) if nb else None  # separate pool: xq8 / s_x usually live in the primary workspace
+    _lib.check(lib.flatq_gemm_w4a8(_ptr(xq8), _ptr(s_x), _ptr(w_packed), _ptr(s_w), _ptr(bias), m, n, k, _ptr(y),
+                                   _DT[out_dtype], _ptr(ws), ws.numel() if ws is not None else 0, _stream()), "gemm_w4a8")
     return y
 
 

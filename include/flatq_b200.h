@@ -105,8 +105,8 @@ int flatq_quantize_rows(const void* x_f16, int64_t tokens, int64_t K, float clip
  *      == OnlineTrans -> Quantizer -> Linear4bit of benchmarks/qlinear_benchmark.py:70-74).
  *      x fp16 [M, K=n1*n2]; left/right may be NULL (no transform / single-sided);
  *      w_packed [N, K/2]; s_w fp32 [N]; bias out_dtype [N] or NULL; y [M, N] out_dtype.
- *      workspace >= flatq_linear_fused_workspace_bytes(M, K). */
-size_t flatq_linear_fused_workspace_bytes(int64_t M, int64_t K);
+ *      workspace >= flatq_linear_fused_workspace_bytes(M, N, K). */
+size_t flatq_linear_fused_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int flatq_linear_fused(const void* x_f16, const void* left_f16, const void* right_f16, int n1, int n2,
                        float clip_max, float clip_min, const uint8_t* w_packed, const float* s_w, const void* bias,
                        int64_t M, int64_t N, void* y, int out_dtype, void* workspace, size_t workspace_bytes,
@@ -121,8 +121,12 @@ int flatq_linear_fused(const void* x_f16, const void* left_f16, const void* righ
  *      flatq_gemm_w4a8: y[M,N] = (xq8 . W^T) * s_x[m] * s_w[n] (+bias), W packed [N, K/2]; K % 32 == 0. */
 int flatq_act_quant(const void* x_f16, const void* left_f16, const void* right_f16, int n1, int n2, float clip_max,
                     float clip_min, int64_t M, int8_t* xq8, float* s_x, flatq_stream_t stream);
+/*      workspace (may be NULL): with flatq_gemm_w4a8_workspace_bytes(M, N, K) bytes, decode shapes (M <= 64) split K
+ *      across CTAs (int32 atomics + a finalize pass) so that the packed-weight stream uses the whole chip. */
+size_t flatq_gemm_w4a8_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed, const float* s_w, const void* bias,
-                    int64_t M, int64_t N, int64_t K, void* y, int out_dtype, flatq_stream_t stream);
+                    int64_t M, int64_t N, int64_t K, void* y, int out_dtype, void* workspace, size_t workspace_bytes,
+                    flatq_stream_t stream);
 
 /* ---- a14: qattention side path ------------------------------------------------------------------
  * flatq_hadamard: out = scale * x . H_n per row, n a power of two in [8, 32768], fp16 in/out, fp32 butterflies.

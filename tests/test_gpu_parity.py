@@ -470,3 +470,29 @@ def test_kernel_level_api(dev):
     qz = torch.clamp(torch.round(z / s[:, None]), -8, 7).numpy().astype(np.int32)
     d = np.abs(O.unpack_i4(pb.quantized_x.cpu().numpy()) - qz)
     assert d.max() <= 1 and (d != 0).mean() < 0.02
+
+
+@pytest.mark.parametrize("m,k,n,n1,n2", [(1, 4096, 4096, 64, 64), (16, 4096, 6144, 64, 64), (64, 14336, 4096, 112, 128),
+                                         (5, 256, 128, 16, 16)])
+def test_decode_split_k_path(ops, dev, m, k, n, n1, n2):
+    """Decode shapes (M <= 64) take the split-K route (int32 atomics + finalize); results must be identical to the
+    oracle arithmetic on the kernel's own codes, and run-to-run deterministic (integer atomics commute)."""
+    torch.manual_seed(m + n)
+    x = torch.randn(m, k, device=dev).half()
+    L = (torch.randn(n1, n1, device=dev) / n1 ** 0.5).half()
+    R = (torch.randn(n2, n2, device=dev) / n2 ** 0.5).half()
+    wq = torch.randint(-8, 8, (n, k), dtype=torch.int8, device=dev)
+    wp = ops.pack_i4(wq)
+    s_w = torch.rand(n, device=dev) * 0.02 + 0.01
+    bias = torch.randn(n, device=dev).half()
+    y = ops.linear_fused(x, L, R, n1, n2, 0.97, 0.99, wp, s_w, bias)
+    y_again = ops.linear_fused(x, L, R, n1, n2, 0.97, 0.99, wp, s_w, bias)
+    assert torch.equal(y, y_again)
+    xq8, sx = ops.act_quant(x, L, R, n1, n2, 0.97, 0.99)
+    perm = np.array([0, 2, 4, 6, 1, 3, 5, 7])
+    c8 = xq8.cpu().numpy().reshape(m, k // 8, 8)
+    codes = np.empty_like(c8)
+    codes[:, :, perm] = c8
+    acc = O.gemm_i4(codes.reshape(m, k), wq.cpu().numpy())
+    ref = O.sym_dequant(acc, sx.cpu().numpy(), s_w.cpu().numpy(), bias.float().cpu().numpy()).astype(np.float16)
+    assert np.array_equal(y.cpu().numpy(), ref)
