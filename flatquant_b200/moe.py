@@ -1,0 +1,63 @@
+"""Routed-expert FlatLinears of the DeepSeek-V3 block (BASELINE configs[4]); semantics of
+flatquant/model_tools/deepseekv3_utils.py:365-455 (`FlatQuantMoEExpert`, `FlatQuantMoE.forward`):
+
+    x_t = w1_trans(x)                                   # ONE transform for all experts (:432-433)
+    for each expert e with tokens idx_e:
+        h = silu(w1_e(x_t[idx_e])) * w3_e(x_t[idx_e])   # w1/w3 share the activation quantiser (:377-378, :424)
+        y[idx_e] += w2_e(routed_w2_trans(h)) * gate_weight
+
+B200 arrangement with the existing kernels: the transform AND the per-token quantisation run once for all tokens
+(`act_quant`), the experts gather rows of the int8 operand (a byte gather, not a re-quantisation), w1 and w3 are one
+fused GEMM per expert ([2*inter, K] packed), the second transform+quantise runs on the gathered rows of all experts
+at once (per-token scales make it order independent), then one GEMM per expert.  Small per-expert token counts take
+the split-K route automatically.  A grouped GEMM (one launch over an (expert, tile) table on the stacked packed
+weights) is the next step; tokens are sorted by expert already, which is the layout it needs.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class FlatQuantRoutedExperts:
+    def __init__(self, w13_packed, s_w13, w2_packed, s_w2, w1_factors, w2_factors, clip1=(1.0, 1.0), clip2=(1.0, 1.0)):
+        """w13_packed [E, 2*inter, dim/2] u8 (rows: w1 then w3), s_w13 [E, 2*inter] f32, w2_packed [E, dim, inter/2],
+        s_w2 [E, dim]; w1_factors / w2_factors = (left, right) fp16 Kronecker pairs; clip = post-sigmoid factors."""
+        self.w13, self.s13, self.w2, self.s2 = w13_packed, s_w13, w2_packed, s_w2
+        self.f1, self.f2, self.clip1, self.clip2 = w1_factors, w2_factors, clip1, clip2
+        self.n_experts = w13_packed.shape[0]
+        self.inter = w2_packed.shape[2] * 2
+        self.dim = w13_packed.shape[2] * 2
+
+    def __call__(self, x: torch.Tensor, weights: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
+        """x [T, dim] fp16, weights / indices [T, top_k] from the (unquantised) gate -> y [T, dim] fp16."""
+        T, top_k = indices.shape
+        L1, R1 = self.f1
+        xq8, sx = ops.act_quant(x.contiguous(), L1, R1, L1.shape[0], R1.shape[0], *self.clip1)  # once for all experts
+        # sort the (token, slot) pairs by expert
+        flat_e = indices.reshape(-1)
+        order = torch.argsort(flat_e, stable=True)
+        tok = (order // top_k)
+        counts = torch.bincount(flat_e, minlength=self.n_experts).tolist()
+        xs8, sxs = xq8[tok].contiguous(), sx[tok].contiguous()
+        h = torch.empty((tok.numel(), self.inter), dtype=torch.float16, device=x.device)
+        off = 0
+        for e, c in enumerate(counts):
+            if c:
+                gu = ops.gemm_w4a8(xs8[off:off + c], sxs[off:off + c], self.w13[e], self.s13[e])
+                g, u = gu[:, :self.inter], gu[:, self.inter:]
+                h[off:off + c] = torch.nn.functional.silu(g.float()).mul_(u.float()).half()
+            off += c
+        L2, R2 = self.f2
+        hq8, sh = ops.act_quant(h, L2, R2, L2.shape[0], R2.shape[0], *self.clip2)  # all experts' rows in one launch
+        out = torch.empty((tok.numel(), self.dim), dtype=torch.float16, device=x.device)
+        off = 0
+        for e, c in enumerate(counts):
+            if c:
+                ops.gemm_w4a8(hq8[off:off + c], sh[off:off + c], self.w2[e], self.s2[e], out=out[off:off + c])
+            off += c
+        w_sorted = weights.reshape(-1)[order].to(torch.float32)
+        y = torch.zeros((T, self.dim), dtype=torch.float32, device=x.device)
+        y.index_add_(0, tok, out.float() * w_sorted[:, None])
+        return y.half()

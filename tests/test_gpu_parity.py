@@ -496,3 +496,39 @@ def test_decode_split_k_path(ops, dev, m, k, n, n1, n2):
     acc = O.gemm_i4(codes.reshape(m, k), wq.cpu().numpy())
     ref = O.sym_dequant(acc, sx.cpu().numpy(), s_w.cpu().numpy(), bias.float().cpu().numpy()).astype(np.float16)
     assert np.array_equal(y.cpu().numpy(), ref)
+
+
+def test_moe_routed_experts_configs4(dev):
+    """DeepSeek-V3 routed experts (configs[4]) at reduced width: shared w1_trans / quantiser, per-expert w1,w3,w2."""
+    from flatquant_b200 import ops as _ops
+    from flatquant_b200.moe import FlatQuantRoutedExperts
+    torch.manual_seed(9)
+    T_, dim, inter, E, top_k = 48, 256, 128, 4, 2
+    (a1, b1), (a2, b2) = O.get_decompose_dim(dim), O.get_decompose_dim(inter)
+    x = torch.randn(T_, dim).half()
+    L1, R1 = (torch.randn(a1, a1) / a1 ** 0.5).half(), (torch.randn(b1, b1) / b1 ** 0.5).half()
+    L2, R2 = (torch.randn(a2, a2) / a2 ** 0.5).half(), (torch.randn(b2, b2) / b2 ** 0.5).half()
+    w13 = torch.randint(-8, 8, (E, 2 * inter, dim), dtype=torch.int8)
+    w2 = torch.randint(-8, 8, (E, dim, inter), dtype=torch.int8)
+    s13, s2 = torch.rand(E, 2 * inter) * 0.02 + 0.01, torch.rand(E, dim) * 0.02 + 0.01
+    indices = torch.stack([torch.randperm(E)[:top_k] for _ in range(T_)])
+    indices[:, 0] = torch.where(indices[:, 0] == 3, torch.zeros_like(indices[:, 0]), indices[:, 0])  # skew the load
+    weights = torch.rand(T_, top_k)
+    moe = FlatQuantRoutedExperts(torch.stack([T(O.pack_i4(w13[e].numpy())) for e in range(E)]).to(dev), s13.to(dev),
+                                 torch.stack([T(O.pack_i4(w2[e].numpy())) for e in range(E)]).to(dev), s2.to(dev),
+                                 (L1.to(dev), R1.to(dev)), (L2.to(dev), R2.to(dev)), (0.98, 0.98), (0.98, 0.98))
+    y = moe(x.to(dev), weights.to(dev), indices.to(dev)).float().cpu()
+    # oracle with the reference's structure (python loop over experts), fp32 arithmetic, raw clip = logit(0.98)
+    raw = float(torch.logit(torch.tensor(0.98)))
+    z = O.kronecker_matmul(x.float(), L1.float(), R1.float())
+    ref = torch.zeros(T_, dim)
+    for e in range(E):
+        idx, top = torch.where(indices == e)
+        if idx.numel() == 0:
+            continue
+        gu = torch.from_numpy(O.flat_linear_int(z[idx], None, None, raw, raw, w13[e].numpy(), s13[e].numpy())["y"])
+        hh = torch.nn.functional.silu(gu[:, :inter]) * gu[:, inter:]
+        out = torch.from_numpy(O.flat_linear_int(hh, L2.float(), R2.float(), raw, raw, w2[e].numpy(), s2[e].numpy())["y"])
+        ref[idx] += out * weights[idx, top, None]
+    err = (y - ref).abs()
+    assert err.max() <= 0.06 * ref.abs().max() and err.mean() <= 0.01 * ref.abs().max()  # two quantised stages

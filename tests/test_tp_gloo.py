@@ -80,7 +80,7 @@ def test_shard_plans():
 
 def test_row_and_column_parallel_world2():
     K, N, M, world = 512, 96, 9, 2
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), K, N, M, ret), nprocs=world, join=True)
     x, w, s_w, bias, facs = _problem(K, N, M, world)
