@@ -511,8 +511,7 @@ def test_moe_routed_experts_configs4(dev):
     w13 = torch.randint(-8, 8, (E, 2 * inter, dim), dtype=torch.int8)
     w2 = torch.randint(-8, 8, (E, dim, inter), dtype=torch.int8)
     s13, s2 = torch.rand(E, 2 * inter) * 0.02 + 0.01, torch.rand(E, dim) * 0.02 + 0.01
-    indices = torch.stack([torch.randperm(E)[:top_k] for _ in range(T_)])
-    indices[:, 0] = torch.where(indices[:, 0] == 3, torch.zeros_like(indices[:, 0]), indices[:, 0])  # skew the load
+    indices = torch.multinomial(torch.tensor([0.45, 0.3, 0.2, 0.05]).repeat(T_, 1), top_k)  # skewed load, distinct experts per token
     weights = torch.rand(T_, top_k)
     moe = FlatQuantRoutedExperts(torch.stack([T(O.pack_i4(w13[e].numpy())) for e in range(E)]).to(dev), s13.to(dev),
                                  torch.stack([T(O.pack_i4(w2[e].numpy())) for e in range(E)]).to(dev), s2.to(dev),
