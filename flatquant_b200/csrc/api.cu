@@ -241,7 +241,7 @@ int launch_kron_tc_t(const KronParams& p, cudaStream_t st) {
                          CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     const int groups = (p.tokens + T - 1) / T;
-    const int cap = 2 * num_sms();
+    const int cap = C::kMinCtas * num_sms();
     FLATQ_CUDA(launch_pdl(kern, dim3(groups < cap ? groups : cap), dim3(C::kThreads), (size_t)C::kSmemBytes, st, tx, p));
     return FLATQ_OK;
 }
