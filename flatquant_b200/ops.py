@@ -115,6 +115,8 @@ def gemm_i4(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         raise RuntimeError("matmul: A and B disagree on K")
     lib = _lib.load()
     c = torch.empty((m, n), dtype=torch.int32, device=dev)
+    if m == 0 or n == 0:
+        return c
     nb = lib.flatq_gemm_i4_workspace_bytes(m, kp * 2)
     ws = _ws.get(dev, nb)
     _lib.check(lib.flatq_gemm_i4(_ptr(a), _ptr(b), m, n, kp * 2, _ptr(c), _ptr(ws), ws.numel(), _stream()), "gemm_i4")
@@ -191,6 +193,8 @@ def linear_fused(x: torch.Tensor, left, right, n1: int, n2: int, clip_max: float
     n = w_packed.shape[0]
     lib = _lib.load()
     y = torch.empty(x.shape[:-1] + (n,), dtype=out_dtype, device=dev)
+    if m == 0:  # empty batch: nothing to launch (torch ops in the reference return an empty tensor too)
+        return y
     ws = _ws.get(dev, lib.flatq_linear_fused_workspace_bytes(m, n, k))
     _lib.check(lib.flatq_linear_fused(_ptr(x), _ptr(left), _ptr(right), n1, n2, float(clip_max), float(clip_min),
                                       _ptr(w_packed), _ptr(s_w), _ptr(bias), m, n, _ptr(y), _DT[out_dtype], _ptr(ws),

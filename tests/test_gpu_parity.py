@@ -533,3 +533,27 @@ def test_moe_routed_experts_configs4(dev):
     # two chained quantised stages at tiny K (256, 128): a single +-1 code flip moves y by several % of max|y|
     rmax = float(ref.abs().max())
     assert err.max() <= 0.15 * rmax and err.mean() <= 0.02 * rmax, (float(err.max()), float(err.mean()), rmax)
+
+
+def test_empty_and_maximum_shapes(ops, dev):
+    """Edge cases: empty batch; the largest K of the configs (28672, factors (128, 224) -> HMMA transform kernel)."""
+    k = 4096
+    wp = torch.zeros((128, k // 2), dtype=torch.uint8, device=dev)
+    y = ops.linear_fused(torch.zeros((0, k), dtype=torch.float16, device=dev), None, None, 1, k, 1.0, 1.0, wp,
+                         torch.ones(128, device=dev))
+    assert y.shape == (0, 128)
+    assert ops.gemm_i4(torch.zeros((0, k // 2), dtype=torch.uint8, device=dev), wp).shape == (0, 128)
+    torch.manual_seed(12)
+    m, n, n1, n2 = 70, 256, 128, 224
+    k = n1 * n2
+    x = torch.randn(m, k, device=dev).half()
+    L = (torch.randn(n1, n1, device=dev) / n1 ** 0.5).half()
+    R = (torch.randn(n2, n2, device=dev) / n2 ** 0.5).half()
+    wq = torch.randint(-8, 8, (n, k), dtype=torch.int8, device=dev)
+    s_w = torch.rand(n, device=dev) * 0.01 + 0.005
+    y = ops.linear_fused(x, L, R, n1, n2, 0.98, 0.98, ops.pack_i4(wq), s_w)
+    xq, _, s32 = ops.transform_quant(x, L, R, n1, n2, 0.98, 0.98)
+    acc = O.gemm_i4(O.unpack_i4(xq.cpu().numpy()), wq.cpu().numpy())
+    ref = O.sym_dequant(acc, s32.cpu().numpy(), s_w.cpu().numpy()).astype(np.float16)
+    assert np.array_equal(y.cpu().numpy(), ref)
+    assert np.abs(acc).max() < 2 ** 24  # the folded-shift fast path of the epilogue is exact only below this
