@@ -482,18 +482,24 @@ int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed
     FLATQ_CHECK(out_dtype == FLATQ_F16 || out_dtype == FLATQ_BF16, FLATQ_ERR_INVALID, "gemm_w4a8: out_dtype");
     FLATQ_CHECK(K % 32 == 0, FLATQ_ERR_INVALID, "gemm_w4a8: K=%lld must be a multiple of 32", (long long)K);
     cudaStream_t st = (cudaStream_t)stream;
-    if (M <= 16) {  // decode: dp4a GEMV at one weight row per lane streams the packed weight at HBM speed
+    if (M <= 2 && (size_t)M * K <= 96 * 1024) {  // decode: dp4a GEMV streams the packed weight at HBM speed
         FLATQ_CHECK(aligned16(xq8) && aligned16(w_packed), FLATQ_ERR_INVALID, "gemm_w4a8: alignment");
         GemvParams g;
         g.w = w_packed; g.x = xq8; g.s_x = s_x; g.s_w = s_w; g.bias = bias; g.out = y;
         g.M = (int)M; g.N = (int)N; g.K = (int)K; g.bf16_out = out_dtype == FLATQ_BF16;
-        const dim3 grid((unsigned)((N + kGemvRows - 1) / kGemvRows)), block(kGemvWarps * 32);
-        cudaError_t e;
-        if (M == 1) e = launch_pdl(gemv_w4a8_kernel<1>, grid, block, 0, st, g);
-        else if (M <= 4) e = launch_pdl(gemv_w4a8_kernel<4>, grid, block, 0, st, g);
-        else if (M <= 8) e = launch_pdl(gemv_w4a8_kernel<8>, grid, block, 0, st, g);
-        else e = launch_pdl(gemv_w4a8_kernel<16>, grid, block, 0, st, g);
-        FLATQ_CUDA(e);
+        int64_t ctas = (N + kGemvWarps - 1) / kGemvWarps;
+        const int64_t cap = (int64_t)num_sms() * 6;
+        const dim3 grid((unsigned)(ctas < cap ? ctas : cap)), block(kGemvWarps * 32);
+        const size_t smem = (size_t)(M == 1 ? 1 : 2) * K;
+        auto k1 = gemv_w4a8_kernel<1>;
+        auto k2 = gemv_w4a8_kernel<2>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            FLATQ_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            FLATQ_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_set = true;
+        }
+        FLATQ_CUDA(M == 1 ? launch_pdl(k1, grid, block, smem, st, g) : launch_pdl(k2, grid, block, smem, st, g));
         return FLATQ_OK;
     }
     const int splits = (ws && ws_bytes >= flatq_gemm_w4a8_workspace_bytes(M, N, K)) ? decode_splits(M, N, K) : 1;
