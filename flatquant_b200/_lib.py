@@ -10,7 +10,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libflatq_b200.so")
+# FLATQ_B200_LIB: load another build of the same library (A/B timing of kernel variants); never a fallback
+LIB_PATH = os.environ.get("FLATQ_B200_LIB") or os.path.join(_HERE, "lib", "libflatq_b200.so")
 
 # name -> (restype, argtypes); must list every symbol of include/flatq_b200.h
 SIGNATURES = {

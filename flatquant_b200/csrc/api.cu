@@ -151,6 +151,8 @@ int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, i
     FLATQ_CHECK(K % 32 == 0, FLATQ_ERR_INVALID, "K=%lld must be a multiple of 32", (long long)K);
     FLATQ_CHECK(K <= 65536 && M < (1ll << 31) && N < (1ll << 31), FLATQ_ERR_UNSUPPORTED, "GEMM too large");
     FLATQ_CHECK(mode == kEpiI32 || N % 2 == 0, FLATQ_ERR_UNSUPPORTED, "N=%lld must be even for 16-bit outputs", (long long)N);
+    FLATQ_CHECK(mode == kEpiI32 || (M + 256) * N < (1ll << 32), FLATQ_ERR_UNSUPPORTED,
+                "output of %lld x %lld exceeds the 32-bit element index of the store path", (long long)M, (long long)N);
     const int tn = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
     CUtensorMap tw, tx;
     int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_128B);

@@ -25,11 +25,13 @@
 //   * Stage contents: packed W tile 128 rows x 128 B (SWIZZLE_128B), int8 X tile = two TMA boxes of
 //     TN rows x 128 B (SWIZZLE_128B).
 //
-// Warp roles (27 warps, persistent over output tiles):
-//   warp 0  X TMA producer     warp 1  MMA issuer (+ TMEM alloc)     warp 2  W TMA producer
-//   warps 3-10  nibble expanders (2 groups x 4 lane-quadrants; a group takes every other stage)
-//   warps 11-26 epilogue (4 per lane-quadrant, each a quarter of the token columns): dequantise the
-//               accumulator into registers, release the TMEM buffer, then store.
+// Warp roles (28 warps = 7 warpgroups, persistent over output tiles; registers re-partitioned with setmaxnreg):
+//   warp 0  X TMA producer     warp 1  MMA issuer (+ TMEM alloc)     warp 2  W TMA producer     warp 3 idle   (40 regs)
+//   warps 4-11  nibble expanders (2 groups x 4 lane-quadrants; a group takes every other stage)              (72 regs)
+//   warps 12-27 epilogue (4 per lane-quadrant, each a quarter of the token columns)                           (80 regs):
+//               copy the RAW accumulator columns into registers (one tcgen05.ld batch), hand the TMEM buffer
+//               back to the MMA issuer at once, and only then dequantise and store -- the accumulator is
+//               single-buffered at TN = 256, so everything before the release is exposed tensor-pipe idle time.
 //
 // Barriers per stage s:  full[s]  <- X bytes (expect_tx) + 4 expander warps;   empty[s] <- tcgen05.commit
 //                        wfull[s] <- W bytes;                                  wempty[s] <- 4 expander warps
@@ -59,7 +61,17 @@ struct FoldFalse { static constexpr bool value = false; };
 
 constexpr int kGemmBlockW = 128;   // weight rows per tile
 constexpr int kGemmBlockK = 256;   // K elements per stage
-constexpr int kGemmWarps = 27;
+constexpr int kGemmWarps = 28;
+#ifndef FLATQ_REGS_EPI
+#define FLATQ_REGS_EPI 80
+#endif
+#ifndef FLATQ_REGS_CTL
+#define FLATQ_REGS_CTL 40
+#endif
+#ifndef FLATQ_REGS_EXP
+#define FLATQ_REGS_EXP 72
+#endif
+constexpr int kRegsCtl = FLATQ_REGS_CTL, kRegsExpand = FLATQ_REGS_EXP, kRegsEpi = FLATQ_REGS_EPI;  
 constexpr int kGemmThreads = kGemmWarps * 32;
 constexpr int kStagesW = 2;        // packed-W smem ring
 constexpr int kTmemColsA0 = 256;   // accumulator(s) in columns [0,256): one 256-wide or two 128-wide buffers
@@ -76,7 +88,7 @@ struct GemmParams {
     const void* bias;     // [N] same dtype as out, or nullptr
     int k_splits;         // > 1: split-K over CTAs, int32 atomics into `out` (MODE == kEpiI32 only; decode shapes)
     long long* prof;      // debug: per-CTA role timers (PROF instantiation only)
-    int dbg;              // debug (PROF only): 1 skip TMEM stores, 2 skip MMA issue, 4 skip epilogue, 8 no X TMA, 16 no W TMA/LDS
+    int dbg;              // debug (PROF only): 1 skip TMEM stores, 2 skip MMA issue, 4 skip epilogue, 8 no X TMA, 16 no W TMA/LDS, 32 weight-blocks-fastest raster
 };
 
 template <int TN>
@@ -85,7 +97,7 @@ struct GemmSmem {
     static constexpr int kXStageBytes = 2 * kXHalfBytes;    // 256 K-bytes per row, as two swizzle atoms
     static constexpr int kStages = TN > 128 ? 3 : 4;        // X smem ring == TMEM A ring (64 columns per stage)
     static constexpr int kAccBufs = TN > 128 ? 1 : 2;       // TMEM accumulator buffers
-    static constexpr int kBytes = kStages * kXStageBytes + kStagesW * kWStageBytes + 1024 /*align*/ + 512 /*bars*/;
+    static constexpr int kBytes = kStages * kXStageBytes + kStagesW * kWStageBytes + 1024 /*align*/ + 512 /*bars*/ + 1024 /*per-token scales of the tile being stored*/;
 };
 
 template <int TN, int MODE, bool PROF = false>
@@ -109,6 +121,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     uint64_t* full_acc = wempty + kStagesW;    // [2]
     uint64_t* empty_acc = full_acc + 2;        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_acc + 2);
+    float* sx_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // [256], 16-B aligned
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -118,7 +131,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 5); mbar_init(&empty[i], 1); }
         for (int i = 0; i < kStagesW; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 4); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&full_acc[i], 1); mbar_init(&empty_acc[i], 512); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&full_acc[i], 1); mbar_init(&empty_acc[i], 16); }
         fence_mbar_init();
     }
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_x);
@@ -135,6 +148,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     const int nb_m = (p.M + TN - 1) / TN;
     // tile order: token blocks fastest, so the CTAs running concurrently share few weight tiles (each packed W tile
     // is fetched from HBM once and re-read from L2 by its other token blocks) while all of X stays L2-resident
+    const bool w_fast = PROF && (p.dbg & 32);  // debug: the other raster order (weight blocks fastest)
     const int KB_all = (p.K + kGemmBlockK - 1) / kGemmBlockK;
     const int splits = p.k_splits > 1 ? p.k_splits : 1;
     const int n_tiles = nb_w * nb_m * splits;  // work units: (output tile, K range)
@@ -145,13 +159,17 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     const int kb1 = (int)((long long)KB_all * (split_ + 1) / splits); \
     (void)tile; (void)kb0; (void)kb1;
 
-    if (warp == 0) {
+    // setmaxnreg sits at the top of each warpgroup's own branch so that ptxas allocates every role's code against
+    // that role's budget
+    if (warp < 4) {
+      reg_dealloc<kRegsCtl>();
+      if (warp == 0) {
         // ================================ X producer ================================
         if (lane == 0) {
             uint32_t it = 0;
             for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x) {
                 FLATQ_UNIT(unit)
-                const int m0 = (tile % nb_m) * TN;
+                const int m0 = (w_fast ? tile / nb_w : tile % nb_m) * TN;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                     FLATQ_TWAIT(0, mbar_wait(&empty[s], ph ^ 1));
@@ -162,13 +180,13 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 }
             }
         }
-    } else if (warp == 2) {
+      } else if (warp == 2) {
         // ================================ W producer ================================
         if (lane == 0) {
             uint32_t it = 0;
             for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x) {
                 FLATQ_UNIT(unit)
-                const int n0 = (tile / nb_m) * kGemmBlockW;
+                const int n0 = (w_fast ? tile % nb_w : tile / nb_m) * kGemmBlockW;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const uint32_t s = it % kStagesW, ph = (it / kStagesW) & 1;
                     FLATQ_TWAIT(0, mbar_wait(&wempty[s], ph ^ 1));
@@ -178,7 +196,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // ================================ MMA issuer ================================
         constexpr uint32_t idesc = make_idesc(kDS32, kFmtS8, kFmtS8, 0, 0, kGemmBlockW, TN);
         uint32_t it = 0, tile_iter = 0;
@@ -209,13 +227,16 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 __syncwarp();
             }
         }
-    } else if (warp < 11) {
+      }  // warp 3 idles: it only completes the control warpgroup for setmaxnreg
+    } else if (warp < 12) {
         // ================================ nibble expanders ================================
-        const int grp = (warp - 3) >> 2;  // handles stage iterations with it % 2 == grp
+        if constexpr (kRegsExpand < 72) reg_dealloc<kRegsExpand>();
+        const int grp = (warp - 4) >> 2;  // handles stage iterations with it % 2 == grp
         const int q = warp & 3;           // TMEM lane quadrant this warp may touch
         const uint32_t row = q * 32 + lane;
-        const uint32_t swz = row & 7;     // SWIZZLE_128B: 16-B chunk index ^= (row % 8)
-        const uint32_t ws_addr = smem_u32(ws) + row * 128;
+        // SWIZZLE_128B: 16-B chunk index ^= (row % 8).  Stage bases are 1024-B aligned, so chunk c of this row lives at
+        // (row base | (row % 8) << 4) ^ (c << 4): one XOR with an immediate per load, no per-chunk address registers
+        const uint32_t ws_addr = smem_u32(ws) + row * 128 + ((row & 7) << 4);
         uint32_t it = 0;
         for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x) {
             FLATQ_UNIT(unit)
@@ -224,11 +245,11 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 const uint32_t sw = it % kStagesW, phw = (it / kStagesW) & 1;
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                 FLATQ_TWAIT(0, mbar_wait(&wfull[sw], phw));
-                uint4 v[8];
+                uint4 v[8];  // this row's 128 packed bytes, fetched while the A slot may still be busy
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     if (PROF && (p.dbg & 16)) v[c] = make_uint4(it, c, lane, 7);
-                    else v[c] = ld_shared_v4(ws_addr + sw * kWStageBytes + ((c ^ swz) << 4));
+                    else v[c] = ld_shared_v4((ws_addr + sw * kWStageBytes) ^ (c << 4));
                 }
                 FLATQ_TWAIT(1, mbar_wait(&empty[s], ph ^ 1));
                 tc_fence_after();
@@ -259,15 +280,16 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         }
     } else {
         // ================================ epilogue ================================
-        const int ew = warp - 11;          // 0..15
-        const int q = warp & 3;            // TMEM lane quadrant (warps 11.. -> 3,0,1,2,3,0,1,2,...)
+        reg_alloc<kRegsEpi>();
+        const int ew = warp - 12;          // 0..15
+        const int q = warp & 3;            // TMEM lane quadrant
         const int half = ew >> 2;          // which quarter of the token columns
         uint32_t tile_iter = 0;
         constexpr int COLS = TN / 4 < 16 ? 16 : TN / 4;   // token columns per epilogue warp (small TN: some quarters idle)
         for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x, ++tile_iter) {
             FLATQ_UNIT(unit)
-            const int n0 = (tile / nb_m) * kGemmBlockW;
-            const int m0 = (tile % nb_m) * TN;
+            const int n0 = (w_fast ? tile % nb_w : tile / nb_m) * kGemmBlockW;
+            const int m0 = (w_fast ? tile / nb_w : tile % nb_m) * TN;
             const uint32_t b = tile_iter % NBUF, phb = (tile_iter / NBUF) & 1;
             const int n = n0 + q * 32 + lane;
             const bool n_ok = n < p.N;
@@ -282,26 +304,33 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                     }
                 }
             }
-            // per-token scales of this warp's columns, one (two) per lane; fetched while the MMAs still run
-            float sx_lo = 0.f, sx_hi = 0.f;
-            if (MODE != kEpiI32) {
-                const int ma = m0 + c0 + lane, mb = m0 + c0 + 32 + lane;
-                if (lane < COLS && ma < p.M) sx_lo = p.s_x[ma];
-                if (COLS > 32 && mb < p.M) sx_hi = p.s_x[mb];
+            // Per-token scales of this quarter's columns go through shared memory: one broadcast LDS.128 then serves
+            // four columns (a SHFL per column costs as much shared-memory bandwidth as an MMA operand row, and the
+            // tensor pipe needs that bandwidth).  Staged while the MMAs of this tile still run.
+            const bool fold = p.acc_shift == 4 && p.K <= 16384;
+            if (MODE != kEpiI32 && c0 < TN) {
+                named_bar_sync(1 + half, 128);   // the quarter's four warps have finished reading the previous tile's scales
+                if (q == 0) {
+#pragma unroll
+                    for (int i = lane; i < COLS; i += 32) {
+                        const int m = m0 + c0 + i;
+                        const float v = m < p.M ? p.s_x[m] : 0.f;
+                        sx_s[c0 + i] = fold ? v * 0.0625f : v;
+                    }
+                }
+                named_bar_sync(1 + half, 128);   // staged
             }
             FLATQ_TWAIT(0, mbar_wait(&full_acc[b], phb));
             tc_fence_after();
             const long long t_epi0 = PROF ? clock64() : 0;
-            // Drain this warp's COLS accumulator columns into registers as dequantised fp16 pairs, hand the
-            // TMEM buffer back to the MMA issuer, and only then do the (slow) global stores.
-            uint32_t yh[COLS / 2];  // MODE != I32: half2 / bf16x2 of tokens (2i, 2i+1); I32 keeps raw values in two passes
+            const uint32_t t_acc = tmem + ((uint32_t)(q * 32) << 16) + b * 128 + c0;
+            const bool live = c0 < TN && !(PROF && (p.dbg & 4));
             if (MODE == kEpiI32) {
-                if (c0 < TN) {
+                if (live) {
 #pragma unroll 1
                     for (int c = 0; c < COLS / 16; ++c) {
-                        if (PROF && (p.dbg & 4)) break;
                         uint32_t r[16];
-                        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + b * 128 + c0 + c * 16, r);
+                        tmem_ld_x16(t_acc + c * 16, r);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -315,59 +344,54 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&empty_acc[b]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_acc[b]);
             } else {
-                // fast path: the raw accumulator (16x the true one) is exactly representable in fp32 (|raw| <= 2^10 K), so
-                // the power-of-two factor moves into the per-token scale instead of a per-element shift
-                const bool fold = p.acc_shift == 4 && p.K <= 16384;
-                const bool has_bias = p.bias != nullptr;
-                if (fold) { sx_lo *= 0.0625f; sx_hi *= 0.0625f; }
-                auto drain = [&](auto fold_c) {
-                    constexpr bool FOLD = decltype(fold_c)::value;
+                // Copy this warp's COLS raw accumulator columns into registers with one batch of tcgen05.ld, then
+                // release the TMEM buffer: the next tile's MMAs overlap all the arithmetic and the stores below.
+                uint32_t r[COLS];
+                if (live) {
+                    if constexpr (COLS == 16) {
+                        tmem_ld_x16(t_acc, r);
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < COLS / 16; ++c) {
-                        uint32_t r[16];
-                        tmem_ld_x16(tmem + ((uint32_t)(q * 32) << 16) + b * 128 + c0 + c * 16, r);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            // per-token scales live one per lane (loaded before the accumulator was ready)
-                            const float s0 = __shfl_sync(0xffffffffu, (c * 16 + j) >= 32 ? sx_hi : sx_lo, (c * 16 + j) & 31);
-                            const float s1 = __shfl_sync(0xffffffffu, (c * 16 + j + 1) >= 32 ? sx_hi : sx_lo, (c * 16 + j + 1) & 31);
-                            const int32_t a0 = FOLD ? static_cast<int32_t>(r[j]) : static_cast<int32_t>(r[j]) >> p.acc_shift;
-                            const int32_t a1 = FOLD ? static_cast<int32_t>(r[j + 1]) : static_cast<int32_t>(r[j + 1]) >> p.acc_shift;
-                            // explicit _rn ops: no FMA contraction, so the result equals the oracle's fp32 arithmetic
-                            float y0 = __fmul_rn(__fmul_rn((float)a0, s0), sw_n);
-                            float y1 = __fmul_rn(__fmul_rn((float)a1, s1), sw_n);
-                            if (has_bias) { y0 = __fadd_rn(y0, bias_n); y1 = __fadd_rn(y1, bias_n); }
-                            if (MODE == kEpiF16) {
-                                yh[c * 8 + j / 2] = pack_half2(y0, y1);
-                            } else {
-                                __nv_bfloat162 v = __floats2bfloat162_rn(y0, y1);
-                                yh[c * 8 + j / 2] = *reinterpret_cast<uint32_t*>(&v);
-                            }
-                        }
+                        for (int c = 0; c < COLS / 32; ++c) tmem_ld_x32(t_acc + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
                     }
-                };
-                if (c0 < TN && !(PROF && (p.dbg & 4))) {
-                    if (fold) drain(FoldTrue{}); else drain(FoldFalse{});
+                    tmem_ld_wait();
                 }
                 tc_fence_before();
-                mbar_arrive(&empty_acc[b]);  // accumulator free: the next tile's MMAs overlap the stores below
-                if (c0 < TN && !(PROF && (p.dbg & 4))) {
-                    // lanes (2i, 2i+1) swap halves so that each stores 4 bytes: even lane -> (token m; n, n+1),
-                    // odd lane -> (token m+1; n-1, n).  N is even (checked on the host).
-                    const bool odd = lane & 1;
-                    uint32_t* out32 = reinterpret_cast<uint32_t*>(p.out);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_acc[b]);
+                if (live) {
+                    // fast path (fold): the raw accumulator (16x the true one) is exactly representable in fp32
+                    // (|raw| <= 2^10 K), so the power-of-two factor sits in the staged per-token scale instead of a shift
+                    const bool has_bias = p.bias != nullptr;
+                    // 16-bit stores: lane = output feature n, so a warp store covers 64 contiguous bytes of one token row.
+                    // (M + 256) * N < 2^32 is checked on the host.
+                    uint16_t* const out16 = reinterpret_cast<uint16_t*>(p.out);
+                    uint32_t idx = (uint32_t)(m0 + c0) * (uint32_t)p.N + (uint32_t)n;
+                    const int j_end = n_ok ? p.M - (m0 + c0) : 0;  // store only tokens m0 + c0 + j < M
+                    auto finish = [&](auto fold_c) {
+                        constexpr bool FOLD = decltype(fold_c)::value;
 #pragma unroll
-                    for (int i = 0; i < COLS / 2; ++i) {
-                        const uint32_t mine = yh[i];
-                        const uint32_t send = odd ? (mine & 0xFFFFu) : (mine >> 16);
-                        const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
-                        const uint32_t outv = odd ? (recv | (mine & 0xFFFF0000u)) : ((mine & 0xFFFFu) | (recv << 16));
-                        const int m = m0 + c0 + 2 * i + (odd ? 1 : 0);
-                        if (m < p.M && n_ok) out32[((size_t)m * p.N + (n & ~1)) >> 1] = outv;  // n_ok is pair-uniform: N even
-                    }
+                        for (int j = 0; j < COLS; j += 4) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(&sx_s[c0 + j]);
+                            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int32_t a = FOLD ? static_cast<int32_t>(r[j + i]) : static_cast<int32_t>(r[j + i]) >> p.acc_shift;
+                                // explicit _rn ops: no FMA contraction, so the result equals the oracle's fp32 arithmetic
+                                float y = __fmul_rn(__fmul_rn((float)a, sv[i]), sw_n);
+                                if (has_bias) y = __fadd_rn(y, bias_n);
+                                uint16_t h;
+                                if (MODE == kEpiF16) h = __half_as_ushort(__float2half_rn(y));
+                                else h = __bfloat16_as_ushort(__float2bfloat16_rn(y));
+                                if (j + i < j_end) out16[idx] = h;
+                                idx += (uint32_t)p.N;
+                            }
+                        }
+                    };
+                    if (fold) finish(FoldTrue{}); else finish(FoldFalse{});
                 }
             }
             if (PROF) tacc[1] += clock64() - t_epi0;

@@ -12,6 +12,7 @@ fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64] * 3 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
 dev = torch.device("cuda:0")
 shapes = [(2048, 4096, 4096), (2048, 28672, 4096), (2048, 4096, 14336), (2048, 6144, 4096)]
+NW = int(os.environ.get("FLATQ_PROF_WARPS", "28"))  # warps per CTA of the build under test
 if len(sys.argv) > 1:
     shapes = [tuple(int(v) for v in sys.argv[1].split("x"))]
 for (m, n, k) in shapes:
@@ -21,8 +22,8 @@ for (m, n, k) in shapes:
     sw = torch.rand(n, device=dev)
     y = torch.empty(m, n, dtype=torch.float16, device=dev)
     grid = min(148, ((n + 127) // 128) * ((m + 255) // 256))
-    for dbg in (0, 4):
-        prof = torch.zeros(grid, 27, 5, dtype=torch.int64, device=dev)
+    for dbg in [int(v) for v in os.environ.get("FLATQ_PROF_DBG", "0,4").split(",")]:
+        prof = torch.zeros(grid, NW, 5, dtype=torch.int64, device=dev)
         st = torch.cuda.current_stream().cuda_stream
         for _ in range(2):
             rc = fn(x8.data_ptr(), sx.data_ptr(), w.data_ptr(), sw.data_ptr(), m, n, k, y.data_ptr(), prof.data_ptr(), dbg, st)
@@ -40,7 +41,7 @@ for (m, n, k) in shapes:
         print(f"== M={m} N={n} K={k} dbg={dbg}: {us:.1f} us, {2*m*n*k/us/1e6:.0f} TOPS; kernel cycles {p[0,4]:.0f}; k-blocks/CTA {kb_total:.0f} -> {p[0,4]/kb_total:.0f} cyc/k-block")
         print(f"   producers: X wait empty {p[0,0]:.0f}   W wait wempty {p[2,0]:.0f}")
         print(f"   mma     : wait full {p[1,0]:.0f}  wait empty_acc {p[1,2]:.0f}")
-        ex = p[3:11]
+        ex = p[NW - 24:NW - 16]
         print(f"   expander: wait wfull {ex[:,0].mean():.0f}  wait empty {ex[:,1].mean():.0f}  tmem st wait {ex[:,2].mean():.0f}  (per warp; each does half the stages)")
-        ep = p[11:27]
+        ep = p[NW - 16:NW]
         print(f"   epilogue: wait full_acc {ep[:,0].mean():.0f}  busy {ep[:,1].mean():.0f}")
