@@ -11,8 +11,11 @@
 #include <string>
 
 #include "../../include/flatq_b200.h"
+#include <atomic>
+#include <random>
 #include "elementwise.cuh"
 #include "gemm_w4a8.cuh"
+#include "gemm_w4a8_2sm.cuh"
 #include "gemv_w4a8.cuh"
 #include "kron_quant.cuh"
 #include "kron_quant_tc.cuh"
@@ -132,6 +135,22 @@ int launch_gemm_t(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams
     return FLATQ_OK;
 }
 
+// CTA-pair kernel (prefill): grid = 2 x min(tiles of 256 weight rows x 256 tokens, SM pairs)
+template <int MODE>
+int launch_gemm_2sm(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, cudaStream_t st) {
+    auto kern = gemm_w4a8_2sm_kernel<MODE>;
+    static bool attr_set = false;  // benign race: idempotent
+    if (!attr_set) {
+        FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2smBytes));
+        attr_set = true;
+    }
+    const int nb_w2 = ((p.N + kGemmBlockW - 1) / kGemmBlockW + 1) / 2, nb_m = (p.M + k2smTokens - 1) / k2smTokens;
+    const int tiles = nb_w2 * nb_m, pairs = num_sms() / 2;
+    const int grid = 2 * (tiles < pairs ? tiles : pairs);
+    FLATQ_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), k2smBytes, st, tw, tx, p));
+    return FLATQ_OK;
+}
+
 template <int MODE>
 int launch_gemm_m(int tn, const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, cudaStream_t st) {
     switch (tn) {
@@ -144,8 +163,24 @@ int launch_gemm_m(int tn, const CUtensorMap& tw, const CUtensorMap& tx, const Ge
 }
 
 // w_packed [N, K/2]; x8 [M, K] int8 in the permuted operand format
+// stream-K workspace of the prefill GEMM: per CTA one 128 x TN int32 partial + 16 flags (see GemmParams::streamk)
+static size_t streamk_ws_bytes(int tn) {
+    return align_up((size_t)num_sms() * kGemmBlockW * tn * 4, 256) + align_up((size_t)num_sms() * 16 * 8, 256);
+}
+
+static unsigned long long next_epoch() {
+    static std::atomic<unsigned long long> ctr{0};
+    static const unsigned long long salt = [] {
+        std::random_device rd;
+        return ((unsigned long long)rd() << 32) ^ ((unsigned long long)rd() << 11);
+    }();
+    unsigned long long e = salt + ctr.fetch_add(1) + 1;
+    return e ? e : 1;
+}
+
 int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, int64_t K, int acc_shift, void* out,
-                int mode, const float* sx, const float* sw, const void* bias, cudaStream_t st, int k_splits = 1) {
+                int mode, const float* sx, const float* sw, const void* bias, cudaStream_t st, int k_splits = 1,
+                void* sk_ws = nullptr, size_t sk_ws_bytes = 0) {
     FLATQ_CHECK(M > 0 && N > 0 && K > 0, FLATQ_ERR_INVALID, "empty GEMM %lldx%lldx%lld", (long long)M, (long long)N,
                 (long long)K);
     FLATQ_CHECK(K % 32 == 0, FLATQ_ERR_INVALID, "K=%lld must be a multiple of 32", (long long)K);
@@ -154,14 +189,41 @@ int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, i
     FLATQ_CHECK(mode == kEpiI32 || (M + 256) * N < (1ll << 32), FLATQ_ERR_UNSUPPORTED,
                 "output of %lld x %lld exceeds the 32-bit element index of the store path", (long long)M, (long long)N);
     const int tn = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+    // prefill: two SMs share a 256 x 256 tile (each loads half of the activation tile)
+    static const bool one_sm = getenv("FLATQ_GEMM_1SM") != nullptr;
+    const bool pair = tn == 256 && k_splits == 1 && !one_sm;
     CUtensorMap tw, tx;
     int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_map_u8(&tx, x8, M, K, K, 128, tn, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_map_u8(&tx, x8, M, K, K, 128, pair ? 128 : tn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     GemmParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = acc_shift;
     p.out = out; p.s_x = sx; p.s_w = sw; p.bias = bias; p.prof = nullptr; p.dbg = 0; p.k_splits = k_splits;
+    p.streamk = 0; p.sk_part = nullptr; p.sk_flags = nullptr; p.epoch = 0;
+    {
+        // Stream-K on the partial last wave: worth it when the tail's K stages, dealt to all SMs, finish at least two
+        // stages earlier than whole tiles would, and every part is long enough to amortise its fix-up.
+        const int64_t G = num_sms(), T = ((N + kGemmBlockW - 1) / kGemmBlockW) * ((M + tn - 1) / tn);
+        const int64_t KB = (K + kGemmBlockK - 1) / kGemmBlockK, R = T % G;
+        static const bool off = getenv("FLATQ_STREAMK") == nullptr;  // measured: no gain under the power limit
+        static const int min_share = getenv("FLATQ_STREAMK_MIN") ? atoi(getenv("FLATQ_STREAMK_MIN")) : 1;
+        if (!off && !pair && mode != kEpiI32 && k_splits == 1 && sk_ws && aligned16(sk_ws) && sk_ws_bytes >= streamk_ws_bytes(tn) &&
+            T > G && R > 0 && R * KB / G >= min_share && KB - (R * KB + G - 1) / G >= 2) {
+            p.streamk = 1;
+            p.sk_part = reinterpret_cast<int32_t*>(sk_ws);
+            p.sk_flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(sk_ws) +
+                                                               align_up((size_t)G * kGemmBlockW * tn * 4, 256));
+            p.epoch = next_epoch();
+        }
+    }
+    if (pair) {
+        switch (mode) {
+            case kEpiI32: return launch_gemm_2sm<kEpiI32>(tw, tx, p, st);
+            case kEpiF16: return launch_gemm_2sm<kEpiF16>(tw, tx, p, st);
+            case kEpiBF16: return launch_gemm_2sm<kEpiBF16>(tw, tx, p, st);
+        }
+    }
     switch (mode) {
         case kEpiI32: return launch_gemm_m<kEpiI32>(tn, tw, tx, p, st);
         case kEpiF16: return launch_gemm_m<kEpiF16>(tn, tw, tx, p, st);
@@ -450,13 +512,14 @@ static int decode_splits(int64_t M, int64_t N, int64_t K) {
     return s < 2 ? 1 : (int)s;
 }
 
-size_t flatq_linear_fused_workspace_bytes(int64_t M, int64_t N, int64_t K) {
-    return align_up((size_t)M * K, 256) + align_up((size_t)M * 4, 256) + (M <= 64 ? align_up((size_t)M * N * 4, 256) : 0);
-}
-
 size_t flatq_gemm_w4a8_workspace_bytes(int64_t M, int64_t N, int64_t K) {
     (void)K;
-    return M <= 64 ? align_up((size_t)M * N * 4, 256) : 0;
+    if (M <= 64) return align_up((size_t)M * N * 4, 256);          // split-K accumulator (decode)
+    return streamk_ws_bytes(M <= 128 ? 128 : 256);                  // stream-K partials + flags (prefill)
+}
+
+size_t flatq_linear_fused_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    return align_up((size_t)M * K, 256) + align_up((size_t)M * 4, 256) + flatq_gemm_w4a8_workspace_bytes(M, N, K);
 }
 
 int flatq_act_quant(const void* x, const void* left, const void* right, int n1, int n2, float clip_max, float clip_min,
@@ -506,7 +569,8 @@ int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed
     }
     const int splits = (ws && ws_bytes >= flatq_gemm_w4a8_workspace_bytes(M, N, K)) ? decode_splits(M, N, K) : 1;
     if (splits == 1)
-        return launch_gemm(w_packed, xq8, M, N, K, 4, y, out_dtype == FLATQ_F16 ? kEpiF16 : kEpiBF16, s_x, s_w, bias, st);
+        return launch_gemm(w_packed, xq8, M, N, K, 4, y, out_dtype == FLATQ_F16 ? kEpiF16 : kEpiBF16, s_x, s_w, bias, st, 1,
+                           M > 64 ? ws : nullptr, M > 64 ? ws_bytes : 0);
     // split-K: zero the int32 workspace, accumulate partial tiles with atomics, dequantise in a finalize pass
     FLATQ_CHECK(aligned16(ws), FLATQ_ERR_INVALID, "gemm_w4a8: workspace alignment");
     FLATQ_CUDA(cudaMemsetAsync(ws, 0, (size_t)M * N * 4, st));
@@ -534,11 +598,11 @@ int flatq_linear_fused(const void* x, const void* left, const void* right, int n
     int8_t* x8 = reinterpret_cast<int8_t*>(ws);
     uint8_t* p = reinterpret_cast<uint8_t*>(ws) + align_up((size_t)M * K, 256);
     float* sx = reinterpret_cast<float*>(p);
-    void* acc_ws = M <= 64 ? p + align_up((size_t)M * 4, 256) : nullptr;
+    void* acc_ws = p + align_up((size_t)M * 4, 256);  // split-K accumulator (decode) or stream-K partials (prefill)
     int rc = flatq_act_quant(x, left, right, n1, n2, clip_max, clip_min, M, x8, sx, stream);
     if (rc) return rc;
-    return flatq_gemm_w4a8(x8, sx, w_packed, s_w, bias, M, N, K, y, out_dtype, acc_ws, acc_ws ? align_up((size_t)M * N * 4, 256) : 0,
-                           stream);
+    return flatq_gemm_w4a8(x8, sx, w_packed, s_w, bias, M, N, K, y, out_dtype, acc_ws,
+                           flatq_gemm_w4a8_workspace_bytes(M, N, K), stream);
 }
 
 int flatq_hadamard(const void* x, void* out, int64_t rows, int n, float scale, flatq_stream_t stream) {
@@ -609,6 +673,7 @@ int flatq_debug_gemm_profile(const int8_t* xq8, const float* s_x, const uint8_t*
     GemmParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = 4;
     p.out = y; p.s_x = s_x; p.s_w = s_w; p.bias = nullptr; p.prof = prof; p.dbg = dbg; p.k_splits = 1;
+    p.streamk = 0; p.sk_part = nullptr; p.sk_flags = nullptr; p.epoch = 0;
     auto kern = gemm_w4a8_kernel<256, kEpiF16, true>;
     constexpr int smem = GemmSmem<256>::kBytes;
     FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

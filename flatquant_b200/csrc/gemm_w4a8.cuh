@@ -87,9 +87,66 @@ struct GemmParams {
     const float* s_w;     // [N]  per-channel scale (dequant modes)
     const void* bias;     // [N] same dtype as out, or nullptr
     int k_splits;         // > 1: split-K over CTAs, int32 atomics into `out` (MODE == kEpiI32 only; decode shapes)
+    // stream-K for the last, partial wave of tiles (16-bit output modes): its tiles' K ranges are dealt evenly to all
+    // CTAs; a CTA that continues a tile begun by its predecessor publishes a raw int32 partial, the CTA that began the
+    // tile adds the partials of its successors in its epilogue.  Integer sums: the result is bit-identical.
+    int streamk;                       // 0 / 1
+    int32_t* sk_part;                  // [grid][TN columns][128 rows] int32 partial of CTA c's continued tile
+    unsigned long long* sk_flags;      // [grid][16 epilogue warps]: == epoch once that warp's slice is published
+    unsigned long long epoch;          // unique per launch (no zeroing of the workspace between launches)
     long long* prof;      // debug: per-CTA role timers (PROF instantiation only)
     int dbg;              // debug (PROF only): 1 skip TMEM stores, 2 skip MMA issue, 4 skip epilogue, 8 no X TMA, 16 no W TMA/LDS, 32 weight-blocks-fastest raster
 };
+
+// ---- work schedule: every warp role walks the same list of units of its CTA
+struct GemmUnit { int tile, kb0, kb1, kind; };  // kind 0: whole tile (or one atomic split-K slice); 1: stream-K continued
+                                                // part (publish partial); 2: stream-K first part (collect partials)
+struct GemmSched {
+    int G, cta, KB, splits, T;   // grid, this CTA, K stages per tile, uniform split-K factor, output tiles
+    int streamk, F;              // stream-K on the last T - F tiles (F = multiple of G tiles run whole)
+    int Q;                       // (T - F) * KB: K stages of the stream-K region, CTA c owns [Q c / G, Q (c + 1) / G)
+    __device__ __forceinline__ int lo(int c) const { return (int)((unsigned)Q * (unsigned)c / (unsigned)G); }  // Q G < 2^31 (host)
+    __device__ __forceinline__ GemmUnit get(int i) const {   // kind < 0: no more work
+        GemmUnit u;
+        u.tile = 0; u.kb0 = 0; u.kb1 = 0; u.kind = -1;
+        if (!streamk) {
+            const int unit = cta + i * G;
+            if (unit < T * splits) {
+                const int sp = unit % splits;
+                u.tile = unit / splits;
+                u.kb0 = KB * sp / splits;   // KB <= 256
+                u.kb1 = KB * (sp + 1) / splits;
+                u.kind = 0;
+            }
+            return u;
+        }
+        const int l = lo(cta), h = lo(cta + 1);   // share < KB: the range touches at most two tiles
+        const int t0 = l / KB, r0 = l - t0 * KB;
+        const int b1 = (t0 + 1) * KB;
+        const bool has_peer = r0 != 0;                   // continues a tile begun by an earlier CTA
+        const bool has_own = has_peer ? h > b1 : h > l;  // begins a tile (finished by later CTAs)
+        const int i_own = has_peer ? 1 : 0, i_dp = i_own + (has_own ? 1 : 0);
+        if (has_peer && i == 0) {
+            u.tile = F + t0; u.kb0 = r0; u.kb1 = (h < b1 ? h : b1) - t0 * KB; u.kind = 1;
+        } else if (has_own && i == i_own) {
+            const int t1 = has_peer ? t0 + 1 : t0;
+            u.tile = F + t1; u.kb0 = 0; u.kb1 = h - t1 * KB; u.kind = 2;
+        } else {
+            const int tile = cta + (i - i_dp) * G;   // whole tiles of the full waves
+            if (tile < F) { u.tile = tile; u.kb0 = 0; u.kb1 = KB; u.kind = 0; }
+        }
+        return u;
+    }
+};
+
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 template <int TN>
 struct GemmSmem {
@@ -151,14 +208,11 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     const bool w_fast = PROF && (p.dbg & 32);  // debug: the other raster order (weight blocks fastest)
     const int KB_all = (p.K + kGemmBlockK - 1) / kGemmBlockK;
     const int splits = p.k_splits > 1 ? p.k_splits : 1;
-    const int n_tiles = nb_w * nb_m * splits;  // work units: (output tile, K range)
-    // unit -> output tile and K-stage range [kb0, kb1)
-#define FLATQ_UNIT(unit)                                              \
-    const int tile = (unit) / splits, split_ = (unit) % splits;       \
-    const int kb0 = (int)((long long)KB_all * split_ / splits);       \
-    const int kb1 = (int)((long long)KB_all * (split_ + 1) / splits); \
-    (void)tile; (void)kb0; (void)kb1;
-
+    GemmSched sc;
+    sc.G = (int)gridDim.x; sc.cta = (int)blockIdx.x; sc.KB = KB_all; sc.splits = splits; sc.T = nb_w * nb_m;
+    sc.streamk = p.streamk;
+    sc.F = sc.T - sc.T % sc.G;
+    sc.Q = (sc.T - sc.F) * KB_all;
     // setmaxnreg sits at the top of each warpgroup's own branch so that ptxas allocates every role's code against
     // that role's budget
     if (warp < 4) {
@@ -167,10 +221,11 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         // ================================ X producer ================================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x) {
-                FLATQ_UNIT(unit)
-                const int m0 = (w_fast ? tile / nb_w : tile % nb_m) * TN;
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            for (int ui = 0;; ++ui) {
+                const GemmUnit u = sc.get(ui);
+                if (u.kind < 0) break;
+                const int m0 = (w_fast ? u.tile / nb_w : u.tile % nb_m) * TN;
+                for (int kb = u.kb0; kb < u.kb1; ++kb, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                     FLATQ_TWAIT(0, mbar_wait(&empty[s], ph ^ 1));
                     if (PROF && (p.dbg & 8)) { mbar_arrive(&full[s]); continue; }
@@ -184,10 +239,11 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         // ================================ W producer ================================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x) {
-                FLATQ_UNIT(unit)
-                const int n0 = (w_fast ? tile % nb_w : tile / nb_m) * kGemmBlockW;
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            for (int ui = 0;; ++ui) {
+                const GemmUnit u = sc.get(ui);
+                if (u.kind < 0) break;
+                const int n0 = (w_fast ? u.tile % nb_w : u.tile / nb_m) * kGemmBlockW;
+                for (int kb = u.kb0; kb < u.kb1; ++kb, ++it) {
                     const uint32_t s = it % kStagesW, ph = (it / kStagesW) & 1;
                     FLATQ_TWAIT(0, mbar_wait(&wempty[s], ph ^ 1));
                     if (PROF && (p.dbg & 16)) { mbar_arrive(&wfull[s]); continue; }
@@ -200,8 +256,10 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         // ================================ MMA issuer ================================
         constexpr uint32_t idesc = make_idesc(kDS32, kFmtS8, kFmtS8, 0, 0, kGemmBlockW, TN);
         uint32_t it = 0, tile_iter = 0;
-        for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x, ++tile_iter) {
-            FLATQ_UNIT(unit)
+        for (;; ++tile_iter) {
+            const GemmUnit u = sc.get((int)tile_iter);
+            if (u.kind < 0) break;
+            const int kb0 = u.kb0, kb1 = u.kb1;
             const uint32_t b = tile_iter % NBUF, phb = (tile_iter / NBUF) & 1;
             FLATQ_TWAIT(2, mbar_wait(&empty_acc[b], phb ^ 1));
             tc_fence_after();
@@ -238,9 +296,10 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         // (row base | (row % 8) << 4) ^ (c << 4): one XOR with an immediate per load, no per-chunk address registers
         const uint32_t ws_addr = smem_u32(ws) + row * 128 + ((row & 7) << 4);
         uint32_t it = 0;
-        for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x) {
-            FLATQ_UNIT(unit)
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        for (int ui = 0;; ++ui) {
+                const GemmUnit u = sc.get(ui);
+                if (u.kind < 0) break;
+            for (int kb = u.kb0; kb < u.kb1; ++kb, ++it) {
                 if ((it & 1) != (uint32_t)grp) continue;
                 const uint32_t sw = it % kStagesW, phw = (it / kStagesW) & 1;
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
@@ -286,10 +345,11 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const int half = ew >> 2;          // which quarter of the token columns
         uint32_t tile_iter = 0;
         constexpr int COLS = TN / 4 < 16 ? 16 : TN / 4;   // token columns per epilogue warp (small TN: some quarters idle)
-        for (int unit = blockIdx.x; unit < n_tiles; unit += gridDim.x, ++tile_iter) {
-            FLATQ_UNIT(unit)
-            const int n0 = (w_fast ? tile % nb_w : tile / nb_m) * kGemmBlockW;
-            const int m0 = (w_fast ? tile / nb_w : tile % nb_m) * TN;
+        for (;; ++tile_iter) {
+            const GemmUnit u = sc.get((int)tile_iter);
+            if (u.kind < 0) break;
+            const int n0 = (w_fast ? u.tile % nb_w : u.tile / nb_m) * kGemmBlockW;
+            const int m0 = (w_fast ? u.tile / nb_w : u.tile % nb_m) * TN;
             const uint32_t b = tile_iter % NBUF, phb = (tile_iter / NBUF) & 1;
             const int n = n0 + q * 32 + lane;
             const bool n_ok = n < p.N;
@@ -362,6 +422,44 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_acc[b]);
+                if (u.kind == 1) {
+                    // stream-K continued part: publish this warp's slice of the raw partial ([column][row], 128-B rows)
+                    if (live) {
+                        int32_t* part = p.sk_part + (size_t)blockIdx.x * (kGemmBlockW * TN) + c0 * kGemmBlockW + q * 32 + lane;
+#ifndef FLATQ_SK_NO_WRITE
+#pragma unroll
+                        for (int j = 0; j < COLS; ++j) part[j * kGemmBlockW] = static_cast<int32_t>(r[j]);
+                        __threadfence();
+#endif
+                        __syncwarp();
+                        if (lane == 0) st_release_u64(&p.sk_flags[blockIdx.x * 16 + ew], p.epoch);
+                    }
+                    continue;
+                }
+                if (u.kind == 2 && live) {
+                    // stream-K first part: the following CTAs continue this tile; add their partials (published early
+                    // in their own schedules) before dequantising
+                    const int tile_end = (u.tile - sc.F + 1) * sc.KB;
+                    for (int c2 = sc.cta + 1; sc.lo(c2) < tile_end; ++c2) {
+                        if (lane == 0) {
+                            // peers publish in the first unit of their schedule; a wait of ~1 s means a broken launch
+                            // (e.g. a workspace shared by concurrent launches): fail loudly rather than hang
+                            uint32_t spins = 0;
+                            while (ld_acquire_u64(&p.sk_flags[c2 * 16 + ew]) != p.epoch) {
+                                __nanosleep(64);
+                                if (++spins > (1u << 24)) asm volatile("trap;");
+                            }
+                        }
+                        __syncwarp();
+                        const int32_t* part = p.sk_part + (size_t)c2 * (kGemmBlockW * TN) + c0 * kGemmBlockW + q * 32 + lane;
+#ifndef FLATQ_SK_NO_READ
+#pragma unroll
+                        for (int j = 0; j < COLS; ++j) r[j] += static_cast<uint32_t>(__ldcg(part + j * kGemmBlockW));
+#else
+                        (void)part;
+#endif
+                    }
+                }
                 if (live) {
                     // fast path (fold): the raw accumulator (16x the true one) is exactly representable in fp32
                     // (|raw| <= 2^10 K), so the power-of-two factor sits in the staged per-token scale instead of a shift

@@ -122,7 +122,10 @@ int flatq_linear_fused(const void* x_f16, const void* left_f16, const void* righ
 int flatq_act_quant(const void* x_f16, const void* left_f16, const void* right_f16, int n1, int n2, float clip_max,
                     float clip_min, int64_t M, int8_t* xq8, float* s_x, flatq_stream_t stream);
 /*      workspace (may be NULL): with flatq_gemm_w4a8_workspace_bytes(M, N, K) bytes, decode shapes (M <= 64) split K
- *      across CTAs (int32 atomics + a finalize pass) so that the packed-weight stream uses the whole chip. */
+ *      across CTAs (int32 atomics + a finalize pass) so that the packed-weight stream uses the whole chip, and
+ *      prefill shapes whose last wave of output tiles is partial deal that wave's K ranges to all SMs (stream-K:
+ *      raw int32 partials + per-launch epoch flags in the workspace; needs no zeroing, must not be shared by
+ *      launches that may run concurrently).  Results are bit-identical with and without the workspace. */
 size_t flatq_gemm_w4a8_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed, const float* s_w, const void* bias,
                     int64_t M, int64_t N, int64_t K, void* y, int out_dtype, void* workspace, size_t workspace_bytes,

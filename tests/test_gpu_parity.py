@@ -500,6 +500,38 @@ def test_decode_split_k_path(ops, dev, m, k, n, n1, n2):
     assert np.array_equal(y.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("m,n,k", [(2048, 4096, 4096), (2048, 6144, 4096), (2048, 5120, 8192), (1500, 4100, 2048),
+                                   (2048, 4096, 14336), (4096, 2560, 1024), (2048, 28672, 4096)])
+def test_prefill_stream_k_bit_identical(ops, dev, m, n, k):
+    """Prefill shapes whose last wave of tiles is partial take the stream-K schedule when a workspace is given
+    (csrc/gemm_w4a8.cuh GemmSched): int32 partial sums move between CTAs, so the result must equal the plain
+    schedule bit for bit, the oracle arithmetic exactly (sampled rows), and be run-to-run deterministic."""
+    from flatquant_b200 import _lib
+    torch.manual_seed(m + n + k)
+    xq8 = torch.randint(-8, 8, (m, k), dtype=torch.int8, device=dev)
+    sx = torch.rand(m, device=dev) * 0.05 + 0.01
+    wq = torch.randint(-8, 8, (n, k), dtype=torch.int8, device=dev)
+    wp = ops.pack_i4(wq)
+    sw = torch.rand(n, device=dev) * 0.02 + 0.01
+    bias = torch.randn(n, device=dev).half()
+    y_sk = ops.gemm_w4a8(xq8, sx, wp, sw, bias, torch.float16)           # ops passes the stream-K workspace
+    y_sk2 = ops.gemm_w4a8(xq8, sx, wp, sw, bias, torch.float16)
+    lib = _lib.load()
+    y_plain = torch.empty_like(y_sk)
+    _lib.check(lib.flatq_gemm_w4a8(xq8.data_ptr(), sx.data_ptr(), wp.data_ptr(), sw.data_ptr(), bias.data_ptr(), m, n, k,
+                                   y_plain.data_ptr(), 0, None, 0, torch.cuda.current_stream().cuda_stream), "gemm_w4a8")
+    torch.cuda.synchronize()
+    assert torch.equal(y_sk, y_plain) and torch.equal(y_sk, y_sk2)
+    rows = np.unique(np.concatenate([np.arange(0, m, max(1, m // 23)), [m - 1]]))
+    perm = np.array([0, 2, 4, 6, 1, 3, 5, 7])
+    c8 = xq8[rows].cpu().numpy().reshape(len(rows), k // 8, 8)
+    codes = np.empty_like(c8)
+    codes[:, :, perm] = c8
+    acc = O.gemm_i4(codes.reshape(len(rows), k), wq.cpu().numpy())
+    ref = O.sym_dequant(acc, sx[rows].cpu().numpy(), sw.cpu().numpy(), bias.float().cpu().numpy()).astype(np.float16)
+    assert np.array_equal(y_sk[rows].cpu().numpy(), ref)
+
+
 def test_moe_routed_experts_configs4(dev):
     """DeepSeek-V3 routed experts (configs[4]) at reduced width: shared w1_trans / quantiser, per-expert w1,w3,w2."""
     from flatquant_b200 import ops as _ops
