@@ -64,22 +64,38 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout_s=5.0):
+        """nvidia-smi takes a while to come up on a fresh box: block until it delivers (warm-up runs meanwhile)."""
+        t_end = time.time() + timeout_s
+        while self.proc is not None and not self.rows and time.time() < t_end:
+            time.sleep(0.01)
+
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= t1 + 0.03)]
+        window = "timed region"
+        if not rows:  # region shorter than one sampling period: fall back to everything seen under the same load
+            rows, window = [r for (_, r) in self.rows], "warm-up + timed region"
+        self.rows = rows
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
         # "under load": the upper half of the samples (idle samples at the edges pull the median down)
         sm_sorted = sorted(sm)
         load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window,
+                "power_w": (statistics.median(pw) if pw else None)}
 
 
 def make_layers(dev, n_layers, gen):
@@ -295,18 +311,22 @@ def main():
     hy = torch.empty(SEQ, HIDDEN, dtype=torch.float16).pin_memory()
     run.set_input(hx, hi)
 
-    for _ in range(max(3, args.warmup)):
-        run.step()
-    torch.cuda.synchronize()
-
-    # ---- device-resident timing (value)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(3, args.warmup)):
+        run.step()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.wait_first()
+
+    # ---- device-resident timing (value)
     run.launches = 0
+    t_mark0 = sampler.mark()
     ms = timed(run.step, args.steps, barrier)
+    t_mark1 = sampler.mark()
     launches = run.launches
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_mark0, t_mark1) if rank == 0 else None
 
     # ---- end-to-end through the public API with host buffers (e2e): H2D inputs + D2H result every step
     def e2e_step():
