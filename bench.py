@@ -130,15 +130,20 @@ class Runner:
         self.x[HIDDEN].copy_(x_hidden, non_blocking=True)
         self.x[INTER].copy_(x_inter, non_blocking=True)
 
-    def step(self):
+    def step(self, x=None, y_last=None):
+        """One pass over all layers.  x: input buffers to read (default: the resident ones); y_last: where the last
+        layer's down projection goes (the step's result)."""
         ops, cm = self.ops, self.cm
+        x = x or self.x
+        last = self.layers[-1]
         for layer in self.layers:
             for name, k, n, (n1, n2) in LINEARS:
                 p = layer[name]
-                ops.act_quant(self.x[k], p["left"], p["right"], n1, n2, cm, cm, out=self.xq[k])
-                ops.gemm_w4a8(self.xq[k][0], self.xq[k][1], p["w"], p["s_w"], out=self.y[name])
+                out = y_last if (y_last is not None and layer is last and name == "down") else self.y[name]
+                ops.act_quant(x[k], p["left"], p["right"], n1, n2, cm, cm, out=self.xq[k])
+                ops.gemm_w4a8(self.xq[k][0], self.xq[k][1], p["w"], p["s_w"], out=out)
                 self.launches += 2
-        return self.y["down"]
+        return y_last if y_last is not None else self.y["down"]
 
     def gemm_only(self):
         for layer in self.layers:
@@ -328,14 +333,54 @@ def main():
     launches = run.launches
     clocks = sampler.stop(t_mark0, t_mark1) if rank == 0 else None
 
-    # ---- end-to-end through the public API with host buffers (e2e): H2D inputs + D2H result every step
-    def e2e_step():
-        run.set_input(hx, hi)
-        y = run.step()
-        hy.copy_(y, non_blocking=True)
+    # ---- end-to-end through the public API with host buffers (e2e): every step copies ITS inputs from pinned host
+    # memory and its result back, inside the timed region.  Serving-style double buffering: while step i computes, the
+    # copy stream brings in step i+1's inputs and takes step i-1's result out; the first copy-in and the last copy-out
+    # have nothing to hide behind and are exposed.
+    class E2E:
+        def __init__(self, steps):
+            self.steps, self.i = steps, 0
+            self.copy = torch.cuda.Stream(device=dev)
+            self.xb = [run.x, {k: torch.empty_like(v) for k, v in run.x.items()}]
+            self.yb = [torch.empty(SEQ, HIDDEN, dtype=torch.float16, device=dev) for _ in range(2)]
+            self.in_ready = [torch.cuda.Event() for _ in range(2)]
+            self.done = [torch.cuda.Event() for _ in range(2)]      # compute of the step that used buffer pair b
+            self.out_done = [torch.cuda.Event() for _ in range(2)]  # D2H of that step's result
+
+        def h2d(self, j):
+            b = j % 2
+            with torch.cuda.stream(self.copy):
+                if j >= 2:
+                    self.copy.wait_event(self.done[b])   # step j-2 no longer reads these buffers
+                self.xb[b][HIDDEN].copy_(hx, non_blocking=True)
+                self.xb[b][INTER].copy_(hi, non_blocking=True)
+                self.in_ready[b].record(self.copy)
+
+        def __call__(self):
+            i, b = self.i, self.i % 2
+            main = torch.cuda.current_stream()
+            if i == 0:
+                self.h2d(0)
+            main.wait_event(self.in_ready[b])
+            if i + 1 < self.steps:
+                self.h2d(i + 1)
+            if i >= 2:
+                main.wait_event(self.out_done[b])        # result buffer b has been read back
+            y = run.step(self.xb[b], self.yb[b])
+            self.done[b].record(main)
+            with torch.cuda.stream(self.copy):
+                self.copy.wait_event(self.done[b])
+                hy.copy_(y, non_blocking=True)
+                self.out_done[b].record(self.copy)
+            if i + 1 == self.steps:
+                main.wait_event(self.out_done[b])        # the timed region ends after the last result is on the host
+            self.i += 1
+
+    warm = E2E(2)
     for _ in range(2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, args.steps, barrier)
+        warm()
+    torch.cuda.synchronize()
+    ms_e2e = timed(E2E(args.steps), args.steps, barrier)
 
     # ---- roofline pass: the dominant kernel (tcgen05 GEMM) alone, same weights / shapes
     ms_gemm = timed(run.gemm_only, args.steps, barrier)
@@ -366,9 +411,10 @@ def main():
             "tops_gemm": OPS_PER_TOKEN_LAYER * SEQ * args.layers * args.steps / (ms * 1e-3) / 1e12,
             "clocks": clocks,
             "e2e": {"value": tok_s_e2e, "unit": "tokens/s",
-                    "h2d_bytes_per_step": hx.numel() * 2 + hi.numel() * 2, "d2h_bytes_per_step": hy.numel() * 2},
+                    "h2d_bytes_per_step": hx.numel() * 2 + hi.numel() * 2, "d2h_bytes_per_step": hy.numel() * 2,
+                    "pipeline": "double-buffered: step i+1's H2D and step i-1's D2H run on a copy stream under step i"},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "gemm_w4a8_kernel (tcgen05.mma kind::i8)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_w4a8_2sm_kernel (tcgen05.mma.cta_group::2 kind::i8)",
                          "achieved": achieved, "peak": peak_i8, "unit": "TOP/s", "frac": achieved / peak_i8,
                          "peak_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({src})",
                          "avg_launch_us": ms_gemm * 1e3 / n_gemm, "launches": n_gemm,
