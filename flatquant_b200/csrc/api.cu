@@ -305,15 +305,23 @@ int launch_kron_tc_t(const KronParams& p, cudaStream_t st) {
     int rc = make_map_u8(&tx, p.x, (uint64_t)p.tokens * p.n1, (uint64_t)N2 * 2, (uint64_t)N2 * 2, 128, C::kXRows,
                          CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+    CUtensorMap tr = tx, tl = tx;  // EXACT: the factors as row-major 2-D byte tensors, 64-column (128 B) panels
+    if (EXACT) {
+        rc = make_map_u8(&tr, p.right, N2, (uint64_t)N2 * 2, (uint64_t)N2 * 2, 128, N2, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        rc = make_map_u8(&tl, p.left, N1P, (uint64_t)N1P * 2, (uint64_t)N1P * 2, 128, N1P, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
     const int groups = (p.tokens + T - 1) / T;
     const int cap = C::kMinCtas * num_sms();
-    FLATQ_CUDA(launch_pdl(kern, dim3(groups < cap ? groups : cap), dim3(C::kThreads), (size_t)C::kSmemBytes, st, tx, p));
+    FLATQ_CUDA(launch_pdl(kern, dim3(groups < cap ? groups : cap), dim3(C::kThreads), (size_t)C::kSmemBytes, st, tx, tr, tl, p));
     return FLATQ_OK;
 }
 
 template <int N2, int N1P, int T>
 int launch_kron_tc_o(const KronParams& p, cudaStream_t st) {
-    if (p.n1 == N1P) return p.xq8 ? launch_kron_tc_t<N2, N1P, T, true, true>(p, st) : launch_kron_tc_t<N2, N1P, T, false, true>(p, st);
+    // EXACT: no padding and both factors present and TMA-addressable -> factor panels by TMA, MN-major operands
+    if (p.n1 == N1P && p.left && p.right && aligned16(p.left) && aligned16(p.right)) return p.xq8 ? launch_kron_tc_t<N2, N1P, T, true, true>(p, st) : launch_kron_tc_t<N2, N1P, T, false, true>(p, st);
     return p.xq8 ? launch_kron_tc_t<N2, N1P, T, true, false>(p, st) : launch_kron_tc_t<N2, N1P, T, false, false>(p, st);
 }
 

@@ -120,6 +120,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_kmajor(uint32_t smem_addr, ui
     d |= static_cast<uint64_t>(layout & 7) << 61;
     return d;
 }
+// MN-major operand (the M / N index is the contiguous one), 128-byte swizzle: 64-element panels of [K rows][128 B];
+// 8-row groups along K are `sbo_bytes` apart, 64-element blocks along M / N are `lbo_bytes` apart
+// (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
+__device__ __forceinline__ uint64_t make_smem_desc_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                           uint32_t layout) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(layout & 7) << 61;
+    return d;
+}
 constexpr uint32_t kLayoutSw128 = 2, kLayoutSw64 = 4, kLayoutSw32 = 6, kLayoutNone = 0;
 
 // Instruction descriptor (upper 32 bits of the "idesc" operand).
