@@ -164,6 +164,8 @@ def run_tp70(args, rank, world, local):
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout, where only the JSON line belongs
         dist.init_process_group("nccl", device_id=dev)
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
     gen = torch.Generator(device=dev).manual_seed(77 + rank)
@@ -303,6 +305,8 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout, where only the JSON line belongs
         dist.init_process_group("nccl", device_id=dev)
         barrier = lambda: dist.barrier()  # noqa: E731
     else:
