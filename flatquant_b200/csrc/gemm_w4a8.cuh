@@ -199,7 +199,9 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     grid_dep_launch();  // PDL: the next kernel may begin its prologue as SMs free up
-    grid_dep_wait();    // everything above overlapped the previous kernel's tail; its outputs are visible from here
+    // everything above overlapped the previous kernel's tail; its outputs are visible after the wait.  The W producer
+    // (warp 2) skips it: the packed weights are static, so their first stages stream in while the dependency resolves.
+    if (warp != 2) grid_dep_wait();
 
     const int nb_w = (p.N + kGemmBlockW - 1) / kGemmBlockW;
     const int nb_m = (p.M + TN - 1) / TN;

@@ -71,7 +71,10 @@ gemm_w4a8_2sm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     grid_dep_launch();
-    grid_dep_wait();
+    // Programmatic dependent launch: only what the previous kernel produced (activation codes, scales, the output
+    // buffer) needs the dependency.  The packed weights are static, so the W producer starts streaming them at once
+    // and the first stages are already in shared memory when the transform kernel's tail retires.
+    if (warp != 2) grid_dep_wait();
 
     const int nb_w = (p.N + kGemmBlockW - 1) / kGemmBlockW;
     const int nb_w2 = (nb_w + 1) / 2;            // pairs of weight blocks (an odd last block pairs with TMA zero fill)
