@@ -163,6 +163,20 @@ int launch_gemm_m(int tn, const CUtensorMap& tw, const CUtensorMap& tx, const Ge
 }
 
 // w_packed [N, K/2]; x8 [M, K] int8 in the permuted operand format
+// Kernel-variant switches (A/B timing and the parity tests of the non-default variants; defaults from the environment):
+//   FLATQ_GEMM_1SM=1  prefill on the single-CTA kernel instead of CTA pairs
+//   FLATQ_STREAMK=1   stream-K on the partial last wave of the single-CTA kernel (measured: no gain, see
+//                     profiles/r01_streamk_power_bound.md)
+static int g_gemm_1sm = -1, g_streamk = -1;
+static bool opt_gemm_1sm() {
+    if (g_gemm_1sm < 0) g_gemm_1sm = getenv("FLATQ_GEMM_1SM") != nullptr;
+    return g_gemm_1sm != 0;
+}
+static bool opt_streamk() {
+    if (g_streamk < 0) g_streamk = getenv("FLATQ_STREAMK") != nullptr;
+    return g_streamk != 0;
+}
+
 // stream-K workspace of the prefill GEMM: per CTA one 128 x TN int32 partial + 16 flags (see GemmParams::streamk)
 static size_t streamk_ws_bytes(int tn) {
     return align_up((size_t)num_sms() * kGemmBlockW * tn * 4, 256) + align_up((size_t)num_sms() * 16 * 8, 256);
@@ -190,8 +204,7 @@ int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, i
                 "output of %lld x %lld exceeds the 32-bit element index of the store path", (long long)M, (long long)N);
     const int tn = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
     // prefill: two SMs share a 256 x 256 tile (each loads half of the activation tile)
-    static const bool one_sm = getenv("FLATQ_GEMM_1SM") != nullptr;
-    const bool pair = tn == 256 && k_splits == 1 && !one_sm;
+    const bool pair = tn == 256 && k_splits == 1 && !opt_gemm_1sm();
     CUtensorMap tw, tx;
     int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -206,9 +219,8 @@ int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, i
         // stages earlier than whole tiles would, and every part is long enough to amortise its fix-up.
         const int64_t G = num_sms(), T = ((N + kGemmBlockW - 1) / kGemmBlockW) * ((M + tn - 1) / tn);
         const int64_t KB = (K + kGemmBlockK - 1) / kGemmBlockK, R = T % G;
-        static const bool off = getenv("FLATQ_STREAMK") == nullptr;  // measured: no gain under the power limit
-        static const int min_share = getenv("FLATQ_STREAMK_MIN") ? atoi(getenv("FLATQ_STREAMK_MIN")) : 1;
-        if (!off && !pair && mode != kEpiI32 && k_splits == 1 && sk_ws && aligned16(sk_ws) && sk_ws_bytes >= streamk_ws_bytes(tn) &&
+        const int min_share = 1;
+        if (opt_streamk() && !pair && mode != kEpiI32 && k_splits == 1 && sk_ws && aligned16(sk_ws) && sk_ws_bytes >= streamk_ws_bytes(tn) &&
             T > G && R > 0 && R * KB / G >= min_share && KB - (R * KB + G - 1) / G >= 2) {
             p.streamk = 1;
             p.sk_part = reinterpret_cast<int32_t*>(sk_ws);
@@ -668,6 +680,9 @@ int flatq_kv_decode_i4(const void* q, void* o, const uint8_t* kv_data, const voi
     FLATQ_CUDA(cudaGetLastError());
     return FLATQ_OK;
 }
+
+// Debug only (not part of the public header): select the GEMM variants listed at opt_gemm_1sm(); -1 = from the environment
+void flatq_debug_set_gemm_options(int one_sm, int streamk) { g_gemm_1sm = one_sm; g_streamk = streamk; }
 
 // Debug only (not part of the public header): role-level cycle counters of the GEMM, TN=128 fp16 epilogue.
 // prof: int64 [grid, kGemmWarps, 5]

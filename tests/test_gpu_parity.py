@@ -502,10 +502,12 @@ def test_decode_split_k_path(ops, dev, m, k, n, n1, n2):
 
 @pytest.mark.parametrize("m,n,k", [(2048, 4096, 4096), (2048, 6144, 4096), (2048, 5120, 8192), (1500, 4100, 2048),
                                    (2048, 4096, 14336), (4096, 2560, 1024), (2048, 28672, 4096)])
-def test_prefill_stream_k_bit_identical(ops, dev, m, n, k):
-    """Prefill shapes whose last wave of tiles is partial take the stream-K schedule when a workspace is given
-    (csrc/gemm_w4a8.cuh GemmSched): int32 partial sums move between CTAs, so the result must equal the plain
-    schedule bit for bit, the oracle arithmetic exactly (sampled rows), and be run-to-run deterministic."""
+def test_prefill_gemm_variants_bit_identical(ops, dev, m, n, k):
+    """Prefill GEMM variants must agree bit for bit (integer accumulation, same fp32 epilogue): the default CTA-pair
+    kernel (csrc/gemm_w4a8_2sm.cuh), the single-CTA kernel, and the single-CTA kernel with the stream-K schedule on
+    the partial last wave (int32 partials between CTAs, csrc/gemm_w4a8.cuh GemmSched); all equal to the oracle
+    arithmetic (sampled rows) and run-to-run deterministic."""
+    import ctypes
     from flatquant_b200 import _lib
     torch.manual_seed(m + n + k)
     xq8 = torch.randint(-8, 8, (m, k), dtype=torch.int8, device=dev)
@@ -514,14 +516,21 @@ def test_prefill_stream_k_bit_identical(ops, dev, m, n, k):
     wp = ops.pack_i4(wq)
     sw = torch.rand(n, device=dev) * 0.02 + 0.01
     bias = torch.randn(n, device=dev).half()
-    y_sk = ops.gemm_w4a8(xq8, sx, wp, sw, bias, torch.float16)           # ops passes the stream-K workspace
-    y_sk2 = ops.gemm_w4a8(xq8, sx, wp, sw, bias, torch.float16)
     lib = _lib.load()
-    y_plain = torch.empty_like(y_sk)
-    _lib.check(lib.flatq_gemm_w4a8(xq8.data_ptr(), sx.data_ptr(), wp.data_ptr(), sw.data_ptr(), bias.data_ptr(), m, n, k,
-                                   y_plain.data_ptr(), 0, None, 0, torch.cuda.current_stream().cuda_stream), "gemm_w4a8")
-    torch.cuda.synchronize()
-    assert torch.equal(y_sk, y_plain) and torch.equal(y_sk, y_sk2)
+    setopt = lib.flatq_debug_set_gemm_options
+    setopt.restype, setopt.argtypes = None, [ctypes.c_int, ctypes.c_int]
+    try:
+        y_pair = ops.gemm_w4a8(xq8, sx, wp, sw, bias, torch.float16)
+        y_pair2 = ops.gemm_w4a8(xq8, sx, wp, sw, bias, torch.float16)
+        setopt(1, 0)
+        y_1sm = ops.gemm_w4a8(xq8, sx, wp, sw, bias, torch.float16)
+        setopt(1, 1)
+        y_sk = ops.gemm_w4a8(xq8, sx, wp, sw, bias, torch.float16)   # ops passes the stream-K workspace
+        y_sk2 = ops.gemm_w4a8(xq8, sx, wp, sw, bias, torch.float16)
+        torch.cuda.synchronize()
+    finally:
+        setopt(-1, -1)
+    assert torch.equal(y_pair, y_pair2) and torch.equal(y_pair, y_1sm) and torch.equal(y_pair, y_sk) and torch.equal(y_sk, y_sk2)
     rows = np.unique(np.concatenate([np.arange(0, m, max(1, m // 23)), [m - 1]]))
     perm = np.array([0, 2, 4, 6, 1, 3, 5, 7])
     c8 = xq8[rows].cpu().numpy().reshape(len(rows), k // 8, 8)
@@ -529,7 +538,7 @@ def test_prefill_stream_k_bit_identical(ops, dev, m, n, k):
     codes[:, :, perm] = c8
     acc = O.gemm_i4(codes.reshape(len(rows), k), wq.cpu().numpy())
     ref = O.sym_dequant(acc, sx[rows].cpu().numpy(), sw.cpu().numpy(), bias.float().cpu().numpy()).astype(np.float16)
-    assert np.array_equal(y_sk[rows].cpu().numpy(), ref)
+    assert np.array_equal(y_pair[rows].cpu().numpy(), ref)
 
 
 def test_moe_routed_experts_configs4(dev):
