@@ -40,15 +40,53 @@ class MultiLayerPagedKVCache4Bit:
     def page_cnt_from_length(self, length):
         return (length + self.page_size - 1) // self.page_size
 
+    @property
     def seen_tokens(self):
         return self.length
+
+    def get_seq_length(self, layer_idx=0) -> int:
+        """Length of the cached sequences (kv_cache.py:378-380)."""
+        return self.length
+
+    def get_usable_length(self, new_seq_length=0, layer_idx=0) -> int:
+        return self.length
+
+    def get_max_length(self):
+        """No hard maximum: the page pool grows on demand (kv_cache.py:382-384)."""
+        return None
+
+    def to_legacy_cache(self):
+        return self
+
+    def _ensure_page_cnt_per_batch(self, expected):
+        """Grow the page pool (at least doubling, kv_cache.py:212-231).  Sequence b keeps the contiguous page range
+        [b * max_page_cnt, (b + 1) * max_page_cnt), so the pool is re-laid out with the new per-sequence count."""
+        if expected <= self.max_page_cnt:
+            return
+        new_cnt = max(expected, 2 * self.max_page_cnt)
+        for name in ("pages", "scales"):
+            old = getattr(self, name)
+            grown = torch.zeros((self.batch_size, new_cnt) + tuple(old.shape[1:]), dtype=old.dtype, device=old.device)
+            grown[:, :self.max_page_cnt] = old.view((self.batch_size, self.max_page_cnt) + tuple(old.shape[1:]))
+            setattr(self, name, grown.view((self.batch_size * new_cnt,) + tuple(old.shape[1:])))
+        self.max_page_cnt = new_cnt
+        self.max_seq_len = new_cnt * self.page_size
+        self._page_base = torch.arange(self.batch_size, dtype=torch.int32, device=self.device) * new_cnt
+
+    def get_cache_specs_for_flash_infer(self, attention_mask=None):
+        """Page-table view of the cache under the reference's argument names (kv_cache.py:356-376)."""
+        if attention_mask is not None:
+            raise NotImplementedError("padded batches: all sequences of a batch share one length here")
+        kw = self._attention_kwargs()
+        return dict(kv_data=self.pages, kv_param=self.scales, kv_indptr=kw["kv_indptr"], kv_indices=kw["kv_indices"],
+                    last_page_offset=kw["last_page_len"])
 
     def _transform(self, x, matrix):
         """K (and Q at decode) <- x . T_k: 128x128 matmul ('matmul*') or H_128/sqrt(128) ('had')."""
         if self.trans == "had":
-            return ops.hadamard(x.to(torch.float16).contiguous(), 1.0 / math.sqrt(x.shape[-1]))
+            return ops.hadamard(x.to(self.trans_dtype).contiguous(), 1.0 / math.sqrt(x.shape[-1]))
         if self.trans.startswith("matmul"):
-            flat = x.to(torch.float16).reshape(-1, x.shape[-1]).contiguous()
+            flat = x.to(self.trans_dtype).reshape(-1, x.shape[-1]).contiguous()
             n = flat.shape[-1]
             return ops.kron_transform(flat, None, matrix.to(flat).contiguous(), 1, n).view(x.shape)
         return x
@@ -80,9 +118,9 @@ class MultiLayerPagedKVCache4Bit:
         assert b == self.batch_size
         key_t = self._transform(key_states, k_mat)
         if layer_idx == 0:
-            start = self.length
+            self._ensure_page_cnt_per_batch(self.page_cnt_from_length(self.length + added))
+            self._start = self.length
             self.length += added
-            self._start = start
         slots = self._slots(self._start, added)
         kq = key_t.reshape(b * added, heads, d).to(torch.float16).contiguous()
         vq = value_states.reshape(b * added, heads, d).to(torch.float16).contiguous()
@@ -94,3 +132,28 @@ class MultiLayerPagedKVCache4Bit:
         assert added == 1
         return functools.partial(self._decode, num_kv_heads=heads, attention_kwargs=self._attention_kwargs(),
                                  layer_idx=layer_idx, k_inv_t=k_inv_t if self.trans.startswith("matmul") else None)
+
+
+class HFCacheAdapter:
+    """Forwarding wrapper with the `Cache` protocol the reference hands to HF's LlamaModel (kv_cache.py:390-412)."""
+
+    def __init__(self, inner):
+        self.inner = inner
+
+    def __getattr__(self, name):  # page pool, trans mode, ... are read straight from the wrapped cache
+        return getattr(self.inner, name)
+
+    def get_usable_length(self, kv_seq_len=0, layer_idx=0) -> int:
+        return self.inner.get_usable_length(kv_seq_len, layer_idx)
+
+    def get_seq_length(self, layer_idx=0) -> int:
+        return self.inner.get_seq_length()
+
+    def get_max_length(self):
+        return self.inner.get_max_length()
+
+    def update(self, key_states, value_states, layer_idx, cache_kwargs=None):
+        return self.inner.update(key_states, value_states, layer_idx, cache_kwargs)
+
+    def to_legacy_cache(self):
+        return self.inner.to_legacy_cache()

@@ -1,0 +1,491 @@
+"""Real-quant W4A4 Llama on the B200 kernels -- the direct caller of the FlatLinear hot path (SURVEY.md section 8(f)
+row 1; reference: deploy/transformers/modeling_llama.py:28-542, benchmarks/benchmark_model.py:176-261).
+
+Module tree, buffer names and the checkpoint key map are the reference's, so a checkpoint written by
+`flatquant.flat_utils.save_quantized_weights_with_safetensors` (packed INT4 safetensors, fake-quant key names) loads
+through `FlatQuantLlamaForCausalLM.from_pretrained` exactly as it does there.  The execution is not the reference's:
+
+  reference (per decoder layer)                               here
+  ----------------------------------------------------------  -------------------------------------------------------
+  3x OnlineTrans+quant of the same hidden state for q/k/v     one transform+quantise launch per distinct clip-factor
+  (modeling_llama.py:66-78), 3 GEMMs + 3 dequant kernels      pair (1 if q/k/v agree), ONE GEMM over the concatenated
+                                                              [q;k;v] packed weight with the dequant in its epilogue
+  o_proj: transpose to [.., head_dim, heads], block_matmul,   Z = O^T . A is the Kronecker transform with
+  packed transposed result, reshape (:146-148)                left = O [heads, heads]: no transposes, same kernel
+  gate/up: 2x OnlineTrans+quant, 2 GEMMs                      one quantise (when the clip factors agree) + ONE GEMM over
+                                                              [gate;up]
+  K.T_k, ~15 torch kernels to quantise K/V, append kernel     one transform launch + one quantise/pack/scatter launch
+  (kv_cache.py:263-353)                                       per K and V (kv_cache.py of this package)
+
+HF `transformers` is not imported: the reference subclasses `LlamaFlashAttention2`, which no longer exists in the
+transformers release of this image; RoPE / RMSNorm / SDPA glue is plain torch (library code, not the hot path).
+Everything that touches INT4 data goes through `flatquant_b200.ops` (CUDA-only, no fallback)."""
+from __future__ import annotations
+
+import json
+import math
+import os
+from types import SimpleNamespace
+
+import torch
+import torch.nn.functional as F
+
+from ... import ops
+from ...function_utils import get_decompose_dim
+from ..nn import Linear4bit, OnlineTrans, Quantizer, RMSNorm
+from .kv_cache import MultiLayerPagedKVCache4Bit
+
+# Activation / factor dtype handed to the kernels.  The CUDA library takes fp16; the host-logic tests run this very
+# file on the oracle-backed CPU stand-ins with ACT_DTYPE = float32 to check the wiring against the reference's fp32
+# fake-quant run without W4A4 code-flip noise (tests/test_llama_model_host.py).
+ACT_DTYPE = torch.float16
+
+LEFT_ONLY_VERIFIED = {(32, 128)}
+
+DEFAULT_ONLINE_TRANS = ("qk", "o_proj", "down_proj", "qkv_proj", "up_gate_proj")
+
+# fake-quant checkpoint name -> deployed module name, applied in order to every key
+# (the contract of deploy/transformers/modeling_llama.py:479-507; order matters: specific before generic)
+KEY_RENAMES = (
+    ("q_proj.linear", "q_proj"), ("q_proj.act_quantizer", "inp_trans_q"),
+    ("k_proj.linear", "k_proj"), ("k_proj.act_quantizer", "inp_trans_k"),
+    ("v_proj.linear", "v_proj"), ("v_proj.act_quantizer", "inp_trans_v"),
+    ("o_proj.linear", "o_proj.1"), ("o_proj.act_quantizer", "o_proj_trans"),
+    ("ln_trans.matrix_left", "left_matrix"), ("ln_trans.matrix_right", "right_matrix"), ("ln_trans", "inp_trans_k"),
+    ("o_trans.matrix", "o_proj_trans.right_matrix"),
+    ("gate_proj.linear", "gate_proj"), ("gate_proj.act_quantizer", "inp_trans_g"),
+    ("up_proj.linear", "up_proj"), ("up_proj.act_quantizer", "inp_trans_u"),
+    ("down_proj.linear", "down_proj.2"), ("down_proj.act_quantizer", "down_proj.0"),
+    ("down_trans.matrix_left", "down_proj.0.left_matrix"), ("down_trans.matrix_right", "down_proj.0.right_matrix"),
+    ("down_trans", "down_proj.0"),
+    ("up_gate_trans.matrix_left", "left_matrix"), ("up_gate_trans.matrix_right", "right_matrix"),
+    ("up_gate_trans", "inp_trans_g"),
+    ("k_cache_quantizer.clip", "kclip"), ("v_cache_quantizer.clip", "vclip"),
+    ("kcache_trans.matrix", "trans_matrix_k"), ("vcache_trans.matrix", "trans_matrix_v"),
+)
+SCALE_RENAMES = (("linear", "weight_scales"), ("mlp.down_proj.weight_scales", "mlp.down_proj.2.weight_scales"),
+                 ("self_attn.o_proj.weight_scales", "self_attn.o_proj.1.weight_scales"))
+
+
+def convert_checkpoint_keys(state_dict):
+    """Fake-quant safetensors keys -> (deployed model keys, per-linear weight scales).  `quantizer.<layer>.scale`
+    entries become `<layer>.weight_scales`; `.zero` / `.maxq` are dropped (symmetric path) as the reference does
+    (modeling_llama.py:456-476, 509-513)."""
+    weights, scales = {}, {}
+    for key, value in state_dict.items():
+        if key.startswith("quantizer."):
+            layer, kind = key[len("quantizer."):].rsplit(".", 1)
+            if kind == "scale":
+                for old, new in SCALE_RENAMES:
+                    layer = layer.replace(old, new)
+                scales[layer] = value
+            continue
+        for old, new in KEY_RENAMES:
+            key = key.replace(old, new)
+        weights[key] = value
+    return weights, scales
+
+
+class FlatQuantLlamaConfig:
+    """The fields of HF's LlamaConfig this path reads, from `config.json` (model_type "llama_FlatQuant")."""
+    model_type = "llama_FlatQuant"
+
+    def __init__(self, hidden_size=4096, intermediate_size=14336, num_attention_heads=32, num_key_value_heads=None,
+                 num_hidden_layers=32, vocab_size=128256, rms_norm_eps=1e-5, rope_theta=500000.0, rope_scaling=None,
+                 max_position_embeddings=8192, head_dim=None, quantization_config=None, **unused):
+        self.hidden_size, self.intermediate_size = hidden_size, intermediate_size
+        self.num_attention_heads = num_attention_heads
+        self.num_key_value_heads = num_key_value_heads or num_attention_heads
+        self.num_hidden_layers, self.vocab_size = num_hidden_layers, vocab_size
+        self.rms_norm_eps, self.rope_theta, self.rope_scaling = rms_norm_eps, rope_theta, rope_scaling
+        self.max_position_embeddings = max_position_embeddings
+        self.head_dim = head_dim or hidden_size // num_attention_heads
+        self.quantization_config = quantization_config or {}
+
+    @classmethod
+    def from_pretrained(cls, path):
+        with open(os.path.join(path, "config.json")) as f:
+            return cls(**json.load(f))
+
+
+def options_from_config(config) -> SimpleNamespace:
+    """The `args` object of the reference (modeling_llama.py:371-379)."""
+    qc = config.quantization_config
+    return SimpleNamespace(fuseLN=qc.get("fuseLN", False), trans=qc.get("trans", "matmul"),
+                           online_trans=set(qc.get("online_trans", DEFAULT_ONLINE_TRANS)))
+
+
+# ---------------------------------------------------------------------------------------------- torch glue (fp16)
+class LlamaRMSNorm(torch.nn.Module):
+    """HF LlamaRMSNorm: fp32 statistics, learned scale applied after the cast back (the FlatQuant diagonal scale is
+    folded into `weight` offline, flat_utils.py:20-27)."""
+
+    def __init__(self, dim, eps=1e-5):
+        super().__init__()
+        self.weight = torch.nn.Parameter(torch.ones(dim), requires_grad=False)
+        self.variance_epsilon = eps
+
+    def forward(self, x):
+        xf = x.float()
+        xf = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + self.variance_epsilon)
+        return self.weight * xf.to(x.dtype)
+
+
+def rope_inv_freq(config, device=None):
+    d = config.head_dim
+    inv = 1.0 / (config.rope_theta ** (torch.arange(0, d, 2, dtype=torch.float32, device=device) / d))
+    rs = config.rope_scaling
+    if rs and rs.get("rope_type", rs.get("type")) == "llama3":  # Llama-3.1 frequency-dependent scaling
+        factor, lo, hi = rs["factor"], rs.get("low_freq_factor", 1.0), rs.get("high_freq_factor", 4.0)
+        old = rs.get("original_max_position_embeddings", 8192)
+        wavelen = 2 * math.pi / inv
+        smooth = ((old / wavelen) - lo) / (hi - lo)
+        scaled = torch.where(wavelen > old / lo, inv / factor, inv)
+        mid = (1 - smooth) * inv / factor + smooth * inv
+        inv = torch.where((wavelen <= old / lo) & (wavelen >= old / hi), mid, scaled)
+    return inv
+
+
+def rope_cos_sin(inv_freq, positions, dtype):
+    """positions int [b, s] -> cos, sin [b, s, 1, head_dim] (fp32 angles, cast like HF's LlamaRotaryEmbedding)."""
+    ang = positions[..., None].float() * inv_freq[None, None, :]
+    emb = torch.cat((ang, ang), dim=-1)
+    return emb.cos().to(dtype)[:, :, None, :], emb.sin().to(dtype)[:, :, None, :]
+
+
+def apply_rope(x, cos, sin):
+    """x [b, s, heads, d]; the rotate_half convention of HF Llama."""
+    h = x.shape[-1] // 2
+    rot = torch.cat((-x[..., h:], x[..., :h]), dim=-1)
+    return x * cos + rot * sin
+
+
+def _sig(v) -> float:
+    return 1.0 / (1.0 + math.exp(-float(v)))
+
+
+def _f16(t):
+    return t.detach().to(ACT_DTYPE).contiguous()
+
+
+class _QuantGroup:
+    """Projections that share one quantised activation (equal clip factors): one act_quant + one GEMM."""
+
+    def __init__(self, clip, names, linears):
+        self.clip, self.names = clip, names
+        self.w = torch.cat([l.weight for l in linears], 0).contiguous()
+        self.s_w = torch.cat([l.weight_scales.reshape(-1).float() for l in linears], 0).contiguous()
+        self.sizes = [l.weight.shape[0] for l in linears]
+        row = 0
+        for l, n in zip(linears, self.sizes):  # the modules keep their buffers as views: no second copy of the weights
+            l.weight = self.w[row:row + n]
+            row += n
+        biases = [l.bias for l in linears]
+        self.bias = None if all(b is None for b in biases) else torch.cat(
+            [torch.zeros(l.weight.shape[0], dtype=ACT_DTYPE, device=l.weight.device) if b is None else b.to(ACT_DTYPE)
+             for l, b in zip(linears, biases)]).contiguous()
+
+
+def _group_by_clip(names, linears, clips):
+    groups = {}
+    for name, lin, clip in zip(names, linears, clips):
+        groups.setdefault(clip, ([], []))
+        groups[clip][0].append(name)
+        groups[clip][1].append(lin)
+    return [_QuantGroup(clip, n, l) for clip, (n, l) in groups.items()]
+
+
+def _flat_linears(x2, left, right, n1, n2, groups, lac):
+    """x2 fp16 [M, K] -> {name: y fp16 [M, N_name]}: transform + quantise once per clip pair, one GEMM per group."""
+    out = {}
+    for g in groups:
+        cmax, cmin = (_sig(g.clip[0]), _sig(g.clip[1])) if lac else (1.0, 1.0)
+        xq8, s_x = ops.act_quant(x2, left, right, n1, n2, cmax, cmin)
+        y = ops.gemm_w4a8(xq8, s_x, g.w, g.s_w, g.bias, out_dtype=ACT_DTYPE)
+        for name, part in zip(g.names, torch.split(y, g.sizes, dim=-1)):
+            out[name] = part
+    return out
+
+
+class FlatQuantLlamaAttention(torch.nn.Module):
+    """deploy/transformers/modeling_llama.py:156-237 (module / buffer names) + :44-153 (forward semantics)."""
+
+    def __init__(self, options, config, layer_idx):
+        super().__init__()
+        self.options, self.config, self.layer_idx = options, config, layer_idx
+        self.isFlatQ = getattr(options, "trans", None) == "matmul"
+        self.hidden_size, self.num_heads = config.hidden_size, config.num_attention_heads
+        self.num_key_value_heads, self.head_dim = config.num_key_value_heads, config.head_dim
+        hs, hd = self.hidden_size, self.head_dim
+        self.quantizer_q, self.quantizer_k, self.quantizer_v = (Quantizer(lac=self.isFlatQ) for _ in range(3))
+        self.q_proj = Linear4bit(hs, self.num_heads * hd)
+        self.k_proj = Linear4bit(hs, self.num_key_value_heads * hd)
+        self.v_proj = Linear4bit(hs, self.num_key_value_heads * hd)
+        self.o_proj_trans = torch.nn.Identity()
+        if "o_proj" in options.online_trans:
+            self.o_proj_trans = OnlineTrans(self.num_heads, trans=options.trans, decompose=False)
+        self.o_proj = torch.nn.Sequential(Quantizer(lac=self.isFlatQ), Linear4bit(self.num_heads * hd, hs))
+        self.inp_trans_q = self.inp_trans_k = self.inp_trans_v = torch.nn.Identity()
+        if "qkv_proj" in options.online_trans and not options.fuseLN:
+            self.inp_trans_q, self.inp_trans_k, self.inp_trans_v = (OnlineTrans(hs, trans=options.trans) for _ in range(3))
+        self.register_buffer("trans_matrix_k", torch.eye(hd))
+        self.register_buffer("trans_matrix_k_inv_t", torch.eye(hd))
+        self.register_buffer("trans_matrix_v", torch.eye(hd))
+        for n in ("kclip_factor_a_max", "kclip_factor_a_min", "vclip_factor_a_max", "vclip_factor_a_min"):
+            self.register_buffer(n, torch.tensor(4.0))
+        n1, n2 = get_decompose_dim(hs)
+        self.register_buffer("left_matrix", torch.eye(n1))
+        self.register_buffer("right_matrix", torch.eye(n2))
+        self._rt = None
+
+    def _runtime(self, dev):
+        """Kernel-ready operands, built once per device from the loaded buffers."""
+        if self._rt is not None and self._rt.dev == dev:
+            return self._rt
+        rt = SimpleNamespace(dev=dev)
+        rt.left, rt.right = _f16(self.left_matrix), _f16(self.right_matrix)
+        rt.n1, rt.n2 = rt.left.shape[0], rt.right.shape[0]
+        clips = [(float(t.clip_factor_a_max), float(t.clip_factor_a_min)) if isinstance(t, OnlineTrans) else (4.0, 4.0)
+                 for t in (self.inp_trans_q, self.inp_trans_k, self.inp_trans_v)]
+        rt.qkv = _group_by_clip(("q", "k", "v"), (self.q_proj, self.k_proj, self.v_proj), clips)
+        # o_proj: Z = O^T . reshape(a, heads, head_dim) == Kronecker transform with left = O, right = I
+        if isinstance(self.o_proj_trans, OnlineTrans):
+            rt.o_left = _f16(self.o_proj_trans.right_matrix)
+            rt.o_clip = (float(self.o_proj_trans.clip_factor_a_max), float(self.o_proj_trans.clip_factor_a_min))
+        else:
+            rt.o_left = torch.eye(self.num_heads, dtype=ACT_DTYPE, device=dev)
+            rt.o_clip = (float(self.o_proj[0].clip_factor_a_max), float(self.o_proj[0].clip_factor_a_min))
+        # left-only launch for the factor shapes whose single-sided kernel configuration has been verified on the GPU
+        # (tests/test_gpu_parity.py::test_kernel_level_api); an explicit identity right factor otherwise, which keeps
+        # other head counts on the two-factor configuration every parity test exercises (exact: X . I == X in fp16)
+        left_only = (self.num_heads, self.head_dim) in LEFT_ONLY_VERIFIED
+        rt.o_right = None if left_only else torch.eye(self.head_dim, dtype=ACT_DTYPE, device=dev)
+        rt.o = _group_by_clip(("o",), (self.o_proj[1],), (rt.o_clip,))
+        rt.k_inv_t = _f16(self.trans_matrix_k_inv_t)
+        rt.cache_kwargs = dict(trans_matrix_k=_f16(self.trans_matrix_k), trans_matrix_k_inv_t=rt.k_inv_t,
+                               trans_matrix_v=_f16(self.trans_matrix_v))
+        self._rt = rt
+        return rt
+
+    def qkv(self, hidden_states):
+        """Stage 1: the q/k/v FlatLinears on the normalised hidden state -> q [b,s,H,d], k, v [b,s,Hkv,d] (pre-RoPE)."""
+        b, s, _ = hidden_states.shape
+        rt = self._runtime(hidden_states.device)
+        x2 = hidden_states.reshape(b * s, self.hidden_size).to(ACT_DTYPE).contiguous()
+        qkv = _flat_linears(x2, rt.left, rt.right, rt.n1, rt.n2, rt.qkv, self.isFlatQ)
+        return (qkv["q"].reshape(b, s, self.num_heads, self.head_dim),
+                qkv["k"].reshape(b, s, self.num_key_value_heads, self.head_dim),
+                qkv["v"].reshape(b, s, self.num_key_value_heads, self.head_dim))
+
+    def attend(self, q, k, v, cos, sin, past_key_value):
+        """Stage 2: RoPE, K/Q cache transform, KV quantise + append, attention -> [b, s, H*d]."""
+        b, s = q.shape[:2]
+        rt = self._runtime(q.device)
+        q, k = apply_rope(q, cos, sin), apply_rope(k, cos, sin)
+        cache_out = past_key_value.update(k.contiguous(), v.contiguous(), self.layer_idx, rt.cache_kwargs)
+        if isinstance(cache_out, tuple):  # prefill: causal attention over the transformed fp16 states
+            k_t, v_t = cache_out
+            if past_key_value.trans.startswith("matmul"):
+                q = ops.kron_transform(q.reshape(-1, self.head_dim).contiguous(), None, rt.k_inv_t, 1,
+                                       self.head_dim).view(q.shape)
+            elif past_key_value.trans == "had":
+                q = ops.hadamard(q.contiguous(), 1.0 / math.sqrt(self.head_dim))
+            attn = F.scaled_dot_product_attention(q.transpose(1, 2), k_t.transpose(1, 2), v_t.transpose(1, 2),
+                                                  is_causal=True, enable_gqa=self.num_heads != self.num_key_value_heads)
+            attn = attn.transpose(1, 2)
+        else:  # decode: single-query attention over the packed INT4 cache
+            attn = cache_out(q.contiguous())
+        return attn.reshape(b, s, self.num_heads * self.head_dim)
+
+    def project_out(self, attn):
+        """Stage 3: the o_proj FlatLinear; its online transform O^T . A runs as the left factor of the same kernel."""
+        b, s, _ = attn.shape
+        rt = self._runtime(attn.device)
+        a2 = attn.reshape(b * s, self.num_heads * self.head_dim).to(ACT_DTYPE).contiguous()
+        y = _flat_linears(a2, rt.o_left, rt.o_right, self.num_heads, self.head_dim, rt.o, self.isFlatQ)["o"]
+        return y.reshape(b, s, self.hidden_size)
+
+    def forward(self, hidden_states, cos, sin, past_key_value):
+        """hidden_states [b, s, hidden] (already normalised) -> [b, s, hidden]."""
+        q, k, v = self.qkv(hidden_states)
+        return self.project_out(self.attend(q, k, v, cos, sin, past_key_value))
+
+
+class FlatQuantLlamaMLP(torch.nn.Module):
+    """deploy/transformers/modeling_llama.py:239-283."""
+
+    def __init__(self, options, config):
+        super().__init__()
+        self.options, self.config = options, config
+        self.isFlatQ = getattr(options, "trans", None) == "matmul"
+        hs, inter = config.hidden_size, config.intermediate_size
+        self.hidden_size, self.intermediate_size = hs, inter
+        self.quantizer_g, self.quantizer_u = Quantizer(lac=self.isFlatQ), Quantizer(lac=self.isFlatQ)
+        self.up_proj, self.gate_proj = Linear4bit(hs, inter), Linear4bit(hs, inter)
+        if "down_proj" in options.online_trans:
+            self.down_proj = torch.nn.Sequential(OnlineTrans(inter, trans=options.trans), Quantizer(lac=self.isFlatQ),
+                                                 Linear4bit(inter, hs))
+        else:
+            self.down_proj = torch.nn.Sequential(Quantizer(lac=self.isFlatQ), Linear4bit(inter, hs))
+        if "up_gate_proj" in options.online_trans and not options.fuseLN:
+            self.inp_trans_g, self.inp_trans_u = OnlineTrans(hs, trans=options.trans), OnlineTrans(hs, trans=options.trans)
+        n1, n2 = get_decompose_dim(hs)
+        self.register_buffer("left_matrix", torch.eye(n1))
+        self.register_buffer("right_matrix", torch.eye(n2))
+        self._rt = None
+
+    def _runtime(self, dev):
+        if self._rt is not None and self._rt.dev == dev:
+            return self._rt
+        rt = SimpleNamespace(dev=dev)
+        if hasattr(self, "inp_trans_g"):
+            rt.left, rt.right = _f16(self.left_matrix), _f16(self.right_matrix)
+            rt.n1, rt.n2 = rt.left.shape[0], rt.right.shape[0]
+            clips = [(float(t.clip_factor_a_max), float(t.clip_factor_a_min)) for t in (self.inp_trans_g, self.inp_trans_u)]
+        else:  # plain per-token quantiser shared by gate and up (modeling_llama.py:274-277)
+            rt.left = rt.right = None
+            rt.n1, rt.n2 = 1, self.hidden_size
+            c = (float(self.quantizer_g.clip_factor_a_max), float(self.quantizer_g.clip_factor_a_min))
+            clips = [c, c]
+        rt.gate_up = _group_by_clip(("gate", "up"), (self.gate_proj, self.up_proj), clips)
+        first = self.down_proj[0]
+        if isinstance(first, OnlineTrans):
+            rt.d_left, rt.d_right = _f16(first.left_matrix), _f16(first.right_matrix)
+            rt.d_n1, rt.d_n2 = rt.d_left.shape[0], rt.d_right.shape[0]
+        else:
+            rt.d_left = rt.d_right = None
+            rt.d_n1, rt.d_n2 = 1, self.intermediate_size
+        rt.down = _group_by_clip(("down",), (self.down_proj[-1],),
+                                 ((float(first.clip_factor_a_max), float(first.clip_factor_a_min)),))
+        self._rt = rt
+        return rt
+
+    def gate_up(self, x):
+        """Stage 1: gate and up FlatLinears on the normalised hidden state -> (gate, up) [b, s, inter]."""
+        b, s, _ = x.shape
+        rt = self._runtime(x.device)
+        x2 = x.reshape(b * s, self.hidden_size).to(ACT_DTYPE).contiguous()
+        gu = _flat_linears(x2, rt.left, rt.right, rt.n1, rt.n2, rt.gate_up, self.isFlatQ)
+        return gu["gate"].reshape(b, s, -1), gu["up"].reshape(b, s, -1)
+
+    def down(self, act):
+        """Stage 2: the down FlatLinear (own Kronecker pair) on silu(gate) * up."""
+        b, s, _ = act.shape
+        rt = self._runtime(act.device)
+        a2 = act.reshape(b * s, self.intermediate_size).to(ACT_DTYPE).contiguous()
+        y = _flat_linears(a2, rt.d_left, rt.d_right, rt.d_n1, rt.d_n2, rt.down, self.isFlatQ)["down"]
+        return y.reshape(b, s, self.hidden_size)
+
+    def forward(self, x):
+        gate, up = self.gate_up(x)
+        return self.down(F.silu(gate) * up)
+
+
+class FlatQuantLlamaDecoderLayer(torch.nn.Module):
+    def __init__(self, options, config, layer_idx):
+        super().__init__()
+        norm = (lambda: RMSNorm(config.hidden_size, eps=config.rms_norm_eps)) if options.fuseLN else \
+            (lambda: LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps))
+        self.self_attn = FlatQuantLlamaAttention(options, config, layer_idx)
+        self.mlp = FlatQuantLlamaMLP(options, config)
+        self.input_layernorm, self.post_attention_layernorm = norm(), norm()
+
+    def forward(self, h, cos, sin, past_key_value):
+        h = h + self.self_attn(self.input_layernorm(h), cos, sin, past_key_value)
+        return h + self.mlp(self.post_attention_layernorm(h))
+
+
+class FlatQuantLlamaModel(torch.nn.Module):
+    def __init__(self, options, config):
+        super().__init__()
+        self.embed_tokens = torch.nn.Embedding(config.vocab_size, config.hidden_size)
+        self.layers = torch.nn.ModuleList(FlatQuantLlamaDecoderLayer(options, config, i)
+                                          for i in range(config.num_hidden_layers))
+        self.norm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+
+
+class FlatQuantLlamaForCausalLM(torch.nn.Module):
+    """deploy/transformers/modeling_llama.py:342-542.  `forward(input_ids, past_key_values=None)` returns
+    (logits fp16 [b, s, vocab], cache); the first call builds the paged INT4 cache (prefill), later one-token calls
+    with the returned cache decode."""
+    config_class = FlatQuantLlamaConfig
+
+    def __init__(self, args, config):
+        super().__init__()
+        self.config, self.args = config, args
+        self.trans, self.online_trans = args.trans, set(args.online_trans)
+        self.model = FlatQuantLlamaModel(args, config)
+        self.lm_head = torch.nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.cache_dtype = "int4"
+        self._expected_max_length = None
+        self._inv_freq = None
+
+    def build_cache(self, batch_size, page_size, max_length):
+        cfg = self.config
+        return MultiLayerPagedKVCache4Bit(
+            batch_size=batch_size, page_size=page_size, max_seq_len=max_length, device=self.lm_head.weight.device,
+            n_layers=len(self.model.layers), num_heads=cfg.num_key_value_heads, head_dim=cfg.head_dim,
+            disable_quant=False, trans_dtype=ACT_DTYPE, trans=self.trans if "qk" in self.online_trans else "none",
+            group_size=1)  # GQA is resolved by index in the decode kernel: the cache holds kv heads, not repeats
+
+    def forward(self, input_ids, past_key_values=None, max_length=None):
+        b, s = input_ids.shape
+        if past_key_values is None:
+            max_length = max(max_length or self._expected_max_length or 0, s)
+            past_key_values = self.build_cache(b, page_size=min(2048, max_length), max_length=max_length)
+        start = past_key_values.get_seq_length()
+        dev = input_ids.device
+        if self._inv_freq is None or self._inv_freq.device != dev:
+            self._inv_freq = rope_inv_freq(self.config, dev)
+        pos = torch.arange(start, start + s, device=dev)[None].expand(b, s)
+        h = self.model.embed_tokens(input_ids)
+        cos, sin = rope_cos_sin(self._inv_freq, pos, h.dtype)
+        for layer in self.model.layers:
+            h = layer(h, cos, sin, past_key_values)
+        return self.lm_head(self.model.norm(h)), past_key_values
+
+    # ------------------------------------------------------------------------------------------ checkpoint ingest
+    @classmethod
+    def from_pretrained(cls, path, device=None):
+        """Load a directory written by save_quantized_weights_with_safetensors (single or sharded safetensors +
+        config.json).  Local directories only: the reference's hub download branch needs a network."""
+        from safetensors.torch import load_file
+        if not os.path.isdir(path):
+            raise RuntimeError(f"from_pretrained: {path} is not a local directory (no hub access in this build)")
+        config = cls.config_class.from_pretrained(path)
+        model = cls(options_from_config(config), config)
+        index = os.path.join(path, "model.safetensors.index.json")
+        state = {}
+        if os.path.exists(index):
+            with open(index) as f:
+                for shard in sorted(set(json.load(f)["weight_map"].values())):
+                    state.update(load_file(os.path.join(path, shard)))
+        else:
+            state = load_file(os.path.join(path, "model.safetensors"))
+        model.load_flatquant_state_dict(state)
+        return model.to(device) if device is not None else model
+
+    def load_flatquant_state_dict(self, state_dict):
+        """Returns (missing, unexpected) after the key conversion; raises if a packed weight or scale is absent."""
+        weights, scales = convert_checkpoint_keys(state_dict)
+        own = self.state_dict()
+        for key, t in list(weights.items()):  # [1] clip factors are stored as shape-[1] tensors; buffers are scalars
+            if key in own and own[key].dim() == 0 and t.numel() == 1:
+                weights[key] = t.reshape(())
+        res = self.load_state_dict({**weights, **scales}, strict=False)
+        need = [k for k in res.missing_keys if k.endswith((".weight", ".weight_scales")) and "layernorm" not in k]
+        if need:
+            raise RuntimeError(f"checkpoint lacks packed weights / scales: {need[:4]}{'...' if len(need) > 4 else ''}")
+        for layer in self.model.layers:  # one Kronecker pair per block, shared by its input transforms (:517-528)
+            at, mlp = layer.self_attn, layer.mlp
+            for t in (at.inp_trans_q, at.inp_trans_k, at.inp_trans_v):
+                if isinstance(t, OnlineTrans):
+                    t.left_matrix, t.right_matrix = at.left_matrix, at.right_matrix
+            for t in (getattr(mlp, "inp_trans_g", None), getattr(mlp, "inp_trans_u", None)):
+                if isinstance(t, OnlineTrans):
+                    t.left_matrix, t.right_matrix = mlp.left_matrix, mlp.right_matrix
+            at._rt = mlp._rt = None
+        for m in (self.model.embed_tokens, self.model.norm, self.lm_head,
+                  *(n for l in self.model.layers for n in (l.input_layernorm, l.post_attention_layernorm))):
+            m.to(ACT_DTYPE)
+        return res.missing_keys, res.unexpected_keys

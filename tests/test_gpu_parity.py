@@ -428,7 +428,7 @@ def test_kv_cache_module_prefill_then_decode(dev):
     for layer in range(L):
         kt, vt = cache.update(k, v, layer)
         assert kt.shape == k.shape and torch.equal(vt, v)
-    assert cache.seen_tokens() == T
+    assert cache.seen_tokens == T and cache.get_seq_length() == T
     k1 = torch.randn(B, 1, H, D, device=dev).half()
     v1 = torch.randn(B, 1, H, D, device=dev).half()
     q = torch.randn(B, 1, 2 * H, D, device=dev).half()  # GQA: 2 query heads per kv head
