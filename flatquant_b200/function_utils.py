@@ -38,3 +38,15 @@ def get_init_weight(dim):
 def get_inverse(matrix):
     """fp64 inverse cast back to the input dtype (flatquant/function_utils.py:35-37)."""
     return torch.linalg.inv(matrix.double()).to(matrix.dtype)
+
+
+def get_paras_dict_by_name(model, required_names, destination=None, prefix=""):
+    """Parameters whose name contains one of `required_names`, grouped in the order of `required_names`
+    (flatquant/function_utils.py:51-58) -- the layout of flat_matrices.pth."""
+    from collections import OrderedDict
+    out = OrderedDict() if destination is None else destination
+    for wanted in required_names:
+        for name, param in model.named_parameters():
+            if wanted in name:
+                out[prefix + name] = param.detach()
+    return out
