@@ -225,6 +225,105 @@ def run_tp70(args, rank, world, local):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------- configs[2]: Llama-3-8B end to end (model stack)
+def run_model(args, rank, world, local):
+    """BASELINE configs[2]: the whole random-init Llama-3-8B W4A4 model (flatquant_b200.deploy.transformers) -- embedding,
+    32 decoder layers (FlatLinears + RoPE + KV transform/quantise + attention), final norm, fp16 lm_head -- prefill at
+    seq 2048 and CUDA-event-timed decode steps at bsz 1 and 16 over the paged INT4 cache
+    (benchmarks/benchmark_model.py:264-305 protocol).  Data-parallel replicas for N > 1."""
+    from flatquant_b200 import ops
+    from flatquant_b200.deploy.transformers import FlatQuantLlamaConfig, FlatQuantLlamaForCausalLM
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+    cfg = FlatQuantLlamaConfig(num_hidden_layers=args.layers)  # defaults = Llama-3-8B
+    model = FlatQuantLlamaForCausalLM.random_init(cfg, dev, seed=1234 + rank)
+    counted = {"n": 0}
+    for name in ("act_quant", "gemm_w4a8", "kron_transform", "kv_quant", "kv_decode_i4", "hadamard"):
+        def wrap(fn):
+            def inner(*a, **k):
+                counted["n"] += 1
+                return fn(*a, **k)
+            return inner
+        setattr(ops, name, wrap(getattr(ops, name)))
+    gen = torch.Generator().manual_seed(rank)
+    ids_host = torch.randint(100, 200, (1, SEQ), generator=gen).pin_memory()  # benchmark_model.py:281
+    ids = ids_host.to(dev)
+    decode_len = 64
+    cache = model.build_cache(1, page_size=2048, max_length=SEQ + decode_len)
+    out_host = torch.empty(1, cfg.vocab_size, dtype=torch.float16).pin_memory()
+
+    def prefill():
+        cache.reset()
+        with torch.no_grad():
+            return model(ids, past_key_values=cache)[0]
+
+    def prefill_e2e():
+        cache.reset()
+        with torch.no_grad():
+            logits = model(ids_host.to(dev, non_blocking=True), past_key_values=cache)[0]
+        out_host.copy_(logits[:, -1], non_blocking=True)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(3, args.warmup)):
+        prefill()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.wait_first()
+    counted["n"] = 0
+    t0 = sampler.mark()
+    ms = timed(prefill, args.steps, barrier)
+    t1 = sampler.mark()
+    launches = counted["n"]
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_e2e = timed(prefill_e2e, args.steps, barrier)
+
+    def decode_ms(bsz):
+        c = model.build_cache(bsz, page_size=2048, max_length=SEQ + decode_len)
+        tok = torch.randint(100, 200, (bsz, 1), device=dev)
+        with torch.no_grad():
+            model(ids.expand(bsz, SEQ).contiguous(), past_key_values=c, logits_to_keep=1)
+            for _ in range(4):
+                model(tok, past_key_values=c)
+
+            def steps():
+                for _ in range(decode_len - 8):
+                    model(tok, past_key_values=c)
+            return timed(steps, 1, barrier) / (decode_len - 8)
+    dec = {f"bsz{b}_ms_per_token": decode_ms(b) for b in (1, 16)}
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank == 0:
+        scale = N_LAYERS / args.layers
+        line = {"metric": "Llama-3-8B W4A4 end-to-end prefill tokens/sec/GPU (whole model, seq 2048, bsz 1)",
+                "value": world * SEQ * args.steps / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "s4 x s4 -> s32 linears, f16 attention / lm_head", "data": "synthetic",
+                "config": {"workload": "llama3-8b whole-model prefill seq 2048 + decode bsz 1/16, random-init weights",
+                           "l2": "inputs larger than L2: 3.5 GB of packed weights + 1 GB lm_head per step",
+                           "parallelism": f"dp{world} (independent replicas)", "layers": args.layers},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": world * SEQ * args.steps / (ms_e2e * 1e-3), "unit": "tokens/s",
+                        "h2d_bytes_per_step": ids_host.numel() * 8, "d2h_bytes_per_step": out_host.numel() * 2},
+                "decode": dec}
+        if scale != 1:
+            line["INVALID"] = "debug run with fewer layers"
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def timed(fn, steps, dist_barrier):
     dist_barrier()
     torch.cuda.synchronize()
@@ -272,8 +371,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=N_LAYERS, help="debug only: fewer layers => INVALID as a bench value")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="llama8b", choices=["llama8b", "llama70b-tp"],
-                    help="llama8b = BASELINE configs[1] (default, data-parallel replicas); llama70b-tp = configs[3]")
+    ap.add_argument("--workload", default="llama8b", choices=["llama8b", "llama70b-tp", "llama8b-model"],
+                    help="llama8b = BASELINE configs[1] (default, data-parallel replicas); llama70b-tp = configs[3]; "
+                         "llama8b-model = configs[2] (whole model: prefill + decode)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -300,6 +400,8 @@ def main():
 
     if args.workload == "llama70b-tp":
         return run_tp70(args, rank, world, local)
+    if args.workload == "llama8b-model":
+        return run_model(args, rank, world, local)
 
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)

@@ -37,6 +37,11 @@ class MultiLayerPagedKVCache4Bit:
         # sequence b owns pages [b * max_page_cnt, (b + 1) * max_page_cnt)
         self._page_base = torch.arange(batch_size, dtype=torch.int32, device=device) * self.max_page_cnt
 
+    def reset(self):
+        """Forget the cached sequences (the page pool is kept): the next update per layer is a prefill again."""
+        self._needs_init = [True] * self.n_layers
+        self.length = 0
+
     def page_cnt_from_length(self, length):
         return (length + self.page_size - 1) // self.page_size
 

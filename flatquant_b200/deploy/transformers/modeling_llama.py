@@ -428,7 +428,8 @@ class FlatQuantLlamaForCausalLM(torch.nn.Module):
             disable_quant=False, trans_dtype=ACT_DTYPE, trans=self.trans if "qk" in self.online_trans else "none",
             group_size=1)  # GQA is resolved by index in the decode kernel: the cache holds kv heads, not repeats
 
-    def forward(self, input_ids, past_key_values=None, max_length=None):
+    def forward(self, input_ids, past_key_values=None, max_length=None, logits_to_keep=0):
+        """`logits_to_keep` > 0 computes the lm_head for the last positions only (HF's `num_logits_to_keep`)."""
         b, s = input_ids.shape
         if past_key_values is None:
             max_length = max(max_length or self._expected_max_length or 0, s)
@@ -442,7 +443,53 @@ class FlatQuantLlamaForCausalLM(torch.nn.Module):
         cos, sin = rope_cos_sin(self._inv_freq, pos, h.dtype)
         for layer in self.model.layers:
             h = layer(h, cos, sin, past_key_values)
+        if logits_to_keep:
+            h = h[:, -logits_to_keep:]
         return self.lm_head(self.model.norm(h)), past_key_values
+
+    @classmethod
+    def random_init(cls, config, device, seed=0, weight_scale=0.002):
+        """Synthetic model of the given architecture for benchmarks (BASELINE.json configs[2]: "random-init weights"):
+        uniform random INT4 weight codes, per-channel scales sized so that activations stay O(1) in fp16, random
+        well-conditioned transform factors, LAC clip factors at their initial value 4.0 (benchmark_model.py:176-261
+        builds its model the same way, from `from_float` of random linears)."""
+        with torch.device(device):
+            model = cls(options_from_config(config), config)
+        gen = torch.Generator(device=device).manual_seed(seed)
+
+        def fill_linear(lin):
+            lin.weight.random_(0, 256, generator=gen)
+            lin.weight_scales.fill_(weight_scale)
+
+        def fill_matrix(buf):
+            n = buf.shape[0]
+            buf.copy_(torch.eye(n, device=device) * 0.75 + torch.randn(n, n, device=device, generator=gen) * (0.5 / n ** 0.5))
+
+        for layer in model.model.layers:
+            at, mlp = layer.self_attn, layer.mlp
+            for lin in (at.q_proj, at.k_proj, at.v_proj, at.o_proj[1], mlp.gate_proj, mlp.up_proj, mlp.down_proj[-1]):
+                fill_linear(lin)
+            for buf in (at.left_matrix, at.right_matrix, mlp.left_matrix, mlp.right_matrix, at.trans_matrix_k):
+                fill_matrix(buf)
+            at.trans_matrix_k_inv_t.copy_(torch.linalg.inv(at.trans_matrix_k.double()).t().float())
+            if isinstance(at.o_proj_trans, OnlineTrans):
+                at.o_proj_trans.right_matrix.copy_(
+                    (torch.eye(at.num_heads, device=device) * 0.75 + torch.randn(at.num_heads, at.num_heads, device=device,
+                                                                                  generator=gen) * (0.5 / at.num_heads ** 0.5)))
+            if isinstance(mlp.down_proj[0], OnlineTrans):
+                fill_matrix(mlp.down_proj[0].left_matrix)
+                fill_matrix(mlp.down_proj[0].right_matrix)
+            for t in (at.inp_trans_q, at.inp_trans_k, at.inp_trans_v, at.o_proj_trans, getattr(mlp, "inp_trans_g", None),
+                      getattr(mlp, "inp_trans_u", None), mlp.down_proj[0]):
+                if isinstance(t, OnlineTrans):
+                    t.clip_factor_a_max.fill_(4.0)
+                    t.clip_factor_a_min.fill_(4.0)
+        model.model.embed_tokens.weight.data.normal_(0, 1.0, generator=gen)
+        model.lm_head.weight.data.normal_(0, config.hidden_size ** -0.5, generator=gen)
+        for m in (model.model.embed_tokens, model.model.norm, model.lm_head,
+                  *(n for l in model.model.layers for n in (l.input_layernorm, l.post_attention_layernorm))):
+            m.to(ACT_DTYPE)
+        return model
 
     # ------------------------------------------------------------------------------------------ checkpoint ingest
     @classmethod

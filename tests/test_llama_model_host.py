@@ -251,3 +251,25 @@ def test_cache_growth_and_adapter():
     assert a.get_seq_length() == 0 and a.seen_tokens == 0 and a.to_legacy_cache() is c and a.trans == "none"
     specs = c.get_cache_specs_for_flash_infer(None)
     assert set(specs) == {"kv_data", "kv_param", "kv_indptr", "kv_indices", "last_page_offset"}
+
+
+def test_random_init_model_runs_prefill_and_decode(monkeypatch):
+    """The synthetic model bench.py --workload llama8b-model builds (here: a tiny architecture with 32 heads so that
+    the left-only o_proj transform of the Llama-3-8B shape is taken) stays finite and O(1) through prefill + decode,
+    with q/k/v and gate/up sharing one quantisation each (uncalibrated clip factors are equal)."""
+    from flatquant_b200.deploy.transformers import FlatQuantLlamaConfig, FlatQuantLlamaForCausalLM
+    cpu_ops.install(monkeypatch)
+    cfg = FlatQuantLlamaConfig(hidden_size=4096, intermediate_size=512, num_attention_heads=32, num_key_value_heads=8,
+                               num_hidden_layers=2, vocab_size=48, rope_theta=500000.0)
+    model = FlatQuantLlamaForCausalLM.random_init(cfg, torch.device("cpu"), seed=3)
+    ids = torch.randint(0, 48, (1, 12), generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        logits, cache = model(ids, max_length=16)
+        step, _ = model(ids[:, -1:], past_key_values=cache)
+    at = model.model.layers[0].self_attn
+    assert len(at._rt.qkv) == 1 and at._rt.qkv[0].w.shape == (4096 + 2 * 1024, 2048) and at._rt.o_right is None
+    assert len(model.model.layers[0].mlp._rt.gate_up) == 1
+    assert torch.isfinite(logits).all() and torch.isfinite(step).all() and 0.05 < float(logits.float().std()) < 20
+    assert cache.get_seq_length() == 13
+    cache.reset()
+    assert cache.get_seq_length() == 0 and all(cache._needs_init)
