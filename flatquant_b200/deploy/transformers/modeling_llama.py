@@ -160,6 +160,28 @@ def apply_rope(x, cos, sin):
     return x * cos + rot * sin
 
 
+class TensorParallel:
+    """Where a module sits in a tensor-parallel group (vllm_custom/.../llama_flatquant.py:75-126,148-289): q/k/v and
+    gate/up are column-parallel (heads / intermediate channels split, replicated input transform, no communication);
+    o_proj and down_proj are row-parallel -- each rank owns its OWN online transform sized for its shard
+    (o: (heads/tp)^2, down: get_decompose_dim(inter/tp)), its own per-token scale and clip factors, and the partial
+    products are summed with ONE all-reduce per linear, i.e. two per decoder layer."""
+
+    def __init__(self, size=1, rank=0, group=None):
+        self.size, self.rank, self.group = size, rank, group
+
+    def shard(self, n, what):
+        if n % self.size:
+            raise ValueError(f"{what}={n} is not divisible by the tensor-parallel size {self.size}")
+        return n // self.size
+
+    def all_reduce(self, y):
+        if self.size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
+        return y
+
+
 def _sig(v) -> float:
     return 1.0 / (1.0 + math.exp(-float(v)))
 
@@ -210,12 +232,20 @@ def _flat_linears(x2, left, right, n1, n2, groups, lac):
 class FlatQuantLlamaAttention(torch.nn.Module):
     """deploy/transformers/modeling_llama.py:156-237 (module / buffer names) + :44-153 (forward semantics)."""
 
-    def __init__(self, options, config, layer_idx):
+    def __init__(self, options, config, layer_idx, tp=None):
         super().__init__()
         self.options, self.config, self.layer_idx = options, config, layer_idx
+        self.tp = tp or TensorParallel()
         self.isFlatQ = getattr(options, "trans", None) == "matmul"
-        self.hidden_size, self.num_heads = config.hidden_size, config.num_attention_heads
-        self.num_key_value_heads, self.head_dim = config.num_key_value_heads, config.head_dim
+        self.hidden_size, self.head_dim = config.hidden_size, config.head_dim
+        # this rank's heads; kv heads are replicated when there are fewer of them than ranks (llama_flatquant.py:152-163)
+        self.num_heads = self.tp.shard(config.num_attention_heads, "num_attention_heads")
+        if config.num_key_value_heads >= self.tp.size:
+            self.num_key_value_heads = self.tp.shard(config.num_key_value_heads, "num_key_value_heads")
+        else:
+            if self.tp.size % config.num_key_value_heads:
+                raise ValueError("the tensor-parallel size must be a multiple of num_key_value_heads to replicate them")
+            self.num_key_value_heads = 1
         hs, hd = self.hidden_size, self.head_dim
         self.quantizer_q, self.quantizer_k, self.quantizer_v = (Quantizer(lac=self.isFlatQ) for _ in range(3))
         self.q_proj = Linear4bit(hs, self.num_heads * hd)
@@ -303,7 +333,7 @@ class FlatQuantLlamaAttention(torch.nn.Module):
         rt = self._runtime(attn.device)
         a2 = attn.reshape(b * s, self.num_heads * self.head_dim).to(ACT_DTYPE).contiguous()
         y = _flat_linears(a2, rt.o_left, rt.o_right, self.num_heads, self.head_dim, rt.o, self.isFlatQ)["o"]
-        return y.reshape(b, s, self.hidden_size)
+        return self.tp.all_reduce(y).reshape(b, s, self.hidden_size)
 
     def forward(self, hidden_states, cos, sin, past_key_value):
         """hidden_states [b, s, hidden] (already normalised) -> [b, s, hidden]."""
@@ -314,11 +344,12 @@ class FlatQuantLlamaAttention(torch.nn.Module):
 class FlatQuantLlamaMLP(torch.nn.Module):
     """deploy/transformers/modeling_llama.py:239-283."""
 
-    def __init__(self, options, config):
+    def __init__(self, options, config, tp=None):
         super().__init__()
         self.options, self.config = options, config
+        self.tp = tp or TensorParallel()
         self.isFlatQ = getattr(options, "trans", None) == "matmul"
-        hs, inter = config.hidden_size, config.intermediate_size
+        hs, inter = config.hidden_size, self.tp.shard(config.intermediate_size, "intermediate_size")
         self.hidden_size, self.intermediate_size = hs, inter
         self.quantizer_g, self.quantizer_u = Quantizer(lac=self.isFlatQ), Quantizer(lac=self.isFlatQ)
         self.up_proj, self.gate_proj = Linear4bit(hs, inter), Linear4bit(hs, inter)
@@ -374,7 +405,7 @@ class FlatQuantLlamaMLP(torch.nn.Module):
         rt = self._runtime(act.device)
         a2 = act.reshape(b * s, self.intermediate_size).to(ACT_DTYPE).contiguous()
         y = _flat_linears(a2, rt.d_left, rt.d_right, rt.d_n1, rt.d_n2, rt.down, self.isFlatQ)["down"]
-        return y.reshape(b, s, self.hidden_size)
+        return self.tp.all_reduce(y).reshape(b, s, self.hidden_size)
 
     def forward(self, x):
         gate, up = self.gate_up(x)
@@ -382,12 +413,12 @@ class FlatQuantLlamaMLP(torch.nn.Module):
 
 
 class FlatQuantLlamaDecoderLayer(torch.nn.Module):
-    def __init__(self, options, config, layer_idx):
+    def __init__(self, options, config, layer_idx, tp=None):
         super().__init__()
         norm = (lambda: RMSNorm(config.hidden_size, eps=config.rms_norm_eps)) if options.fuseLN else \
             (lambda: LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps))
-        self.self_attn = FlatQuantLlamaAttention(options, config, layer_idx)
-        self.mlp = FlatQuantLlamaMLP(options, config)
+        self.self_attn = FlatQuantLlamaAttention(options, config, layer_idx, tp)
+        self.mlp = FlatQuantLlamaMLP(options, config, tp)
         self.input_layernorm, self.post_attention_layernorm = norm(), norm()
 
     def forward(self, h, cos, sin, past_key_value):
@@ -396,10 +427,10 @@ class FlatQuantLlamaDecoderLayer(torch.nn.Module):
 
 
 class FlatQuantLlamaModel(torch.nn.Module):
-    def __init__(self, options, config):
+    def __init__(self, options, config, tp=None):
         super().__init__()
         self.embed_tokens = torch.nn.Embedding(config.vocab_size, config.hidden_size)
-        self.layers = torch.nn.ModuleList(FlatQuantLlamaDecoderLayer(options, config, i)
+        self.layers = torch.nn.ModuleList(FlatQuantLlamaDecoderLayer(options, config, i, tp)
                                           for i in range(config.num_hidden_layers))
         self.norm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
 
@@ -410,11 +441,14 @@ class FlatQuantLlamaForCausalLM(torch.nn.Module):
     with the returned cache decode."""
     config_class = FlatQuantLlamaConfig
 
-    def __init__(self, args, config):
+    def __init__(self, args, config, tp=None):
+        """`tp`: a TensorParallel placement -- every rank builds the same module tree with its shard's shapes
+        (embedding, norms and lm_head replicated), so per-rank checkpoints load through the same key map."""
         super().__init__()
         self.config, self.args = config, args
+        self.tp = tp or TensorParallel()
         self.trans, self.online_trans = args.trans, set(args.online_trans)
-        self.model = FlatQuantLlamaModel(args, config)
+        self.model = FlatQuantLlamaModel(args, config, self.tp)
         self.lm_head = torch.nn.Linear(config.hidden_size, config.vocab_size, bias=False)
         self.cache_dtype = "int4"
         self._expected_max_length = None
@@ -424,7 +458,8 @@ class FlatQuantLlamaForCausalLM(torch.nn.Module):
         cfg = self.config
         return MultiLayerPagedKVCache4Bit(
             batch_size=batch_size, page_size=page_size, max_seq_len=max_length, device=self.lm_head.weight.device,
-            n_layers=len(self.model.layers), num_heads=cfg.num_key_value_heads, head_dim=cfg.head_dim,
+            n_layers=len(self.model.layers), num_heads=self.model.layers[0].self_attn.num_key_value_heads,
+            head_dim=cfg.head_dim,
             disable_quant=False, trans_dtype=ACT_DTYPE, trans=self.trans if "qk" in self.online_trans else "none",
             group_size=1)  # GQA is resolved by index in the decode kernel: the cache holds kv heads, not repeats
 
@@ -448,20 +483,22 @@ class FlatQuantLlamaForCausalLM(torch.nn.Module):
         return self.lm_head(self.model.norm(h)), past_key_values
 
     @classmethod
-    def random_init(cls, config, device, seed=0, weight_scale=0.002):
+    def random_init(cls, config, device, seed=0, weight_scale=0.002, tp=None):
         """Synthetic model of the given architecture for benchmarks (BASELINE.json configs[2]: "random-init weights"):
         uniform random INT4 weight codes, per-channel scales sized so that activations stay O(1) in fp16, random
         well-conditioned transform factors, LAC clip factors at their initial value 4.0 (benchmark_model.py:176-261
         builds its model the same way, from `from_float` of random linears)."""
         with torch.device(device):
-            model = cls(options_from_config(config), config)
-        gen = torch.Generator(device=device).manual_seed(seed)
+            model = cls(options_from_config(config), config, tp)
+        tp_ = model.tp
+        rep = torch.Generator(device=device).manual_seed(seed)                       # replicated across ranks
+        own = torch.Generator(device=device).manual_seed(seed * 1009 + 7 + tp_.rank)  # this rank's shard
 
         def fill_linear(lin):
-            lin.weight.random_(0, 256, generator=gen)
+            lin.weight.random_(0, 256, generator=own)
             lin.weight_scales.fill_(weight_scale)
 
-        def fill_matrix(buf):
+        def fill_matrix(buf, gen):
             n = buf.shape[0]
             buf.copy_(torch.eye(n, device=device) * 0.75 + torch.randn(n, n, device=device, generator=gen) * (0.5 / n ** 0.5))
 
@@ -470,20 +507,19 @@ class FlatQuantLlamaForCausalLM(torch.nn.Module):
             for lin in (at.q_proj, at.k_proj, at.v_proj, at.o_proj[1], mlp.gate_proj, mlp.up_proj, mlp.down_proj[-1]):
                 fill_linear(lin)
             for buf in (at.left_matrix, at.right_matrix, mlp.left_matrix, mlp.right_matrix, at.trans_matrix_k):
-                fill_matrix(buf)
+                fill_matrix(buf, rep)  # input-side transforms see the full hidden state on every rank
             at.trans_matrix_k_inv_t.copy_(torch.linalg.inv(at.trans_matrix_k.double()).t().float())
-            if isinstance(at.o_proj_trans, OnlineTrans):
-                at.o_proj_trans.right_matrix.copy_(
-                    (torch.eye(at.num_heads, device=device) * 0.75 + torch.randn(at.num_heads, at.num_heads, device=device,
-                                                                                  generator=gen) * (0.5 / at.num_heads ** 0.5)))
+            if isinstance(at.o_proj_trans, OnlineTrans):  # row-parallel: one transform per rank
+                fill_matrix(at.o_proj_trans.right_matrix, own)
             if isinstance(mlp.down_proj[0], OnlineTrans):
-                fill_matrix(mlp.down_proj[0].left_matrix)
-                fill_matrix(mlp.down_proj[0].right_matrix)
+                fill_matrix(mlp.down_proj[0].left_matrix, own)
+                fill_matrix(mlp.down_proj[0].right_matrix, own)
             for t in (at.inp_trans_q, at.inp_trans_k, at.inp_trans_v, at.o_proj_trans, getattr(mlp, "inp_trans_g", None),
                       getattr(mlp, "inp_trans_u", None), mlp.down_proj[0]):
                 if isinstance(t, OnlineTrans):
                     t.clip_factor_a_max.fill_(4.0)
                     t.clip_factor_a_min.fill_(4.0)
+        gen = rep
         model.model.embed_tokens.weight.data.normal_(0, 1.0, generator=gen)
         model.lm_head.weight.data.normal_(0, config.hidden_size ** -0.5, generator=gen)
         for m in (model.model.embed_tokens, model.model.norm, model.lm_head,
