@@ -21,11 +21,15 @@ from . import ops
 
 
 class FlatQuantRoutedExperts:
-    def __init__(self, w13_packed, s_w13, w2_packed, s_w2, w1_factors, w2_factors, clip1=(1.0, 1.0), clip2=(1.0, 1.0)):
+    def __init__(self, w13_packed, s_w13, w2_packed, s_w2, w1_factors, w2_factors, clip1=(1.0, 1.0), clip2=(1.0, 1.0),
+                 diag1=None, diag2=None):
         """w13_packed [E, 2*inter, dim/2] u8 (rows: w1 then w3), s_w13 [E, 2*inter] f32, w2_packed [E, dim, inter/2],
-        s_w2 [E, dim]; w1_factors / w2_factors = (left, right) fp16 Kronecker pairs; clip = post-sigmoid factors."""
+        s_w2 [E, dim]; w1_factors / w2_factors = (left, right) fp16 Kronecker pairs; clip = post-sigmoid factors;
+        diag1 [dim] / diag2 [inter]: the transforms' per-channel `diag_scale` (add_diag; the DeepSeek wrappers keep it
+        online, trans_utils.py:86-90), applied to the activation in front of the Kronecker factors."""
         self.w13, self.s13, self.w2, self.s2 = w13_packed, s_w13, w2_packed, s_w2
         self.f1, self.f2, self.clip1, self.clip2 = w1_factors, w2_factors, clip1, clip2
+        self.diag1, self.diag2 = diag1, diag2
         self.n_experts = w13_packed.shape[0]
         self.inter = w2_packed.shape[2] * 2
         self.dim = w13_packed.shape[2] * 2
@@ -34,6 +38,9 @@ class FlatQuantRoutedExperts:
         """x [T, dim] fp16, weights / indices [T, top_k] from the (unquantised) gate -> y [T, dim] fp16."""
         T, top_k = indices.shape
         L1, R1 = self.f1
+        dt = x.dtype
+        if self.diag1 is not None:
+            x = x * self.diag1
         xq8, sx = ops.act_quant(x.contiguous(), L1, R1, L1.shape[0], R1.shape[0], *self.clip1)  # once for all experts
         # sort the (token, slot) pairs by expert
         flat_e = indices.reshape(-1)
@@ -41,23 +48,25 @@ class FlatQuantRoutedExperts:
         tok = (order // top_k)
         counts = torch.bincount(flat_e, minlength=self.n_experts).tolist()
         xs8, sxs = xq8[tok].contiguous(), sx[tok].contiguous()
-        h = torch.empty((tok.numel(), self.inter), dtype=torch.float16, device=x.device)
+        h = torch.empty((tok.numel(), self.inter), dtype=dt, device=x.device)
         off = 0
         for e, c in enumerate(counts):
             if c:
-                gu = ops.gemm_w4a8(xs8[off:off + c], sxs[off:off + c], self.w13[e], self.s13[e])
+                gu = ops.gemm_w4a8(xs8[off:off + c], sxs[off:off + c], self.w13[e], self.s13[e], out_dtype=dt)
                 g, u = gu[:, :self.inter], gu[:, self.inter:]
-                h[off:off + c] = torch.nn.functional.silu(g.float()).mul_(u.float()).half()
+                h[off:off + c] = torch.nn.functional.silu(g.float()).mul_(u.float()).to(dt)
             off += c
         L2, R2 = self.f2
+        if self.diag2 is not None:
+            h = h * self.diag2
         hq8, sh = ops.act_quant(h, L2, R2, L2.shape[0], R2.shape[0], *self.clip2)  # all experts' rows in one launch
-        out = torch.empty((tok.numel(), self.dim), dtype=torch.float16, device=x.device)
+        out = torch.empty((tok.numel(), self.dim), dtype=dt, device=x.device)
         off = 0
         for e, c in enumerate(counts):
             if c:
-                ops.gemm_w4a8(hq8[off:off + c], sh[off:off + c], self.w2[e], self.s2[e], out=out[off:off + c])
+                ops.gemm_w4a8(hq8[off:off + c], sh[off:off + c], self.w2[e], self.s2[e], out_dtype=dt, out=out[off:off + c])
             off += c
         w_sorted = weights.reshape(-1)[order].to(torch.float32)
         y = torch.zeros((T, self.dim), dtype=torch.float32, device=x.device)
         y.index_add_(0, tok, out.float() * w_sorted[:, None])
-        return y.half()
+        return y.to(dt)

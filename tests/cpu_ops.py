@@ -45,7 +45,12 @@ def act_quant(x, left, right, n1, n2, clip_max=1.0, clip_min=1.0, out=None):
     """(codes int8 [M, K] -- natural K order, the format is opaque to callers --, s_x fp32 [M])"""
     k = n1 * n2
     z = _transform(x.reshape(-1, k), left, right, n1, n2)
-    return _scale_codes(z, clip_max, clip_min)
+    q, s = _scale_codes(z, clip_max, clip_min)
+    if out is not None:
+        out[0].copy_(q)
+        out[1].copy_(s)
+        return out
+    return q, s
 
 
 def transform_quant(x, left, right, n1, n2, clip_max=1.0, clip_min=1.0):
@@ -62,7 +67,11 @@ def gemm_w4a8(xq8, s_x, w_packed, s_w, bias=None, out_dtype=torch.float16, out=N
     wq = O.unpack_i4(w_packed.numpy())
     acc = O.gemm_i4(xq8.numpy(), wq)
     y = O.sym_dequant(acc, s_x.numpy(), s_w.float().numpy(), None if bias is None else bias.float().numpy())
-    return torch.from_numpy(y).to(out_dtype)
+    y = torch.from_numpy(y).to(out_dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
 
 
 def linear_fused(x, left, right, n1, n2, clip_max, clip_min, w_packed, s_w, bias=None, out_dtype=torch.float16):
