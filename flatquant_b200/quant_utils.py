@@ -51,8 +51,6 @@ class ActivationQuantizer(torch.nn.Module):
 
     def __init__(self, bits, sym=False, lac=False, groupsize=-1, clip_ratio=None):
         super().__init__()
-        if groupsize > 0:
-            raise NotImplementedError("Not support per-group quantization for activation yet.")
         self.bits, self.sym, self.lac, self.groupsize = bits, sym, lac, groupsize
         self.q_max, self.q_min = get_qmin_qmax(bits, sym)
         self._clip_ratio = clip_ratio
@@ -70,13 +68,20 @@ class ActivationQuantizer(torch.nn.Module):
         r = 1.0 if self._clip_ratio is None else float(self._clip_ratio)
         return r, r
 
-    def forward(self, x):
+    def forward(self, x, scale=None, zero=None):
+        """`scale` / `zero`: precomputed quantisation parameters, and `groupsize` > 0: groups of that many channels
+        quantised on their own -- the form of the vLLM copy (vllm_custom/.../fake_quant_utils.py:69-88, used for the
+        grouped KV-cache quantisers); the main-repo class raises on groupsize > 0 (quant_utils.py:52-53)."""
         if self.bits == 16 or not self.enable:
             return x
-        return self.fake_quant(x)
+        if self.groupsize > 0:
+            shape = x.shape
+            return self.fake_quant(x.reshape(-1, self.groupsize), scale, zero).reshape(shape)
+        return self.fake_quant(x, scale, zero)
 
-    def fake_quant(self, x):
-        scale, zero = self.get_scale_zero(x)
+    def fake_quant(self, x, scale=None, zero=None):
+        if scale is None or zero is None:
+            scale, zero = self.get_scale_zero(x)
         qm = self.q_max.to(x)
         out = sym_quant_dequant(x, scale, qm) if self.sym else asym_quant_dequant(x, scale, zero, qm)
         return out.to(x.dtype)

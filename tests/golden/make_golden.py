@@ -170,6 +170,23 @@ def main():
             cases[f"{name}_fq_h"] = aq(xh).numpy()
     np.savez_compressed(f"{OUT}/act_quant.npz", x=x.numpy(), **cases)
 
+    # ---- a4 (vLLM copy): grouped quantisation and caller-supplied scale/zero (vllm_custom/.../fake_quant_utils.py:69-88)
+    vq = load_by_path("ref_vllm_fake_quant",
+                      f"{REF}/vllm_custom/model_executor/layers/quantization/utils/fake_quant_utils.py")
+    torch.manual_seed(31)
+    xv = torch.randn(5, 3, 128)
+    vcases = {"x": xv.numpy()}
+    with torch.no_grad():
+        gq = vq.ActivationQuantizer(bits=4, sym=False, lac=True, groupsize=64)
+        gq.clip_factor_a_max.fill_(3.0)
+        gq.clip_factor_a_min.fill_(5.0)
+        vcases["grouped_asym_lac"] = gq(xv).numpy()
+        sq = vq.ActivationQuantizer(bits=4, sym=True)
+        s_given, z_given = sq.get_scale_zero(xv * 1.5)
+        vcases["given_scale"], vcases["given_zero"] = s_given.numpy(), z_given.numpy()
+        vcases["sym_given"] = sq(xv, s_given, z_given).numpy()
+    np.savez_compressed(f"{OUT}/act_quant_vllm.npz", **vcases)
+
     # ---- a5: WeightQuantizer RTN
     torch.manual_seed(4)
     w = torch.randn(32, 128) * torch.rand(32, 1)

@@ -117,3 +117,19 @@ def test_host_modules_match_oracle_on_cpu(golden):
         y = fl2(torch.from_numpy(g2["z"]))
     assert torch.allclose(y, torch.from_numpy(g2["y"]), atol=2e-5)
     assert O.get_decompose_dim(256) == (16, 16)
+
+
+def test_activation_quantizer_vllm_signature(golden):
+    """forward(x, scale=None, zero=None) and groupsize > 0 of the vLLM copy (vllm_custom/.../fake_quant_utils.py:69-88);
+    fixture generated from that file by tests/golden/make_golden.py."""
+    from flatquant_b200.quant_utils import ActivationQuantizer
+    g = golden("act_quant_vllm")
+    x = torch.from_numpy(g["x"])
+    gq = ActivationQuantizer(bits=4, sym=False, lac=True, groupsize=64)
+    with torch.no_grad():
+        gq.clip_factor_a_max.fill_(3.0)
+        gq.clip_factor_a_min.fill_(5.0)
+        assert torch.equal(gq(x), torch.from_numpy(g["grouped_asym_lac"]))
+        sq = ActivationQuantizer(bits=4, sym=True)
+        assert torch.equal(sq(x, torch.from_numpy(g["given_scale"]), torch.from_numpy(g["given_zero"])),
+                           torch.from_numpy(g["sym_given"]))
