@@ -324,6 +324,85 @@ def run_model(args, rank, world, local):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------- configs[4]: DeepSeek-V3 single block
+def run_deepseek(args, rank, world, local):
+    """BASELINE configs[4]: one random-init DeepSeek-V3 MoE block at the public V3 shape (dim 7168, 128 heads, MLA
+    ranks 1536 / 512, 256 routed experts top-8 + 1 shared, moe_inter 2048; 5.8 GB of packed expert weights), prefill of
+    2048 tokens.  Data-parallel replicas for N > 1."""
+    from types import SimpleNamespace
+
+    from flatquant_b200 import ops
+    from flatquant_b200.deploy.transformers import modeling_deepseek as MD
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+    a = SimpleNamespace(**MD.V3_ARGS)
+    block = MD.FlatQuantDeepSeekBlock(a, MD.random_block_params(a, dev, seed=99 + rank), dev)
+    counted = {"n": 0}
+    for name in ("act_quant", "gemm_w4a8"):
+        def wrap(fn):
+            def inner(*aa, **k):
+                counted["n"] += 1
+                return fn(*aa, **k)
+            return inner
+        setattr(ops, name, wrap(getattr(ops, name)))
+    x_host = torch.randn(1, SEQ, a.dim, generator=torch.Generator().manual_seed(rank)).half().pin_memory()
+    x = x_host.to(dev)
+    y_host = torch.empty(1, SEQ, a.dim, dtype=torch.float16).pin_memory()
+    cos, sin = MD.precompute_freqs(a, SEQ, dev)
+
+    def step():
+        with torch.no_grad():
+            return block(x, 0, cos, sin)
+
+    def step_e2e():
+        with torch.no_grad():
+            y_host.copy_(block(x_host.to(dev, non_blocking=True), 0, cos, sin), non_blocking=True)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.wait_first()
+    counted["n"] = 0
+    t0 = sampler.mark()
+    ms = timed(step, args.steps, barrier)
+    t1 = sampler.mark()
+    launches = counted["n"]
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, barrier)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank == 0:
+        qk = a.qk_nope_head_dim + a.qk_rope_head_dim
+        ops_tok = 2 * (a.dim * (a.q_lora_rank + a.kv_lora_rank + a.qk_rope_head_dim) + a.q_lora_rank * a.n_heads * qk +
+                       a.n_heads * a.v_head_dim * a.dim + 3 * a.dim * a.moe_inter_dim * (a.n_activated_experts + a.n_shared_experts))
+        line = {"metric": "DeepSeek-V3 single MoE block W4A4 prefill tokens/sec/GPU (seq 2048)",
+                "value": world * SEQ * args.steps / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "s4 x s4 -> s32 FlatLinears, f16 attention / gate", "data": "synthetic",
+                "config": {"workload": "deepseek-v3 MoE block (public 671B shape), MLA + 256 routed experts top-8 + shared, seq 2048",
+                           "l2": "inputs larger than L2: 5.8 GB of packed expert weights",
+                           "parallelism": f"dp{world} (independent replicas)"},
+                "tops_flatlinear": ops_tok * SEQ * args.steps / (ms * 1e-3) / 1e12, "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": world * SEQ * args.steps / (ms_e2e * 1e-3), "unit": "tokens/s",
+                        "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": y_host.numel() * 2}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def timed(fn, steps, dist_barrier):
     dist_barrier()
     torch.cuda.synchronize()
@@ -371,9 +450,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=N_LAYERS, help="debug only: fewer layers => INVALID as a bench value")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="llama8b", choices=["llama8b", "llama70b-tp", "llama8b-model"],
+    ap.add_argument("--workload", default="llama8b", choices=["llama8b", "llama70b-tp", "llama8b-model", "deepseek-block"],
                     help="llama8b = BASELINE configs[1] (default, data-parallel replicas); llama70b-tp = configs[3]; "
-                         "llama8b-model = configs[2] (whole model: prefill + decode)")
+                         "llama8b-model = configs[2] (whole model: prefill + decode); deepseek-block = configs[4]")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -402,6 +481,8 @@ def main():
         return run_tp70(args, rank, world, local)
     if args.workload == "llama8b-model":
         return run_model(args, rank, world, local)
+    if args.workload == "deepseek-block":
+        return run_deepseek(args, rank, world, local)
 
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)

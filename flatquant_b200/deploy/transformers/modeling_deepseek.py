@@ -204,3 +204,49 @@ class FlatQuantDeepSeekBlock(torch.nn.Module):
     def forward(self, x, start_pos, cos, sin):
         x = x + self.attention(_rms(x, self.w_attn_norm), start_pos, cos, sin)
         return x + self.moe(_rms(x, self.w_ffn_norm))
+
+
+# Public DeepSeek-V3 architecture (the reference's configs/config_671B.json is git-ignored)
+V3_ARGS = dict(max_batch_size=1, max_seq_len=4096, dim=7168, moe_inter_dim=2048, n_heads=128, n_routed_experts=256,
+               n_shared_experts=1, n_activated_experts=8, n_expert_groups=1, n_limited_groups=1, score_func="sigmoid",
+               route_scale=2.5, q_lora_rank=1536, kv_lora_rank=512, qk_nope_head_dim=128, qk_rope_head_dim=64,
+               v_head_dim=128, original_seq_len=4096, rope_theta=10000.0, rope_factor=40, beta_fast=32, beta_slow=1,
+               mscale=1.0)
+
+
+def random_block_params(args, device, seed=0, weight_scale=0.002):
+    """Synthetic parameters of one MoE block in the fixture layout (random INT4 codes, well-conditioned transform
+    factors, unit diagonal scales, LAC clip factors at their initial 4.0) for benchmarks."""
+    from ...function_utils import get_decompose_dim
+    a = args if not isinstance(args, dict) else SimpleNamespace(**args)
+    gen = torch.Generator(device=device).manual_seed(seed)
+    p = {}
+
+    def trans(name, k):
+        n1, n2 = get_decompose_dim(k)
+        for side, n in (("left", n1), ("right", n2)):
+            p[f"{name}.matrix_{side}"] = (torch.eye(n, device=device) * 0.75 +
+                                          torch.randn(n, n, device=device, generator=gen) * (0.5 / n ** 0.5))
+        p[f"{name}.diag_scale"] = torch.ones(k, device=device)
+
+    def linear(name, k, n):
+        p[f"{name}.w_packed"] = torch.randint(0, 256, (n, k // 2), dtype=torch.uint8, device=device, generator=gen)
+        p[f"{name}.s_w"] = torch.full((n, 1), weight_scale, device=device)
+        p[f"{name}.clip_a"] = torch.tensor([4.0, 4.0])
+
+    qk = a.qk_nope_head_dim + a.qk_rope_head_dim
+    shared_inter = a.n_shared_experts * a.moe_inter_dim
+    trans("qkv_trans", a.dim), trans("wqb_trans", a.q_lora_rank), trans("wo_trans", a.n_heads * a.v_head_dim)
+    trans("w1_trans", a.dim), trans("w2_trans", shared_inter), trans("routed_w2_trans", a.moe_inter_dim)
+    linear("wq_a", a.dim, a.q_lora_rank), linear("wkv_a", a.dim, a.kv_lora_rank + a.qk_rope_head_dim)
+    linear("wq_b", a.q_lora_rank, a.n_heads * qk), linear("wo", a.n_heads * a.v_head_dim, a.dim)
+    linear("shared.w1", a.dim, shared_inter), linear("shared.w3", a.dim, shared_inter), linear("shared.w2", shared_inter, a.dim)
+    for e in range(a.n_routed_experts):
+        linear(f"experts.{e}.w1", a.dim, a.moe_inter_dim), linear(f"experts.{e}.w3", a.dim, a.moe_inter_dim)
+        linear(f"experts.{e}.w2", a.moe_inter_dim, a.dim)
+    for n, k in (("attn_norm", a.dim), ("ffn_norm", a.dim), ("q_norm", a.q_lora_rank), ("kv_norm", a.kv_lora_rank)):
+        p[n] = torch.ones(k, device=device)
+    p["wkv_b"] = torch.randn(a.n_heads * (a.qk_nope_head_dim + a.v_head_dim), a.kv_lora_rank, device=device,
+                             generator=gen) * a.kv_lora_rank ** -0.5
+    p["gate"] = torch.randn(a.n_routed_experts, a.dim, device=device, generator=gen) * 0.05
+    return p

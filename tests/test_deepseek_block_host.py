@@ -112,3 +112,18 @@ def test_block_stages_teacher_forced_fp16(monkeypatch):
     c = torch.nn.functional.cosine_similarity(y.float().flatten(), torch.from_numpy(g["y"]).flatten(), dim=0)
     print("block output cosine", float(c))
     assert c > 0.97  # the residual stream dominates; the quantised branches are checked stage by stage above
+
+
+def test_random_block_runs(monkeypatch):
+    """The synthetic block bench.py --workload deepseek-block builds (here at reduced width) stays finite."""
+    from flatquant_b200.deploy.transformers import modeling_deepseek as MD
+    cpu_ops.install(monkeypatch)
+    args = SimpleNamespace(**dict(MD.V3_ARGS, dim=512, moe_inter_dim=256, n_heads=4, n_routed_experts=6,
+                                  n_activated_experts=2, q_lora_rank=256, kv_lora_rank=64, qk_nope_head_dim=32,
+                                  qk_rope_head_dim=32, v_head_dim=64, max_batch_size=1, max_seq_len=16))
+    block = MD.FlatQuantDeepSeekBlock(args, MD.random_block_params(args, "cpu", seed=1), "cpu")
+    cos, sin = MD.precompute_freqs(args, 10)
+    with torch.no_grad():
+        y = block(torch.randn(1, 10, 512).half(), 0, cos, sin)
+    assert y.shape == (1, 10, 512) and torch.isfinite(y).all()
+    assert len(block.g_qkv) == 1 and block.g_qkv[0].w.shape[0] == 256 + 64 + 32  # equal clips: wq_a and wkv_a fused
