@@ -300,6 +300,27 @@ def run_model(args, rank, world, local):
             return timed(steps, 1, barrier) / (decode_len - 8)
     dec = {f"bsz{b}_ms_per_token": decode_ms(b) for b in (1, 16)}
 
+    def decode_graph_ms(bsz):
+        """The same steps replayed from one CUDA graph (position on the device, graphs.GraphedDecoder)."""
+        from flatquant_b200.deploy.transformers.graphs import GraphedDecoder
+        c = model.build_cache(bsz, page_size=SEQ + decode_len, max_length=SEQ + decode_len)
+        tok = torch.randint(100, 200, (bsz, 1), device=dev)
+        with torch.no_grad():
+            model(ids.expand(bsz, SEQ).contiguous(), past_key_values=c, logits_to_keep=1)
+        g = GraphedDecoder(model, c)
+        for _ in range(4):
+            g.step(tok)
+
+        def steps():
+            for _ in range(decode_len - 8):
+                g.step(tok)
+        return timed(steps, 1, barrier) / (decode_len - 8)
+    for b in (1, 16):
+        try:
+            dec[f"bsz{b}_graph_ms_per_token"] = decode_graph_ms(b)
+        except Exception as e:  # a capture problem must not lose the eager numbers of the same run
+            dec[f"bsz{b}_graph_error"] = f"{type(e).__name__}: {e}"[:200]
+
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -41,6 +41,7 @@ class MultiLayerPagedKVCache4Bit:
         """Forget the cached sequences (the page pool is kept): the next update per layer is a prefill again."""
         self._needs_init = [True] * self.n_layers
         self.length = 0
+        self._step_key = None
 
     def page_cnt_from_length(self, length):
         return (length + self.page_size - 1) // self.page_size
@@ -116,8 +117,42 @@ class MultiLayerPagedKVCache4Bit:
         o = ops.kv_decode_i4(qt.contiguous(), self.pages, self.scales, layer=layer_idx, **attention_kwargs)
         return o.unsqueeze(1)
 
+    # ---- decode with the position held on the device: every launch argument of a step is then either static or a
+    # device tensor updated in place, so the whole step can be captured in a CUDA graph and replayed (graphs.py)
+    def begin_static_decode(self):
+        if self.max_page_cnt != 1:
+            raise RuntimeError("static (graph-capturable) decode needs one page per sequence: page_size >= max_seq_len, "
+                               "which is how the reference sizes its cache too (modeling_llama.py:337)")
+        b, dev = self.batch_size, self.device
+        self.pos_dev = torch.full((1,), self.length, dtype=torch.int32, device=dev)  # tokens cached so far
+        self._static_attn = dict(kv_indptr=torch.arange(b + 1, dtype=torch.int32, device=dev),
+                                 kv_indices=self._page_base.clone(),
+                                 last_page_len=torch.empty(b, dtype=torch.int32, device=dev))
+        self._static_slots = torch.empty(b, dtype=torch.int32, device=dev)
+        self._static_mode = True
+
+    def end_static_decode(self):
+        self._static_mode = False
+
+    def _update_static(self, key_states, value_states, layer_idx, cache_kwargs):
+        k_mat, k_inv_t = cache_kwargs.get("trans_matrix_k"), cache_kwargs.get("trans_matrix_k_inv_t")
+        b, added, heads, d = key_states.shape
+        assert b == self.batch_size and added == 1
+        key_t = self._transform(key_states, k_mat)
+        if layer_idx == 0:  # slot of the new token and the attended length, from the device-side position
+            self._static_slots.copy_(self._page_base * self.page_size + self.pos_dev)
+            self._static_attn["last_page_len"].copy_((self.pos_dev + 1).expand(b))
+        kq = key_t.reshape(b, heads, d).to(torch.float16).contiguous()
+        vq = value_states.reshape(b, heads, d).to(torch.float16).contiguous()
+        ops.kv_quant(kq, self.pages, self.scales, self._static_slots, layer_idx, 0)
+        ops.kv_quant(vq, self.pages, self.scales, self._static_slots, layer_idx, 1)
+        return functools.partial(self._decode, num_kv_heads=heads, attention_kwargs=self._static_attn,
+                                 layer_idx=layer_idx, k_inv_t=k_inv_t if self.trans.startswith("matmul") else None)
+
     def update(self, key_states, value_states, layer_idx, cache_kwargs=None):
         cache_kwargs = cache_kwargs or {}
+        if getattr(self, "_static_mode", False):
+            return self._update_static(key_states, value_states, layer_idx, cache_kwargs)
         k_mat, k_inv_t = cache_kwargs.get("trans_matrix_k"), cache_kwargs.get("trans_matrix_k_inv_t")
         b, added, heads, d = key_states.shape
         assert b == self.batch_size
@@ -126,7 +161,11 @@ class MultiLayerPagedKVCache4Bit:
             self._ensure_page_cnt_per_batch(self.page_cnt_from_length(self.length + added))
             self._start = self.length
             self.length += added
-        slots = self._slots(self._start, added)
+        # slot indices and the page table are the same for every layer of a step: build them once, not per layer
+        key = (self._start, added, self.max_page_cnt)
+        if getattr(self, "_step_key", None) != key:
+            self._step_key, self._step_slots, self._step_attn = key, self._slots(self._start, added), None
+        slots = self._step_slots
         kq = key_t.reshape(b * added, heads, d).to(torch.float16).contiguous()
         vq = value_states.reshape(b * added, heads, d).to(torch.float16).contiguous()
         ops.kv_quant(kq, self.pages, self.scales, slots, layer_idx, 0)
@@ -135,7 +174,9 @@ class MultiLayerPagedKVCache4Bit:
             self._needs_init[layer_idx] = False
             return key_t, value_states  # prefill: attention runs on the (transformed) fp16 states
         assert added == 1
-        return functools.partial(self._decode, num_kv_heads=heads, attention_kwargs=self._attention_kwargs(),
+        if self._step_attn is None:
+            self._step_attn = self._attention_kwargs()
+        return functools.partial(self._decode, num_kv_heads=heads, attention_kwargs=self._step_attn,
                                  layer_idx=layer_idx, k_inv_t=k_inv_t if self.trans.startswith("matmul") else None)
 
 

@@ -527,6 +527,26 @@ class FlatQuantLlamaForCausalLM(torch.nn.Module):
             m.to(ACT_DTYPE)
         return model
 
+    def decode_static(self, input_ids, cache):
+        """One decode step whose position comes from the device (`cache.pos_dev`, after `cache.begin_static_decode()`):
+        same arithmetic as `forward` on one token, but nothing in it depends on host-side integers, which makes the
+        step capturable in a CUDA graph (graphs.GraphedDecoder).  Advances `cache.pos_dev`; the caller advances
+        `cache.length`."""
+        dev = input_ids.device
+        if self._inv_freq is None or self._inv_freq.device != dev:
+            self._inv_freq = rope_inv_freq(self.config, dev)
+        table = getattr(self, "_rope_table", None)
+        if table is None or table[0].device != dev or table[0].shape[1] < cache.max_seq_len:
+            pos = torch.arange(cache.max_seq_len, device=dev)[None]
+            self._rope_table = table = rope_cos_sin(self._inv_freq, pos, ACT_DTYPE)  # [1, L, 1, d] each
+        row = cache.pos_dev.long()
+        cos, sin = table[0].index_select(1, row), table[1].index_select(1, row)
+        h = self.model.embed_tokens(input_ids)
+        for layer in self.model.layers:
+            h = layer(h, cos, sin, cache)
+        cache.pos_dev.add_(1)
+        return self.lm_head(self.model.norm(h))
+
     # ------------------------------------------------------------------------------------------ checkpoint ingest
     @classmethod
     def from_pretrained(cls, path, device=None):

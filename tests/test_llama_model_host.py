@@ -273,3 +273,33 @@ def test_random_init_model_runs_prefill_and_decode(monkeypatch):
     assert cache.get_seq_length() == 13
     cache.reset()
     assert cache.get_seq_length() == 0 and all(cache._needs_init)
+
+
+def test_static_decode_equals_eager_decode(monkeypatch):
+    """The graph-capturable decode step (position on the device) computes exactly what the eager step computes, for
+    several consecutive tokens, and leaves identical cache contents."""
+    cpu_ops.install(monkeypatch)
+    g = np.load(os.path.join(GOLDEN, "llama_model.npz"))
+    model = _load_model()
+    ids = torch.from_numpy(g["ids"])
+    n_pre, n_dec = 9, 4
+    with torch.no_grad():
+        _, eager = model(ids[:, :n_pre], max_length=ids.shape[1])
+        _, static = model(ids[:, :n_pre], max_length=ids.shape[1])
+        static.begin_static_decode()
+        for t in range(n_pre, n_pre + n_dec):
+            want, _ = model(ids[:, t:t + 1], past_key_values=eager)
+            got = model.decode_static(ids[:, t:t + 1], static)
+            static.length += 1
+            assert torch.equal(got, want), t
+    assert int(static.pos_dev) == n_pre + n_dec == eager.get_seq_length()
+    assert torch.equal(static.pages, eager.pages) and torch.equal(static.scales, eager.scales)
+    static.end_static_decode()
+    with torch.no_grad():  # back in eager mode the cache continues where the static steps left it
+        a, _ = model(ids[:, -1:], past_key_values=static)
+        b, _ = model(ids[:, -1:], past_key_values=eager)
+    assert torch.equal(a, b)
+    import pytest
+    from flatquant_b200.deploy.transformers import MultiLayerPagedKVCache4Bit
+    with pytest.raises(RuntimeError, match="one page per sequence"):
+        MultiLayerPagedKVCache4Bit(1, 4, 16, torch.device("cpu"), 1, 1, 128, trans="none").begin_static_decode()

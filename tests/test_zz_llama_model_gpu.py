@@ -97,3 +97,34 @@ def test_decode_attention_over_paged_int4_cache(model, g, dev):
     got = outs[1].reshape(b, hq, hd).float().cpu()
     # fp16 K.T_k products can round differently from the CPU restatement and move a few 4-bit codes of the cache
     assert (got - want).abs().max() < 0.05 * want.abs().max(), (got - want).abs().max()
+
+
+def test_graphed_steps_equal_eager(model, g, dev):
+    """CUDA-graph replay of the decode step (device-side position) and of the fixed-shape prefill reproduces the eager
+    results: same kernels, same inputs; only the cuBLAS lm_head may pick a different algorithm under capture."""
+    from flatquant_b200.deploy.transformers.graphs import GraphedDecoder, GraphedPrefill
+    ids = torch.from_numpy(g["ids"]).to(dev)
+    b, s = ids.shape
+    n_pre = 9
+
+    def close(a, w):
+        return float((a.float() - w.float()).abs().max()) <= 2e-3 * float(w.float().abs().max())
+    with torch.no_grad():
+        _, eager = model(ids[:, :n_pre], max_length=s)
+        _, c2 = model(ids[:, :n_pre], max_length=s)
+    dec = GraphedDecoder(model, c2)
+    for t in range(n_pre, s):
+        with torch.no_grad():
+            want, _ = model(ids[:, t:t + 1], past_key_values=eager)
+        got = dec.step(ids[:, t:t + 1]).clone()
+        assert close(got, want), t
+    torch.cuda.synchronize()
+    assert int(c2.pos_dev) == s == c2.get_seq_length()
+    assert torch.equal(c2.pages, eager.pages) and torch.equal(c2.scales, eager.scales)
+    pf = GraphedPrefill(model, b, s)
+    for _ in range(2):  # replays are repeatable
+        logits, cache = pf(ids)
+        with torch.no_grad():
+            want, wc = model(ids)
+        assert close(logits, want) and cache.get_seq_length() == s
+        assert torch.equal(cache.pages, wc.pages)
