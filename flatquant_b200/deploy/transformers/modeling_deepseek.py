@@ -91,17 +91,24 @@ def _clip(params, name):
 
 
 class FlatQuantDeepSeekBlock(torch.nn.Module):
-    def __init__(self, args, params, device):
+    def __init__(self, args, params, device, tp=None):
+        """`tp` (modeling_llama.TensorParallel): the reference's sharding of the block (deepseek_v3/model.py:205-264,
+        404-441, 633-691) -- wq_b / wkv_b column-parallel over heads, wo row-parallel with this rank's own transform,
+        routed experts range-partitioned, the shared expert column/row-parallel over its intermediate channels; `params`
+        then holds this rank's shard (local shapes, local experts under their GLOBAL indices).  Two all-reduces per
+        block: after wo, and one for routed + shared together (the reference issues them separately)."""
         super().__init__()
         self.args = a = args if not isinstance(args, dict) else SimpleNamespace(**args)
+        self.tp = tp or ML.TensorParallel()
         dev = self.dev = torch.device(device)
         p = {k: (torch.as_tensor(v) if not isinstance(v, torch.Tensor) else v) for k, v in params.items()}
-        self.n_heads, self.qk_head_dim = a.n_heads, a.qk_nope_head_dim + a.qk_rope_head_dim
+        self.n_heads = self.tp.shard(a.n_heads, "n_heads")  # local heads
+        self.qk_head_dim = a.qk_nope_head_dim + a.qk_rope_head_dim
         self.softmax_scale = float(p["softmax_scale"]) if "softmax_scale" in p else self.qk_head_dim ** -0.5
         for n in ("attn_norm", "ffn_norm", "q_norm", "kv_norm", "gate"):
             setattr(self, f"w_{n}", p[n].to(dev, torch.float32))
         self.w_gate_bias = p["gate_bias"].to(dev, torch.float32) if "gate_bias" in p else None
-        self.wkv_b = p["wkv_b"].to(dev, _act()).view(a.n_heads, a.qk_nope_head_dim + a.v_head_dim, a.kv_lora_rank)
+        self.wkv_b = p["wkv_b"].to(dev, _act()).view(self.n_heads, a.qk_nope_head_dim + a.v_head_dim, a.kv_lora_rank)
         self.t_qkv, self.t_wqb, self.t_wo = (_Trans(p, n, dev) for n in ("qkv_trans", "wqb_trans", "wo_trans"))
         self.t_w1, self.t_w2, self.t_rw2 = (_Trans(p, n, dev) for n in ("w1_trans", "w2_trans", "routed_w2_trans"))
         grp = ML._group_by_clip
@@ -112,20 +119,23 @@ class FlatQuantDeepSeekBlock(torch.nn.Module):
         self.g_s13 = grp(("w1", "w3"), [_linear(p, f"shared.{n}", dev) for n in ("w1", "w3")],
                          [_clip(p, f"shared.{n}") for n in ("w1", "w3")])
         self.g_s2 = grp(("w2",), [_linear(p, "shared.w2", dev)], [_clip(p, "shared.w2")])
-        E = a.n_routed_experts
-        w13 = torch.stack([torch.cat([p[f"experts.{e}.w1.w_packed"], p[f"experts.{e}.w3.w_packed"]], 0) for e in range(E)])
-        s13 = torch.stack([torch.cat([p[f"experts.{e}.w1.s_w"], p[f"experts.{e}.w3.s_w"]], 0).reshape(-1) for e in range(E)])
-        w2 = torch.stack([p[f"experts.{e}.w2.w_packed"] for e in range(E)])
-        s2 = torch.stack([p[f"experts.{e}.w2.s_w"].reshape(-1) for e in range(E)])
-        c1, c2 = _clip(p, "experts.0.w1"), _clip(p, "experts.0.w2")  # one shared quantiser per stage (:413-415)
-        for e in range(E):
+        n_local = self.tp.shard(a.n_routed_experts, "n_routed_experts")
+        first = self.tp.rank * n_local
+        E = range(first, first + n_local)
+        w13 = torch.stack([torch.cat([p[f"experts.{e}.w1.w_packed"], p[f"experts.{e}.w3.w_packed"]], 0) for e in E])
+        s13 = torch.stack([torch.cat([p[f"experts.{e}.w1.s_w"], p[f"experts.{e}.w3.s_w"]], 0).reshape(-1) for e in E])
+        w2 = torch.stack([p[f"experts.{e}.w2.w_packed"] for e in E])
+        s2 = torch.stack([p[f"experts.{e}.w2.s_w"].reshape(-1) for e in E])
+        c1, c2 = _clip(p, f"experts.{first}.w1"), _clip(p, f"experts.{first}.w2")  # one shared quantiser per stage (:413-415)
+        for e in E:
             if _clip(p, f"experts.{e}.w1") != c1 or _clip(p, f"experts.{e}.w3") != c1 or _clip(p, f"experts.{e}.w2") != c2:
                 raise RuntimeError("routed experts must share their activation quantisers (deepseekv3_utils.py:413-415)")
         sig = ML._sig
         self.routed = FlatQuantRoutedExperts(
             w13.to(dev).contiguous(), s13.to(dev, torch.float32).contiguous(), w2.to(dev).contiguous(),
             s2.to(dev, torch.float32).contiguous(), (self.t_w1.left, self.t_w1.right), (self.t_rw2.left, self.t_rw2.right),
-            (sig(c1[0]), sig(c1[1])), (sig(c2[0]), sig(c2[1])), self.t_w1.diag, self.t_rw2.diag)
+            (sig(c1[0]), sig(c1[1])), (sig(c2[0]), sig(c2[1])), self.t_w1.diag, self.t_rw2.diag,
+            expert_offset=first if self.tp.size > 1 else None)
         self.kv_cache = torch.zeros(a.max_batch_size, a.max_seq_len, a.kv_lora_rank, dtype=_act(), device=dev)
         self.pe_cache = torch.zeros(a.max_batch_size, a.max_seq_len, a.qk_rope_head_dim, dtype=_act(), device=dev)
 
@@ -151,7 +161,7 @@ class FlatQuantDeepSeekBlock(torch.nn.Module):
         a = self.args
         b, s = q.shape[:2]
         end = start_pos + s
-        q = q.view(b, s, a.n_heads, self.qk_head_dim)
+        q = q.view(b, s, self.n_heads, self.qk_head_dim)
         q_nope, q_pe = torch.split(q, [a.qk_nope_head_dim, a.qk_rope_head_dim], dim=-1)
         q_pe = apply_rotary(q_pe, cos, sin)
         kv, k_pe = torch.split(kv, [a.kv_lora_rank, a.qk_rope_head_dim], dim=-1)
@@ -169,7 +179,7 @@ class FlatQuantDeepSeekBlock(torch.nn.Module):
         return torch.einsum("bshc,hdc->bshd", o, self.wkv_b[:, -a.v_head_dim:]).flatten(2)
 
     def attn_out(self, o):
-        return self._fl(o, self.t_wo, self.g_wo)["wo"]
+        return self.tp.all_reduce(self._fl(o, self.t_wo, self.g_wo)["wo"])
 
     def attention(self, xn, start_pos, cos, sin):
         q1, kv = self.attn_in(xn)
@@ -199,7 +209,7 @@ class FlatQuantDeepSeekBlock(torch.nn.Module):
         x2 = xn.reshape(-1, shape[-1]).to(_act())
         weights, indices = routing if routing is not None else self.gate(x2)
         y = self.routed(x2, weights, indices)
-        return (y + self.shared_expert(x2)).view(shape)
+        return self.tp.all_reduce(y + self.shared_expert(x2)).view(shape)
 
     def forward(self, x, start_pos, cos, sin):
         x = x + self.attention(_rms(x, self.w_attn_norm), start_pos, cos, sin)
@@ -214,39 +224,47 @@ V3_ARGS = dict(max_batch_size=1, max_seq_len=4096, dim=7168, moe_inter_dim=2048,
                mscale=1.0)
 
 
-def random_block_params(args, device, seed=0, weight_scale=0.002):
+def random_block_params(args, device, seed=0, weight_scale=0.002, tp_size=1, tp_rank=0):
     """Synthetic parameters of one MoE block in the fixture layout (random INT4 codes, well-conditioned transform
-    factors, unit diagonal scales, LAC clip factors at their initial 4.0) for benchmarks."""
+    factors, unit diagonal scales, LAC clip factors at their initial 4.0) for benchmarks.  With tp_size > 1: this
+    rank's shard -- replicated tensors are drawn from `seed`, sharded ones from a per-rank stream."""
     from ...function_utils import get_decompose_dim
     a = args if not isinstance(args, dict) else SimpleNamespace(**args)
-    gen = torch.Generator(device=device).manual_seed(seed)
+    rep = torch.Generator(device=device).manual_seed(seed)
+    own = torch.Generator(device=device).manual_seed(seed * 1009 + 7 + tp_rank)
     p = {}
 
-    def trans(name, k):
+    def trans(name, k, gen):
         n1, n2 = get_decompose_dim(k)
         for side, n in (("left", n1), ("right", n2)):
             p[f"{name}.matrix_{side}"] = (torch.eye(n, device=device) * 0.75 +
                                           torch.randn(n, n, device=device, generator=gen) * (0.5 / n ** 0.5))
         p[f"{name}.diag_scale"] = torch.ones(k, device=device)
 
-    def linear(name, k, n):
+    def linear(name, k, n, gen):
         p[f"{name}.w_packed"] = torch.randint(0, 256, (n, k // 2), dtype=torch.uint8, device=device, generator=gen)
         p[f"{name}.s_w"] = torch.full((n, 1), weight_scale, device=device)
         p[f"{name}.clip_a"] = torch.tensor([4.0, 4.0])
 
     qk = a.qk_nope_head_dim + a.qk_rope_head_dim
-    shared_inter = a.n_shared_experts * a.moe_inter_dim
-    trans("qkv_trans", a.dim), trans("wqb_trans", a.q_lora_rank), trans("wo_trans", a.n_heads * a.v_head_dim)
-    trans("w1_trans", a.dim), trans("w2_trans", shared_inter), trans("routed_w2_trans", a.moe_inter_dim)
-    linear("wq_a", a.dim, a.q_lora_rank), linear("wkv_a", a.dim, a.kv_lora_rank + a.qk_rope_head_dim)
-    linear("wq_b", a.q_lora_rank, a.n_heads * qk), linear("wo", a.n_heads * a.v_head_dim, a.dim)
-    linear("shared.w1", a.dim, shared_inter), linear("shared.w3", a.dim, shared_inter), linear("shared.w2", shared_inter, a.dim)
-    for e in range(a.n_routed_experts):
-        linear(f"experts.{e}.w1", a.dim, a.moe_inter_dim), linear(f"experts.{e}.w3", a.dim, a.moe_inter_dim)
-        linear(f"experts.{e}.w2", a.moe_inter_dim, a.dim)
+    heads = a.n_heads // tp_size
+    shared_inter = a.n_shared_experts * a.moe_inter_dim // tp_size
+    n_local = a.n_routed_experts // tp_size
+    # replicated: the input-side transforms, wq_a / wkv_a (plain Linear in model.py:418-421), norms, the gate
+    trans("qkv_trans", a.dim, rep), trans("wqb_trans", a.q_lora_rank, rep), trans("w1_trans", a.dim, rep)
+    trans("routed_w2_trans", a.moe_inter_dim, rep)
+    linear("wq_a", a.dim, a.q_lora_rank, rep), linear("wkv_a", a.dim, a.kv_lora_rank + a.qk_rope_head_dim, rep)
+    p["gate"] = torch.randn(a.n_routed_experts, a.dim, device=device, generator=rep) * 0.05
     for n, k in (("attn_norm", a.dim), ("ffn_norm", a.dim), ("q_norm", a.q_lora_rank), ("kv_norm", a.kv_lora_rank)):
         p[n] = torch.ones(k, device=device)
-    p["wkv_b"] = torch.randn(a.n_heads * (a.qk_nope_head_dim + a.v_head_dim), a.kv_lora_rank, device=device,
-                             generator=gen) * a.kv_lora_rank ** -0.5
-    p["gate"] = torch.randn(a.n_routed_experts, a.dim, device=device, generator=gen) * 0.05
+    # sharded: heads, the row-parallel transforms (sized by the local K), the shared expert's channels, the experts
+    trans("wo_trans", heads * a.v_head_dim, own), trans("w2_trans", shared_inter, own)
+    linear("wq_b", a.q_lora_rank, heads * qk, own), linear("wo", heads * a.v_head_dim, a.dim, own)
+    linear("shared.w1", a.dim, shared_inter, own), linear("shared.w3", a.dim, shared_inter, own)
+    linear("shared.w2", shared_inter, a.dim, own)
+    for e in range(tp_rank * n_local, (tp_rank + 1) * n_local):
+        linear(f"experts.{e}.w1", a.dim, a.moe_inter_dim, own), linear(f"experts.{e}.w3", a.dim, a.moe_inter_dim, own)
+        linear(f"experts.{e}.w2", a.moe_inter_dim, a.dim, own)
+    p["wkv_b"] = torch.randn(heads * (a.qk_nope_head_dim + a.v_head_dim), a.kv_lora_rank, device=device,
+                             generator=own) * a.kv_lora_rank ** -0.5
     return p

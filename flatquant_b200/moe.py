@@ -22,14 +22,16 @@ from . import ops
 
 class FlatQuantRoutedExperts:
     def __init__(self, w13_packed, s_w13, w2_packed, s_w2, w1_factors, w2_factors, clip1=(1.0, 1.0), clip2=(1.0, 1.0),
-                 diag1=None, diag2=None):
+                 diag1=None, diag2=None, expert_offset=None):
         """w13_packed [E, 2*inter, dim/2] u8 (rows: w1 then w3), s_w13 [E, 2*inter] f32, w2_packed [E, dim, inter/2],
         s_w2 [E, dim]; w1_factors / w2_factors = (left, right) fp16 Kronecker pairs; clip = post-sigmoid factors;
         diag1 [dim] / diag2 [inter]: the transforms' per-channel `diag_scale` (add_diag; the DeepSeek wrappers keep it
-        online, trans_utils.py:86-90), applied to the activation in front of the Kronecker factors."""
+        online, trans_utils.py:86-90), applied to the activation in front of the Kronecker factors;
+        expert_offset: expert parallelism -- this rank holds global experts [offset, offset + E) and skips the
+        (token, slot) pairs routed elsewhere (deepseek_v3/model.py:657-660, 677-683)."""
         self.w13, self.s13, self.w2, self.s2 = w13_packed, s_w13, w2_packed, s_w2
         self.f1, self.f2, self.clip1, self.clip2 = w1_factors, w2_factors, clip1, clip2
-        self.diag1, self.diag2 = diag1, diag2
+        self.diag1, self.diag2, self.expert_offset = diag1, diag2, expert_offset
         self.n_experts = w13_packed.shape[0]
         self.inter = w2_packed.shape[2] * 2
         self.dim = w13_packed.shape[2] * 2
@@ -44,7 +46,13 @@ class FlatQuantRoutedExperts:
         xq8, sx = ops.act_quant(x.contiguous(), L1, R1, L1.shape[0], R1.shape[0], *self.clip1)  # once for all experts
         # sort the (token, slot) pairs by expert
         flat_e = indices.reshape(-1)
-        order = torch.argsort(flat_e, stable=True)
+        if self.expert_offset is None:
+            order = torch.argsort(flat_e, stable=True)
+        else:  # keep the pairs of the local experts only
+            flat_e = flat_e - self.expert_offset
+            mine = ((flat_e >= 0) & (flat_e < self.n_experts)).nonzero().squeeze(1)
+            order = mine[torch.argsort(flat_e[mine], stable=True)]
+            flat_e = flat_e[mine]
         tok = (order // top_k)
         counts = torch.bincount(flat_e, minlength=self.n_experts).tolist()
         xs8, sxs = xq8[tok].contiguous(), sx[tok].contiguous()
@@ -56,6 +64,8 @@ class FlatQuantRoutedExperts:
                 g, u = gu[:, :self.inter], gu[:, self.inter:]
                 h[off:off + c] = torch.nn.functional.silu(g.float()).mul_(u.float()).to(dt)
             off += c
+        if tok.numel() == 0:  # no token of this batch is routed to a local expert
+            return torch.zeros((T, self.dim), dtype=dt, device=x.device)
         L2, R2 = self.f2
         if self.diag2 is not None:
             h = h * self.diag2
