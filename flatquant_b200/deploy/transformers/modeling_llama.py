@@ -92,7 +92,8 @@ class FlatQuantLlamaConfig:
 
     def __init__(self, hidden_size=4096, intermediate_size=14336, num_attention_heads=32, num_key_value_heads=None,
                  num_hidden_layers=32, vocab_size=128256, rms_norm_eps=1e-5, rope_theta=500000.0, rope_scaling=None,
-                 max_position_embeddings=8192, head_dim=None, quantization_config=None, **unused):
+                 max_position_embeddings=8192, head_dim=None, quantization_config=None, attention_bias=False,
+                 mlp_bias=False, **unused):
         self.hidden_size, self.intermediate_size = hidden_size, intermediate_size
         self.num_attention_heads = num_attention_heads
         self.num_key_value_heads = num_key_value_heads or num_attention_heads
@@ -101,6 +102,9 @@ class FlatQuantLlamaConfig:
         self.max_position_embeddings = max_position_embeddings
         self.head_dim = head_dim or hidden_size // num_attention_heads
         self.quantization_config = quantization_config or {}
+        # q/k/v (and o) biases as in Qwen2 / attention_bias Llamas (flatquant/model_tools/qwen_utils.py wraps the same
+        # FlatQuantizedLinear around biased linears; v_proj's bias is transformed offline, flat_linear.py:95-96)
+        self.attention_bias, self.mlp_bias = attention_bias, mlp_bias
 
     @classmethod
     def from_pretrained(cls, path):
@@ -248,9 +252,10 @@ class FlatQuantLlamaAttention(torch.nn.Module):
             self.num_key_value_heads = 1
         hs, hd = self.hidden_size, self.head_dim
         self.quantizer_q, self.quantizer_k, self.quantizer_v = (Quantizer(lac=self.isFlatQ) for _ in range(3))
-        self.q_proj = Linear4bit(hs, self.num_heads * hd)
-        self.k_proj = Linear4bit(hs, self.num_key_value_heads * hd)
-        self.v_proj = Linear4bit(hs, self.num_key_value_heads * hd)
+        ab = bool(getattr(config, "attention_bias", False))
+        self.q_proj = Linear4bit(hs, self.num_heads * hd, bias=ab)
+        self.k_proj = Linear4bit(hs, self.num_key_value_heads * hd, bias=ab)
+        self.v_proj = Linear4bit(hs, self.num_key_value_heads * hd, bias=ab)
         self.o_proj_trans = torch.nn.Identity()
         if "o_proj" in options.online_trans:
             self.o_proj_trans = OnlineTrans(self.num_heads, trans=options.trans, decompose=False)

@@ -303,3 +303,30 @@ def test_static_decode_equals_eager_decode(monkeypatch):
     from flatquant_b200.deploy.transformers import MultiLayerPagedKVCache4Bit
     with pytest.raises(RuntimeError, match="one page per sequence"):
         MultiLayerPagedKVCache4Bit(1, 4, 16, torch.device("cpu"), 1, 1, 128, trans="none").begin_static_decode()
+
+
+def test_attention_bias_is_applied_after_dequant(monkeypatch):
+    """attention_bias (Qwen2-style q/k/v biases): y = dequant(acc) + b per projection, also inside a fused group."""
+    from oracle import flatq_oracle as O
+
+    from flatquant_b200.deploy.transformers import FlatQuantLlamaConfig, FlatQuantLlamaForCausalLM
+    from flatquant_b200.deploy.transformers import modeling_llama as ML
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(cpu_ops, "EMULATE_FP16", False)
+    monkeypatch.setattr(ML, "ACT_DTYPE", torch.float32)
+    cfg = FlatQuantLlamaConfig(hidden_size=512, intermediate_size=512, num_attention_heads=4, num_key_value_heads=2,
+                               num_hidden_layers=1, vocab_size=16, attention_bias=True)
+    model = FlatQuantLlamaForCausalLM.random_init(cfg, torch.device("cpu"), seed=2)
+    at = model.model.layers[0].self_attn
+    torch.manual_seed(0)
+    for lin in (at.q_proj, at.k_proj, at.v_proj):
+        lin.bias = torch.randn(lin.weight.shape[0])
+    x = torch.randn(1, 5, 512)
+    with torch.no_grad():
+        q, k, v = at.qkv(x)
+    assert len(at._rt.qkv) == 1 and at._rt.qkv[0].bias.shape == (1024,)
+    for got, lin in ((q, at.q_proj), (k, at.k_proj), (v, at.v_proj)):
+        want = O.flat_linear_int(x.reshape(5, 512), at.left_matrix, at.right_matrix, 4.0, 4.0,
+                                 O.unpack_i4(lin.weight.numpy()), lin.weight_scales.reshape(-1).numpy(),
+                                 lin.bias.numpy())["y"]
+        assert np.abs(got.reshape(5, -1).numpy() - want).max() < 1e-4 * np.abs(want).max()
