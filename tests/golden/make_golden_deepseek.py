@@ -57,7 +57,10 @@ def jitter_(t, lo, hi):
         t.copy_(lo + (hi - lo) * torch.rand_like(t))
 
 
-def main():
+def build_block(DU=DU):
+    """The fixture's block, built from a fixed RNG state on the wrapper classes of `DU` (the reference's
+    deepseekv3_utils; tests/test_dropin_reference_wrappers.py passes a copy of that file whose flatquant.* imports
+    resolve to flatquant_b200.*).  Returns (block, args, transforms, linears)."""
     torch.manual_seed(2024)
     np.random.seed(2024)
     args = M.ModelArgs(**ARGS)
@@ -96,7 +99,20 @@ def main():
         jitter_(fl.clip_factor_w_min, 3.0, 5.0)
     attn.reparameterize()
     ffn.reparameterize()
+    return block, args, transforms, linears
 
+
+def fixture_input(args):
+    torch.manual_seed(7)
+    x = torch.randn(BSZ, SEQ, args.dim)
+    freqs = M.precompute_freqs_cis(args)[:SEQ]
+    mask = torch.full((SEQ, SEQ), float("-inf")).triu_(1)
+    return x, freqs, mask
+
+
+def main():
+    block, args, transforms, linears = build_block()
+    attn, ffn = block.attn, block.ffn
     rec = {f"arg_{k}": np.asarray(v) for k, v in ARGS.items()}
     for name, tr in transforms.items():
         rec[f"{name}.matrix_left"] = tr.matrix_left.data.numpy()
@@ -120,10 +136,7 @@ def main():
         rec[name] = t.data.numpy()
     rec["softmax_scale"] = np.float32(attn.softmax_scale)
 
-    torch.manual_seed(7)
-    x = torch.randn(BSZ, SEQ, args.dim)
-    freqs = M.precompute_freqs_cis(args)[:SEQ]
-    mask = torch.full((SEQ, SEQ), float("-inf")).triu_(1)
+    x, freqs, mask = fixture_input(args)
     caps = {}
     hooks = []
 
