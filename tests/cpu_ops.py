@@ -13,6 +13,96 @@ from oracle import flatq_oracle as O
 
 EMULATE_FP16 = True
 
+# ---------------------------------------------------------------------------------------------------------------------
+# STRICT: every stand-in first applies the argument checks the real call would apply -- the ones of flatquant_b200/ops.py
+# (contiguity) and of the C ABI (flatquant_b200/csrc/api.cu: shapes, divisibility, 16-byte alignment, supported factor
+# sizes) plus the element types the kernels read through raw pointers (an fp16 tensor handed to a `const float*` is
+# silent garbage on the GPU and invisible to an oracle-backed stand-in that calls .float()).  A host-logic test that
+# passes here therefore only makes calls the CUDA library accepts.  Activation dtype checks apply in the deployed mode
+# (EMULATE_FP16); the fp32 wiring tests run the same code with ACT_DTYPE = float32 on purpose.
+STRICT = True
+CALLS = []  # (op, config) of every call, for tests that want to see which kernel configurations a model exercises
+
+
+class AbiViolation(AssertionError):
+    pass
+
+
+def _req(cond, msg):
+    if STRICT and not cond:
+        raise AbiViolation(msg)
+
+
+def _contig(**ts):
+    for name, t in ts.items():
+        if t is not None:
+            _req(t.is_contiguous(), f"{name}: ops._need_cuda needs contiguous tensors")
+
+
+def _al16(t, elem_bytes, name):
+    """16-byte alignment of the address the GPU would see (allocations are >= 256-byte aligned; the offset counts)."""
+    if t is not None:
+        _req((t.storage_offset() * elem_bytes) % 16 == 0, f"{name}: not 16-byte aligned (offset {t.storage_offset()} elements)")
+
+
+def _act_dtype(t, name):
+    if EMULATE_FP16 and t is not None:
+        _req(t.dtype == torch.float16, f"{name}: the kernels read fp16, got {t.dtype}")
+
+
+def _dtype(t, want, name):
+    if t is not None:
+        _req(t.dtype == want, f"{name}: the kernel reads {want}, got {t.dtype}")
+
+
+def _check_kron(tokens, n1, n2, left, right, quant, z_out, x, out8):
+    """launch_kron / launch_kron_tc of api.cu: which kernel a (n1, n2) request lands on, or a refusal."""
+    _req(tokens > 0, "kron: no tokens (api.cu launch_kron)")
+    _al16(x, 2, "kron x")
+    _act_dtype(x, "kron x"), _act_dtype(left, "left factor"), _act_dtype(right, "right factor")
+    if left is not None:
+        _req(tuple(left.shape) == (n1, n1), f"left factor {tuple(left.shape)} != ({n1}, {n1})")
+    if right is not None:
+        _req(tuple(right.shape) == (n2, n2), f"right factor {tuple(right.shape)} != ({n2}, {n2})")
+    if quant and not z_out and (n1 * n2) % 32 == 0:
+        if (n2 == 64 and (32 <= n1 <= 64)) or (n2 == 128 and 32 < n1 <= 128):
+            return "tcgen05"
+    _req(1 <= n1 <= 256 and 16 <= n2 <= 256 and n2 % 16 == 0,
+         f"unsupported Kronecker factor sizes ({n1}, {n2}): need n2 % 16 == 0 and n1, n2 <= 256")
+    p1 = (n1 + 15) // 16 * 16
+    wpt, kt2 = p1 // 16, n2 // 16
+    _req(wpt * 32 <= (512 if kt2 <= 8 else 256), f"Kronecker factors ({n1}, {n2}) need {wpt} warps per token")
+    smem = ((p1 * (p1 + 8) * 2 if left is not None else 0) + (n2 * (n2 + 8) * 2 if right is not None else 0) +
+            p1 * (n2 + 8) * 2 + 16 * 2 * 4 + 16)  # one token per CTA
+    _req(smem <= 227 * 1024, f"Kronecker factors ({n1}, {n2}) exceed shared memory")
+    return "hmma"
+
+
+def _check_rowquant(x, tokens, k):
+    _req(tokens > 0 and k > 0 and k % 8 == 0, f"quantize_rows: K={k} must be a multiple of 8 and tokens > 0")
+    _al16(x, 2, "rowquant x"), _act_dtype(x, "rowquant x")
+
+
+def _check_gemm(m, n, k, xq8, s_x, w_packed, s_w, bias, out, out_dtype):
+    _req(m > 0 and n > 0 and k > 0, f"empty GEMM {m}x{n}x{k} (api.cu launch_gemm)")
+    _req(k % 32 == 0, f"gemm_w4a8: K={k} must be a multiple of 32")
+    _req(k <= 65536, "GEMM too large")
+    _req(n % 2 == 0, f"N={n} must be even for 16-bit outputs")
+    _req((m + 256) * n < (1 << 32), "output exceeds the 32-bit element index of the store path")
+    _req(tuple(w_packed.shape) == (n, k // 2), f"w_packed {tuple(w_packed.shape)} != ({n}, {k // 2})")
+    _dtype(xq8, torch.int8, "xq8"), _dtype(w_packed, torch.uint8, "w_packed")
+    _dtype(s_x, torch.float32, "s_x"), _dtype(s_w, torch.float32, "s_w")
+    _req(s_x.numel() == m and s_w.numel() == n, "scale sizes")
+    _al16(xq8, 1, "xq8 (TMA)"), _al16(w_packed, 1, "w_packed (TMA)")
+    _req(out_dtype in (torch.float16, torch.bfloat16) or not EMULATE_FP16, f"gemm_w4a8: out_dtype {out_dtype}")
+    if bias is not None:
+        _req(bias.numel() == n, "bias size")
+        if EMULATE_FP16:
+            _dtype(bias, out_dtype, "bias (read as the output type)")
+    if out is not None:
+        _req(tuple(out.shape) == (m, n) and out.is_contiguous(), "out must be a contiguous [M, N] tensor")
+        _req((out.storage_offset() * 2) % 4 == 0, "out: 32-bit stores")
+
 
 def _h(t):
     return t.half().float() if EMULATE_FP16 else t.float()
@@ -28,8 +118,16 @@ def _transform(x2, left, right, n1, n2):
 
 
 def kron_transform(x, left, right, n1, n2):
+    _contig(x=x, left=left, right=right)
     if left is None:
+        rows = x.numel() // n2
+        g = next(c for c in (16, 8, 4, 2, 1) if rows % c == 0)  # the grouping ops.kron_transform applies
+        CALLS.append(("kron_transform", (g, n2, False, right is not None)))
+        _check_kron(rows // g, g, n2, None, right, False, True, x, False)
         n1 = 1
+    else:
+        CALLS.append(("kron_transform", (n1, n2, True, right is not None)))
+        _check_kron(x.numel() // (n1 * n2), n1, n2, left, right, False, True, x, False)
     return _transform(x.reshape(-1, n1 * n2), left, right, n1, n2).to(x.dtype).reshape(x.shape)
 
 
@@ -44,6 +142,19 @@ def _scale_codes(z, clip_max, clip_min):
 def act_quant(x, left, right, n1, n2, clip_max=1.0, clip_min=1.0, out=None):
     """(codes int8 [M, K] -- natural K order, the format is opaque to callers --, s_x fp32 [M])"""
     k = n1 * n2
+    _contig(x=x, left=left, right=right)
+    _req(k % 32 == 0, f"act_quant: K={k} must be a multiple of 32")
+    m = x.numel() // k
+    if left is None and right is None:
+        _check_rowquant(x, m, k)
+        CALLS.append(("act_quant", ("rowquant", k)))
+    else:
+        CALLS.append(("act_quant", (_check_kron(m, n1, n2, left, right, True, False, x, True), n1, n2,
+                                    left is not None, right is not None)))
+    if out is not None:
+        _contig(xq8=out[0], s_x=out[1])
+        _dtype(out[0], torch.int8, "act_quant out codes"), _dtype(out[1], torch.float32, "act_quant out scales")
+        _al16(out[0], 1, "act_quant xq8")
     z = _transform(x.reshape(-1, k), left, right, n1, n2)
     q, s = _scale_codes(z, clip_max, clip_min)
     if out is not None:
@@ -54,16 +165,25 @@ def act_quant(x, left, right, n1, n2, clip_max=1.0, clip_min=1.0, out=None):
 
 
 def transform_quant(x, left, right, n1, n2, clip_max=1.0, clip_min=1.0):
+    _req((n1 * n2) % 32 == 0 or (left is None and right is None), "transform_quant: packed rows must be 16-byte multiples")
     q, s = act_quant(x, left, right, n1, n2, clip_max, clip_min)
     return torch.from_numpy(O.pack_i4(q.numpy())), s.half(), s
 
 
 def quantize_rows(x, clip_max=1.0, clip_min=1.0, half_math=True):
+    _contig(x=x)
+    _check_rowquant(x, x.numel() // x.shape[-1], x.shape[-1])
     q, s = _scale_codes(x.reshape(-1, x.shape[-1]).float(), clip_max, clip_min)
     return torch.from_numpy(O.pack_i4(q.numpy())), s.half(), s
 
 
 def gemm_w4a8(xq8, s_x, w_packed, s_w, bias=None, out_dtype=torch.float16, out=None):
+    _contig(xq8=xq8, s_x=s_x, w_packed=w_packed, s_w=s_w, bias=bias)
+    m, k = xq8.shape
+    n = w_packed.shape[0]
+    _check_gemm(m, n, k, xq8, s_x, w_packed, s_w, bias, out, out_dtype)
+    CALLS.append(("gemm_w4a8", ("gemv" if m <= 2 and m * k <= 96 * 1024 else "split-k" if m <= 64 else
+                                "1sm-128" if m <= 128 else "2sm", m, n, k)))
     wq = O.unpack_i4(w_packed.numpy())
     acc = O.gemm_i4(xq8.numpy(), wq)
     y = O.sym_dequant(acc, s_x.numpy(), s_w.float().numpy(), None if bias is None else bias.float().numpy())
@@ -76,19 +196,46 @@ def gemm_w4a8(xq8, s_x, w_packed, s_w, bias=None, out_dtype=torch.float16, out=N
 
 def linear_fused(x, left, right, n1, n2, clip_max, clip_min, w_packed, s_w, bias=None, out_dtype=torch.float16):
     k = n1 * n2
+    _contig(x=x, left=left, right=right, w_packed=w_packed, s_w=s_w, bias=bias)
+    _req(x.shape[-1] == k and w_packed.shape[1] * 2 == k, "linear_fused: K mismatch")
+    _act_dtype(x, "linear_fused x"), _dtype(s_w, torch.float32, "linear_fused s_w")
+    if x.numel() == 0:
+        return torch.empty(x.shape[:-1] + (w_packed.shape[0],), dtype=out_dtype)
     q, s = act_quant(x.reshape(-1, k), left, right, n1, n2, clip_max, clip_min)
     return gemm_w4a8(q, s, w_packed, s_w, bias, out_dtype).reshape(x.shape[:-1] + (w_packed.shape[0],))
 
 
 def pack_i4(q):
+    _contig(q=q)
+    _req(q.shape[-1] % 16 == 0, f"pack_i4: cols={q.shape[-1]} must be a multiple of 16")
+    _al16(q, 1, "pack_i4 q")
     return torch.from_numpy(O.pack_i4(q.numpy()))
 
 
 def hadamard(x, scale=1.0):
+    _contig(x=x)
+    n = x.shape[-1]
+    _req(8 <= n <= 32768 and n & (n - 1) == 0, f"hadamard: n={n} must be a power of two in [8, 32768]")
+    _req(x.numel() > 0, "hadamard: rows"), _al16(x, 2, "hadamard x"), _act_dtype(x, "hadamard x")
     return torch.from_numpy(O.hadamard_transform(x.float().numpy(), scale)).to(x.dtype)
 
 
 def kv_quant(x, kv_data=None, kv_param=None, slot=None, layer=0, kv_select=0):
+    _contig(x=x, kv_data=kv_data, kv_param=kv_param, slot=slot)
+    tokens, heads, d = x.shape
+    _req(d == 128, f"kv_quant: head_dim={d} (only 128)")
+    _req(tokens > 0 and heads > 0, "kv_quant: empty")
+    _dtype(x, torch.float16, "kv_quant x")
+    if kv_data is not None:
+        _req(kv_param is not None and slot is not None and kv_select in (0, 1) and 0 <= layer < kv_data.shape[1],
+             "kv_quant: paged-cache arguments")
+        _dtype(kv_data, torch.uint8, "kv_data"), _dtype(kv_param, torch.float16, "kv_param"), _dtype(slot, torch.int32, "slot")
+        _req(slot.numel() == tokens, "kv_quant: one slot per token")
+        _req(kv_data.dim() == 6 and kv_data.shape[2] == 2 and kv_data.shape[3] == heads and kv_data.shape[5] == d // 2,
+             f"kv_data layout {tuple(kv_data.shape)}")
+        _req(tuple(kv_param.shape) == tuple(kv_data.shape[:5]) + (2,), f"kv_param layout {tuple(kv_param.shape)}")
+        _req(int(slot.max()) < kv_data.shape[0] * kv_data.shape[4] and int(slot.min()) >= 0, "kv_quant: slot out of the page pool")
+    CALLS.append(("kv_quant", (heads, kv_data is not None)))
     packed, s, z = O.kv_asym_quant(x)  # x fp16 [tokens, heads, d]: the reference's fp16 op-by-op arithmetic
     par = torch.cat([s, z], -1).to(torch.float16)
     if kv_data is not None:
@@ -100,8 +247,18 @@ def kv_quant(x, kv_data=None, kv_param=None, slot=None, layer=0, kv_select=0):
 
 
 def kv_decode_i4(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, layer=0, sm_scale=None):
+    _contig(q=q, kv_data=kv_data, kv_param=kv_param, kv_indptr=kv_indptr, kv_indices=kv_indices, last_page_len=last_page_len)
     b, hq, d = q.shape
     hkv, ps = kv_data.shape[3], kv_data.shape[4]
+    _req(d == 128, f"kv_decode: head_dim={d} (only 128)")
+    _req(b > 0 and hq > 0 and hkv > 0 and hq % hkv == 0, "kv_decode: heads")
+    _act_dtype(q, "kv_decode q"), _dtype(kv_data, torch.uint8, "kv_data"), _dtype(kv_param, torch.float16, "kv_param")
+    for name, t in (("kv_indptr", kv_indptr), ("kv_indices", kv_indices), ("last_page_len", last_page_len)):
+        _dtype(t, torch.int32, name)
+    _req(kv_indptr.numel() == b + 1 and last_page_len.numel() == b, "kv_decode: page-table sizes")
+    _req(int(kv_indices.max()) < kv_data.shape[0], "kv_decode: page index out of the pool")
+    _req(0 < int(last_page_len.min()) and int(last_page_len.max()) <= ps, "kv_decode: last_page_len in (0, page_size]")
+    CALLS.append(("kv_decode_i4", (hq, hkv, ps)))
     outs = []
     for i in range(b):
         pages = kv_indices[kv_indptr[i]:kv_indptr[i + 1]].long()
