@@ -214,6 +214,7 @@ int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, i
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = acc_shift;
     p.out = out; p.s_x = sx; p.s_w = sw; p.bias = bias; p.prof = nullptr; p.dbg = 0; p.k_splits = k_splits;
     p.streamk = 0; p.sk_part = nullptr; p.sk_flags = nullptr; p.epoch = 0;
+    p.grp_off = nullptr; p.grp_tile = nullptr; p.n_groups = 0; p.t_upper = 0;
     {
         // Stream-K on the partial last wave: worth it when the tail's K stages, dealt to all SMs, finish at least two
         // stages earlier than whole tiles would, and every part is long enough to amortise its fix-up.
@@ -242,6 +243,32 @@ int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, i
         case kEpiBF16: return launch_gemm_m<kEpiBF16>(tn, tw, tx, p, st);
     }
     return fail(FLATQ_ERR_INVALID, "bad epilogue mode %d", mode);
+}
+
+// ---- grouped (mixture-of-experts) GEMM: the single-CTA kernel with the schedule of csrc/grouped_sched.h
+template <int TN, int MODE>
+int launch_gemm_grouped_t(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, cudaStream_t st) {
+    auto kern = gemm_w4a8_kernel<TN, MODE, false, true>;
+    constexpr int smem = GemmSmem<TN>::kBytes;
+    static bool attr_set = false;  // benign race: idempotent
+    if (!attr_set) {
+        FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int grid = p.t_upper < num_sms() ? p.t_upper : num_sms();
+    FLATQ_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, st, tw, tx, p));
+    return FLATQ_OK;
+}
+
+template <int MODE>
+int launch_gemm_grouped_m(int tn, const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, cudaStream_t st) {
+    switch (tn) {
+        case 16: return launch_gemm_grouped_t<16, MODE>(tw, tx, p, st);
+        case 32: return launch_gemm_grouped_t<32, MODE>(tw, tx, p, st);
+        case 64: return launch_gemm_grouped_t<64, MODE>(tw, tx, p, st);
+        case 128: return launch_gemm_grouped_t<128, MODE>(tw, tx, p, st);
+        default: return launch_gemm_grouped_t<256, MODE>(tw, tx, p, st);
+    }
 }
 
 // ---- Kronecker transform (+quant) launch
@@ -608,6 +635,49 @@ int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed
     return FLATQ_OK;
 }
 
+size_t flatq_gemm_w4a8_grouped_workspace_bytes(int n_groups) {
+    return align_up((size_t)(n_groups > 0 ? n_groups + 1 : 1) * sizeof(int32_t), 256);
+}
+
+int flatq_gemm_w4a8_grouped(const int8_t* xq8, const float* s_x, const uint8_t* w_packed, const float* s_w,
+                            const void* bias, const int32_t* group_offsets, int n_groups, int64_t M, int64_t N, int64_t K,
+                            int rows_per_group_hint, void* y, int out_dtype, void* ws, size_t ws_bytes,
+                            flatq_stream_t stream) {
+    FLATQ_CHECK(xq8 && s_x && w_packed && s_w && group_offsets && y && ws, FLATQ_ERR_INVALID, "gemm_w4a8_grouped: null pointer");
+    FLATQ_CHECK(out_dtype == FLATQ_F16 || out_dtype == FLATQ_BF16, FLATQ_ERR_INVALID, "gemm_w4a8_grouped: out_dtype");
+    FLATQ_CHECK(n_groups >= 1 && n_groups <= 65536, FLATQ_ERR_INVALID, "gemm_w4a8_grouped: n_groups=%d", n_groups);
+    FLATQ_CHECK(M > 0 && N > 0 && K > 0, FLATQ_ERR_INVALID, "gemm_w4a8_grouped: empty GEMM %lldx%lldx%lld", (long long)M,
+                (long long)N, (long long)K);
+    FLATQ_CHECK(K % 32 == 0 && K <= 65536, FLATQ_ERR_INVALID, "gemm_w4a8_grouped: K=%lld must be a multiple of 32, <= 65536",
+                (long long)K);
+    FLATQ_CHECK(N % 2 == 0, FLATQ_ERR_UNSUPPORTED, "gemm_w4a8_grouped: N=%lld must be even", (long long)N);
+    FLATQ_CHECK((M + 256) * N < (1ll << 32) && (int64_t)n_groups * N < (1ll << 31), FLATQ_ERR_UNSUPPORTED,
+                "gemm_w4a8_grouped: output / stacked weight exceeds the 32-bit index of the store path");
+    FLATQ_CHECK(ws_bytes >= flatq_gemm_w4a8_grouped_workspace_bytes(n_groups) && (reinterpret_cast<uintptr_t>(ws) & 3) == 0,
+                FLATQ_ERR_WORKSPACE, "gemm_w4a8_grouped: workspace too small or misaligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t hint = rows_per_group_hint > 0 ? rows_per_group_hint : (M + n_groups - 1) / n_groups;
+    const int tn = hint <= 16 ? 16 : hint <= 32 ? 32 : hint <= 64 ? 64 : hint <= 128 ? 128 : 256;
+    const int64_t nb_w = (N + kGemmBlockW - 1) / kGemmBlockW;
+    const int64_t t_upper = nb_w * ((M + tn - 1) / tn + n_groups);  // every group adds at most one partial token block
+    FLATQ_CHECK(t_upper < (1ll << 31), FLATQ_ERR_UNSUPPORTED, "gemm_w4a8_grouped: too many tiles");
+    CUtensorMap tw, tx;
+    int rc = make_map_u8(&tw, w_packed, (uint64_t)n_groups * N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_u8(&tx, xq8, M, K, K, 128, tn, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    int* tile_prefix = reinterpret_cast<int*>(ws);
+    grouped_prefix_kernel<<<1, 32, 0, st>>>(group_offsets, n_groups, tn, (int)nb_w, tile_prefix);
+    FLATQ_CUDA(cudaGetLastError());
+    GemmParams p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = 4;
+    p.out = y; p.s_x = s_x; p.s_w = s_w; p.bias = bias; p.prof = nullptr; p.dbg = 0; p.k_splits = 1;
+    p.streamk = 0; p.sk_part = nullptr; p.sk_flags = nullptr; p.epoch = 0;
+    p.grp_off = group_offsets; p.grp_tile = tile_prefix; p.n_groups = n_groups; p.t_upper = (int)t_upper;
+    return out_dtype == FLATQ_F16 ? launch_gemm_grouped_m<kEpiF16>(tn, tw, tx, p, st)
+                                  : launch_gemm_grouped_m<kEpiBF16>(tn, tw, tx, p, st);
+}
+
 int flatq_linear_fused(const void* x, const void* left, const void* right, int n1, int n2, float clip_max,
                        float clip_min, const uint8_t* w_packed, const float* s_w, const void* bias, int64_t M, int64_t N,
                        void* y, int out_dtype, void* ws, size_t ws_bytes, flatq_stream_t stream) {
@@ -697,6 +767,7 @@ int flatq_debug_gemm_profile(const int8_t* xq8, const float* s_x, const uint8_t*
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = 4;
     p.out = y; p.s_x = s_x; p.s_w = s_w; p.bias = nullptr; p.prof = prof; p.dbg = dbg; p.k_splits = 1;
     p.streamk = 0; p.sk_part = nullptr; p.sk_flags = nullptr; p.epoch = 0;
+    p.grp_off = nullptr; p.grp_tile = nullptr; p.n_groups = 0; p.t_upper = 0;
     auto kern = gemm_w4a8_kernel<256, kEpiF16, true>;
     constexpr int smem = GemmSmem<256>::kBytes;
     FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

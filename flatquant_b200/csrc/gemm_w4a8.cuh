@@ -36,6 +36,7 @@
 // Barriers per stage s:  full[s]  <- X bytes (expect_tx) + 4 expander warps;   empty[s] <- tcgen05.commit
 //                        wfull[s] <- W bytes;                                  wempty[s] <- 4 expander warps
 #pragma once
+#include "grouped_sched.h"
 #include "ptx.cuh"
 
 namespace flatq {
@@ -96,6 +97,13 @@ struct GemmParams {
     unsigned long long epoch;          // unique per launch (no zeroing of the workspace between launches)
     long long* prof;      // debug: per-CTA role timers (PROF instantiation only)
     int dbg;              // debug (PROF only): 1 skip TMEM stores, 2 skip MMA issue, 4 skip epilogue, 8 no X TMA, 16 no W TMA/LDS, 32 weight-blocks-fastest raster
+    // grouped (mixture-of-experts) launch, GROUPED instantiations only (csrc/grouped_sched.h): n_groups GEMMs sharing
+    // N and K; M = total rows of the sorted activation, s_w / bias are [n_groups, N], the W tensor map spans the
+    // stacked [n_groups * N, K / 2] weight.  Appended so that the plain instantiations' parameter offsets are unchanged.
+    const int* grp_off;   // [n_groups + 1] first row of every group (device; written by the router)
+    const int* grp_tile;  // [n_groups + 1] tile prefix (device; grouped_prefix_kernel, same stream, just before)
+    int n_groups;
+    int t_upper;          // host-side bound on the number of tiles: nb_w * (ceil(M / TN) + n_groups)
 };
 
 // ---- work schedule: every warp role walks the same list of units of its CTA
@@ -157,7 +165,7 @@ struct GemmSmem {
     static constexpr int kBytes = kStages * kXStageBytes + kStagesW * kWStageBytes + 1024 /*align*/ + 512 /*bars*/ + 1024 /*per-token scales of the tile being stored*/;
 };
 
-template <int TN, int MODE, bool PROF = false>
+template <int TN, int MODE, bool PROF = false, bool GROUPED = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                  const GemmParams p) {
@@ -201,7 +209,8 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     grid_dep_launch();  // PDL: the next kernel may begin its prologue as SMs free up
     // everything above overlapped the previous kernel's tail; its outputs are visible after the wait.  The W producer
     // (warp 2) skips it: the packed weights are static, so their first stages stream in while the dependency resolves.
-    if (warp != 2) grid_dep_wait();
+    // (a grouped launch reads its schedule from memory written by the preceding kernels: every role waits)
+    if (GROUPED || warp != 2) grid_dep_wait();
 
     const int nb_w = (p.N + kGemmBlockW - 1) / kGemmBlockW;
     const int nb_m = (p.M + TN - 1) / TN;
@@ -212,6 +221,10 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     const int splits = p.k_splits > 1 ? p.k_splits : 1;
     GemmSched sc;
     sc.G = (int)gridDim.x; sc.cta = (int)blockIdx.x; sc.KB = KB_all; sc.splits = splits; sc.T = nb_w * nb_m;
+    if constexpr (GROUPED) {
+        const int t_dev = __ldg(p.grp_tile + p.n_groups);   // tiles of this routing; never more than the host bound
+        sc.T = t_dev < p.t_upper ? t_dev : p.t_upper;
+    }
     sc.streamk = p.streamk;
     sc.F = sc.T - sc.T % sc.G;
     sc.Q = (sc.T - sc.F) * KB_all;
@@ -226,7 +239,9 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             for (int ui = 0;; ++ui) {
                 const GemmUnit u = sc.get(ui);
                 if (u.kind < 0) break;
-                const int m0 = (w_fast ? u.tile / nb_w : u.tile % nb_m) * TN;
+                int m0;
+                if constexpr (GROUPED) m0 = grouped_tile(p.grp_off, p.grp_tile, p.n_groups, TN, kGemmBlockW, u.tile).m0;
+                else m0 = (w_fast ? u.tile / nb_w : u.tile % nb_m) * TN;
                 for (int kb = u.kb0; kb < u.kb1; ++kb, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                     FLATQ_TWAIT(0, mbar_wait(&empty[s], ph ^ 1));
@@ -244,7 +259,13 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             for (int ui = 0;; ++ui) {
                 const GemmUnit u = sc.get(ui);
                 if (u.kind < 0) break;
-                const int n0 = (w_fast ? u.tile % nb_w : u.tile / nb_m) * kGemmBlockW;
+                int n0;  // row of the (stacked) packed weight
+                if constexpr (GROUPED) {
+                    const GroupTile gt = grouped_tile(p.grp_off, p.grp_tile, p.n_groups, TN, kGemmBlockW, u.tile);
+                    n0 = gt.group * p.N + gt.n0;
+                } else {
+                    n0 = (w_fast ? u.tile % nb_w : u.tile / nb_m) * kGemmBlockW;
+                }
                 for (int kb = u.kb0; kb < u.kb1; ++kb, ++it) {
                     const uint32_t s = it % kStagesW, ph = (it / kStagesW) & 1;
                     FLATQ_TWAIT(0, mbar_wait(&wempty[s], ph ^ 1));
@@ -350,8 +371,15 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         for (;; ++tile_iter) {
             const GemmUnit u = sc.get((int)tile_iter);
             if (u.kind < 0) break;
-            const int n0 = (w_fast ? u.tile % nb_w : u.tile / nb_m) * kGemmBlockW;
-            const int m0 = (w_fast ? u.tile / nb_w : u.tile % nb_m) * TN;
+            int n0, m0, m_end, ch0;  // ch0: offset of the group's per-channel scale / bias rows
+            if constexpr (GROUPED) {
+                const GroupTile gt = grouped_tile(p.grp_off, p.grp_tile, p.n_groups, TN, kGemmBlockW, u.tile);
+                n0 = gt.n0; m0 = gt.m0; m_end = gt.m_end < p.M ? gt.m_end : p.M; ch0 = gt.group * p.N;
+            } else {
+                n0 = (w_fast ? u.tile % nb_w : u.tile / nb_m) * kGemmBlockW;
+                m0 = (w_fast ? u.tile / nb_w : u.tile % nb_m) * TN;
+                m_end = p.M; ch0 = 0;
+            }
             const uint32_t b = tile_iter % NBUF, phb = (tile_iter / NBUF) & 1;
             const int n = n0 + q * 32 + lane;
             const bool n_ok = n < p.N;
@@ -359,10 +387,10 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             float sw_n = 0.f, bias_n = 0.f;
             if (MODE != kEpiI32) {
                 if (n_ok) {
-                    sw_n = p.s_w[n];
+                    sw_n = p.s_w[ch0 + n];
                     if (p.bias) {
-                        bias_n = MODE == kEpiF16 ? __half2float(reinterpret_cast<const __half*>(p.bias)[n])
-                                                 : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
+                        bias_n = MODE == kEpiF16 ? __half2float(reinterpret_cast<const __half*>(p.bias)[ch0 + n])
+                                                 : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[ch0 + n]);
                     }
                 }
             }
@@ -376,7 +404,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
 #pragma unroll
                     for (int i = lane; i < COLS; i += 32) {
                         const int m = m0 + c0 + i;
-                        const float v = m < p.M ? p.s_x[m] : 0.f;
+                        const float v = m < m_end ? p.s_x[m] : 0.f;
                         sx_s[c0 + i] = fold ? v * 0.0625f : v;
                     }
                 }
@@ -397,7 +425,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const int m = m0 + c0 + c * 16 + j;
-                            if (m < p.M && n_ok) {
+                            if (m < m_end && n_ok) {
                                 int32_t* dst = reinterpret_cast<int32_t*>(p.out) + (size_t)m * p.N + n;
                                 const int32_t val = static_cast<int32_t>(r[j]) >> p.acc_shift;  // exact per partial sum
                                 if (splits > 1) atomicAdd(dst, val); else *dst = val;
@@ -470,7 +498,7 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                     // (M + 256) * N < 2^32 is checked on the host.
                     uint16_t* const out16 = reinterpret_cast<uint16_t*>(p.out);
                     uint32_t idx = (uint32_t)(m0 + c0) * (uint32_t)p.N + (uint32_t)n;
-                    const int j_end = n_ok ? p.M - (m0 + c0) : 0;  // store only tokens m0 + c0 + j < M
+                    const int j_end = n_ok ? m_end - (m0 + c0) : 0;  // store only tokens m0 + c0 + j < M (< the group's end)
                     auto finish = [&](auto fold_c) {
                         constexpr bool FOLD = decltype(fold_c)::value;
 #pragma unroll
@@ -509,6 +537,11 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         tc_fence_after();
         tmem_dealloc<512>(tmem);
     }
+}
+
+// Tile prefix of a grouped launch, built on the device from the router's row offsets (no host read of the routing).
+__global__ void grouped_prefix_kernel(const int* __restrict__ off, int n_groups, int tn, int nb_w, int* __restrict__ tile_prefix) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) grouped_build_prefix(off, n_groups, tn, nb_w, tile_prefix);
 }
 
 }  // namespace flatq

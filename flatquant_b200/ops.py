@@ -60,6 +60,7 @@ class _Workspace:
 
 _ws = _Workspace()
 _ws2 = _Workspace()
+_ws3 = _Workspace()  # tile-prefix tables of grouped launches
 
 
 def pack_i4(q: torch.Tensor) -> torch.Tensor:
@@ -227,6 +228,32 @@ def gemm_w4a8(xq8: torch.Tensor, s_x: torch.Tensor, w_packed: torch.Tensor, s_w:
     ws = _ws2.get(dev, nb) if nb else None  # separate pool: xq8 / s_x usually live in the primary workspace
     _lib.check(lib.flatq_gemm_w4a8(_ptr(xq8), _ptr(s_x), _ptr(w_packed), _ptr(s_w), _ptr(bias), m, n, k, _ptr(y),
                                    _DT[out_dtype], _ptr(ws), ws.numel() if ws is not None else 0, _stream()), "gemm_w4a8")
+    return y
+
+
+def gemm_w4a8_grouped(xq8: torch.Tensor, s_x: torch.Tensor, w_packed: torch.Tensor, s_w: torch.Tensor,
+                      group_offsets: torch.Tensor, bias=None, out_dtype=torch.float16, out=None,
+                      rows_per_group_hint: int = 0) -> torch.Tensor:
+    """One launch for the FlatLinears of all routed experts of a stage (DeepSeek block, BASELINE configs[4]):
+    rows [group_offsets[e], group_offsets[e + 1]) of xq8 [M, K] (tokens sorted by expert) are multiplied with
+    w_packed[e] ([E, N, K/2]) and scaled by s_x[m] * s_w[e, n] (+ bias[e, n]) -> y [M, N].  `group_offsets` is an int32
+    DEVICE tensor [E + 1]; nothing of the routing is read on the host.  Bit-identical to E gemm_w4a8 calls."""
+    dev = _need_cuda(xq8, s_x, w_packed, s_w, group_offsets, bias)
+    m, k = xq8.shape
+    e, n, kp = w_packed.shape
+    if kp * 2 != k or tuple(s_w.shape) != (e, n) or group_offsets.numel() != e + 1:
+        raise RuntimeError(f"gemm_w4a8_grouped: shapes xq8 {tuple(xq8.shape)}, w_packed {tuple(w_packed.shape)}, "
+                           f"s_w {tuple(s_w.shape)}, group_offsets {tuple(group_offsets.shape)}")
+    if group_offsets.dtype != torch.int32 or s_x.dtype != torch.float32 or s_w.dtype != torch.float32:
+        raise RuntimeError("gemm_w4a8_grouped: group_offsets must be int32, scales float32")
+    y = out if out is not None else torch.empty((m, n), dtype=out_dtype, device=dev)
+    if m == 0:
+        return y
+    lib = _lib.load()
+    ws = _ws3.get(dev, lib.flatq_gemm_w4a8_grouped_workspace_bytes(e))
+    _lib.check(lib.flatq_gemm_w4a8_grouped(_ptr(xq8), _ptr(s_x), _ptr(w_packed), _ptr(s_w), _ptr(bias),
+                                           _ptr(group_offsets), e, m, n, k, int(rows_per_group_hint), _ptr(y),
+                                           _DT[out_dtype], _ptr(ws), ws.numel(), _stream()), "gemm_w4a8_grouped")
     return y
 
 

@@ -131,6 +131,21 @@ int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed
                     int64_t M, int64_t N, int64_t K, void* y, int out_dtype, void* workspace, size_t workspace_bytes,
                     flatq_stream_t stream);
 
+/* ---- a6 for mixture-of-experts layers: the routed-expert FlatLinears of the DeepSeek block (BASELINE configs[4];
+ *      deepseek_v3/model.py:677-683 -- a Python loop over experts, each `expert(x[idx])` -- under
+ *      flatquant/model_tools/deepseekv3_utils.py:413-470).  ONE launch for all experts of a stage:
+ *        rows [group_offsets[e], group_offsets[e+1]) of xq8 / s_x / y belong to expert e  (tokens sorted by expert),
+ *        w_packed [n_groups, N, K/2], s_w [n_groups, N], bias [n_groups, N] or NULL,
+ *        y[m, :] = (xq8[m] . W_e^T) * s_x[m] * s_w[e, :] (+ bias[e, :])   -- bit-identical to n_groups flatq_gemm_w4a8 calls.
+ *      group_offsets is a DEVICE array (int32, n_groups + 1, non-decreasing, [0] == 0, [n_groups] <= M): the host does
+ *      not read the routing result.  rows_per_group_hint picks the token tile (<= 0: M / n_groups).
+ *      workspace >= flatq_gemm_w4a8_grouped_workspace_bytes(n_groups), 4-byte aligned. */
+size_t flatq_gemm_w4a8_grouped_workspace_bytes(int n_groups);
+int flatq_gemm_w4a8_grouped(const int8_t* xq8, const float* s_x, const uint8_t* w_packed, const float* s_w,
+                            const void* bias, const int32_t* group_offsets, int n_groups, int64_t M, int64_t N, int64_t K,
+                            int rows_per_group_hint, void* y, int out_dtype, void* workspace, size_t workspace_bytes,
+                            flatq_stream_t stream);
+
 /* ---- a14: qattention side path ------------------------------------------------------------------
  * flatq_hadamard: out = scale * x . H_n per row, n a power of two in [8, 32768], fp16 in/out, fp32 butterflies.
  *   Replaces fast_hadamard_transform.hadamard_transform (third-party/fast-hadamard-transform/csrc/

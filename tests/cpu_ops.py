@@ -194,6 +194,29 @@ def gemm_w4a8(xq8, s_x, w_packed, s_w, bias=None, out_dtype=torch.float16, out=N
     return y
 
 
+def gemm_w4a8_grouped(xq8, s_x, w_packed, s_w, group_offsets, bias=None, out_dtype=torch.float16, out=None,
+                      rows_per_group_hint=0):
+    _contig(xq8=xq8, s_x=s_x, w_packed=w_packed, s_w=s_w, group_offsets=group_offsets, bias=bias)
+    m, k = xq8.shape
+    e, n, kp = w_packed.shape
+    _req(kp * 2 == k and tuple(s_w.shape) == (e, n) and group_offsets.numel() == e + 1, "gemm_w4a8_grouped: shapes")
+    _dtype(group_offsets, torch.int32, "group_offsets"), _dtype(xq8, torch.int8, "xq8"), _dtype(w_packed, torch.uint8, "w_packed")
+    _dtype(s_x, torch.float32, "s_x"), _dtype(s_w, torch.float32, "s_w")
+    _req(m > 0 and n > 0 and k % 32 == 0 and k <= 65536 and n % 2 == 0, f"gemm_w4a8_grouped: {m}x{n}x{k}")
+    _req((m + 256) * n < (1 << 32) and e * n < (1 << 31), "gemm_w4a8_grouped: 32-bit index of the store path")
+    _al16(xq8, 1, "xq8 (TMA)"), _al16(w_packed, 1, "w_packed (TMA)")
+    off = group_offsets.tolist()
+    _req(off[0] == 0 and off[-1] <= m and all(a <= b for a, b in zip(off, off[1:])), f"group_offsets {off[:4]}...")
+    CALLS.append(("gemm_w4a8_grouped", (e, m, n, k)))
+    y = out if out is not None else torch.zeros((m, n), dtype=out_dtype)
+    for g in range(e):
+        if off[g + 1] > off[g]:
+            r = slice(off[g], off[g + 1])
+            y[r] = gemm_w4a8(xq8[r], s_x[r], w_packed[g], s_w[g], None if bias is None else bias[g], out_dtype)
+            CALLS.pop()
+    return y
+
+
 def linear_fused(x, left, right, n1, n2, clip_max, clip_min, w_packed, s_w, bias=None, out_dtype=torch.float16):
     k = n1 * n2
     _contig(x=x, left=left, right=right, w_packed=w_packed, s_w=s_w, bias=bias)
@@ -274,7 +297,8 @@ def kv_decode_i4(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, lay
     return torch.cat(outs).to(q.dtype)
 
 
-FUNCTIONS = ("kron_transform", "act_quant", "transform_quant", "quantize_rows", "gemm_w4a8", "linear_fused", "pack_i4",
+FUNCTIONS = ("kron_transform", "act_quant", "transform_quant", "quantize_rows", "gemm_w4a8", "gemm_w4a8_grouped",
+             "linear_fused", "pack_i4",
              "hadamard", "kv_quant", "kv_decode_i4")
 
 

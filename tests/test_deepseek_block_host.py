@@ -127,3 +127,40 @@ def test_random_block_runs(monkeypatch):
         y = block(torch.randn(1, 10, 512).half(), 0, cos, sin)
     assert y.shape == (1, 10, 512) and torch.isfinite(y).all()
     assert len(block.g_qkv) == 1 and block.g_qkv[0].w.shape[0] == 256 + 64 + 32  # equal clips: wq_a and wkv_a fused
+
+
+def test_grouped_routed_experts_equal_the_per_expert_loop(monkeypatch):
+    """`FlatQuantRoutedExperts(grouped=True)` -- one grouped GEMM launch per stage, row offsets of the expert-sorted
+    tokens kept on the device -- computes exactly what the per-expert loop computes (integer accumulation, same fp32
+    epilogue), with and without expert parallelism, including experts that receive no token."""
+    from flatquant_b200.moe import FlatQuantRoutedExperts
+    cpu_ops.install(monkeypatch)
+    torch.manual_seed(4)
+    T_, dim, inter, E, top_k = 23, 256, 128, 6, 2
+    mk = lambda n: (torch.eye(n) * 0.75 + torch.randn(n, n) * (0.5 / n ** 0.5)).half()  # noqa: E731
+    f1, f2 = (mk(16), mk(16)), (mk(8), mk(16))
+    w13 = torch.randint(0, 256, (E, 2 * inter, dim // 2), dtype=torch.uint8)
+    w2 = torch.randint(0, 256, (E, dim, inter // 2), dtype=torch.uint8)
+    s13, s2 = torch.rand(E, 2 * inter) * 0.02 + 0.01, torch.rand(E, dim) * 0.02 + 0.01
+    d1, d2 = (torch.rand(dim) + 0.5).half(), (torch.rand(inter) + 0.5).half()
+    x = torch.randn(T_, dim).half()
+    probs = torch.tensor([0.4, 0.3, 0.0, 0.2, 0.1, 0.0]).repeat(T_, 1)  # experts 2 and 5 receive nothing
+    indices = torch.multinomial(probs, top_k)
+    weights = torch.rand(T_, top_k).half()
+    for offset, sl in ((None, slice(0, E)), (0, slice(0, 3)), (3, slice(3, 6))):
+        args = (w13[sl].contiguous(), s13[sl].contiguous(), w2[sl].contiguous(), s2[sl].contiguous(), f1, f2,
+                (0.98, 0.97), (0.99, 0.98), d1, d2)
+        loop = FlatQuantRoutedExperts(*args, expert_offset=offset, grouped=False)
+        grouped = FlatQuantRoutedExperts(*args, expert_offset=offset, grouped=True)
+        cpu_ops.CALLS.clear()
+        y_loop = loop(x, weights, indices)
+        n_loop = sum(op == "gemm_w4a8" for op, _ in cpu_ops.CALLS)
+        cpu_ops.CALLS.clear()
+        y_grouped = grouped(x, weights, indices)
+        assert torch.equal(y_loop, y_grouped), offset
+        launched = [op for op, _ in cpu_ops.CALLS if op.startswith("gemm")]
+        assert launched == ["gemm_w4a8_grouped"] * 2 and n_loop > 2, (launched, n_loop)
+    # no pair for the local experts: both paths return zeros without launching
+    none = FlatQuantRoutedExperts(w13[2:3].contiguous(), s13[2:3].contiguous(), w2[2:3].contiguous(), s2[2:3].contiguous(),
+                                  f1, f2, expert_offset=2, grouped=True)
+    assert not none(x, weights, indices).any()
