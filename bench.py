@@ -463,6 +463,23 @@ def cpu_reference_pass(n_layers_sample, threads, reps, warm):
     return SEQ / (t_layer * N_LAYERS), t_layer
 
 
+def reference_gpu_kernels(device_index, our_gemm_ms_per_step):
+    """Baseline leg: the reference's own CUTLASS s4 GEMM + dequant kernels (oracle/_ref, built from /root/reference for
+    sm_100a) over the work of our GEMM-only pass, in a SUBPROCESS (tools/ref_kernels_bench.py) so that a fault inside a
+    reference kernel cannot touch this process's CUDA context.  Reported next to our number; never on our path."""
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_kernels_bench.py"), "--device",
+                              str(device_index)], capture_output=True, text=True, timeout=300)
+        last = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+        res = json.loads(last[-1]) if last else {"unavailable": (out.stderr or "no output")[-300:]}
+    except Exception as e:  # noqa: BLE001
+        res = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    if "ms_per_step" in res:
+        res["our_gemm_pass_ms_per_step"] = our_gemm_ms_per_step
+        res["speedup_of_our_gemm_pass"] = res["ms_per_step"] / our_gemm_ms_per_step
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -632,6 +649,16 @@ def main():
                          "traffic": 62.9e6, "traffic_unit": "bytes/launch", "algorithmic_bytes_per_launch": 85.0e6,
                          "issue_peak_note": "tcgen05 kind::i8 issue peak measured by tools/mma_rate.cu: 8185 MAC/cycle/SM"},
         }
+        # sustained figure of the same file: what a kernel timed inside a long step can be held against
+        try:
+            sus = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained")
+        except (OSError, ValueError):
+            sus = None
+        if sus:
+            line["roofline"]["peak_sustained"] = 2 * sus
+            line["roofline"]["frac_of_sustained"] = achieved / (2 * sus)
+        if world == 1 and args.layers == N_LAYERS:
+            line["reference_gpu_kernels"] = reference_gpu_kernels(local, ms_gemm / args.steps)
         if not args.no_cpu_baseline and world == 1:
             v, t_layer = cpu_reference_pass(1, threads, 2, 1)
             line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
