@@ -12,7 +12,7 @@
 // std::runtime_error (include/common.h:16-23); an exception crossing a ctypes call would abort the process, so every
 // wrapper catches and returns a status.  All reference kernels launch on the legacy default stream.
 //
-// Used by tests/test_zzr_reference_cuda_kernels_gpu.py (bit-level GPU parity of flatq_gemm_i4 / flatq_sym_quant /
+// Used by tests/test_zy_reference_cuda_kernels_gpu.py (bit-level GPU parity of flatq_gemm_i4 / flatq_sym_quant /
 // flatq_sym_dequant(mode 1) / flatq_kv_decode_i4 against the reference's kernels on the same B200) and by
 // tools/ref_kernels_bench.py (the reference's GEMM + dequant timed next to ours).
 #include <flashinfer.h>

@@ -8,8 +8,8 @@ GPU box, the reference tree does not):
     flatq_kv_decode_i4          ~=  FlashInferBatchDecodeKernel_i4<128> (flashinfer.cu:9-47) on the same paged INT4
                                     cache bytes (written by flatq_kv_quant): the storage layout is the reference's
 
-Sorted after the verified suite and the model-stack files: this is its first run on hardware (written after round 1's
-GPU minutes were spent).  If the reference library is absent, or the reference kernel itself refuses to run on this
+Sorted after the verified suite and before the model-stack files (zz): this is its first run on hardware (written after
+round 1's GPU minutes were spent), and under the driver's `-x` the simplest first-run checks go first.  If the reference library is absent, or the reference kernel itself refuses to run on this
 GPU, the test SKIPS with the reason -- a mismatch of results fails."""
 import numpy as np
 import pytest
