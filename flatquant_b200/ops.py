@@ -45,14 +45,19 @@ def _need_cuda(*ts):
 
 
 class _Workspace:
-    """Grow-only per-device scratch so steady-state calls do not allocate (CUDA-graph friendly)."""
+    """Grow-only per-device scratch so steady-state calls do not allocate (CUDA-graph friendly).  A buffer that is
+    outgrown is retired, not freed: a captured CUDA graph may still hold its address, and handing that memory back to
+    the allocator would let a later replay write into somebody else's tensor."""
 
     def __init__(self):
         self.buf = {}
+        self.retired = []
 
     def get(self, dev, nbytes):
         b = self.buf.get(dev)
         if b is None or b.numel() < nbytes:
+            if b is not None:
+                self.retired.append(b)
             b = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
             self.buf[dev] = b
         return b
