@@ -11,38 +11,45 @@ def round_ste(x):
 
 
 def get_qmin_qmax(bits, sym):
-    if sym:
-        hi = 2 ** (bits - 1) - 1
-        return torch.tensor(hi), torch.tensor(-hi - 1)
-    return torch.tensor(2 ** bits - 1), 0
+    """(q_max, q_min) of a `bits`-wide grid: symmetric [-2^(b-1), 2^(b-1)-1] as tensors, asymmetric [0, 2^b - 1]."""
+    if not sym:
+        return torch.tensor((1 << bits) - 1), 0
+    top = (1 << (bits - 1)) - 1
+    return torch.tensor(top), torch.tensor(-top - 1)
+
+
+def _to_grid(x, scale, zero, lo, hi):
+    """clamp(round_ste(x / scale) + zero, lo, hi): the one rounding step behind all four public helpers below."""
+    q = round_ste(x / scale)
+    return torch.clamp(q if zero is None else q + zero, lo, hi)
 
 
 def sym_quant(x, scale, maxq):
-    scale = scale.to(x.device)
-    return torch.clamp(round_ste(x / scale), -(maxq + 1), maxq), scale
-
-
-def sym_dequant(q, scale):
-    return scale * q
-
-
-def sym_quant_dequant(x, scale, maxq):
-    q, s = sym_quant(x, scale, maxq)
-    return sym_dequant(q, s)
+    """-> (codes in [-(maxq+1), maxq], scale on x's device)  (quant_utils.py:19-23)"""
+    s = scale.to(x.device)
+    return _to_grid(x, s, None, -(maxq + 1), maxq), s
 
 
 def asym_quant(x, scale, zero, maxq):
-    scale, zero = scale.to(x.device), zero.to(x.device)
-    return torch.clamp(round_ste(x / scale) + zero, 0, maxq), scale, zero
+    """-> (codes in [0, maxq], scale, zero)  (quant_utils.py:33-38)"""
+    s, z = scale.to(x.device), zero.to(x.device)
+    return _to_grid(x, s, z, 0, maxq), s, z
+
+
+def sym_dequant(q, scale):
+    return q * scale
 
 
 def asym_dequant(q, scale, zero):
-    return scale * (q - zero)
+    return (q - zero) * scale
+
+
+def sym_quant_dequant(x, scale, maxq):
+    return sym_dequant(*sym_quant(x, scale, maxq))
 
 
 def asym_quant_dequant(x, scale, zero, maxq):
-    q, s, z = asym_quant(x, scale, zero, maxq)
-    return asym_dequant(q, s, z)
+    return asym_dequant(*asym_quant(x, scale, zero, maxq))
 
 
 class ActivationQuantizer(torch.nn.Module):
