@@ -133,3 +133,40 @@ def test_activation_quantizer_vllm_signature(golden):
         sq = ActivationQuantizer(bits=4, sym=True)
         assert torch.equal(sq(x, torch.from_numpy(g["given_scale"]), torch.from_numpy(g["given_zero"])),
                            torch.from_numpy(g["sym_given"]))
+
+
+def test_c_abi_argument_errors_without_a_gpu(lib):
+    """SURVEY 8(b) "Errors": every entry point validates its arguments before touching the device and reports through
+    the status + flatq_last_error() pair (the reference throws std::runtime_error from `ensure()`).  The pointers below
+    are never dereferenced: each call is rejected by a host-side check."""
+    import ctypes
+    l = lib.load()
+    fake = ctypes.c_void_p(0x1000)   # non-null, 16-byte aligned, never touched
+    odd = ctypes.c_void_p(0x1004)    # misaligned
+    INVALID, UNSUPPORTED, WORKSPACE = -1, -2, -4
+
+    def err():
+        return l.flatq_last_error().decode()
+
+    assert l.flatq_pack_i4(None, fake, 4, 16, None) == INVALID and "null" in err()
+    assert l.flatq_pack_i4(fake, fake, 4, 24, None) == INVALID and "multiple of 16" in err()
+    assert l.flatq_unpack_i4(fake, fake, 4, 6, None) == INVALID and "multiple of 4" in err()
+    assert l.flatq_sym_quant(fake, fake, 4, 20, fake, None) == INVALID and "multiple of 8" in err()
+    assert l.flatq_gemm_i4(fake, fake, 8, 8, 48, fake, fake, 1 << 20, None) == INVALID and "multiple of 64" in err()
+    assert l.flatq_gemm_i4(fake, fake, 8, 8, 64, fake, fake, 16, None) == WORKSPACE and "workspace" in err()
+    assert l.flatq_hadamard(fake, fake, 4, 12, 1.0, None) == UNSUPPORTED and "power of two" in err()
+    assert l.flatq_kv_quant(fake, 4, 2, 64, fake, fake, None, None, None, 0, 1, 0, 1, None) == UNSUPPORTED and "head_dim" in err()
+    assert l.flatq_kv_decode_i4(fake, fake, fake, fake, fake, fake, fake, 1, 6, 4, 128, 16, 0, 1, 1.0, None) == INVALID
+    assert l.flatq_kron_transform(odd, None, fake, 4, 1, 128, fake, None) == INVALID and "aligned" in err()
+    assert l.flatq_act_quant(fake, fake, fake, 3, 5, 1.0, 1.0, 4, fake, fake, None) == INVALID and "multiple of 32" in err()
+    assert l.flatq_gemm_w4a8(fake, fake, fake, fake, None, 4, 8, 48, fake, 0, None, 0, None) == INVALID
+    assert l.flatq_gemm_w4a8(fake, fake, fake, fake, None, 4, 8, 64, fake, 7, None, 0, None) == INVALID and "out_dtype" in err()
+    assert l.flatq_linear_fused(fake, None, None, 1, 64, 1.0, 1.0, fake, fake, None, 4, 8, fake, 0, fake, 8, None) == WORKSPACE
+    g = l.flatq_gemm_w4a8_grouped
+    ws = l.flatq_gemm_w4a8_grouped_workspace_bytes(8)
+    assert ws >= 9 * 4
+    assert g(fake, fake, fake, fake, None, None, 8, 64, 128, 256, 0, fake, 0, fake, ws, None) == INVALID and "null" in err()
+    assert g(fake, fake, fake, fake, None, fake, 0, 64, 128, 256, 0, fake, 0, fake, ws, None) == INVALID and "n_groups" in err()
+    assert g(fake, fake, fake, fake, None, fake, 8, 64, 127, 256, 0, fake, 0, fake, ws, None) == UNSUPPORTED and "even" in err()
+    assert g(fake, fake, fake, fake, None, fake, 8, 64, 128, 250, 0, fake, 0, fake, ws, None) == INVALID
+    assert g(fake, fake, fake, fake, None, fake, 8, 64, 128, 256, 0, fake, 0, fake, 8, None) == WORKSPACE
