@@ -354,3 +354,82 @@ def test_vllm_custom_utility_copies_are_interchangeable_with_ours():
         theirs.configure(4, **kw), mine.configure(4, **kw)
         theirs.find_params(w), mine.find_params(w)
         assert torch.equal(mine.scale, theirs.scale) and torch.equal(mine.quantize(w), theirs.quantize(w)), kw
+
+
+@pytest.mark.parametrize("family", ["llama31_utils", "qwen_utils"])
+def test_other_model_families_wrappers_on_our_modules(family):
+    """The Llama-3.1 and Qwen2 wrappers of flatquant/model_tools (position_embeddings calling convention; Qwen2 with
+    q/k/v biases, whose v bias goes through the value-cache transform in reparameterize, flat_linear.py:95-96): same
+    check as for llama_utils -- reference modules vs flatquant_b200 modules under the unmodified wrapper file."""
+    from transformers import LlamaConfig, Qwen2Config
+    from transformers.models.llama.modeling_llama import LlamaAttention, LlamaMLP, LlamaRotaryEmbedding
+    from transformers.models.qwen2.modeling_qwen2 import Qwen2Attention, Qwen2MLP
+    _stub_missing_modules()
+    sys.path.insert(0, REF)
+    try:
+        path = os.path.join(REF, "flatquant", "model_tools", family + ".py")
+        ref_lu = _load_by_path(f"ref_{family}_on_reference_ops", path)
+        saved = {n: sys.modules.get(f"flatquant.{n}") for n in SWAPPED}
+        try:
+            for n in SWAPPED:
+                sys.modules[f"flatquant.{n}"] = importlib.import_module(f"flatquant_b200.{n}")
+            our_lu = _load_by_path(f"ref_{family}_on_b200_ops", path)
+        finally:
+            for n, m in saved.items():
+                if m is None:
+                    sys.modules.pop(f"flatquant.{n}", None)
+                else:
+                    sys.modules[f"flatquant.{n}"] = m
+    finally:
+        sys.path.remove(REF)
+    qwen = family == "qwen_utils"
+    kw = dict(CFG)
+    if qwen:
+        kw.pop("attention_bias"), kw.pop("mlp_bias")
+        cfg = Qwen2Config(**kw)
+    else:
+        cfg = LlamaConfig(**kw)
+    cfg._attn_implementation = "eager"
+    torch.manual_seed(7)
+    attn = (Qwen2Attention if qwen else LlamaAttention)(cfg, 0).float()
+    mlp = (Qwen2MLP if qwen else LlamaMLP)(cfg).float()
+    with torch.no_grad():
+        for p in list(attn.parameters()) + list(mlp.parameters()):
+            if p.dim() == 2:
+                p.normal_(0, 1.0 / p.shape[1] ** 0.5)
+            else:
+                p.normal_(0, 0.3)  # Qwen2's q/k/v biases
+    names = ("FlatQuantQwen2Attention", "FlatQuantQwen2MLP") if qwen else ("FlatQuantLlamaAttention", "FlatQuantLlamaMLP")
+    torch.manual_seed(3)
+    x = torch.randn(BSZ, SEQ, cfg.hidden_size)
+    pos = torch.arange(SEQ)[None].expand(BSZ, SEQ)
+    cos_sin = LlamaRotaryEmbedding(LlamaConfig(**CFG))(x, pos)
+    mask = torch.full((SEQ, SEQ), float("-inf")).triu(1)[None, None].expand(BSZ, 1, SEQ, SEQ)
+    outs = []
+    for lu in (ref_lu, our_lu):
+        args = types.SimpleNamespace(**ARGS)
+        torch.manual_seed(11)
+        np.random.seed(11)
+        at = getattr(lu, names[0])(args, copy.deepcopy(attn))
+        ml = getattr(lu, names[1])(args, copy.deepcopy(mlp))
+        at.num_heads, at.num_key_value_heads, at.hidden_size = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.hidden_size
+        gen = torch.Generator().manual_seed(5)
+        with torch.no_grad():
+            for name, p in list(at.named_parameters()) + list(ml.named_parameters()):
+                if "clip_factor" in name:
+                    p.copy_(2.5 + 2.5 * torch.rand(p.shape, generator=gen))
+                elif "linear_diag" in name or "diag_scale" in name:
+                    p.copy_(0.8 + 0.45 * torch.rand(p.shape, generator=gen))
+            a = at(x, mask, pos, None, False, False, position_embeddings=cos_sin)[0]
+            m = ml(x + a)
+            at.reparameterize(), ml.reparameterize()
+        outs.append((at, ml, a, m))
+    (r_at, r_ml, ra, rm), (o_at, o_ml, oa, om) = outs
+    from flatquant_b200.flat_linear import FlatQuantizedLinear
+    assert isinstance(o_at.v_proj, FlatQuantizedLinear) and not isinstance(r_at.v_proj, FlatQuantizedLinear)
+    assert torch.allclose(oa, ra, rtol=1e-5, atol=1e-6 * float(ra.abs().max()))
+    assert torch.allclose(om, rm, rtol=1e-5, atol=1e-6 * float(rm.abs().max()))
+    _same_state(r_at, o_at, exact=False)   # after reparameterize: baked weights, transformed v bias (Qwen2), eval matrices
+    _same_state(r_ml, o_ml, exact=False)
+    if qwen:
+        assert o_at.v_proj.linear.bias is not None and not torch.equal(o_at.v_proj.linear.bias, attn.v_proj.bias)
