@@ -21,6 +21,7 @@ run 600 verified_suite.log python -m pytest tests/test_gpu_parity.py -q
 run 300 ref_kernels.log python -m pytest tests/test_zy_reference_cuda_kernels_gpu.py -q -s
 run 300 zz_llama.log python -m pytest tests/test_zz_llama_model_gpu.py -q -s
 run 300 zz_deepseek.log python -m pytest tests/test_zz_deepseek_block_gpu.py -q -s
+run 300 zzv_shapes.log python -m pytest tests/test_zzv_full_size_transform_shapes_gpu.py -q -s
 FLATQ_RUN_UNVERIFIED=1 run 300 zzz_grouped.log python -m pytest tests/test_zzz_grouped_gemm_gpu.py -q -s
 run 400 bench_default.json python bench.py --steps 10 --warmup 3
 run 120 ref_kernels_bench.json python tools/ref_kernels_bench.py
