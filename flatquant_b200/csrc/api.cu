@@ -751,6 +751,55 @@ int flatq_kv_decode_i4(const void* q, void* o, const uint8_t* kv_data, const voi
     return FLATQ_OK;
 }
 
+// split-KV decode attention: partial softmax states of up to kDecMaxSplits splits per (batch, query head)
+static constexpr int kDecMaxSplits = 64;
+
+size_t flatq_kv_decode_i4_split_workspace_bytes(int batch, int q_heads) {
+    return align_up((size_t)(batch > 0 ? batch : 0) * (q_heads > 0 ? q_heads : 0) * kDecMaxSplits * kDecPartStride * sizeof(float), 256);
+}
+
+int flatq_kv_decode_i4_split(const void* q, void* o, const uint8_t* kv_data, const void* kv_param, const int32_t* kv_indptr,
+                             const int32_t* kv_indices, const int32_t* last_page_len, int batch, int q_heads, int kv_heads,
+                             int head_dim, int page_size, int layer, int n_layers, float sm_scale, int max_tokens_hint,
+                             void* ws, size_t ws_bytes, flatq_stream_t stream) {
+    FLATQ_CHECK(q && o && kv_data && kv_param && kv_indptr && kv_indices && last_page_len && ws, FLATQ_ERR_INVALID,
+                "kv_decode_split: null pointer");
+    FLATQ_CHECK(head_dim == 128, FLATQ_ERR_UNSUPPORTED, "kv_decode_split: head_dim=%d (only 128)", head_dim);
+    FLATQ_CHECK(batch > 0 && q_heads > 0 && kv_heads > 0 && q_heads % kv_heads == 0, FLATQ_ERR_INVALID, "kv_decode_split: heads");
+    FLATQ_CHECK(page_size > 0 && n_layers > 0 && layer >= 0 && layer < n_layers, FLATQ_ERR_INVALID, "kv_decode_split: cache arguments");
+    FLATQ_CHECK(aligned16(q) && aligned16(kv_data) && (reinterpret_cast<uintptr_t>(ws) & 15) == 0, FLATQ_ERR_INVALID,
+                "kv_decode_split: alignment");
+    FLATQ_CHECK(ws_bytes >= flatq_kv_decode_i4_split_workspace_bytes(batch, q_heads), FLATQ_ERR_WORKSPACE,
+                "kv_decode_split: workspace too small");
+    const int G = q_heads / kv_heads;
+    const int gh = G % 4 == 0 ? 4 : G % 2 == 0 ? 2 : 1;
+    const int64_t base = (int64_t)batch * kv_heads * (G / gh);
+    // enough CTAs for two per SM, but no split shorter than 64 tokens (4 chunks of 16) when the caller bounds the length
+    int64_t splits = (2 * (int64_t)num_sms() + base - 1) / base;
+    if (max_tokens_hint > 0) {
+        const int64_t by_len = ((int64_t)max_tokens_hint + 63) / 64;
+        if (splits > by_len) splits = by_len;
+    }
+    if (splits > kDecMaxSplits) splits = kDecMaxSplits;
+    if (splits < 1) splits = 1;
+    DecodeParams p;
+    p.q = reinterpret_cast<const __half*>(q); p.o = reinterpret_cast<__half*>(o);
+    p.kv_data = kv_data; p.kv_param = reinterpret_cast<const __half*>(kv_param);
+    p.kv_indptr = kv_indptr; p.kv_indices = kv_indices; p.last_page_len = last_page_len;
+    p.batch = batch; p.q_heads = q_heads; p.kv_heads = kv_heads; p.D = head_dim; p.page_size = page_size;
+    p.layer = layer; p.n_layers = n_layers; p.sm_scale = sm_scale;
+    float* part = reinterpret_cast<float*>(ws);
+    const dim3 grid((unsigned)splits, (unsigned)(kv_heads * (G / gh)), (unsigned)batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gh == 4) decode_attn_i4_split_kernel<4><<<grid, kDecSplitThreads, 0, st>>>(p, (int)splits, part);
+    else if (gh == 2) decode_attn_i4_split_kernel<2><<<grid, kDecSplitThreads, 0, st>>>(p, (int)splits, part);
+    else decode_attn_i4_split_kernel<1><<<grid, kDecSplitThreads, 0, st>>>(p, (int)splits, part);
+    FLATQ_CUDA(cudaGetLastError());
+    decode_attn_merge_kernel<<<batch * q_heads, 128, 0, st>>>(part, (int)splits, reinterpret_cast<__half*>(o));
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
 // Debug only (not part of the public header): select the GEMM variants listed at opt_gemm_1sm(); -1 = from the environment
 void flatq_debug_set_gemm_options(int one_sm, int streamk) { g_gemm_1sm = one_sm; g_streamk = streamk; }
 

@@ -208,4 +208,160 @@ __global__ void __launch_bounds__(128) decode_attn_i4_kernel(const DecodeParams 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ split-KV decode attention
+// The kernel above walks a sequence with one CTA per (batch, query head), one warp per token and no loads in flight
+// beyond the current token: at batch 1 that is 32 CTAs on 148 SMs, each serialising ~seq/4 dependent-load round trips,
+// and with grouped-query attention every query head of a group re-reads the same K/V rows.  This variant
+//   * gives a CTA ONE kv head and GH of its query heads (K/V bytes are read once per group, not once per query head),
+//   * splits the sequence over `splits` CTAs (flash-decoding) so that batch x kv_heads x splits fills the chip,
+//   * reads 8 bytes (16 dims) per lane: 8 lanes cover a 64-byte row, a warp covers 4 consecutive tokens = 256
+//     contiguous bytes of a page per load instruction, and the next chunk's loads are issued before the current
+//     chunk's arithmetic (software double buffering),
+//   * keeps, per 8-lane token group, an online-softmax state (m, l, acc[16 dims]) for each of the GH heads in registers;
+//     the 16 groups of a CTA are merged through shared memory, the splits by decode_attn_merge_kernel.
+// Partial results: part[((b * q_heads + hq) * splits + s) * 130 + {0..127: unnormalised output, 128: max, 129: sum}], fp32.
+// Same arithmetic as above (x_hat = nibble * scale - zero in fp32, scores scaled by sm_scale, fp32 online softmax) up to
+// the order of the fp32 sums.  Bytes per (token, kv head): 2 * (64 + 4), read once per head group of GH.
+constexpr int kDecSplitThreads = 128, kDecGroups = kDecSplitThreads / 8, kDecPartStride = 130;
+
+struct DecKvChunk { uint2 k, v; float2 kpar, vpar; };
+
+__device__ __forceinline__ void dec_load_chunk(const DecodeParams& p, int pg0, int hk, int t, int lane8, DecKvChunk& c) {
+    const int page = p.kv_indices[pg0 + t / p.page_size], off = t % p.page_size;
+    const size_t kidx = ((((size_t)page * p.n_layers + p.layer) * 2 + 0) * p.kv_heads + hk) * p.page_size + off;
+    const size_t vidx = kidx + (size_t)p.kv_heads * p.page_size;
+    c.k = reinterpret_cast<const uint2*>(p.kv_data + kidx * (p.D / 2))[lane8];
+    c.v = reinterpret_cast<const uint2*>(p.kv_data + vidx * (p.D / 2))[lane8];
+    c.kpar = __half22float2(reinterpret_cast<const __half2*>(p.kv_param)[kidx]);
+    c.vpar = __half22float2(reinterpret_cast<const __half2*>(p.kv_param)[vidx]);
+}
+
+// 16 nibbles of a uint2 (element 2j in the low nibble of byte j) -> x_hat[16] = nibble * scale - zero
+__device__ __forceinline__ void dec_dequant16(const uint2 raw, const float2 par, float (&x)[16]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        x[j] = fmaf((float)((raw.x >> (4 * j)) & 0xF), par.x, -par.y);
+        x[8 + j] = fmaf((float)((raw.y >> (4 * j)) & 0xF), par.x, -par.y);
+    }
+}
+
+template <int GH>  // query heads of one kv head handled by a CTA (1, 2 or 4)
+__global__ void __launch_bounds__(kDecSplitThreads)
+decode_attn_i4_split_kernel(const DecodeParams p, int splits, float* __restrict__ part) {
+    const int split = blockIdx.x, b = blockIdx.z;
+    const int G = p.q_heads / p.kv_heads, head_groups = G / GH;
+    const int hk = blockIdx.y / head_groups, hq0 = hk * G + (blockIdx.y % head_groups) * GH;
+    const int lane8 = threadIdx.x & 7, grp = threadIdx.x >> 3;   // 16-dim slice of the row; token group 0..15
+    // per token group: GH x 128 partial outputs, stored [d][lane8] (dim 16 * lane8 + d at d * 8 + lane8) and padded by 8
+    // words per group, so that the 4 groups x 8 lanes of a warp write 32 distinct banks
+    constexpr int kGrpStride = GH * 128 + 8;
+    __shared__ float s_m[kDecGroups][GH], s_l[kDecGroups][GH];
+    __shared__ float s_acc[kDecGroups * kGrpStride];
+
+    float qv[GH][16];
+#pragma unroll
+    for (int g = 0; g < GH; ++g) {
+        const uint4* qp = reinterpret_cast<const uint4*>(p.q + ((size_t)b * p.q_heads + hq0 + g) * p.D + 16 * lane8);
+        const uint4 lo = qp[0], hi = qp[1];
+        const __half2* h0 = reinterpret_cast<const __half2*>(&lo);
+        const __half2* h1 = reinterpret_cast<const __half2*>(&hi);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 a = __half22float2(h0[j]), c = __half22float2(h1[j]);
+            qv[g][2 * j] = a.x * p.sm_scale; qv[g][2 * j + 1] = a.y * p.sm_scale;
+            qv[g][8 + 2 * j] = c.x * p.sm_scale; qv[g][8 + 2 * j + 1] = c.y * p.sm_scale;
+        }
+    }
+    float m[GH], l[GH], acc[GH][16];
+#pragma unroll
+    for (int g = 0; g < GH; ++g) {
+        m[g] = -INFINITY; l[g] = 0.f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[g][d] = 0.f;
+    }
+
+    const int pg0 = p.kv_indptr[b], pg1 = p.kv_indptr[b + 1];
+    const int n_tok = (pg1 - pg0 - 1) * p.page_size + p.last_page_len[b];
+    const int per = (n_tok + splits - 1) / splits;           // tokens per split
+    const int t0 = split * per, t1 = min(n_tok, t0 + per);   // empty when t0 >= n_tok
+    const int n_iter = t1 > t0 ? (t1 - t0 + kDecGroups - 1) / kDecGroups : 0;   // uniform over the CTA: shuffles stay converged
+    DecKvChunk cur, nxt;
+    cur.k = cur.v = nxt.k = nxt.v = make_uint2(0, 0);
+    cur.kpar = cur.vpar = nxt.kpar = nxt.vpar = make_float2(0.f, 0.f);
+    if (n_iter > 0 && t0 + grp < t1) dec_load_chunk(p, pg0, hk, t0 + grp, lane8, cur);
+    for (int it = 0; it < n_iter; ++it) {
+        const int t = t0 + it * kDecGroups + grp;
+        const bool valid = t < t1;
+        if (it + 1 < n_iter && t + kDecGroups < t1) dec_load_chunk(p, pg0, hk, t + kDecGroups, lane8, nxt);
+        float xh[16];
+        dec_dequant16(cur.k, cur.kpar, xh);
+        float dot[GH];
+#pragma unroll
+        for (int g = 0; g < GH; ++g) {
+            float a = 0.f;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) a = fmaf(qv[g][d], xh[d], a);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            dot[g] = a;
+        }
+        dec_dequant16(cur.v, cur.vpar, xh);
+        if (valid) {
+#pragma unroll
+            for (int g = 0; g < GH; ++g) {
+                const float m_new = fmaxf(m[g], dot[g]);
+                const float corr = __expf(m[g] - m_new), pexp = __expf(dot[g] - m_new);   // m = -inf at first: corr = 0
+                l[g] = l[g] * corr + pexp;
+#pragma unroll
+                for (int d = 0; d < 16; ++d) acc[g][d] = fmaf(acc[g][d], corr, pexp * xh[d]);
+                m[g] = m_new;
+            }
+        }
+        cur = nxt;
+    }
+
+    // ---- merge the CTA's 16 token groups (thread j owns output dim j), publish one partial per (query head, split)
+#pragma unroll
+    for (int g = 0; g < GH; ++g) {
+        if (lane8 == 0) { s_m[grp][g] = m[g]; s_l[grp][g] = l[g]; }
+#pragma unroll
+        for (int d = 0; d < 16; ++d) s_acc[grp * kGrpStride + g * 128 + d * 8 + lane8] = acc[g][d];
+    }
+    __syncthreads();
+    const int j = threadIdx.x, jj = (j & 15) * 8 + (j >> 4);   // where dim j sits inside a group's [d][lane8] block
+#pragma unroll
+    for (int g = 0; g < GH; ++g) {
+        float mm = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < kDecGroups; ++r) mm = fmaxf(mm, s_m[r][g]);
+        float ll = 0.f, out = 0.f;
+#pragma unroll
+        for (int r = 0; r < kDecGroups; ++r) {
+            const float c = s_m[r][g] == -INFINITY ? 0.f : __expf(s_m[r][g] - mm);
+            ll = fmaf(s_l[r][g], c, ll);
+            out = fmaf(s_acc[r * kGrpStride + g * 128 + jj], c, out);
+        }
+        float* dst = part + (((size_t)b * p.q_heads + hq0 + g) * splits + split) * kDecPartStride;
+        dst[j] = out;
+        if (j == 0) { dst[128] = mm; dst[129] = ll; }
+    }
+}
+
+// grid = batch * q_heads, 128 threads (thread j = output dim j): combine the splits' partial softmax states
+__global__ void __launch_bounds__(128) decode_attn_merge_kernel(const float* __restrict__ part, int splits, __half* __restrict__ o) {
+    const float* src = part + (size_t)blockIdx.x * splits * kDecPartStride;
+    const int j = threadIdx.x;
+    float mm = -INFINITY;
+    for (int s = 0; s < splits; ++s) mm = fmaxf(mm, src[s * kDecPartStride + 128]);
+    float ll = 0.f, out = 0.f;
+    for (int s = 0; s < splits; ++s) {
+        const float ms = src[s * kDecPartStride + 128];
+        const float c = ms == -INFINITY ? 0.f : __expf(ms - mm);
+        ll = fmaf(src[s * kDecPartStride + 129], c, ll);
+        out = fmaf(src[s * kDecPartStride + j], c, out);
+    }
+    o[(size_t)blockIdx.x * 128 + j] = __float2half_rn(ll > 0.f ? out / ll : 0.f);
+}
+
 }  // namespace flatq

@@ -114,7 +114,11 @@ class MultiLayerPagedKVCache4Bit:
         b, q_len, hq, d = q.shape
         assert q_len == 1
         qt = self._transform(q.view(b, hq, d), k_inv_t)
-        o = ops.kv_decode_i4(qt.contiguous(), self.pages, self.scales, layer=layer_idx, **attention_kwargs)
+        # the split-KV kernel (opt-in) sizes its grid from a host-side bound of the length; in static (graph) mode the
+        # length lives on the device, so the bound is the cache capacity
+        bound = self.max_seq_len if getattr(self, "_static_mode", False) else self.length
+        o = ops.kv_decode_i4(qt.contiguous(), self.pages, self.scales, layer=layer_idx, max_tokens_hint=bound,
+                             **attention_kwargs)
         return o.unsqueeze(1)
 
     # ---- decode with the position held on the device: every launch argument of a step is then either static or a

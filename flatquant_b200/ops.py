@@ -6,6 +6,8 @@ current stream only; all compute happens in libflatq_b200.so.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -13,6 +15,8 @@ from . import _lib
 F16, BF16 = 0, 1
 _DT = {torch.float16: F16, torch.bfloat16: BF16}
 _sm_checked = False
+# opt-in until the split-KV decode kernel has run on hardware
+_DECODE_SPLIT = bool(os.environ.get("FLATQ_DECODE_SPLIT"))
 
 
 def _ptr(t):
@@ -66,6 +70,7 @@ class _Workspace:
 _ws = _Workspace()
 _ws2 = _Workspace()
 _ws3 = _Workspace()  # tile-prefix tables of grouped launches
+_ws4 = _Workspace()  # partial softmax states of the split-KV decode attention
 
 
 def pack_i4(q: torch.Tensor) -> torch.Tensor:
@@ -289,15 +294,29 @@ def kv_quant(x: torch.Tensor, kv_data=None, kv_param=None, slot=None, layer: int
 
 
 def kv_decode_i4(q: torch.Tensor, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, layer: int = 0,
-                 sm_scale=None) -> torch.Tensor:
-    """Single-query attention over the paged INT4 cache: q [batch, q_heads, 128] fp16 -> o same shape."""
+                 sm_scale=None, split=None, max_tokens_hint: int = 0) -> torch.Tensor:
+    """Single-query attention over the paged INT4 cache: q [batch, q_heads, 128] fp16 -> o same shape.
+
+    split=True (default: the FLATQ_DECODE_SPLIT environment variable) takes the split-KV kernel
+    (flatq_kv_decode_i4_split: sequence split over CTAs, one CTA per kv head serving its query-head group);
+    `max_tokens_hint` is a host-side upper bound of the sequence lengths (0 = unknown)."""
     dev = _need_cuda(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len)
     batch, q_heads, d = q.shape
     o = torch.empty_like(q)
     if sm_scale is None:
         sm_scale = d ** -0.5
-    _lib.check(_lib.load().flatq_kv_decode_i4(_ptr(q), _ptr(o), _ptr(kv_data), _ptr(kv_param), _ptr(kv_indptr),
-                                              _ptr(kv_indices), _ptr(last_page_len), batch, q_heads, kv_data.shape[3], d,
-                                              kv_data.shape[4], layer, kv_data.shape[1], float(sm_scale), _stream()),
+    lib = _lib.load()
+    if split is None:
+        split = _DECODE_SPLIT
+    if split:
+        ws = _ws4.get(dev, lib.flatq_kv_decode_i4_split_workspace_bytes(batch, q_heads))
+        _lib.check(lib.flatq_kv_decode_i4_split(_ptr(q), _ptr(o), _ptr(kv_data), _ptr(kv_param), _ptr(kv_indptr),
+                                                _ptr(kv_indices), _ptr(last_page_len), batch, q_heads, kv_data.shape[3], d,
+                                                kv_data.shape[4], layer, kv_data.shape[1], float(sm_scale),
+                                                int(max_tokens_hint), _ptr(ws), ws.numel(), _stream()), "kv_decode_i4_split")
+        return o
+    _lib.check(lib.flatq_kv_decode_i4(_ptr(q), _ptr(o), _ptr(kv_data), _ptr(kv_param), _ptr(kv_indptr),
+                                      _ptr(kv_indices), _ptr(last_page_len), batch, q_heads, kv_data.shape[3], d,
+                                      kv_data.shape[4], layer, kv_data.shape[1], float(sm_scale), _stream()),
                "kv_decode_i4")
     return o

@@ -167,6 +167,19 @@ int flatq_kv_decode_i4(const void* q_f16, void* o_f16, const uint8_t* kv_data, c
                        int q_heads, int kv_heads, int head_dim, int page_size, int layer, int n_layers, float sm_scale,
                        flatq_stream_t stream);
 
+/* flatq_kv_decode_i4_split: the same attention with the sequence split over CTAs (flash-decoding) and one CTA per kv head
+ *   serving up to four of its query heads (grouped-query attention reads each K/V row once per group): fills the chip at
+ *   small batch, where flatq_kv_decode_i4 runs batch x q_heads CTAs.  max_tokens_hint (host-side upper bound of the
+ *   sequence lengths, <= 0: unknown) limits the number of splits; the lengths themselves are read on the device.
+ *   workspace >= flatq_kv_decode_i4_split_workspace_bytes(batch, q_heads), 16-byte aligned; results equal
+ *   flatq_kv_decode_i4's up to fp32 summation order.  Opt-in until its first run on hardware. */
+size_t flatq_kv_decode_i4_split_workspace_bytes(int batch, int q_heads);
+int flatq_kv_decode_i4_split(const void* q_f16, void* o_f16, const uint8_t* kv_data, const void* kv_param_f16,
+                             const int32_t* kv_indptr, const int32_t* kv_indices, const int32_t* last_page_len, int batch,
+                             int q_heads, int kv_heads, int head_dim, int page_size, int layer, int n_layers,
+                             float sm_scale, int max_tokens_hint, void* workspace, size_t workspace_bytes,
+                             flatq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -269,7 +269,8 @@ def kv_quant(x, kv_data=None, kv_param=None, slot=None, layer=0, kv_select=0):
     return packed, par
 
 
-def kv_decode_i4(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, layer=0, sm_scale=None):
+def kv_decode_i4(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, layer=0, sm_scale=None, split=None,
+                 max_tokens_hint=0):
     _contig(q=q, kv_data=kv_data, kv_param=kv_param, kv_indptr=kv_indptr, kv_indices=kv_indices, last_page_len=last_page_len)
     b, hq, d = q.shape
     hkv, ps = kv_data.shape[3], kv_data.shape[4]
@@ -281,6 +282,9 @@ def kv_decode_i4(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, lay
     _req(kv_indptr.numel() == b + 1 and last_page_len.numel() == b, "kv_decode: page-table sizes")
     _req(int(kv_indices.max()) < kv_data.shape[0], "kv_decode: page index out of the pool")
     _req(0 < int(last_page_len.min()) and int(last_page_len.max()) <= ps, "kv_decode: last_page_len in (0, page_size]")
+    if max_tokens_hint:  # the bound the split-KV kernel sizes its grid from must cover every sequence
+        n_max = max((int(kv_indptr[i + 1] - kv_indptr[i]) - 1) * ps + int(last_page_len[i]) for i in range(b))
+        _req(max_tokens_hint >= n_max, f"kv_decode: max_tokens_hint {max_tokens_hint} < longest sequence {n_max}")
     CALLS.append(("kv_decode_i4", (hq, hkv, ps)))
     outs = []
     for i in range(b):
