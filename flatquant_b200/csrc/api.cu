@@ -51,14 +51,44 @@ int fail(int code, const char* fmt, ...) {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+// cudaFuncSetAttribute is per device: a process that drives several GPUs must opt every kernel in on each of them.
+// One flag (or the largest size opted in so far) per device ordinal; races are benign -- the call is idempotent.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int d = 0;
+    return cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < kMaxDevices ? d : -1;
+}
+struct PerDeviceOnce {
+    bool done[kMaxDevices] = {};
+    bool first_time() {   // true once per device (always true when the device cannot be determined)
+        const int d = current_device();
+        if (d < 0) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
     }
-    return n;
+};
+struct PerDeviceMax {
+    size_t seen[kMaxDevices] = {};
+    bool grows(size_t v) {  // true when v exceeds what this device has been opted in for
+        const int d = current_device();
+        if (d < 0) return true;
+        if (v <= seen[d]) return false;
+        seen[d] = v;
+        return true;
+    }
+};
+
+int num_sms() {
+    static int cached[kMaxDevices] = {};
+    const int dev = current_device();
+    if (dev < 0) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
 }
 
 int grid_for(size_t n_items, int block, int max_waves = 8) {
@@ -124,11 +154,8 @@ template <int TN, int MODE>
 int launch_gemm_t(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, cudaStream_t st) {
     auto kern = gemm_w4a8_kernel<TN, MODE>;
     constexpr int smem = GemmSmem<TN>::kBytes;
-    static bool attr_set = false;  // benign race: idempotent
-    if (!attr_set) {
-        FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr;
+    if (attr.first_time()) FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int tiles = ((p.N + kGemmBlockW - 1) / kGemmBlockW) * ((p.M + TN - 1) / TN) * (p.k_splits > 1 ? p.k_splits : 1);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     FLATQ_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, st, tw, tx, p));
@@ -139,11 +166,8 @@ int launch_gemm_t(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams
 template <int MODE>
 int launch_gemm_2sm(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, cudaStream_t st) {
     auto kern = gemm_w4a8_2sm_kernel<MODE>;
-    static bool attr_set = false;  // benign race: idempotent
-    if (!attr_set) {
-        FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2smBytes));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr;
+    if (attr.first_time()) FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2smBytes));
     const int nb_w2 = ((p.N + kGemmBlockW - 1) / kGemmBlockW + 1) / 2, nb_m = (p.M + k2smTokens - 1) / k2smTokens;
     const int tiles = nb_w2 * nb_m, pairs = num_sms() / 2;
     const int grid = 2 * (tiles < pairs ? tiles : pairs);
@@ -250,11 +274,8 @@ template <int TN, int MODE>
 int launch_gemm_grouped_t(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, cudaStream_t st) {
     auto kern = gemm_w4a8_kernel<TN, MODE, false, true>;
     constexpr int smem = GemmSmem<TN>::kBytes;
-    static bool attr_set = false;  // benign race: idempotent
-    if (!attr_set) {
-        FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr;
+    if (attr.first_time()) FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = p.t_upper < num_sms() ? p.t_upper : num_sms();
     FLATQ_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, st, tw, tx, p));
     return FLATQ_OK;
@@ -275,11 +296,9 @@ int launch_gemm_grouped_m(int tn, const CUtensorMap& tw, const CUtensorMap& tx, 
 template <int KT2>
 int launch_kron_t(const KronParams& p, int threads, size_t smem, int grid, cudaStream_t st) {
     auto kern = kron_quant_mma_kernel<KT2>;
-    static size_t attr_smem = 0;
-    if (smem > 48 * 1024 && smem > attr_smem) {
+    static PerDeviceMax attr;
+    if (smem > 48 * 1024 && attr.grows(smem))
         FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
     FLATQ_CUDA(launch_pdl(kern, dim3(grid), dim3(threads), smem, st, p));
     return FLATQ_OK;
 }
@@ -335,11 +354,8 @@ template <int N2, int N1P, int T, bool OUT8, bool EXACT>
 int launch_kron_tc_t(const KronParams& p, cudaStream_t st) {
     using C = KronTc<N2, N1P, T>;
     auto kern = kron_quant_tc_kernel<N2, N1P, T, OUT8, EXACT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr;
+    if (attr.first_time()) FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     CUtensorMap tx;  // x as a 2-D byte tensor [tokens * n1 rows][n2 * 2 bytes]
     int rc = make_map_u8(&tx, p.x, (uint64_t)p.tokens * p.n1, (uint64_t)N2 * 2, (uint64_t)N2 * 2, 128, C::kXRows,
                          CU_TENSOR_MAP_SWIZZLE_128B);
@@ -605,11 +621,10 @@ int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed
         const size_t smem = (size_t)(M == 1 ? 1 : 2) * K;
         auto k1 = gemv_w4a8_kernel<1>;
         auto k2 = gemv_w4a8_kernel<2>;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr;
+        if (attr.first_time()) {
             FLATQ_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             FLATQ_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr_set = true;
         }
         FLATQ_CUDA(M == 1 ? launch_pdl(k1, grid, block, smem, st, g) : launch_pdl(k2, grid, block, smem, st, g));
         return FLATQ_OK;
@@ -704,11 +719,9 @@ int flatq_hadamard(const void* x, void* out, int64_t rows, int n, float scale, f
     while ((1 << log_n) < n) ++log_n;
     int threads = n / 8 < 32 ? 32 : (n / 8 > 1024 ? 1024 : n / 8);
     const size_t smem = (size_t)(n + n / 32 + 1) * sizeof(float);
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
+    static PerDeviceMax attr;
+    if (smem > 48 * 1024 && attr.grows(smem))
         FLATQ_CUDA(cudaFuncSetAttribute(fht_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
     const int64_t cap = (int64_t)num_sms() * (n <= 1024 ? 8 : 2);
     fht_kernel<<<(int)(rows < cap ? rows : cap), threads, smem, (cudaStream_t)stream>>>(
         reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), (int)rows, n, log_n, scale);
