@@ -41,6 +41,10 @@ def _need_cuda(*ts):
             dev = t.device
         elif t.device != dev:
             raise RuntimeError("flatquant_b200 ops need all tensors on the same GPU")
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        # like the reference's bindings (no device guard, bindings.cpp): kernels launch on the CURRENT device and stream
+        raise RuntimeError(f"flatquant_b200 ops: tensors live on {dev} but the current CUDA device is "
+                           f"cuda:{torch.cuda.current_device()}; call under torch.cuda.device({dev.index})")
     if not _sm_checked:
         if not _lib.load().flatq_device_supported():
             raise RuntimeError("flatquant_b200 needs an sm_100 (B200) device: tcgen05/TMA kernels only")
