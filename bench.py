@@ -145,6 +145,25 @@ class Runner:
                 self.launches += 2
         return y_last if y_last is not None else self.y["down"]
 
+    def fused_per_shape(self, reps, barrier, peak_tops):
+        """BASELINE's second metric ("FlatLinear INT4 TFLOPS vs B200 peak", qlinear_benchmark.py protocol: one shape at a
+        time): GPU time of ONE fused FlatLinear -- transform + quantise + W4A4 GEMM + dequant through ops.linear_fused --
+        per Llama-3-8B shape at 2048 tokens, cycling over the layers' distinct weights.  The 4096 -> 4096 row is the
+        shape the north star quotes its 70 % target on."""
+        out = {}
+        for name, k, n, (n1, n2) in LINEARS:
+            ps = [layer[name] for layer in self.layers]
+
+            def one_pass():
+                for p in ps:
+                    self.ops.linear_fused(self.x[k], p["left"], p["right"], n1, n2, self.cm, self.cm, p["w"], p["s_w"])
+            one_pass()
+            ms = timed(one_pass, reps, barrier)
+            us = ms * 1e3 / (reps * len(ps))
+            tops = 2.0 * SEQ * k * n / us / 1e6
+            out[f"{name} {k}->{n}"] = {"us": us, "tops": tops, "frac_of_peak": tops / peak_tops}
+        return out
+
     def gemm_only(self):
         for layer in self.layers:
             for name, k, n, _ in LINEARS:
@@ -609,6 +628,12 @@ def main():
 
     # ---- roofline pass: the dominant kernel (tcgen05 GEMM) alone, same weights / shapes
     ms_gemm = timed(run.gemm_only, args.steps, barrier)
+    per_shape = None
+    if world == 1:
+        try:
+            per_shape = run.fused_per_shape(3, barrier, 2 * peaks()[1])
+        except Exception as e:  # noqa: BLE001 -- an extra table must never cost the headline line
+            per_shape = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e, ms_gemm], device=dev, dtype=torch.float64)
@@ -649,6 +674,8 @@ def main():
                          "traffic": 62.9e6, "traffic_unit": "bytes/launch", "algorithmic_bytes_per_launch": 85.0e6,
                          "issue_peak_note": "tcgen05 kind::i8 issue peak measured by tools/mma_rate.cu: 8185 MAC/cycle/SM"},
         }
+        if per_shape is not None:
+            line["fused_linear_per_shape"] = per_shape
         # sustained figure of the same file: what a kernel timed inside a long step can be held against
         try:
             sus = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained")
