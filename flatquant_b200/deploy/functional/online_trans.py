@@ -9,13 +9,7 @@ import torch
 
 from ... import ops
 from ...function_utils import get_decompose_dim  # noqa: F401  (re-exported like the reference)
-
-
-def _clip_factor(c):
-    """The reference passes raw clip factors and applies a sigmoid unless the factor is exactly 1.0
-    (online_trans.py:91-99, kron_matmul.py:88-92 always sigmoid-s; module default 1.0 means 'no LAC')."""
-    c = float(c)
-    return c
+from .hadamard import get_hadK, is_pow2, matmul_hadU_cuda  # noqa: F401  (the reference defines them in this module)
 
 
 def quant(x, clip_factor_a_max=1.0, clip_factor_a_min=1.0, input_clip_ratio=1.0):

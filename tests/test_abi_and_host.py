@@ -170,3 +170,36 @@ def test_c_abi_argument_errors_without_a_gpu(lib):
     assert g(fake, fake, fake, fake, None, fake, 8, 64, 127, 256, 0, fake, 0, fake, ws, None) == UNSUPPORTED and "even" in err()
     assert g(fake, fake, fake, fake, None, fake, 8, 64, 128, 250, 0, fake, 0, fake, ws, None) == INVALID
     assert g(fake, fake, fake, fake, None, fake, 8, 64, 128, 256, 0, fake, 0, fake, 8, None) == WORKSPACE
+
+
+def test_hadamard_factors_and_matmul_hadU(monkeypatch):
+    """get_hadK: the reference's choice of K (deploy/functional/online_trans.py:21-71), a generated Hadamard matrix where a
+    prime-field Paley construction exists, a placeholder otherwise; matmul_hadU_cuda == X . (H_K (x) H_{n/K}) / sqrt(n)."""
+    import numpy as np
+    import scipy.linalg
+
+    import cpu_ops
+    from flatquant_b200.deploy import functional as F
+    from flatquant_b200.deploy.functional import hadamard as H
+    from flatquant_b200.deploy.nn import OnlineTrans
+    for n, k in ((4096, 1), (14336, 28), (11008, 172), (13824, 108), (5120, 40), (27648, 108), (8192, 1), (6144, 12)):
+        assert H.hadK_order(n) == k
+    for k in (12, 20, 28, 36, 40, 60, 108, 140):
+        h = H.paley_hadamard(k)
+        assert torch.equal(h @ h.t(), k * torch.eye(k)) and set(h.unique().tolist()) == {-1.0, 1.0}
+    assert H.paley_hadamard(172) is None and torch.isnan(H.get_hadK(11008)[0]).all()
+    assert F.get_hadK(4096) == (None, 1) and F.online_trans.get_hadK is H.get_hadK
+    cpu_ops.install(monkeypatch)
+    torch.manual_seed(0)
+    n, k = 28 * 32, 28
+    x = torch.randn(5, n).half()
+    hk, kk = H.get_hadK(n)
+    got = F.matmul_hadU_cuda(x, hk, kk).float().numpy()
+    full = np.kron(hk.numpy(), scipy.linalg.hadamard(n // k))   # H_K (x) H_{n/K}, applied to row vectors
+    want = x.float().numpy() @ full.T / np.sqrt(n)
+    assert np.abs(got - want).max() < 2e-2 * np.abs(want).max()
+    ot = OnlineTrans(14336, trans="had")   # Llama-3-8B down_proj in the Hadamard baseline mode: constructible
+    assert ot.rem_dim == 28 and ot.had_rem_dim.shape == (28, 28) and "had_rem_dim" in ot.state_dict()
+    bad = OnlineTrans(11008, trans="had")  # order 172: placeholder until a checkpoint provides the table
+    with pytest.raises(RuntimeError, match="placeholder"):
+        bad(torch.zeros(1, 2, 11008, dtype=torch.float16))
