@@ -194,6 +194,30 @@ def _f16(t):
     return t.detach().to(ACT_DTYPE).contiguous()
 
 
+def _had_matrix(n):
+    """Dense H_n / sqrt(n) as the online Hadamard of deploy.nn.OnlineTrans(trans="had") applies it to a row vector:
+    x . (hadK^T (x) H_{n/K}) / sqrt(n) (deploy/functional/online_trans.py:144-151) -- used as a left Kronecker factor."""
+    from ..functional.hadamard import get_hadK
+    hk, k = get_hadK(n)
+    m = n // k
+    h = torch.ones(1, 1)
+    while h.shape[0] < m:  # Sylvester
+        h = torch.cat([torch.cat([h, h], 1), torch.cat([h, -h], 1)], 0)
+    if k > 1:
+        h = torch.kron(hk.t().contiguous(), h)
+    return h / math.sqrt(n)
+
+
+def _is_had(module):
+    return isinstance(module, OnlineTrans) and module.trans == "had"
+
+
+def _pre_hadamard(module, x2):
+    """Hadamard baseline mode (trans="had"): the online transform is an fp16 -> fp16 FHT in front of a plain per-token
+    quantiser (deploy/transformers/modeling_llama.py:146-148, 250-252), not a fused Kronecker transform."""
+    return module(x2) if _is_had(module) else x2
+
+
 class _QuantGroup:
     """Projections that share one quantised activation (equal clip factors): one act_quant + one GEMM."""
 
@@ -278,13 +302,20 @@ class FlatQuantLlamaAttention(torch.nn.Module):
         if self._rt is not None and self._rt.dev == dev:
             return self._rt
         rt = SimpleNamespace(dev=dev)
-        rt.left, rt.right = _f16(self.left_matrix), _f16(self.right_matrix)
-        rt.n1, rt.n2 = rt.left.shape[0], rt.right.shape[0]
+        if isinstance(self.inp_trans_q, OnlineTrans) and self.inp_trans_q.trans == "matmul":
+            rt.left, rt.right = _f16(self.left_matrix), _f16(self.right_matrix)
+            rt.n1, rt.n2 = rt.left.shape[0], rt.right.shape[0]
+        else:  # no online input transform (rotation fused offline / Hadamard applied in front): plain quantiser
+            rt.left = rt.right = None
+            rt.n1, rt.n2 = 1, self.hidden_size
         clips = [(float(t.clip_factor_a_max), float(t.clip_factor_a_min)) if isinstance(t, OnlineTrans) else (4.0, 4.0)
                  for t in (self.inp_trans_q, self.inp_trans_k, self.inp_trans_v)]
         rt.qkv = _group_by_clip(("q", "k", "v"), (self.q_proj, self.k_proj, self.v_proj), clips)
         # o_proj: Z = O^T . reshape(a, heads, head_dim) == Kronecker transform with left = O, right = I
-        if isinstance(self.o_proj_trans, OnlineTrans):
+        if _is_had(self.o_proj_trans):  # Hadamard over the heads axis == a left factor H / sqrt(heads)
+            rt.o_left = _had_matrix(self.num_heads).to(dev, ACT_DTYPE).contiguous()
+            rt.o_clip = (float(self.o_proj[0].clip_factor_a_max), float(self.o_proj[0].clip_factor_a_min))
+        elif isinstance(self.o_proj_trans, OnlineTrans):
             rt.o_left = _f16(self.o_proj_trans.right_matrix)
             rt.o_clip = (float(self.o_proj_trans.clip_factor_a_max), float(self.o_proj_trans.clip_factor_a_min))
         else:
@@ -307,6 +338,7 @@ class FlatQuantLlamaAttention(torch.nn.Module):
         b, s, _ = hidden_states.shape
         rt = self._runtime(hidden_states.device)
         x2 = hidden_states.reshape(b * s, self.hidden_size).to(ACT_DTYPE).contiguous()
+        x2 = _pre_hadamard(self.inp_trans_q, x2)
         qkv = _flat_linears(x2, rt.left, rt.right, rt.n1, rt.n2, rt.qkv, self.isFlatQ)
         return (qkv["q"].reshape(b, s, self.num_heads, self.head_dim),
                 qkv["k"].reshape(b, s, self.num_key_value_heads, self.head_dim),
@@ -374,7 +406,7 @@ class FlatQuantLlamaMLP(torch.nn.Module):
         if self._rt is not None and self._rt.dev == dev:
             return self._rt
         rt = SimpleNamespace(dev=dev)
-        if hasattr(self, "inp_trans_g"):
+        if hasattr(self, "inp_trans_g") and self.inp_trans_g.trans == "matmul":
             rt.left, rt.right = _f16(self.left_matrix), _f16(self.right_matrix)
             rt.n1, rt.n2 = rt.left.shape[0], rt.right.shape[0]
             clips = [(float(t.clip_factor_a_max), float(t.clip_factor_a_min)) for t in (self.inp_trans_g, self.inp_trans_u)]
@@ -385,10 +417,10 @@ class FlatQuantLlamaMLP(torch.nn.Module):
             clips = [c, c]
         rt.gate_up = _group_by_clip(("gate", "up"), (self.gate_proj, self.up_proj), clips)
         first = self.down_proj[0]
-        if isinstance(first, OnlineTrans):
+        if isinstance(first, OnlineTrans) and first.trans == "matmul":
             rt.d_left, rt.d_right = _f16(first.left_matrix), _f16(first.right_matrix)
             rt.d_n1, rt.d_n2 = rt.d_left.shape[0], rt.d_right.shape[0]
-        else:
+        else:  # Hadamard mode (FHT in front, see down()) or no online transform: plain per-token quantiser
             rt.d_left = rt.d_right = None
             rt.d_n1, rt.d_n2 = 1, self.intermediate_size
         rt.down = _group_by_clip(("down",), (self.down_proj[-1],),
@@ -401,6 +433,7 @@ class FlatQuantLlamaMLP(torch.nn.Module):
         b, s, _ = x.shape
         rt = self._runtime(x.device)
         x2 = x.reshape(b * s, self.hidden_size).to(ACT_DTYPE).contiguous()
+        x2 = _pre_hadamard(getattr(self, "inp_trans_g", None), x2)
         gu = _flat_linears(x2, rt.left, rt.right, rt.n1, rt.n2, rt.gate_up, self.isFlatQ)
         return gu["gate"].reshape(b, s, -1), gu["up"].reshape(b, s, -1)
 
@@ -409,6 +442,7 @@ class FlatQuantLlamaMLP(torch.nn.Module):
         b, s, _ = act.shape
         rt = self._runtime(act.device)
         a2 = act.reshape(b * s, self.intermediate_size).to(ACT_DTYPE).contiguous()
+        a2 = _pre_hadamard(self.down_proj[0], a2)
         y = _flat_linears(a2, rt.d_left, rt.d_right, rt.d_n1, rt.d_n2, rt.down, self.isFlatQ)["down"]
         return self.tp.all_reduce(y).reshape(b, s, self.hidden_size)
 
@@ -514,9 +548,9 @@ class FlatQuantLlamaForCausalLM(torch.nn.Module):
             for buf in (at.left_matrix, at.right_matrix, mlp.left_matrix, mlp.right_matrix, at.trans_matrix_k):
                 fill_matrix(buf, rep)  # input-side transforms see the full hidden state on every rank
             at.trans_matrix_k_inv_t.copy_(torch.linalg.inv(at.trans_matrix_k.double()).t().float())
-            if isinstance(at.o_proj_trans, OnlineTrans):  # row-parallel: one transform per rank
+            if isinstance(at.o_proj_trans, OnlineTrans) and at.o_proj_trans.trans == "matmul":  # row-parallel: one per rank
                 fill_matrix(at.o_proj_trans.right_matrix, own)
-            if isinstance(mlp.down_proj[0], OnlineTrans):
+            if isinstance(mlp.down_proj[0], OnlineTrans) and mlp.down_proj[0].trans == "matmul":
                 fill_matrix(mlp.down_proj[0].left_matrix, own)
                 fill_matrix(mlp.down_proj[0].right_matrix, own)
             for t in (at.inp_trans_q, at.inp_trans_k, at.inp_trans_v, at.o_proj_trans, getattr(mlp, "inp_trans_g", None),

@@ -330,3 +330,47 @@ def test_attention_bias_is_applied_after_dequant(monkeypatch):
                                  O.unpack_i4(lin.weight.numpy()), lin.weight_scales.reshape(-1).numpy(),
                                  lin.bias.numpy())["y"]
         assert np.abs(got.reshape(5, -1).numpy() - want).max() < 1e-4 * np.abs(want).max()
+
+
+def test_hadamard_baseline_mode(monkeypatch):
+    """trans="had" (the QuaRot-style baseline the reference benchmarks next to FlatQuant): o_proj's online Hadamard over
+    the heads axis runs as a left Kronecker factor H / sqrt(heads), down_proj's as FHT x dense 28 x 28 factor in front of
+    a plain quantiser (inter = 28 * 64), the K / Q cache transform as FHT; no LAC (clip factors unused)."""
+    from oracle import flatq_oracle as O
+
+    from flatquant_b200.deploy.functional import hadamard as H
+    from flatquant_b200.deploy.transformers import FlatQuantLlamaConfig, FlatQuantLlamaForCausalLM
+    from flatquant_b200.deploy.transformers import modeling_llama as ML
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(cpu_ops, "EMULATE_FP16", False)
+    monkeypatch.setattr(ML, "ACT_DTYPE", torch.float32)
+    cfg = FlatQuantLlamaConfig(hidden_size=512, intermediate_size=28 * 64, num_attention_heads=4, num_key_value_heads=2,
+                               num_hidden_layers=1, vocab_size=16,
+                               quantization_config=dict(trans="had", online_trans=["qk", "o_proj", "down_proj"]))
+    model = FlatQuantLlamaForCausalLM.random_init(cfg, torch.device("cpu"), seed=5)
+    at, mlp = model.model.layers[0].self_attn, model.model.layers[0].mlp
+    assert not at.isFlatQ and at.o_proj_trans.trans == "had" and mlp.down_proj[0].rem_dim == 28
+    torch.manual_seed(1)
+    a = torch.randn(1, 6, 512)
+    with torch.no_grad():
+        y = at.project_out(a)
+    h4 = torch.tensor([[1, 1, 1, 1], [1, -1, 1, -1], [1, 1, -1, -1], [1, -1, -1, 1.]]) / 2
+    z = torch.einsum("hg,thd->tgd", h4, a.reshape(6, 4, 128)).reshape(6, 512)   # Hadamard over the heads axis
+    lin = at.o_proj[1]
+    want = O.flat_linear_int(z, None, None, 50.0, 50.0, O.unpack_i4(lin.weight.numpy()), lin.weight_scales.reshape(-1).numpy())["y"]
+    assert np.abs(y.reshape(6, -1).numpy() - want).max() < 1e-4 * np.abs(want).max()
+    act = torch.randn(1, 6, 28 * 64)
+    with torch.no_grad():
+        yd = mlp.down(act)
+    hk, k = H.get_hadK(28 * 64)
+    full = torch.kron(hk.t().contiguous(), torch.from_numpy(O.hadamard_matrix(64)).float() if hasattr(O, "hadamard_matrix")
+                      else torch.from_numpy(__import__("scipy.linalg", fromlist=["hadamard"]).hadamard(64)).float()) / (28 * 64) ** 0.5
+    zd = act.reshape(6, -1) @ full
+    lin = mlp.down_proj[-1]
+    want = O.flat_linear_int(zd, None, None, 50.0, 50.0, O.unpack_i4(lin.weight.numpy()), lin.weight_scales.reshape(-1).numpy())["y"]
+    assert np.abs(yd.reshape(6, -1).numpy() - want).max() < 1e-3 * np.abs(want).max()
+    ids = torch.randint(0, 16, (1, 7), generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        logits, cache = model(ids, max_length=8)
+        step, _ = model(ids[:, -1:], past_key_values=cache)
+    assert cache.trans == "had" and torch.isfinite(logits).all() and torch.isfinite(step).all()
