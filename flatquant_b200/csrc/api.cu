@@ -682,7 +682,7 @@ int flatq_gemm_w4a8_grouped(const int8_t* xq8, const float* s_x, const uint8_t* 
     rc = make_map_u8(&tx, xq8, M, K, K, 128, tn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     int* tile_prefix = reinterpret_cast<int*>(ws);
-    grouped_prefix_kernel<<<1, 32, 0, st>>>(group_offsets, n_groups, tn, (int)nb_w, tile_prefix);
+    grouped_prefix_kernel<<<1, kPrefixThreads, 0, st>>>(group_offsets, n_groups, tn, (int)nb_w, tile_prefix);
     FLATQ_CUDA(cudaGetLastError());
     GemmParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = 4;

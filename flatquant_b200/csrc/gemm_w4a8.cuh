@@ -539,9 +539,38 @@ gemm_w4a8_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     }
 }
 
-// Tile prefix of a grouped launch, built on the device from the router's row offsets (no host read of the routing).
-__global__ void grouped_prefix_kernel(const int* __restrict__ off, int n_groups, int tn, int nb_w, int* __restrict__ tile_prefix) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) grouped_build_prefix(off, n_groups, tn, nb_w, tile_prefix);
+// Tile prefix of a grouped launch, built on the device from the router's row offsets (no host read of the routing):
+// the parallel form of grouped_build_prefix (csrc/grouped_sched.h) -- one block, one thread per group, a shared-memory
+// inclusive scan per chunk of 1024 groups (a serial walk over 256 experts would cost ~500 dependent loads).
+constexpr int kPrefixThreads = 1024;
+__global__ void __launch_bounds__(kPrefixThreads)
+grouped_prefix_kernel(const int* __restrict__ off, int n_groups, int tn, int nb_w, int* __restrict__ tile_prefix) {
+    __shared__ int s[kPrefixThreads];
+    __shared__ int base;
+    const int t = threadIdx.x;
+    if (t == 0) { base = 0; tile_prefix[0] = 0; }
+    __syncthreads();
+    for (int c0 = 0; c0 < n_groups; c0 += kPrefixThreads) {
+        const int e = c0 + t;
+        int v = 0;
+        if (e < n_groups) {
+            int rows = off[e + 1] - off[e];
+            if (rows < 0) rows = 0;
+            v = nb_w * ((rows + tn - 1) / tn);
+        }
+        s[t] = v;
+        __syncthreads();
+        for (int d = 1; d < kPrefixThreads; d <<= 1) {   // Hillis-Steele inclusive scan
+            const int add = t >= d ? s[t - d] : 0;
+            __syncthreads();
+            s[t] += add;
+            __syncthreads();
+        }
+        if (e < n_groups) tile_prefix[e + 1] = base + s[t];
+        __syncthreads();
+        if (t == kPrefixThreads - 1) base += s[t];
+        __syncthreads();
+    }
 }
 
 }  // namespace flatq
