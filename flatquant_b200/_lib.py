@@ -49,6 +49,9 @@ SIGNATURES = {
     "flatq_kv_decode_i4_split_workspace_bytes": (c_size_t, [c_int, c_int]),
     "flatq_kv_decode_i4_split": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                          c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
+    "flatq_rmsnorm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_float, c_void_p, c_void_p]),
+    "flatq_rope": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "flatq_silu_mul": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "flatq_linear_fused_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "flatq_linear_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
                                    c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),

@@ -17,6 +17,7 @@
 #include "gemm_w4a8.cuh"
 #include "gemm_w4a8_2sm.cuh"
 #include "gemv_w4a8.cuh"
+#include "glue.cuh"
 #include "kron_quant.cuh"
 #include "kron_quant_tc.cuh"
 #include "qattention.cuh"
@@ -809,6 +810,44 @@ int flatq_kv_decode_i4_split(const void* q, void* o, const uint8_t* kv_data, con
     else decode_attn_i4_split_kernel<1><<<grid, kDecSplitThreads, 0, st>>>(p, (int)splits, part);
     FLATQ_CUDA(cudaGetLastError());
     decode_attn_merge_kernel<<<batch * q_heads, 128, 0, st>>>(part, (int)splits, reinterpret_cast<__half*>(o));
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+int flatq_rmsnorm(const void* x, const void* weight, int64_t rows, int64_t K, float mean_dim, float eps, void* y,
+                  flatq_stream_t stream) {
+    FLATQ_CHECK(x && y, FLATQ_ERR_INVALID, "rmsnorm: null pointer");
+    FLATQ_CHECK(rows > 0 && K > 0 && K % 8 == 0 && rows < (1ll << 31) && K < (1ll << 31), FLATQ_ERR_INVALID,
+                "rmsnorm: rows=%lld, K=%lld (K must be a multiple of 8)", (long long)rows, (long long)K);
+    FLATQ_CHECK(mean_dim > 0.f, FLATQ_ERR_INVALID, "rmsnorm: mean_dim");
+    FLATQ_CHECK(aligned16(x) && aligned16(y) && (!weight || aligned16(weight)), FLATQ_ERR_INVALID, "rmsnorm: alignment");
+    const int64_t cap = (int64_t)num_sms() * 8;
+    rmsnorm_f16_kernel<<<(int)(rows < cap ? rows : cap), kNormThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(weight), reinterpret_cast<__half*>(y), (int)rows,
+        (int)K, mean_dim, eps);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+int flatq_rope(void* x, const void* cos_t, const void* sin_t, int64_t tokens, int heads, int head_dim, flatq_stream_t stream) {
+    FLATQ_CHECK(x && cos_t && sin_t, FLATQ_ERR_INVALID, "rope: null pointer");
+    FLATQ_CHECK(head_dim == 128, FLATQ_ERR_UNSUPPORTED, "rope: head_dim=%d (only 128)", head_dim);
+    FLATQ_CHECK(tokens > 0 && heads > 0 && tokens * heads < (1ll << 31), FLATQ_ERR_INVALID, "rope: tokens / heads");
+    FLATQ_CHECK(aligned16(x) && aligned16(cos_t) && aligned16(sin_t), FLATQ_ERR_INVALID, "rope: alignment");
+    rope_f16_kernel<<<grid_for((size_t)tokens * heads * 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<__half*>(x), reinterpret_cast<const __half*>(cos_t), reinterpret_cast<const __half*>(sin_t),
+        (int)tokens, heads);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+int flatq_silu_mul(const void* gu, int64_t rows, int64_t inter, void* out, flatq_stream_t stream) {
+    FLATQ_CHECK(gu && out, FLATQ_ERR_INVALID, "silu_mul: null pointer");
+    FLATQ_CHECK(rows > 0 && inter > 0 && inter % 8 == 0 && rows < (1ll << 31) && inter < (1ll << 30), FLATQ_ERR_INVALID,
+                "silu_mul: rows=%lld, inter=%lld (inter must be a multiple of 8)", (long long)rows, (long long)inter);
+    FLATQ_CHECK(aligned16(gu) && aligned16(out), FLATQ_ERR_INVALID, "silu_mul: alignment");
+    silu_mul_f16_kernel<<<grid_for((size_t)rows * (inter / 8), 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(gu), reinterpret_cast<__half*>(out), (int)rows, (int)inter);
     FLATQ_CUDA(cudaGetLastError());
     return FLATQ_OK;
 }

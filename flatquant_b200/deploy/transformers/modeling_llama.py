@@ -130,6 +130,8 @@ class LlamaRMSNorm(torch.nn.Module):
         self.variance_epsilon = eps
 
     def forward(self, x):
+        if ops.FUSED_GLUE and x.dtype == torch.float16 and self.weight.dtype == torch.float16:
+            return ops.rmsnorm(x.contiguous(), self.weight, self.variance_epsilon)   # one pass (csrc/glue.cuh), opt-in
         xf = x.float()
         xf = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + self.variance_epsilon)
         return self.weight * xf.to(x.dtype)
@@ -159,6 +161,10 @@ def rope_cos_sin(inv_freq, positions, dtype):
 
 def apply_rope(x, cos, sin):
     """x [b, s, heads, d]; the rotate_half convention of HF Llama."""
+    if ops.FUSED_GLUE and x.dtype == torch.float16 and cos.dtype == torch.float16 and x.shape[-1] == 128:
+        b, s_, _, d = x.shape   # one in-place pass over a contiguous copy (csrc/glue.cuh), opt-in
+        expand = lambda t: t.expand(b, s_, 1, d).reshape(b * s_, d).contiguous()  # noqa: E731
+        return ops.rope_(x.contiguous(), expand(cos), expand(sin))
     h = x.shape[-1] // 2
     rot = torch.cat((-x[..., h:], x[..., :h]), dim=-1)
     return x * cos + rot * sin
@@ -245,13 +251,17 @@ def _group_by_clip(names, linears, clips):
     return [_QuantGroup(clip, n, l) for clip, (n, l) in groups.items()]
 
 
-def _flat_linears(x2, left, right, n1, n2, groups, lac):
-    """x2 fp16 [M, K] -> {name: y fp16 [M, N_name]}: transform + quantise once per clip pair, one GEMM per group."""
+def _flat_linears(x2, left, right, n1, n2, groups, lac, raw=False):
+    """x2 fp16 [M, K] -> {name: y fp16 [M, N_name]}: transform + quantise once per clip pair, one GEMM per group.
+    raw=True: {names tuple: the group's undivided GEMM output [M, sum N]} instead."""
     out = {}
     for g in groups:
         cmax, cmin = (_sig(g.clip[0]), _sig(g.clip[1])) if lac else (1.0, 1.0)
         xq8, s_x = ops.act_quant(x2, left, right, n1, n2, cmax, cmin)
         y = ops.gemm_w4a8(xq8, s_x, g.w, g.s_w, g.bias, out_dtype=ACT_DTYPE)
+        if raw:
+            out[tuple(g.names)] = y
+            continue
         for name, part in zip(g.names, torch.split(y, g.sizes, dim=-1)):
             out[name] = part
     return out
@@ -428,12 +438,16 @@ class FlatQuantLlamaMLP(torch.nn.Module):
         self._rt = rt
         return rt
 
-    def gate_up(self, x):
-        """Stage 1: gate and up FlatLinears on the normalised hidden state -> (gate, up) [b, s, inter]."""
+    def gate_up(self, x, fused=False):
+        """Stage 1: gate and up FlatLinears on the normalised hidden state -> (gate, up) [b, s, inter]; fused=True (one
+        shared quantisation, i.e. one GEMM over [gate; up]): the undivided output [b, s, 2 * inter]."""
         b, s, _ = x.shape
         rt = self._runtime(x.device)
         x2 = x.reshape(b * s, self.hidden_size).to(ACT_DTYPE).contiguous()
         x2 = _pre_hadamard(getattr(self, "inp_trans_g", None), x2)
+        if fused:
+            gu = _flat_linears(x2, rt.left, rt.right, rt.n1, rt.n2, rt.gate_up, self.isFlatQ, True)
+            return gu[("gate", "up")].reshape(b, s, -1)
         gu = _flat_linears(x2, rt.left, rt.right, rt.n1, rt.n2, rt.gate_up, self.isFlatQ)
         return gu["gate"].reshape(b, s, -1), gu["up"].reshape(b, s, -1)
 
@@ -447,6 +461,8 @@ class FlatQuantLlamaMLP(torch.nn.Module):
         return self.tp.all_reduce(y).reshape(b, s, self.hidden_size)
 
     def forward(self, x):
+        if ops.FUSED_GLUE and ACT_DTYPE == torch.float16 and len(self._runtime(x.device).gate_up) == 1:
+            return self.down(ops.silu_mul(self.gate_up(x, fused=True)))   # SiLU * up in one pass over the GEMM output
         gate, up = self.gate_up(x)
         return self.down(F.silu(gate) * up)
 

@@ -271,6 +271,46 @@ def gemm_w4a8_grouped(xq8: torch.Tensor, s_x: torch.Tensor, w_packed: torch.Tens
     return y
 
 
+# ---- elementwise glue of a decoder layer (opt-in in the model stack: FLATQ_FUSED_GLUE, see csrc/glue.cuh)
+FUSED_GLUE = bool(os.environ.get("FLATQ_FUSED_GLUE"))
+
+
+def rmsnorm(x: torch.Tensor, weight=None, eps: float = 1e-5, mean_dim=None) -> torch.Tensor:
+    """HF LlamaRMSNorm on fp16: weight * half(float(x) * rsqrt(sum(x^2) / mean_dim + eps)); weight None = weight-less."""
+    dev = _need_cuda(x, weight)
+    if x.dtype != torch.float16 or (weight is not None and weight.dtype != torch.float16):
+        raise RuntimeError("rmsnorm: float16 activations and weight")
+    k = x.shape[-1]
+    y = torch.empty_like(x)
+    _lib.check(_lib.load().flatq_rmsnorm(_ptr(x), _ptr(weight), x.numel() // k, k, float(mean_dim or k), float(eps), _ptr(y),
+                                         _stream()), "rmsnorm")
+    return y
+
+
+def rope_(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+    """In-place HF rotary embedding: x [..., tokens, heads, 128] contiguous fp16, cos / sin with tokens * 128 elements."""
+    _need_cuda(x, cos, sin)
+    heads, d = x.shape[-2], x.shape[-1]
+    tokens = x.numel() // (heads * d)
+    if x.dtype != torch.float16 or cos.dtype != torch.float16 or sin.dtype != torch.float16:
+        raise RuntimeError("rope_: float16 tensors")
+    if cos.numel() != tokens * d or sin.numel() != tokens * d:
+        raise RuntimeError(f"rope_: cos / sin must hold tokens x head_dim = {tokens} x {d} values")
+    _lib.check(_lib.load().flatq_rope(_ptr(x), _ptr(cos), _ptr(sin), tokens, heads, d, _stream()), "rope")
+    return x
+
+
+def silu_mul(gu: torch.Tensor) -> torch.Tensor:
+    """gu [..., 2 * inter] = [gate | up] (fused gate/up GEMM output) -> silu(gate) * up [..., inter], fp16."""
+    dev = _need_cuda(gu)
+    if gu.dtype != torch.float16:
+        raise RuntimeError("silu_mul: float16 activations")
+    inter = gu.shape[-1] // 2
+    out = torch.empty(gu.shape[:-1] + (inter,), dtype=torch.float16, device=dev)
+    _lib.check(_lib.load().flatq_silu_mul(_ptr(gu), gu.numel() // (2 * inter), inter, _ptr(out), _stream()), "silu_mul")
+    return out
+
+
 def hadamard(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
     """out = scale * x . H_n over the last axis (n a power of two), fp16."""
     dev = _need_cuda(x)

@@ -180,6 +180,21 @@ int flatq_kv_decode_i4_split(const void* q_f16, void* o_f16, const uint8_t* kv_d
                              float sm_scale, int max_tokens_hint, void* workspace, size_t workspace_bytes,
                              flatq_stream_t stream);
 
+/* ---- elementwise glue between the FlatLinears of a decoder layer (the callers either side of the path; HF
+ *      transformers' torch expressions in the reference).  One pass each, fp16 in/out, the rounding points of the
+ *      expression replaced.  Opt-in in the model stack until their first run on hardware.
+ * flatq_rmsnorm:  y = weight * half(float(x) * rsqrt(sum(x^2) / mean_dim + eps))   (LlamaRMSNorm.forward; weight NULL =
+ *                 the weight-less norm of deploy/nn/normalization.py:4-23).  x, y [rows, K], K % 8 == 0.
+ * flatq_rope:     in place, x [tokens, heads, 128], cos / sin [tokens, 128]: x * cos + rotate_half(x) * sin with every
+ *                 op rounded to fp16 (apply_rotary_pos_emb of HF Llama on fp16 tensors).
+ * flatq_silu_mul: gu [rows, 2 * inter] = [gate | up] (the fused gate/up GEMM output) -> out [rows, inter] =
+ *                 half(silu_f32(gate)) * up (LlamaMLP.forward: act_fn(gate_proj(x)) * up_proj(x)). */
+int flatq_rmsnorm(const void* x_f16, const void* weight_f16, int64_t rows, int64_t K, float mean_dim, float eps,
+                  void* y_f16, flatq_stream_t stream);
+int flatq_rope(void* x_f16, const void* cos_f16, const void* sin_f16, int64_t tokens, int heads, int head_dim,
+               flatq_stream_t stream);
+int flatq_silu_mul(const void* gu_f16, int64_t rows, int64_t inter, void* out_f16, flatq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -235,6 +235,35 @@ def pack_i4(q):
     return torch.from_numpy(O.pack_i4(q.numpy()))
 
 
+def rmsnorm(x, weight=None, eps=1e-5, mean_dim=None):
+    """the torch expression flatq_rmsnorm replaces (HF LlamaRMSNorm / deploy.nn.RMSNorm)"""
+    _contig(x=x, weight=weight), _al16(x, 2, "rmsnorm x"), _act_dtype(x, "rmsnorm x"), _act_dtype(weight, "rmsnorm weight")
+    _req(x.shape[-1] % 8 == 0, "rmsnorm: K must be a multiple of 8")
+    xf = x.float()
+    n = (xf * torch.rsqrt(xf.pow(2).sum(-1, keepdim=True) / float(mean_dim or x.shape[-1]) + eps)).to(x.dtype)
+    return n if weight is None else weight * n
+
+
+def rope_(x, cos, sin):
+    """in place; the torch expression flatq_rope replaces (apply_rotary_pos_emb, every op rounded to x.dtype)"""
+    _contig(x=x, cos=cos, sin=sin), _al16(x, 2, "rope x"), _al16(cos, 2, "rope cos"), _al16(sin, 2, "rope sin")
+    _act_dtype(x, "rope x"), _act_dtype(cos, "rope cos"), _act_dtype(sin, "rope sin")
+    heads, d = x.shape[-2], x.shape[-1]
+    tokens = x.numel() // (heads * d)
+    _req(d == 128 and cos.numel() == tokens * d and sin.numel() == tokens * d, "rope: shapes")
+    xv, c, s = x.view(tokens, heads, d), cos.reshape(tokens, 1, d), sin.reshape(tokens, 1, d)
+    rot = torch.cat((-xv[..., d // 2:], xv[..., :d // 2]), dim=-1)
+    x.copy_((xv * c + rot * s).view(x.shape))
+    return x
+
+
+def silu_mul(gu):
+    _contig(gu=gu), _al16(gu, 2, "silu_mul gu"), _act_dtype(gu, "silu_mul gu")
+    inter = gu.shape[-1] // 2
+    _req(inter % 8 == 0, "silu_mul: inter must be a multiple of 8")
+    return torch.nn.functional.silu(gu[..., :inter]) * gu[..., inter:]
+
+
 def hadamard(x, scale=1.0):
     _contig(x=x)
     n = x.shape[-1]
@@ -303,7 +332,7 @@ def kv_decode_i4(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, lay
 
 FUNCTIONS = ("kron_transform", "act_quant", "transform_quant", "quantize_rows", "gemm_w4a8", "gemm_w4a8_grouped",
              "linear_fused", "pack_i4",
-             "hadamard", "kv_quant", "kv_decode_i4")
+             "hadamard", "kv_quant", "kv_decode_i4", "rmsnorm", "rope_", "silu_mul")
 
 
 def install(monkeypatch):

@@ -374,3 +374,28 @@ def test_hadamard_baseline_mode(monkeypatch):
         logits, cache = model(ids, max_length=8)
         step, _ = model(ids[:, -1:], past_key_values=cache)
     assert cache.trans == "had" and torch.isfinite(logits).all() and torch.isfinite(step).all()
+
+
+def test_fused_glue_wiring_is_a_no_op_on_results(monkeypatch):
+    """FLATQ_FUSED_GLUE routes RMSNorm, RoPE and SiLU * up through one-pass kernels (csrc/glue.cuh).  Their CPU stand-ins
+    are the torch expressions they replace, so on the host the wiring must not change a bit: prefill, eager decode and the
+    static (graph-capturable) decode, whose cos / sin row is shared by the whole batch."""
+    from flatquant_b200 import ops
+    cpu_ops.install(monkeypatch)
+    g = np.load(os.path.join(GOLDEN, "llama_model.npz"))
+    ids = torch.from_numpy(g["ids"])
+    outs = []
+    for fused in (False, True):
+        monkeypatch.setattr(ops, "FUSED_GLUE", fused)
+        cpu_ops.CALLS.clear()
+        model = _load_model()
+        with torch.no_grad():
+            logits, cache = model(ids[:, :-2], max_length=ids.shape[1])
+            step, _ = model(ids[:, -2:-1], past_key_values=cache)
+            cache.begin_static_decode()
+            static = model.decode_static(ids[:, -1:], cache)
+        outs.append((logits, step, static, cache.pages.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    # layer 0 has one shared gate/up quantisation (fused SiLU path), layer 1 two (torch path): both were exercised
+    assert len(model.model.layers[0].mlp._rt.gate_up) == 1 and len(model.model.layers[1].mlp._rt.gate_up) == 2

@@ -1,0 +1,64 @@
+"""One-pass glue kernels (csrc/glue.cuh: flatq_rmsnorm, flatq_rope, flatq_silu_mul) against the torch expressions they
+replace, on the GPU in fp16.  UNVERIFIED ON HARDWARE, gated like the other zzz files (FLATQ_RUN_UNVERIFIED=1): written
+after round 1's GPU minutes were spent.
+
+    FLATQ_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_zzz_glue_kernels_gpu.py -x -q -s
+    then: FLATQ_FUSED_GLUE=1 python bench.py --workload llama8b-model   vs   without"""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.environ.get("FLATQ_RUN_UNVERIFIED"), reason="kernels not yet run on hardware; "
+                                 "set FLATQ_RUN_UNVERIFIED=1 (see the module docstring)")]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("rows,k", [(5, 512), (2048, 4096), (33, 8192), (7, 14336)])
+def test_rmsnorm_matches_hf_expression(dev, rows, k):
+    from flatquant_b200 import ops
+    torch.manual_seed(rows + k)
+    x = (torch.randn(rows, k, device=dev) * 3).half()
+    w = (torch.rand(k, device=dev) + 0.5).half()
+    xf = x.float()
+    ref = w * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)).half()
+    got = ops.rmsnorm(x, w, 1e-5)
+    # the fp32 sum of squares is accumulated in another order: the normalised value may round differently by one fp16 ulp
+    d = (got.float() - ref.float()).abs()
+    assert float((d / ref.float().abs().clamp(min=1e-3)).max()) < 2.0 ** -9 and float((d > 0).float().mean()) < 0.02
+    bare = (xf * torch.rsqrt(xf.pow(2).sum(-1, keepdim=True) / k + 1e-5)).half()   # the weight-less norm (deploy.nn.RMSNorm)
+    d = (ops.rmsnorm(x, None, 1e-5, mean_dim=k).float() - bare.float()).abs()
+    assert float((d / bare.float().abs().clamp(min=1e-3)).max()) < 2.0 ** -9
+
+
+@pytest.mark.parametrize("b,s,h", [(1, 7, 4), (2, 2048, 32), (16, 1, 8)])
+def test_rope_is_bit_identical_to_the_torch_expression(dev, b, s, h):
+    from flatquant_b200 import ops
+    from flatquant_b200.deploy.transformers import modeling_llama as ML
+    torch.manual_seed(b + s + h)
+    x = torch.randn(b, s, h, 128, device=dev).half()
+    inv = 1.0 / (500000.0 ** (torch.arange(0, 128, 2, dtype=torch.float32, device=dev) / 128))
+    pos = torch.arange(3, 3 + s, device=dev)[None].expand(b, s)
+    cos, sin = ML.rope_cos_sin(inv, pos, torch.float16)
+    half = 64
+    rot = torch.cat((-x[..., half:], x[..., :half]), dim=-1)
+    ref = x * cos + rot * sin
+    got = ops.rope_(x.clone(), cos.reshape(b * s, 128).contiguous(), sin.reshape(b * s, 128).contiguous())
+    assert torch.equal(got, ref)   # same three fp16 roundings per element
+
+
+@pytest.mark.parametrize("rows,inter", [(3, 64), (2048, 14336), (17, 1792)])
+def test_silu_mul_matches_the_torch_expression(dev, rows, inter):
+    from flatquant_b200 import ops
+    torch.manual_seed(rows + inter)
+    gu = (torch.randn(rows, 2 * inter, device=dev) * 2).half()
+    ref = torch.nn.functional.silu(gu[:, :inter]) * gu[:, inter:]
+    got = ops.silu_mul(gu)
+    d = (got.float() - ref.float()).abs()
+    # torch's silu kernel and expf may differ in the last fp32 bit before the fp16 rounding: at most one fp16 ulp, rarely
+    assert float((d / ref.float().abs().clamp(min=1e-3)).max()) < 2.0 ** -9 and float((d > 0).float().mean()) < 1e-3

@@ -23,12 +23,14 @@ run 300 zz_llama.log python -m pytest tests/test_zz_llama_model_gpu.py -q -s
 run 300 zz_deepseek.log python -m pytest tests/test_zz_deepseek_block_gpu.py -q -s
 run 300 zzv_shapes.log python -m pytest tests/test_zzv_full_size_transform_shapes_gpu.py -q -s
 FLATQ_RUN_UNVERIFIED=1 run 300 zzz_grouped.log python -m pytest tests/test_zzz_grouped_gemm_gpu.py -q -s
+FLATQ_RUN_UNVERIFIED=1 run 300 zzz_glue.log python -m pytest tests/test_zzz_glue_kernels_gpu.py -q -s
 FLATQ_RUN_UNVERIFIED=1 run 300 zzz_decode_split.log python -m pytest tests/test_zzz_decode_split_gpu.py -q -s
 run 400 bench_default.json python bench.py --steps 10 --warmup 3
 run 120 ref_kernels_bench.json python tools/ref_kernels_bench.py
 FLATQ_RUN_UNVERIFIED=1 run 300 decode_attn_bench.jsonl python tools/decode_attn_bench.py
 run 600 bench_model.json python bench.py --workload llama8b-model --steps 3 --warmup 3
 FLATQ_DECODE_SPLIT=1 run 600 bench_model_split_decode.json python bench.py --workload llama8b-model --steps 3 --warmup 3
+FLATQ_DECODE_SPLIT=1 FLATQ_FUSED_GLUE=1 run 600 bench_model_split_decode_fused_glue.json python bench.py --workload llama8b-model --steps 3 --warmup 3
 run 400 bench_deepseek_loop.json python bench.py --workload deepseek-block --steps 3 --warmup 3
 FLATQ_GROUPED_MOE=1 run 400 bench_deepseek_grouped.json python bench.py --workload deepseek-block --steps 3 --warmup 3
 run 300 ncu_launches_deepseek.log ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
