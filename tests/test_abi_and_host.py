@@ -162,6 +162,16 @@ def test_c_abi_argument_errors_without_a_gpu(lib):
     assert l.flatq_gemm_w4a8(fake, fake, fake, fake, None, 4, 8, 48, fake, 0, None, 0, None) == INVALID
     assert l.flatq_gemm_w4a8(fake, fake, fake, fake, None, 4, 8, 64, fake, 7, None, 0, None) == INVALID and "out_dtype" in err()
     assert l.flatq_linear_fused(fake, None, None, 1, 64, 1.0, 1.0, fake, fake, None, 4, 8, fake, 0, fake, 8, None) == WORKSPACE
+    assert l.flatq_rmsnorm(fake, None, 4, 20, 20.0, 1e-5, fake, None) == INVALID and "multiple of 8" in err()
+    assert l.flatq_rmsnorm(fake, odd, 4, 64, 64.0, 1e-5, fake, None) == INVALID and "alignment" in err()
+    assert l.flatq_rope(fake, fake, fake, 4, 2, 64, None) == UNSUPPORTED and "head_dim" in err()
+    assert l.flatq_silu_mul(fake, 4, 12, fake, None) == INVALID and "multiple of 8" in err()
+    dws = l.flatq_kv_decode_i4_split_workspace_bytes(2, 8)
+    assert dws >= 2 * 8 * 64 * 130 * 4
+    assert l.flatq_kv_decode_i4_split(fake, fake, fake, fake, fake, fake, fake, 2, 8, 3, 128, 16, 0, 1, 1.0, 0, fake, dws,
+                                      None) == INVALID and "heads" in err()
+    assert l.flatq_kv_decode_i4_split(fake, fake, fake, fake, fake, fake, fake, 2, 8, 2, 128, 16, 0, 1, 1.0, 0, fake, 16,
+                                      None) == WORKSPACE
     g = l.flatq_gemm_w4a8_grouped
     ws = l.flatq_gemm_w4a8_grouped_workspace_bytes(8)
     assert ws >= 9 * 4
