@@ -215,8 +215,8 @@ __global__ void __launch_bounds__(128) decode_attn_i4_kernel(const DecodeParams 
 //   * gives a CTA ONE kv head and GH of its query heads (K/V bytes are read once per group, not once per query head),
 //   * splits the sequence over `splits` CTAs (flash-decoding) so that batch x kv_heads x splits fills the chip,
 //   * reads 8 bytes (16 dims) per lane: 8 lanes cover a 64-byte row, a warp covers 4 consecutive tokens = 256
-//     contiguous bytes of a page per load instruction, and the next chunk's loads are issued before the current
-//     chunk's arithmetic (software double buffering),
+//     contiguous bytes of a page per load instruction, and the loads of the next TWO chunks are in flight while the
+//     current chunk's arithmetic runs (a ring of three register buffers),
 //   * keeps, per 8-lane token group, an online-softmax state (m, l, acc[16 dims]) for each of the GH heads in registers;
 //     the 16 groups of a CTA are merged through shared memory, the splits by decode_attn_merge_kernel.
 // Partial results: part[((b * q_heads + hq) * splits + s) * 130 + {0..127: unnormalised output, 128: max, 129: sum}], fp32.
@@ -285,14 +285,16 @@ decode_attn_i4_split_kernel(const DecodeParams p, int splits, float* __restrict_
     const int per = (n_tok + splits - 1) / splits;           // tokens per split
     const int t0 = split * per, t1 = min(n_tok, t0 + per);   // empty when t0 >= n_tok
     const int n_iter = t1 > t0 ? (t1 - t0 + kDecGroups - 1) / kDecGroups : 0;   // uniform over the CTA: shuffles stay converged
-    DecKvChunk cur, nxt;
-    cur.k = cur.v = nxt.k = nxt.v = make_uint2(0, 0);
-    cur.kpar = cur.vpar = nxt.kpar = nxt.vpar = make_float2(0.f, 0.f);
-    if (n_iter > 0 && t0 + grp < t1) dec_load_chunk(p, pg0, hk, t0 + grp, lane8, cur);
+    // two chunks in flight beyond the one being consumed (a ring of three register buffers)
+    DecKvChunk cur, nxt, nx2;
+    cur.k = cur.v = nxt.k = nxt.v = nx2.k = nx2.v = make_uint2(0, 0);
+    cur.kpar = cur.vpar = nxt.kpar = nxt.vpar = nx2.kpar = nx2.vpar = make_float2(0.f, 0.f);
+    if (t0 + grp < t1) dec_load_chunk(p, pg0, hk, t0 + grp, lane8, cur);
+    if (t0 + kDecGroups + grp < t1) dec_load_chunk(p, pg0, hk, t0 + kDecGroups + grp, lane8, nxt);
     for (int it = 0; it < n_iter; ++it) {
         const int t = t0 + it * kDecGroups + grp;
         const bool valid = t < t1;
-        if (it + 1 < n_iter && t + kDecGroups < t1) dec_load_chunk(p, pg0, hk, t + kDecGroups, lane8, nxt);
+        if (t + 2 * kDecGroups < t1) dec_load_chunk(p, pg0, hk, t + 2 * kDecGroups, lane8, nx2);
         float xh[16];
         dec_dequant16(cur.k, cur.kpar, xh);
         float dot[GH];
@@ -319,6 +321,7 @@ decode_attn_i4_split_kernel(const DecodeParams p, int splits, float* __restrict_
             }
         }
         cur = nxt;
+        nxt = nx2;
     }
 
     // ---- merge the CTA's 16 token groups (thread j owns output dim j), publish one partial per (query head, split)

@@ -3,7 +3,7 @@
 
 UNVERIFIED ON HARDWARE, gated like tests/test_zzz_grouped_gemm_gpu.py: written after round 1's GPU minutes were spent.
 Checked without a GPU: the algorithm (tests/test_decode_split_model.py, numpy restatement of the kernel's schedule), the
-existing kernels' SASS unchanged (tools/sass_diff.py: identical 89, new 4), no spills (-Xptxas: 80 / 128 / 237 registers
+existing kernels' SASS unchanged (tools/sass_diff.py: identical 89, new 4), no spills (-Xptxas: 96 / 127 / 243 registers
 for 1 / 2 / 4 query heads per CTA).  First run:
 
     FLATQ_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_zzz_decode_split_gpu.py -x -q -s
