@@ -362,11 +362,7 @@ class FlatQuantLlamaAttention(torch.nn.Module):
         cache_out = past_key_value.update(k.contiguous(), v.contiguous(), self.layer_idx, rt.cache_kwargs)
         if isinstance(cache_out, tuple):  # prefill: causal attention over the transformed fp16 states
             k_t, v_t = cache_out
-            if past_key_value.trans.startswith("matmul"):
-                q = ops.kron_transform(q.reshape(-1, self.head_dim).contiguous(), None, rt.k_inv_t, 1,
-                                       self.head_dim).view(q.shape)
-            elif past_key_value.trans == "had":
-                q = ops.hadamard(q.contiguous(), 1.0 / math.sqrt(self.head_dim))
+            q = past_key_value._transform(q, rt.k_inv_t)   # Q . T_k^-T (or the Hadamard), like K . T_k in the cache
             attn = F.scaled_dot_product_attention(q.transpose(1, 2), k_t.transpose(1, 2), v_t.transpose(1, 2),
                                                   is_causal=True, enable_gqa=self.num_heads != self.num_key_value_heads)
             attn = attn.transpose(1, 2)

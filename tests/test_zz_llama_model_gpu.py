@@ -36,43 +36,6 @@ def g():
     return np.load(os.path.join(GOLDEN, "llama_model.npz"))
 
 
-def test_right_only_transform_and_matmul_kv_cache(dev):
-    """x . T over the last axis with no left factor (the K / Q cache transform, kv_cache.py `_transform`): the HMMA
-    kernel's right-only configuration at every row grouping ops.kron_transform picks (16 / 8 / 1 rows per "token"), then
-    the paged cache in trans="matmul" mode (prefill + one appended token + single-query attention) against the oracle."""
-    from flatquant_b200 import ops
-    from flatquant_b200.deploy.transformers import MultiLayerPagedKVCache4Bit
-    torch.manual_seed(21)
-    D = 128
-    t_k = (torch.eye(D) * 0.75 + torch.randn(D, D) * (0.5 / D ** 0.5)).half()
-    t_k_inv_t = torch.linalg.inv(t_k.double()).t().float().half()
-    for rows in (48, 8, 3):
-        x = torch.randn(rows, D).half()
-        z = ops.kron_transform(x.to(dev), None, t_k.to(dev), 1, D).float().cpu()
-        ref = x.float() @ t_k.float()
-        assert (z - ref).abs().max() <= 3 * 2.0 ** -11 * float(ref.abs().max()), rows  # one fp16 rounding of the output
-    B, T, H, L = 2, 21, 2, 2
-    kw = dict(trans_matrix_k=t_k.to(dev), trans_matrix_k_inv_t=t_k_inv_t.to(dev))
-    cache = MultiLayerPagedKVCache4Bit(B, 16, 64, dev, L, H, D, trans="matmul")
-    k, v = torch.randn(B, T, H, D).half(), torch.randn(B, T, H, D).half()
-    k1, v1 = torch.randn(B, 1, H, D).half(), torch.randn(B, 1, H, D).half()
-    q = torch.randn(B, 1, 2 * H, D).half()  # GQA: 2 query heads per kv head
-    for layer in range(L):
-        kt, vt = cache.update(k.to(dev), v.to(dev), layer, kw)
-        assert (kt.float().cpu() - k.float() @ t_k.float()).abs().max() <= 3 * 2.0 ** -11 * float((k.float() @ t_k.float()).abs().max())
-        assert torch.equal(vt.cpu(), v)
-    for layer in range(L):
-        o = cache.update(k1.to(dev), v1.to(dev), layer, kw)(q.to(dev))
-    assert o.shape == (B, 1, 2 * H, D) and cache.get_seq_length() == T + 1
-    kk = torch.cat([(k.float() @ t_k.float()).half(), (k1.float() @ t_k.float()).half()], 1)
-    kp, ks, kz = O.kv_asym_quant(kk)
-    vp, vs, vz = O.kv_asym_quant(torch.cat([v, v1], 1))
-    r = lambda t: t.repeat_interleave(2, 2)  # noqa: E731
-    q_t = (q[:, 0].float() @ t_k_inv_t.float()).half()
-    ref = O.decode_attention_i4(q_t, r(kp), r(ks), r(kz), r(vp), r(vs), r(vz))
-    assert (o[:, 0].float().cpu() - ref).abs().max() < 2e-2
-
-
 def test_every_quantised_stage_teacher_forced(model, g, dev):
     """q/k/v, o (with RoPE, K/Q transforms, KV quantise+append and attention in front of it), gate/up and down of both
     layers on the golden input of each stage, vs the reference's fp32 fake-quant output."""
@@ -165,3 +128,41 @@ def test_graphed_steps_equal_eager(model, g, dev):
             want, wc = model(ids)
         assert close(logits, want) and cache.get_seq_length() == s
         assert torch.equal(cache.pages, wc.pages)
+
+
+def test_right_only_transform_and_matmul_kv_cache(dev):
+    """x . T over the last axis with no left factor: the HMMA kernel's right-only configuration at every row grouping
+    ops.kron_transform picks (16 / 8 / 1 rows per "token") -- never run on hardware, hence LAST in this file (the cache
+    itself passes an explicit identity left factor until this has passed: kv_cache.RIGHT_ONLY_VERIFIED) -- then the paged
+    cache in trans="matmul" mode (prefill + one appended token + single-query attention) against the oracle."""
+    from flatquant_b200 import ops
+    from flatquant_b200.deploy.transformers import MultiLayerPagedKVCache4Bit
+    torch.manual_seed(21)
+    D = 128
+    t_k = (torch.eye(D) * 0.75 + torch.randn(D, D) * (0.5 / D ** 0.5)).half()
+    t_k_inv_t = torch.linalg.inv(t_k.double()).t().float().half()
+    for rows in (48, 8, 3):
+        x = torch.randn(rows, D).half()
+        z = ops.kron_transform(x.to(dev), None, t_k.to(dev), 1, D).float().cpu()
+        ref = x.float() @ t_k.float()
+        assert (z - ref).abs().max() <= 3 * 2.0 ** -11 * float(ref.abs().max()), rows  # one fp16 rounding of the output
+    B, T, H, L = 2, 21, 2, 2
+    kw = dict(trans_matrix_k=t_k.to(dev), trans_matrix_k_inv_t=t_k_inv_t.to(dev))
+    cache = MultiLayerPagedKVCache4Bit(B, 16, 64, dev, L, H, D, trans="matmul")
+    k, v = torch.randn(B, T, H, D).half(), torch.randn(B, T, H, D).half()
+    k1, v1 = torch.randn(B, 1, H, D).half(), torch.randn(B, 1, H, D).half()
+    q = torch.randn(B, 1, 2 * H, D).half()  # GQA: 2 query heads per kv head
+    for layer in range(L):
+        kt, vt = cache.update(k.to(dev), v.to(dev), layer, kw)
+        assert (kt.float().cpu() - k.float() @ t_k.float()).abs().max() <= 3 * 2.0 ** -11 * float((k.float() @ t_k.float()).abs().max())
+        assert torch.equal(vt.cpu(), v)
+    for layer in range(L):
+        o = cache.update(k1.to(dev), v1.to(dev), layer, kw)(q.to(dev))
+    assert o.shape == (B, 1, 2 * H, D) and cache.get_seq_length() == T + 1
+    kk = torch.cat([(k.float() @ t_k.float()).half(), (k1.float() @ t_k.float()).half()], 1)
+    kp, ks, kz = O.kv_asym_quant(kk)
+    vp, vs, vz = O.kv_asym_quant(torch.cat([v, v1], 1))
+    r = lambda t: t.repeat_interleave(2, 2)  # noqa: E731
+    q_t = (q[:, 0].float() @ t_k_inv_t.float()).half()
+    ref = O.decode_attention_i4(q_t, r(kp), r(ks), r(kz), r(vp), r(vs), r(vz))
+    assert (o[:, 0].float().cpu() - ref).abs().max() < 2e-2
