@@ -482,20 +482,17 @@ def cpu_reference_pass(n_layers_sample, threads, reps, warm):
     return SEQ / (t_layer * N_LAYERS), t_layer
 
 
-def reference_gpu_kernels(device_index, our_gemm_ms_per_step):
-    """Baseline leg: the reference's own CUTLASS s4 GEMM + dequant kernels (oracle/_ref, built from /root/reference for
-    sm_100a) over the work of our GEMM-only pass, in a SUBPROCESS (tools/ref_kernels_bench.py) so that a fault inside a
-    reference kernel cannot touch this process's CUDA context.  Reported next to our number; never on our path."""
+def reference_gpu_kernels(device_index):
+    """Reference arm only: the reference's own CUTLASS s4 GEMM + dequant kernels (oracle/_ref, built from
+    /root/reference for sm_100a) over the work of our arm's GEMM-only roofline pass, in a SUBPROCESS
+    (tests/tools/ref_kernels_bench.py) so that a fault inside a reference kernel cannot touch this process."""
     try:
-        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_kernels_bench.py"), "--device",
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "ref_kernels_bench.py"), "--device",
                               str(device_index)], capture_output=True, text=True, timeout=300)
         last = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
         res = json.loads(last[-1]) if last else {"unavailable": (out.stderr or "no output")[-300:]}
     except Exception as e:  # noqa: BLE001
         res = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
-    if "ms_per_step" in res:
-        res["our_gemm_pass_ms_per_step"] = our_gemm_ms_per_step
-        res["speedup_of_our_gemm_pass"] = res["ms_per_step"] / our_gemm_ms_per_step
     return res
 
 
@@ -531,6 +528,13 @@ def main():
                 "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": threads, "kind": "port",
                                  "sample": "1 decoder layer (7 linears) at seq 2048 per step, x32"},
                 "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        # extra, GPU boxes only: the reference's own native GEMM + dequant kernels on this GPU (compare with the other
+        # arm's roofline.avg_launch_us x launches / steps, i.e. its GEMM-only pass)
+        try:
+            if torch.cuda.is_available():
+                line["reference_gpu_kernels"] = reference_gpu_kernels(local)
+        except Exception as e:  # noqa: BLE001
+            line["reference_gpu_kernels"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         print(json.dumps(line), flush=True)
         return
 
@@ -684,8 +688,6 @@ def main():
         if sus:
             line["roofline"]["peak_sustained"] = 2 * sus
             line["roofline"]["frac_of_sustained"] = achieved / (2 * sus)
-        if world == 1 and args.layers == N_LAYERS:
-            line["reference_gpu_kernels"] = reference_gpu_kernels(local, ms_gemm / args.steps)
         if not args.no_cpu_baseline and world == 1:
             v, t_layer = cpu_reference_pass(1, threads, 2, 1)
             line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port",

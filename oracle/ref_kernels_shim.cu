@@ -14,7 +14,7 @@
 //
 // Used by tests/test_zy_reference_cuda_kernels_gpu.py (bit-level GPU parity of flatq_gemm_i4 / flatq_sym_quant /
 // flatq_sym_dequant(mode 1) / flatq_kv_decode_i4 against the reference's kernels on the same B200) and by
-// tools/ref_kernels_bench.py (the reference's GEMM + dequant timed next to ours).
+// tests/tools/ref_kernels_bench.py (the reference's GEMM + dequant timed by the reference arm of bench.py).
 #include <flashinfer.h>
 #include <gemm.h>
 #include <quant.h>

@@ -8,7 +8,7 @@ import traceback
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from flatquant_b200 import ops  # noqa: E402
 from oracle import flatq_oracle as O  # noqa: E402

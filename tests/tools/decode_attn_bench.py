@@ -4,14 +4,14 @@ GPU time per launch of (a) flatq_kv_decode_i4 (single pass, verified), (b) flatq
 a cache holding the kv heads repeated to 32 (what the reference's cache stores, kv_cache.py:291-299).
 CUDA events on the legacy default stream, 50 launches after 5 warm-ups; prints one JSON object per (batch, kernel).
 
-    python tools/decode_attn_bench.py            (first run of (b): see tests/test_zzz_decode_split_gpu.py)"""
+    python tests/tools/decode_attn_bench.py            (first run of (b): see tests/test_zzz_decode_split_gpu.py)"""
 import json
 import os
 import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from flatquant_b200 import ops  # noqa: E402
 from oracle import ref_kernels as R  # noqa: E402  (baseline leg only)
 

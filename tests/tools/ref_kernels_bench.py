@@ -5,14 +5,15 @@ pass: 32 layers x {qkv 4096->6144, o 4096->4096, gate_up 4096->28672, down 14336
 weights per layer (3.5 GB, larger than L2).  This is the "reference's own deploy/kernels CUTLASS build on the same box"
 the north star names as the target to beat for a11 + a12; the reference's Triton transform kernels are not part of it.
 
-Prints ONE JSON object.  bench.py runs this file in a subprocess (a fault inside a reference kernel must not take the
-benchmark's CUDA context with it) and attaches the object to its line as "reference_gpu_kernels"."""
+Prints ONE JSON object.  The REFERENCE arm of bench.py (--impl reference) runs this file in a subprocess (a fault
+inside a reference kernel must not take the caller with it) and attaches the object to its line as
+"reference_gpu_kernels"."""
 import argparse
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

@@ -26,8 +26,8 @@ FLATQ_RUN_UNVERIFIED=1 run 300 zzz_grouped.log python -m pytest tests/test_zzz_g
 FLATQ_RUN_UNVERIFIED=1 run 300 zzz_glue.log python -m pytest tests/test_zzz_glue_kernels_gpu.py -q -s
 FLATQ_RUN_UNVERIFIED=1 run 300 zzz_decode_split.log python -m pytest tests/test_zzz_decode_split_gpu.py -q -s
 run 400 bench_default.json python bench.py --steps 10 --warmup 3
-run 120 ref_kernels_bench.json python tools/ref_kernels_bench.py
-FLATQ_RUN_UNVERIFIED=1 run 300 decode_attn_bench.jsonl python tools/decode_attn_bench.py
+run 120 ref_kernels_bench.json python tests/tools/ref_kernels_bench.py
+FLATQ_RUN_UNVERIFIED=1 run 300 decode_attn_bench.jsonl python tests/tools/decode_attn_bench.py
 run 600 bench_model.json python bench.py --workload llama8b-model --steps 3 --warmup 3
 FLATQ_DECODE_SPLIT=1 run 600 bench_model_split_decode.json python bench.py --workload llama8b-model --steps 3 --warmup 3
 FLATQ_DECODE_SPLIT=1 FLATQ_FUSED_GLUE=1 run 600 bench_model_split_decode_fused_glue.json python bench.py --workload llama8b-model --steps 3 --warmup 3
