@@ -3,7 +3,7 @@ stand-ins of tests/cpu_ops.py (STRICT: the C ABI's own argument checks) and devi
 it proves that the test code and the host code it drives are executable and only make calls the CUDA library accepts,
 before GPU minutes are spent on them.  (Graph capture and the kernels' numerics are what remains for the hardware run.)
 
-    python tools/dry_run_gpu_tests_on_cpu.py"""
+    python tests/tools/dry_run_gpu_tests_on_cpu.py"""
 import importlib
 import os
 import sys
@@ -11,7 +11,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import cpu_ops  # noqa: E402
 from flatquant_b200 import ops  # noqa: E402
