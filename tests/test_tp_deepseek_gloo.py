@@ -6,6 +6,7 @@ import os
 import socket
 from types import SimpleNamespace
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -33,16 +34,19 @@ def _block(rank, tp):
     return MD.FlatQuantDeepSeekBlock(a, MD.random_block_params(a, "cpu", seed=SEED, tp_size=WORLD, tp_rank=rank), "cpu", tp)
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, grouped):
     from flatquant_b200 import ops
     from flatquant_b200.deploy.transformers import modeling_deepseek as MD
     from flatquant_b200.deploy.transformers.modeling_llama import TensorParallel
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    if grouped:   # the ranks take the grouped-GEMM path (one launch per expert stage, local experts only)
+        os.environ["FLATQ_GROUPED_MOE"] = "1"
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         for name in cpu_ops.FUNCTIONS:
             setattr(ops, name, getattr(cpu_ops, name))
         block = _block(rank, TensorParallel(world, rank))
+        assert block.routed.grouped == bool(grouped)
         x = _x()
         cos, sin = MD.precompute_freqs(_args(), x.shape[1])
         with torch.no_grad():
@@ -62,12 +66,13 @@ def _free_port():
     return p
 
 
-def test_tp2_block_equals_lockstep_serial_restatement(monkeypatch):
+@pytest.mark.parametrize("grouped", [False, True])
+def test_tp2_block_equals_lockstep_serial_restatement(monkeypatch, grouped):
     from flatquant_b200.deploy.transformers import modeling_deepseek as MD
     from flatquant_b200.deploy.transformers.modeling_llama import TensorParallel
     mgr = mp.get_context("spawn").Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(WORLD, _free_port(), ret), nprocs=WORLD, join=True)
+    mp.spawn(_worker, args=(WORLD, _free_port(), ret, grouped), nprocs=WORLD, join=True)
     assert (ret[0][0] == ret[1][0]).all() and (ret[0][1] == ret[1][1]).all()
 
     cpu_ops.install(monkeypatch)
