@@ -58,10 +58,10 @@ def _case(dev, counts, n, k, out_dtype=torch.float16, with_bias=False, hint=0, s
     ([0, 0, 7, 0], 100, 128, 0),                          # empty groups around one; N < 128 (weight rows of the next
                                                           # expert inside the TMA box must be masked)
     ([1] * 9, 130, 512, 0),                               # decode-like: one row per expert, N = 128 + 2
-    ([37, 0, 64, 3, 129], 384, 1024, 0),                  # ragged, TN = 64 from the mean
-    ([37, 0, 64, 3, 129], 384, 1024, 16),                 # same with the smallest token tile
-    ([300, 0, 0, 1], 4096, 2048, 128),                    # one hot expert, several token blocks, full-width N
-    ([90, 250, 513], 512, 4096, 256),                     # TN = 256 single-CTA tiles
+    ([37, 0, 64, 3, 129], 384, 1024, 0),                  # ragged, token tile from the mean (47 rows -> 128)
+    ([37, 0, 64, 3, 129], 384, 1024, 4),                  # same with the smallest token tile (16)
+    ([300, 0, 0, 1], 4096, 2048, 20),                     # one hot expert, several 64-token blocks, full-width N
+    ([90, 250, 513], 512, 4096, 256),                     # 256-token single-CTA tiles
 ])
 def test_grouped_gemm_equals_per_expert_launches(dev, counts, n, k, hint):
     xq8, sx, w, sw, y = _case(dev, counts, n, k, hint=hint)
