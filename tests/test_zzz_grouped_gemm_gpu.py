@@ -60,6 +60,7 @@ def _case(dev, counts, n, k, out_dtype=torch.float16, with_bias=False, hint=0, s
     ([1] * 9, 130, 512, 0),                               # decode-like: one row per expert, N = 128 + 2
     ([37, 0, 64, 3, 129], 384, 1024, 0),                  # ragged, token tile from the mean (47 rows -> 128)
     ([37, 0, 64, 3, 129], 384, 1024, 4),                  # same with the smallest token tile (16)
+    ([20, 9, 0, 31], 256, 256, 12),                       # 32-token tiles
     ([300, 0, 0, 1], 4096, 2048, 20),                     # one hot expert, several 64-token blocks, full-width N
     ([90, 250, 513], 512, 4096, 256),                     # 256-token single-CTA tiles
 ])
