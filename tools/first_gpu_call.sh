@@ -2,7 +2,7 @@
 # First GPU call of the next session: everything that was written after round 1's GPU minutes were spent, in order of
 # increasing risk, each step under its own timeout, logs into gpurun_out/ (merged back by gpurun).
 #
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/first_gpu_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/first_gpu_call.sh'
 #
 # Reads: DESIGN.md section 10 (status table).  A step that fails does not stop the later ones.
 set -u
