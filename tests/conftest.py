@@ -21,6 +21,12 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         has_gpu = False
     if has_gpu:
+        # a kernel that hangs must cost one test run, not the box: pytest-timeout's thread method ends the process
+        # (signals cannot interrupt a thread blocked inside a CUDA call).  15 minutes is far above the slowest test.
+        if config.pluginmanager.hasplugin("timeout"):
+            for it in items:
+                if "gpu" in it.keywords and it.get_closest_marker("timeout") is None:
+                    it.add_marker(pytest.mark.timeout(900, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:
