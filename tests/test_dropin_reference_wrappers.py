@@ -433,3 +433,32 @@ def test_other_model_families_wrappers_on_our_modules(family):
     _same_state(r_ml, o_ml, exact=False)
     if qwen:
         assert o_at.v_proj.linear.bias is not None and not torch.equal(o_at.v_proj.linear.bias, attn.v_proj.bias)
+
+
+def test_get_hadK_chooses_the_reference_factorisation(monkeypatch):
+    """deploy/functional/online_trans.py:21-71 (loaded with its CUDA-only imports stubbed): for every hidden / intermediate
+    size of the model families the reference lists, our get_hadK picks the same K x 2^m factorisation; the reference's
+    tables are Hadamard matrices, as are the ones we generate for the orders that have a construction."""
+    from flatquant_b200.deploy.functional import hadamard as H
+
+    def stub(name, **attrs):
+        mod = types.ModuleType(name)
+        mod.__path__ = []
+        for k, v in attrs.items():
+            setattr(mod, k, v)
+        monkeypatch.setitem(sys.modules, name, mod)
+    stub("fast_hadamard_transform"), stub("deploy"), stub("deploy.kernels")
+    stub("deploy.kernels.kron_matmul", kron_matmul=None), stub("deploy.kernels.block_matmul", block_matmul=None)
+    ref = _load_by_path("ref_deploy_online_trans", os.path.join(REF, "deploy", "functional", "online_trans.py"))
+    for n in (4096, 14336, 11008, 13824, 5120, 27648, 8192, 6144, 1792, 20 * 64, 36 * 8, 52 * 4, 60 * 2, 140 * 16, 156 * 2,
+              12 * 4, 28 * 2, 40 * 8, 108 * 32):
+        hk, k = ref.get_hadK(n)
+        assert k == H.hadK_order(n), n
+        ours, _ = H.get_hadK(n)
+        if hk is not None:
+            assert torch.equal(hk.float() @ hk.float().t(), k * torch.eye(k))
+            if not torch.isnan(ours).any():
+                assert ours.shape == hk.shape and torch.equal(ours @ ours.t(), k * torch.eye(k))
+    for n in (64, 448, 8192):
+        assert ref.get_decompose_dim(n) == H.__dict__.get("get_decompose_dim", __import__(
+            "flatquant_b200.function_utils", fromlist=["get_decompose_dim"]).get_decompose_dim)(n)
