@@ -213,3 +213,16 @@ def test_hadamard_factors_and_matmul_hadU(monkeypatch):
     bad = OnlineTrans(11008, trans="had")  # order 172: placeholder until a checkpoint provides the table
     with pytest.raises(RuntimeError, match="placeholder"):
         bad(torch.zeros(1, 2, 11008, dtype=torch.float16))
+
+
+def test_integration_md_binding_snippet_is_valid_python_against_the_real_symbols(lib):
+    """The reference-side ctypes binding shown in INTEGRATION.md compiles, and every flatq_* symbol it (and the symbol
+    table) names is exported by the built library."""
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", md, flags=re.S)
+    assert blocks, "no python block in INTEGRATION.md"
+    for src in blocks:
+        compile(src, "INTEGRATION.md", "exec")
+    l = lib.load()
+    for name in set(re.findall(r"\b(flatq_[a-z0-9_]+)\b", md)) - {"flatq_b200"}:   # the header's / library's own name
+        assert hasattr(l, name), f"INTEGRATION.md names {name}, which the library does not export"
