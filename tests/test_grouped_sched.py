@@ -73,3 +73,50 @@ def test_grouped_schedule_v3_shape(shim):
     counts = np.bincount(rng.choice(256, 2048 * 8, p=p), minlength=256)
     _check(shim, counts, 64, 4096)
     _check(shim, counts, 128, 7168)
+
+
+def test_grouped_gemm_tile_level_model_equals_per_expert_gemms(shim):
+    """Tile-level transcription of the GROUPED branches of gemm_w4a8_kernel (csrc/gemm_w4a8.cuh): per output tile the X
+    TMA box rows [m0, m0 + TN) of the sorted activation (rows of the NEXT expert included, rows past M zero-filled), the
+    W TMA box rows [group * N + n0, + 128) of the stacked weight (rows of the next expert included), the epilogue's
+    masks (n < N, m < m_end) and scale offsets (ch0 = group * N) -- against one plain GEMM per expert."""
+    rng = np.random.default_rng(7)
+    for counts, n, k, tn in (([5, 0, 19, 2], 100, 64, 16), ([40, 3, 0, 0, 70], 200, 32, 32), ([1] * 6, 130, 64, 16)):
+        counts = np.asarray(counts, np.int32)
+        e, m = len(counts), int(counts.sum())
+        off = np.zeros(e + 1, np.int32)
+        off[1:] = np.cumsum(counts)
+        nb_w = (n + 127) // 128
+        prefix = np.zeros(e + 1, np.int32)
+        shim.shim_build_prefix(_ptr(off), e, tn, nb_w, _ptr(prefix))
+        x = rng.integers(-8, 8, (m, k)).astype(np.int64)
+        w = rng.integers(-8, 8, (e * n, k)).astype(np.int64)          # stacked [E * N, K]
+        sx, sw = rng.random(m) + 0.5, rng.random(e * n) + 0.5
+        y = np.full((m, n), np.nan)
+        out = np.zeros(4, np.int32)
+        for t in range(int(prefix[-1])):
+            shim.shim_tile(_ptr(off), _ptr(prefix), e, tn, 128, t, _ptr(out))
+            g, m0, m_end, n0 = (int(v) for v in out)
+            m_end = min(m_end, m)
+            w_row0, ch0 = g * n + n0, g * n
+            xt = np.zeros((tn, k), np.int64)
+            rows = x[m0:m0 + tn]                                        # TMA box; out-of-bounds rows are zero-filled
+            xt[:len(rows)] = rows
+            wt = np.zeros((128, k), np.int64)
+            wrows = w[w_row0:w_row0 + 128]
+            wt[:len(wrows)] = wrows
+            acc = wt @ xt.T                                             # D[n, m] of the tile
+            for r in range(128):
+                nn = n0 + r
+                if nn >= n:
+                    continue                                            # n_ok
+                for j in range(tn):
+                    mm = m0 + j
+                    if mm < m_end:
+                        assert np.isnan(y[mm, nn])                      # written exactly once
+                        y[mm, nn] = acc[r, j] * sx[mm] * sw[ch0 + nn]
+        want = np.zeros((m, n))
+        for g in range(e):
+            r = slice(off[g], off[g + 1])
+            want[r] = (x[r] @ w[g * n:(g + 1) * n].T) * sx[r, None] * sw[None, g * n:(g + 1) * n]
+        assert not np.isnan(y).any() and np.array_equal(y, want)
