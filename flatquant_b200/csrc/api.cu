@@ -733,6 +733,31 @@ int flatq_hadamard(const void* x, void* out, int64_t rows, int n, float scale, f
     return FLATQ_OK;
 }
 
+int flatq_hadamard_kn(const void* x, void* out, const void* hadK, int64_t rows, int n, int K, float scale,
+                      flatq_stream_t stream) {
+    FLATQ_CHECK(x && out && hadK, FLATQ_ERR_INVALID, "hadamard_kn: null pointer");
+    FLATQ_CHECK(K >= 4 && K <= 172 && K % 4 == 0 && n % K == 0, FLATQ_ERR_UNSUPPORTED,
+                "hadamard_kn: K=%d must be a multiple of 4 in [4, 172] dividing n=%d", K, n);
+    const int n2 = n / K;
+    FLATQ_CHECK(n2 >= 8 && (n2 & (n2 - 1)) == 0 && n <= 32768, FLATQ_ERR_UNSUPPORTED,
+                "hadamard_kn: n/K=%d must be a power of two >= 8, n <= 32768", n2);
+    FLATQ_CHECK(rows > 0 && aligned16(x) && aligned16(out), FLATQ_ERR_INVALID, "hadamard_kn: rows / alignment");
+    int log_n2 = 0;
+    while ((1 << log_n2) < n2) ++log_n2;
+    const int threads = n / 8 < 128 ? 128 : (n / 8 > 1024 ? 1024 : ((n / 8 + 31) / 32) * 32);
+    const size_t smem = (size_t)(n + n / 32 + 2) * sizeof(float) + (size_t)K * K * 2;
+    FLATQ_CHECK(smem <= 227 * 1024, FLATQ_ERR_UNSUPPORTED, "hadamard_kn: row of n=%d with K=%d does not fit shared memory", n, K);
+    static PerDeviceMax attr;
+    if (smem > 48 * 1024 && attr.grows(smem))
+        FLATQ_CUDA(cudaFuncSetAttribute(fht_kn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t cap = (int64_t)num_sms() * (smem <= 56 * 1024 ? 4 : (smem <= 113 * 1024 ? 2 : 1));
+    fht_kn_kernel<<<(int)(rows < cap ? rows : cap), threads, smem, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), reinterpret_cast<const __half*>(hadK), (int)rows,
+        K, log_n2, scale);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
 int flatq_kv_quant(const void* x, int64_t tokens, int heads, int head_dim, uint8_t* q_out, void* param_out, uint8_t* kv_data,
                    void* kv_param, const int32_t* slot, int layer, int n_layers, int kv_select, int page_size,
                    flatq_stream_t stream) {

@@ -81,6 +81,90 @@ __global__ void __launch_bounds__(1024) fht_kernel(const __half* __restrict__ x,
     }
 }
 
+// ------------------------------------------------------------------------------------------------ FHT, n = K * 2^m
+// matmul_hadU_cuda for the sizes that are not a power of two (deploy/functional/online_trans.py:144-151; the reference
+// runs hadamard_transform over the 2^m axis and then `hadK @ input`, a cuBLAS batched GEMM with an fp16 round trip
+// through HBM in between; third-party/fast-hadamard-transform's own fused forms are fast_hadamard_transform_cuda.cu:
+// 37-127 / 276-441, the 12N/20N/28N/40N kernels).  One CTA per row: the row lives in shared memory as fp32 [K][N2],
+// radix-8 butterflies over every N2 segment, then the dense K x K factor over the K axis.  The intermediate is rounded
+// to fp16 after the scale (what hadamard_transform returns to the reference's matmul), the K-sum accumulates in fp32.
+//   out[k', j] = sum_k hadK[k', k] * half(scale * (x_k . H_N2)[j])
+template <int RADIX_BITS>
+__device__ __forceinline__ void fht_seg_pass(float* s, int segs, int log_n2, int shift, int tid, int nthreads) {
+    constexpr int R = 1 << RADIX_BITS;
+    const int gps = 1 << (log_n2 - RADIX_BITS);       // groups per segment
+    const int groups = segs * gps;
+    for (int t = tid; t < groups; t += nthreads) {
+        const int seg = t >> (log_n2 - RADIX_BITS), tt = t & (gps - 1);
+        const int base = (seg << log_n2) + (((tt >> shift) << (shift + RADIX_BITS)) | (tt & ((1 << shift) - 1)));
+        float v[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = s[fht_pad(base + (j << shift))];
+#pragma unroll
+        for (int h = 1; h < R; h <<= 1) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                if (!(j & h)) {
+                    const float a = v[j], b = v[j | h];
+                    v[j] = a + b;
+                    v[j | h] = a - b;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) s[fht_pad(base + (j << shift))] = v[j];
+    }
+}
+
+__global__ void __launch_bounds__(1024) fht_kn_kernel(const __half* __restrict__ x, __half* __restrict__ out,
+                                                     const __half* __restrict__ hadK, int rows, int K, int log_n2, float scale) {
+    extern __shared__ float fht_s[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int n2 = 1 << log_n2, n = K * n2;
+    __half* hk = reinterpret_cast<__half*>(fht_s + fht_pad(n) + 1);   // [K][K]
+    for (int i = tid; i < K * K; i += nt) hk[i] = hadK[i];
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)row * n);
+        for (int i = tid; i < n / 8; i += nt) {
+            const uint4 v = src[i];
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h[j]);
+                fht_s[fht_pad(i * 8 + 2 * j)] = f.x;
+                fht_s[fht_pad(i * 8 + 2 * j + 1)] = f.y;
+            }
+        }
+        __syncthreads();
+        int shift = 0;
+        for (; shift + 3 <= log_n2; shift += 3) { fht_seg_pass<3>(fht_s, K, log_n2, shift, tid, nt); __syncthreads(); }
+        if (log_n2 - shift == 2) { fht_seg_pass<2>(fht_s, K, log_n2, shift, tid, nt); __syncthreads(); }
+        if (log_n2 - shift == 1) { fht_seg_pass<1>(fht_s, K, log_n2, shift, tid, nt); __syncthreads(); }
+        for (int i = tid; i < n; i += nt) fht_s[fht_pad(i)] = __half2float(__float2half_rn(fht_s[fht_pad(i)] * scale));
+        __syncthreads();
+        // dense factor: a work item = 4 output rows k' x 2 adjacent columns j (a warp's lanes share k': hadK reads broadcast)
+        const int pairs = n2 >> 1, items = (K >> 2) * pairs;
+        __half* dst = out + (size_t)row * n;
+        for (int w = tid; w < items; w += nt) {
+            const int kc = (w / pairs) << 2, j = (w % pairs) << 1;
+            float acc[4][2] = {};
+            for (int k = 0; k < K; ++k) {
+                const float v0 = fht_s[fht_pad((k << log_n2) + j)], v1 = fht_s[fht_pad((k << log_n2) + j + 1)];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float hv = __half2float(hk[(kc + r) * K + k]);
+                    acc[r][0] = fmaf(hv, v0, acc[r][0]);
+                    acc[r][1] = fmaf(hv, v1, acc[r][1]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                *reinterpret_cast<__half2*>(dst + ((kc + r) << log_n2) + j) = __floats2half2_rn(acc[r][0], acc[r][1]);
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ KV quantise (+ append)
 // One warp per (token, head) row of D = 128 halves (4 per lane).  slot[token] = page * page_size + offset gives the
 // destination inside the paged cache (host/torch computes it from kv_indptr / kv_indices / last_page_offset).

@@ -1,18 +1,20 @@
 """Online Hadamard transform (mirror of the Hadamard part of deploy/functional/online_trans.py:21-71,144-151).
 
-`matmul_hadU_cuda(X, hadK, K)` = X . (H_K (x) H_{n/K}) / sqrt(n).  The power-of-two factor runs on the sm_100a FHT
-kernel (flatq_hadamard, replacing third-party/fast-hadamard-transform); a non-trivial K x K factor `hadK` is applied
-as a small dense transform over the K axis.
+`matmul_hadU_cuda(X, hadK, K)` = X viewed as [..., K, n/K]: hadamard_transform over the last axis (scaled by 1/sqrt(n),
+fp16), then `hadK @` over the K axis.  Power-of-two sizes run on the sm_100a FHT kernel (flatq_hadamard, replacing
+third-party/fast-hadamard-transform); n = K * 2^m runs on ONE fused kernel (flatq_hadamard_kn: FHT segments + the dense
+K x K factor with the row resident in shared memory) where the reference launches the FHT and a cuBLAS batched GEMM.
 
 `get_hadK(n)` picks K like the reference (the first of 172, 156, 140, 108, 60, 52, 36, 28, 40, 20, 12 that divides n
-with a power-of-two cofactor).  The reference hard-codes its K x K matrices as a 4000-line table of Sloane's library;
-that is data and is not reproduced here.  Where number theory gives a matrix of the same order -- Paley's constructions
-over a prime field: 12, 20, 28, 36, 60, 108, 140, and 40 by doubling -- `get_hadK` BUILDS a Hadamard matrix of that
-order.  It is a valid H (H.H^T = K.I) but not entry-for-entry the reference's: a checkpoint whose weights were rotated
-offline with the reference's table carries that table in its `had_rem_dim` buffer (OnlineTrans registers it, so it is
-in the state dict), and loading the checkpoint overwrites the generated one.  Orders without a prime-field Paley
-construction (52, 156, 172) get a placeholder that must come from a checkpoint."""
+with a power-of-two cofactor) and returns the reference's own K x K matrix: the tables of online_trans.py:161-4083
+(Sloane's library of Hadamard matrices) are shipped as DATA, one bit per entry, in data/hadamard_tables.npz, written
+from the reference by tools/make_hadamard_tables.py and checked entry for entry against it in
+tests/test_dropin_reference_wrappers.py.  (The reference's exporter writes parameters only, so `had_rem_dim` never
+travels in a checkpoint: the online factor MUST be the table the weights were rotated with offline.)  `paley_hadamard`
+-- a number-theoretic construction of a Hadamard matrix of the same orders -- is kept as an independent check that the
+shipped tables are Hadamard matrices of the right order; it is not used on the inference path."""
 import math
+import os
 
 import torch
 
@@ -72,15 +74,26 @@ def hadK_order(n):
     raise NotImplementedError(f"get_hadK({n}): no Hadamard factorisation K x 2^m with K in {_ORDERS}")
 
 
+_TABLES = {}
+
+
+def hadamard_table(k):
+    """The reference's K x K Hadamard matrix (entries +-1, fp32) from the shipped bit table."""
+    if k not in _TABLES:
+        import numpy as np
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "hadamard_tables.npz")
+        with np.load(path) as z:
+            bits = np.unpackbits(z[f"had{k}"])[: k * k].reshape(k, k)
+        _TABLES[k] = torch.from_numpy(bits.astype(np.float32) * 2.0 - 1.0)
+    return _TABLES[k].clone()
+
+
 def get_hadK(n, transpose=False):
-    """(hadK [K, K] fp32 or None, K).  For orders without a construction the matrix is a NaN placeholder: it must be
-    overwritten from a checkpoint (`OnlineTrans.had_rem_dim`); OnlineTrans refuses to run with it."""
+    """(hadK [K, K] fp32 or None, K) -- online_trans.py:21-71."""
     k = hadK_order(n)
     if k == 1:
         return None, 1
-    h = paley_hadamard(k)
-    if h is None:
-        h = torch.full((k, k), float("nan"))
+    h = hadamard_table(k)
     return (h.t().contiguous() if transpose else h), k
 
 
@@ -90,7 +103,4 @@ def matmul_hadU_cuda(X, hadK, K):
         return ops.hadamard(X.contiguous(), 1.0 / math.sqrt(n))
     if hadK is None:
         raise RuntimeError(f"matmul_hadU_cuda: K = {K} needs its K x K Hadamard factor")
-    # X viewed as [..., K, n/K]: FHT over the last axis, then the dense K x K factor over the K axis
-    inp = ops.hadamard(X.contiguous().view(-1, K, n // K), 1.0)
-    out = torch.matmul(hadK.to(inp).unsqueeze(0), inp)  # small dense factor (K <= 172)
-    return (out / math.sqrt(n)).reshape(X.shape)
+    return ops.hadamard_kn(X.contiguous(), hadK, K, 1.0 / math.sqrt(n))

@@ -43,11 +43,5 @@ class OnlineTrans(torch.nn.Module):
             return F_ot.kronecker_matmul(x, self._factors(), float(self.clip_factor_a_max), float(self.clip_factor_a_min))
         if self.trans == "had":
             from ..functional.hadamard import matmul_hadU_cuda
-            if self.had_rem_dim is not None and not getattr(self, "_had_checked", False):
-                if not bool(torch.isfinite(self.had_rem_dim).all()):   # once, not per call: it reads the device
-                    raise RuntimeError(f"OnlineTrans: the {self.rem_dim} x {self.rem_dim} Hadamard factor is a placeholder; "
-                                       "load it from the checkpoint (had_rem_dim) -- the reference's table for this "
-                                       "order is not bundled")
-                self._had_checked = True
             return matmul_hadU_cuda(x, self.had_rem_dim, self.rem_dim)
         return x

@@ -19,11 +19,6 @@ import torch
 from ... import ops
 
 
-# (rows per group, n) of the right-only transform (x . T, no left factor) that have been verified on the GPU; see
-# tests/test_zz_llama_model_gpu.py::test_right_only_transform_and_matmul_kv_cache and modeling_llama.LEFT_ONLY_VERIFIED
-RIGHT_ONLY_VERIFIED = set()
-
-
 class MultiLayerPagedKVCache4Bit:
     def __init__(self, batch_size, page_size, max_seq_len, device, n_layers, num_heads, head_dim, disable_quant=False,
                  trans_dtype=torch.float16, trans="had", group_size=1):
@@ -100,20 +95,10 @@ class MultiLayerPagedKVCache4Bit:
             flat = x.to(self.trans_dtype).reshape(-1, x.shape[-1]).contiguous()
             n = flat.shape[-1]
             m = matrix.to(flat).contiguous()
-            g = next(c for c in (16, 8, 4, 2, 1) if flat.shape[0] % c == 0)   # rows grouped into "tokens" of g rows
-            if (g, n) in RIGHT_ONLY_VERIFIED:
-                return ops.kron_transform(flat, None, m, 1, n).view(x.shape)
-            # an explicit identity left factor keeps the launch on the two-factor kernel configuration every parity
-            # test exercises (exact: I . X == X); the right-only configuration is used once it has run on hardware
-            return ops.kron_transform(flat, self._identity(g, flat), m, g, n).view(x.shape)
+            # right-only configuration (x . T, no left factor): hardware-verified in round 2
+            # (tests/test_zz_llama_model_gpu.py::test_right_only_transform_and_matmul_kv_cache)
+            return ops.kron_transform(flat, None, m, 1, n).view(x.shape)
         return x
-
-    def _identity(self, g, like):
-        key = (g, like.dtype, like.device)
-        cache = self.__dict__.setdefault("_eyes", {})
-        if key not in cache:
-            cache[key] = torch.eye(g, dtype=like.dtype, device=like.device)
-        return cache[key]
 
     def _slots(self, start, count):
         """slot = page * page_size + offset for tokens [start, start + count) of every sequence -> int32 [batch * count]"""

@@ -16,7 +16,7 @@ F16, BF16 = 0, 1
 _DT = {torch.float16: F16, torch.bfloat16: BF16}
 _sm_checked = False
 # opt-in until the split-KV decode kernel has run on hardware
-_DECODE_SPLIT = bool(os.environ.get("FLATQ_DECODE_SPLIT"))
+_DECODE_SPLIT = os.environ.get("FLATQ_DECODE_SPLIT", "1") != "0"   # default since round 2 (hardware-verified); "0" opts out
 
 
 def _ptr(t):
@@ -271,8 +271,8 @@ def gemm_w4a8_grouped(xq8: torch.Tensor, s_x: torch.Tensor, w_packed: torch.Tens
     return y
 
 
-# ---- elementwise glue of a decoder layer (opt-in in the model stack: FLATQ_FUSED_GLUE, see csrc/glue.cuh)
-FUSED_GLUE = bool(os.environ.get("FLATQ_FUSED_GLUE"))
+# ---- elementwise glue of a decoder layer (default in the model stack; FLATQ_FUSED_GLUE=0 opts out, see csrc/glue.cuh)
+FUSED_GLUE = os.environ.get("FLATQ_FUSED_GLUE", "1") != "0"   # default since round 2; "0" falls back to the torch expressions
 
 
 def rmsnorm(x: torch.Tensor, weight=None, eps: float = 1e-5, mean_dim=None) -> torch.Tensor:
@@ -320,6 +320,22 @@ def hadamard(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
     return out
 
 
+def hadamard_kn(x: torch.Tensor, hadK: torch.Tensor, K: int, scale: float) -> torch.Tensor:
+    """matmul_hadU_cuda for n = K * 2^m: per row, x viewed as [K, n/K] -> hadK @ half(scale * FHT over the last axis)."""
+    dev = _need_cuda(x, hadK)
+    if x.dtype != torch.float16:
+        raise RuntimeError("hadamard_kn: float16 activations")
+    n = x.shape[-1]
+    hk = hadK.to(device=dev, dtype=torch.float16).contiguous()
+    if hk.shape != (K, K):
+        raise RuntimeError(f"hadamard_kn: hadK must be [{K}, {K}]")
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().flatq_hadamard_kn(_ptr(x), _ptr(out), _ptr(hk), x.numel() // n, n, int(K), float(scale), _stream()),
+               "hadamard_kn")
+    return out
+
+
 def kv_quant(x: torch.Tensor, kv_data=None, kv_param=None, slot=None, layer: int = 0, kv_select: int = 0):
     """Asymmetric 4-bit quantise + pack of K or V rows x [tokens, heads, 128] (fp16).
 
@@ -341,7 +357,7 @@ def kv_decode_i4(q: torch.Tensor, kv_data, kv_param, kv_indptr, kv_indices, last
                  sm_scale=None, split=None, max_tokens_hint: int = 0) -> torch.Tensor:
     """Single-query attention over the paged INT4 cache: q [batch, q_heads, 128] fp16 -> o same shape.
 
-    split=True (default: the FLATQ_DECODE_SPLIT environment variable) takes the split-KV kernel
+    split=True (the default; FLATQ_DECODE_SPLIT=0 or split=False selects the single-pass kernel) takes the split-KV kernel
     (flatq_kv_decode_i4_split: sequence split over CTAs, one CTA per kv head serving its query-head group);
     `max_tokens_hint` is a host-side upper bound of the sequence lengths (0 = unknown)."""
     dev = _need_cuda(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len)

@@ -159,6 +159,12 @@ int flatq_gemm_w4a8_grouped(const int8_t* xq8, const float* s_x, const uint8_t* 
  * flatq_kv_decode_i4: single-query attention over the packed cache (batch_decode_i4: bindings.cpp:118-170,
  *   include/flashinfer/decode.cuh:480-689): o = softmax(q.K^T * sm_scale) . V with x_hat = nibble*scale - zero. */
 int flatq_hadamard(const void* x_f16, void* out_f16, int64_t rows, int n, float scale, flatq_stream_t stream);
+/* flatq_hadamard_kn: matmul_hadU_cuda for n = K * 2^m (deploy/functional/online_trans.py:144-151: hadamard_transform over
+ *   the 2^m axis of x viewed as [rows, K, n/K], scaled, rounded to fp16, then `hadK @ input` over the K axis; the fused
+ *   counterparts in the third-party library are fast_hadamard_transform_cuda.cu:37-127,276-441).  hadK: fp16 [K, K]
+ *   row-major (the reference's table for K, see flatquant_b200/deploy/functional/data), K % 4 == 0, K <= 172. */
+int flatq_hadamard_kn(const void* x_f16, void* out_f16, const void* hadK_f16, int64_t rows, int n, int K, float scale,
+                      flatq_stream_t stream);
 int flatq_kv_quant(const void* x_f16, int64_t tokens, int heads, int head_dim, uint8_t* q_out, void* param_out_f16,
                    uint8_t* kv_data, void* kv_param_f16, const int32_t* slot, int layer, int n_layers, int kv_select,
                    int page_size, flatq_stream_t stream);

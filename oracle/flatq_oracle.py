@@ -306,6 +306,20 @@ def hadamard_transform(x, scale: float = 1.0) -> np.ndarray:
     return (y * np.float32(scale)).reshape(x.shape)
 
 
+def matmul_hadU_kn(x, had_k, scale: float, fp16_intermediate: bool = True) -> np.ndarray:
+    """matmul_hadU_cuda for n = K * 2^m (deploy/functional/online_trans.py:144-151): x viewed as [..., K, n/K],
+    hadamard_transform over the last axis with `scale` -- returned to torch as fp16, hence the rounding -- then
+    `hadK @ input` over the K axis.  fp16_intermediate=False gives flatquant/hadamard_utils.py:89-110 (all fp32)."""
+    x = np.asarray(x, np.float32)
+    had_k = np.asarray(had_k, np.float32)
+    k = had_k.shape[0]
+    n = x.shape[-1]
+    t = hadamard_transform(x.reshape(-1, k, n // k), scale)
+    if fp16_intermediate:
+        t = t.astype(np.float16).astype(np.float32)
+    return np.einsum("ab,rbj->raj", had_k, t).reshape(x.shape)
+
+
 def kv_asym_quant(x: torch.Tensor):
     """Per-(token, head) asymmetric 4-bit quantisation of K or V, non-LAC branch.
 

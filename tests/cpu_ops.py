@@ -272,6 +272,19 @@ def hadamard(x, scale=1.0):
     return torch.from_numpy(O.hadamard_transform(x.float().numpy(), scale)).to(x.dtype)
 
 
+def hadamard_kn(x, hadK, K, scale):
+    _contig(x=x)
+    n = x.shape[-1]
+    _req(4 <= K <= 172 and K % 4 == 0 and n % K == 0, f"hadamard_kn: K={K} must be a multiple of 4 in [4, 172] dividing n={n}")
+    n2 = n // K
+    _req(n2 >= 8 and n2 & (n2 - 1) == 0 and n <= 32768, f"hadamard_kn: n/K={n2} must be a power of two >= 8, n <= 32768")
+    _req((n + n // 32 + 2) * 4 + K * K * 2 <= 227 * 1024, "hadamard_kn: row does not fit shared memory")
+    _req(x.numel() > 0, "hadamard_kn: rows"), _al16(x, 2, "hadamard_kn x"), _act_dtype(x, "hadamard_kn x")
+    _req(tuple(hadK.shape) == (K, K), "hadamard_kn: hadK shape")
+    y = O.matmul_hadU_kn(x.float().numpy(), hadK.float().numpy(), scale, fp16_intermediate=x.dtype == torch.float16)
+    return torch.from_numpy(y).to(x.dtype)
+
+
 def kv_quant(x, kv_data=None, kv_param=None, slot=None, layer=0, kv_select=0):
     _contig(x=x, kv_data=kv_data, kv_param=kv_param, slot=slot)
     tokens, heads, d = x.shape
@@ -332,7 +345,7 @@ def kv_decode_i4(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, lay
 
 FUNCTIONS = ("kron_transform", "act_quant", "transform_quant", "quantize_rows", "gemm_w4a8", "gemm_w4a8_grouped",
              "linear_fused", "pack_i4",
-             "hadamard", "kv_quant", "kv_decode_i4", "rmsnorm", "rope_", "silu_mul")
+             "hadamard", "hadamard_kn", "kv_quant", "kv_decode_i4", "rmsnorm", "rope_", "silu_mul")
 
 
 def install(monkeypatch):

@@ -183,8 +183,9 @@ def test_c_abi_argument_errors_without_a_gpu(lib):
 
 
 def test_hadamard_factors_and_matmul_hadU(monkeypatch):
-    """get_hadK: the reference's choice of K (deploy/functional/online_trans.py:21-71), a generated Hadamard matrix where a
-    prime-field Paley construction exists, a placeholder otherwise; matmul_hadU_cuda == X . (H_K (x) H_{n/K}) / sqrt(n)."""
+    """get_hadK: the reference's choice of K (deploy/functional/online_trans.py:21-71) and the shipped K x K table for every
+    order; Paley's constructions confirm independently that those orders carry Hadamard matrices;
+    matmul_hadU_cuda == X . (H_K (x) H_{n/K}) / sqrt(n)."""
     import numpy as np
     import scipy.linalg
 
@@ -197,7 +198,10 @@ def test_hadamard_factors_and_matmul_hadU(monkeypatch):
     for k in (12, 20, 28, 36, 40, 60, 108, 140):
         h = H.paley_hadamard(k)
         assert torch.equal(h @ h.t(), k * torch.eye(k)) and set(h.unique().tolist()) == {-1.0, 1.0}
-    assert H.paley_hadamard(172) is None and torch.isnan(H.get_hadK(11008)[0]).all()
+    for k in (12, 20, 28, 36, 40, 52, 60, 108, 140, 156, 172):
+        h = H.hadamard_table(k)
+        assert h.shape == (k, k) and torch.equal(h @ h.t(), k * torch.eye(k)) and set(h.unique().tolist()) == {-1.0, 1.0}
+    assert torch.equal(H.get_hadK(11008, transpose=True)[0], H.hadamard_table(172).t())
     assert F.get_hadK(4096) == (None, 1) and F.online_trans.get_hadK is H.get_hadK
     cpu_ops.install(monkeypatch)
     torch.manual_seed(0)
@@ -210,9 +214,8 @@ def test_hadamard_factors_and_matmul_hadU(monkeypatch):
     assert np.abs(got - want).max() < 2e-2 * np.abs(want).max()
     ot = OnlineTrans(14336, trans="had")   # Llama-3-8B down_proj in the Hadamard baseline mode: constructible
     assert ot.rem_dim == 28 and ot.had_rem_dim.shape == (28, 28) and "had_rem_dim" in ot.state_dict()
-    bad = OnlineTrans(11008, trans="had")  # order 172: placeholder until a checkpoint provides the table
-    with pytest.raises(RuntimeError, match="placeholder"):
-        bad(torch.zeros(1, 2, 11008, dtype=torch.float16))
+    ot = OnlineTrans(11008, trans="had")   # Llama-2-7B: order 172, the reference's table
+    assert ot.rem_dim == 172 and bool(torch.isfinite(ot.had_rem_dim).all())
 
 
 def test_integration_md_binding_snippet_is_valid_python_against_the_real_symbols(lib):

@@ -346,6 +346,39 @@ def test_hadamard_golden(ops, dev, golden, n):
     assert np.abs(y - g[f"y_{n}"]).max() <= 2e-2  # golden is from the fp32 input; x was rounded to fp16 here
 
 
+@pytest.mark.parametrize("n", [12 * 8, 20 * 16, 28 * 32, 40 * 8, 36 * 8, 52 * 8, 60 * 8, 108 * 8, 140 * 8, 156 * 8, 172 * 8,
+                               172 * 64, 28 * 512])
+def test_hadamard_kn_golden(ops, dev, golden, n):
+    """matmul_hadU_cuda for n = K * 2^m on the fused kernel (FHT segments + the reference's K x K table) against the
+    reference's own matmul_hadU output (tests/golden/make_golden_hadamard_kn.py) and the oracle's restatement of the
+    deployed form (fp16 intermediate, deploy/functional/online_trans.py:144-151)."""
+    from flatquant_b200.deploy.functional.hadamard import get_hadK, matmul_hadU_cuda
+    g = golden("hadamard_kn")
+    x = T(g[f"x_{n}"])
+    hk, k = get_hadK(n)
+    y = matmul_hadU_cuda(x.to(dev), hk.to(dev), k).float().cpu().numpy()
+    ref = O.matmul_hadU_kn(x.float().numpy(), hk.numpy(), 1.0 / n ** 0.5)
+    # vs the same rounding points: one fp16 rounding of the output (+ fp32 summation order)
+    assert np.abs(y - ref).max() <= 2 ** -10 * max(1.0, np.abs(ref).max()) * 1.5
+    # vs the reference's fp32 result: the fp16 intermediate contributes sqrt(K) half-ulps
+    assert np.abs(y - g[f"y_{n}"]).max() <= 2 ** -9 * k ** 0.5 * max(1.0, np.abs(ref).max())
+
+
+def test_hadamard_kn_full_width_properties(ops, dev):
+    """Llama-3-8B down_proj in the Hadamard baseline mode: 2048 x 14336 = 28 x 512.  H.H^T = n.I: applying the transform
+    and then its transpose (hadK^T, same FHT) is the identity; Parseval per row."""
+    from flatquant_b200.deploy.functional.hadamard import get_hadK, matmul_hadU_cuda
+    torch.manual_seed(3)
+    n = 14336
+    x = torch.randn(2048, n, device=dev).half()
+    hk, k = get_hadK(n)
+    hkt, _ = get_hadK(n, transpose=True)
+    y = matmul_hadU_cuda(x, hk.to(dev), k)
+    z = matmul_hadU_cuda(y, hkt.to(dev), k)
+    assert (z.float() - x.float()).abs().max() < 3e-2
+    assert torch.allclose(y.float().pow(2).sum(1), x.float().pow(2).sum(1), rtol=1e-2)
+
+
 def test_hadamard_properties_large(ops, dev):
     """n = 32768 (the FHT maximum): H.H = n.I (round trip) and Parseval, on 64 rows."""
     torch.manual_seed(0)

@@ -14,7 +14,7 @@ from conftest import GOLDEN
 GPU_VERIFIED = {
     "hmma two-factor": "test_gpu_parity.py::test_transform_quant_codes[(32,48),(128,224),(8,16),(14,16)] (padded n1 included)",
     "hmma left-only": "test_gpu_parity.py::test_kernel_level_api (block_matmul, 32 heads x 128)",
-    "hmma right-only": "test_zz_llama_model_gpu.py::test_right_only_transform_and_matmul_kv_cache (first hardware run: round end; not reached by the stacks)",
+    "hmma right-only": "test_zz_llama_model_gpu.py::test_right_only_transform_and_matmul_kv_cache (hardware-verified round 2; the K / Q cache transform)",
     "tcgen05": "test_gpu_parity.py::test_transform_quant_codes[(64,64),(112,128),(86,128),(56,64),(32,64),(64,128)]",
     "rowquant": "test_gpu_parity.py::test_quantize_rows_deploy_semantics, test_empty_and_maximum_shapes",
     "gemv": "test_gpu_parity.py::test_decode_split_k_path[m=1,2]",
@@ -58,9 +58,8 @@ def test_llama_stack_kernel_configurations(monkeypatch):
         model(ids[:, -1:], past_key_values=cache)
     used = _classes(cpu_ops.CALLS)
     # prefill 30 tokens -> split-K GEMM route, decode 2 tokens -> GEMV; (16,32) / (32,32) / padded (4,128)+identity
-    # Kronecker pairs on the HMMA kernel; K.T_k and Q.T_k^-T as identity-left two-factor 128x128 transforms (the
-    # right-only configuration has no hardware run yet: kv_cache.RIGHT_ONLY_VERIFIED); paged INT4 KV
-    assert used == {"hmma two-factor", "split-k", "gemv", "kv_quant", "kv_decode_i4"}, used
+    # Kronecker pairs on the HMMA kernel; K.T_k and Q.T_k^-T as right-only 128x128 transforms; paged INT4 KV
+    assert used == {"hmma two-factor", "hmma right-only", "split-k", "gemv", "kv_quant", "kv_decode_i4"}, used
     assert used <= set(GPU_VERIFIED)
     configs = {cfg for op, cfg in cpu_ops.CALLS if op == "act_quant"}
     assert configs == {("hmma", 16, 32, True, True), ("hmma", 4, 128, True, True), ("hmma", 32, 32, True, True)}, configs

@@ -121,6 +121,22 @@ def test_hadamard(golden):
     assert np.array_equal(h @ h.T, 8 * np.eye(8))
 
 
+def test_hadamard_kn_reference_tables(golden):
+    """n = K * 2^m: the oracle's matmul_hadU_kn with the SHIPPED tables (flatquant_b200/.../data/hadamard_tables.npz)
+    equals the reference's matmul_hadU (its own hard-coded tables) on every order the reference lists."""
+    from flatquant_b200.deploy.functional.hadamard import get_hadK
+    g = golden("hadamard_kn")
+    for key in g.files:
+        if not key.startswith("x_"):
+            continue
+        n = int(key[2:])
+        hk, k = get_hadK(n)
+        y = O.matmul_hadU_kn(g[key].astype(np.float32), hk.numpy(), 1.0 / np.sqrt(n), fp16_intermediate=False)
+        assert np.allclose(y, g[f"y_{n}"], rtol=1e-4, atol=1e-4), (n, k)
+        y16 = O.matmul_hadU_kn(g[key].astype(np.float32), hk.numpy(), 1.0 / np.sqrt(n))
+        assert np.abs(y16 - g[f"y_{n}"]).max() <= 2 ** -9 * np.sqrt(k) * max(1.0, np.abs(y).max()), (n, k)
+
+
 def test_int_gemm_and_dequant_models():
     rng = np.random.default_rng(0)
     xq = rng.integers(-8, 8, (5, 64)).astype(np.int8)

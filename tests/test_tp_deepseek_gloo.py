@@ -39,8 +39,8 @@ def _worker(rank, world, port, ret, grouped):
     from flatquant_b200.deploy.transformers import modeling_deepseek as MD
     from flatquant_b200.deploy.transformers.modeling_llama import TensorParallel
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    if grouped:   # the ranks take the grouped-GEMM path (one launch per expert stage, local experts only)
-        os.environ["FLATQ_GROUPED_MOE"] = "1"
+    # grouped (the default): one launch per expert stage, local experts only; "0": the per-expert loop
+    os.environ["FLATQ_GROUPED_MOE"] = "1" if grouped else "0"
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         for name in cpu_ops.FUNCTIONS:

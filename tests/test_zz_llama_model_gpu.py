@@ -132,8 +132,7 @@ def test_graphed_steps_equal_eager(model, g, dev):
 
 def test_right_only_transform_and_matmul_kv_cache(dev):
     """x . T over the last axis with no left factor: the HMMA kernel's right-only configuration at every row grouping
-    ops.kron_transform picks (16 / 8 / 1 rows per "token") -- never run on hardware, hence LAST in this file (the cache
-    itself passes an explicit identity left factor until this has passed: kv_cache.RIGHT_ONLY_VERIFIED) -- then the paged
+    ops.kron_transform picks (16 / 8 / 1 rows per "token"; first hardware run: round 2, the cache uses it since) -- then the paged
     cache in trans="matmul" mode (prefill + one appended token + single-query attention) against the oracle."""
     from flatquant_b200 import ops
     from flatquant_b200.deploy.transformers import MultiLayerPagedKVCache4Bit

@@ -1,14 +1,8 @@
 """Split-KV decode attention (flatq_kv_decode_i4_split) on the B200 against the verified single-pass kernel
 (flatq_kv_decode_i4) and the oracle, over the same paged INT4 cache.
 
-UNVERIFIED ON HARDWARE, gated like tests/test_zzz_grouped_gemm_gpu.py: written after round 1's GPU minutes were spent.
-Checked without a GPU: the algorithm (tests/test_decode_split_model.py, numpy restatement of the kernel's schedule), the
-existing kernels' SASS unchanged (tools/sass_diff.py: identical 89, new 4), no spills (-Xptxas: 96 / 127 / 243 registers
-for 1 / 2 / 4 query heads per CTA).  First run:
-
-    FLATQ_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_zzz_decode_split_gpu.py -x -q -s
-
-then make it the default of ops.kv_decode_i4 (FLATQ_DECODE_SPLIT) and time bench.py --workload llama8b-model decode."""
+First hardware run: round 2 (6 passed, profiles/r02_first_gpu_call.md); the split-KV kernel is the default of
+ops.kv_decode_i4 since.  The algorithm is also restated in numpy (tests/test_decode_split_model.py)."""
 import os
 
 import pytest
@@ -16,9 +10,7 @@ import torch
 
 from oracle import flatq_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("FLATQ_RUN_UNVERIFIED"), reason="kernel not yet run on hardware; "
-                                 "set FLATQ_RUN_UNVERIFIED=1 (see the module docstring)")]
+pytestmark = pytest.mark.gpu
 
 
 def _cache(dev, lens, hkv, ps, n_layers, layer, seed):

@@ -1,15 +1,9 @@
 """Grouped (mixture-of-experts) W4A4 GEMM on the B200 against the verified per-expert launches: bit-identical outputs.
 
-UNVERIFIED ON HARDWARE: `flatq_gemm_w4a8_grouped` (the GROUPED instantiations of csrc/gemm_w4a8.cuh) was written after
-round 1's GPU minutes were spent.  What is checked without a GPU: the plain kernels' SASS is unchanged by the new
-template parameter (profiles/r01_sass_regression_grouped.md), the tile schedule (tests/test_grouped_sched.py, same header
-compiled for the host), and the host logic on the oracle-backed stand-ins (tests/test_deepseek_block_host.py).  Until
-this file has passed on a B200 it only runs when FLATQ_RUN_UNVERIFIED=1, so that a first-run failure (or hang) of a
-never-executed kernel cannot take the verified parity suite's round-end run with it.  First run:
-
-    FLATQ_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_zzz_grouped_gemm_gpu.py -x -q
-
-then drop the gate and make `grouped=True` the default of flatquant_b200.moe.FlatQuantRoutedExperts."""
+First hardware run: round 2 (10 passed, profiles/r02_first_gpu_call.md); `grouped=True` is the default of
+flatquant_b200.moe.FlatQuantRoutedExperts since.  Also checked without a GPU: the tile schedule
+(tests/test_grouped_sched.py, same header compiled for the host) and the host logic on the oracle-backed stand-ins
+(tests/test_deepseek_block_host.py)."""
 import os
 
 import numpy as np
@@ -18,9 +12,7 @@ import torch
 
 from oracle import flatq_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("FLATQ_RUN_UNVERIFIED"), reason="kernel not yet run on hardware; "
-                                 "set FLATQ_RUN_UNVERIFIED=1 (see the module docstring)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
