@@ -23,6 +23,7 @@ class GraphedDecoder:
         self.model, self.cache = model, cache
         dev = cache.device
         cache.begin_static_decode()
+        self.capacity = min(int(cache.page_size), int(cache.max_seq_len))   # static decode: one page per sequence
         self.tokens = torch.zeros((cache.batch_size, 1), dtype=torch.long, device=dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -37,6 +38,11 @@ class GraphedDecoder:
 
     def step(self, tokens):
         """tokens [batch, 1] -> logits [batch, 1, vocab] (a static buffer, overwritten by the next step)."""
+        # the captured step computes its KV slot and RoPE row on the device from cache.pos_dev and cannot grow the page
+        # pool: past the capacity it would scatter into the next sequence's page (or past the allocation)
+        if self.cache.length >= self.capacity:
+            raise RuntimeError(f"GraphedDecoder.step: the static cache is full ({self.cache.length} of {self.capacity} "
+                               "tokens per sequence); build the cache with a larger max_length")
         self.tokens.copy_(tokens, non_blocking=True)
         self.graph.replay()
         self.cache.length += 1

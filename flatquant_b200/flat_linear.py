@@ -88,25 +88,59 @@ class FlatQuantizedLinear(nn.Module):
         return self._train_forward(hidden_states, qa_trans=qa_trans, out_trans=out_trans)
 
     # ------------------------------------------------------------------ inference on the CUDA library
+    def set_weight_scales(self, weight_scales):
+        """Hand over the quantiser's true per-channel scales [N] / [N, 1] (what main.py holds in its `quantizers` dict
+        after RTN / GPTQ, gptq_utils.py:272-310); pack_weights uses them instead of recovering the grid from the weight."""
+        self._weight_scales = None if weight_scales is None else weight_scales.detach().reshape(-1).float().clone()
+        self._packed = None
+
+    def _grid_scales(self, wf):
+        """Per-channel scale of an int-grid weight.  Order of trust: scales handed over by the caller, this module's own
+        weight_quantizer when it holds per-channel parameters, then recovery from the weight itself: the extreme code of a
+        row is +-7 after RTN but can be -8 or anything below 7 after GPTQ, so amax/7 is only the first candidate."""
+        n = wf.shape[0]
+        given = getattr(self, "_weight_scales", None)
+        if given is not None and given.numel() == n:
+            return given.to(wf).reshape(-1, 1)
+        wq = self.weight_quantizer
+        if getattr(wq, "scale", None) is not None and wq.scale.numel() == n and bool(wq.ready()):
+            # only when it describes THIS weight (a calibration-time forward leaves the scale of the unrounded weight)
+            s = wq.scale.detach().to(wf).reshape(-1, 1)
+            codes = torch.round(wf / s)
+            if torch.allclose(codes * s, wf, rtol=2e-3, atol=0) and codes.max() <= 7 and codes.min() >= -8:
+                return s
+        amax = wf.abs().amax(1, keepdim=True).clamp(min=1e-10)
+        best = amax / 7
+        todo = torch.ones(n, dtype=torch.bool, device=wf.device)
+        for k in (7, 8, 6, 5, 4, 3, 2, 1):   # first candidate whose grid holds the whole row wins
+            s = amax / k
+            codes = torch.round(wf / s)
+            ok = ((codes * s - wf).abs() <= 2e-3 * wf.abs()).all(1) & (codes.amax(1) <= 7) & (codes.amin(1) >= -8)
+            take = todo & ok
+            best = torch.where(take[:, None], s, best)
+            todo &= ~ok
+            if not bool(todo.any()):
+                break
+        return best
+
     def pack_weights(self, weight_scales=None):
         """4-bit pack the int-grid weight: returns (w_packed u8 [N, K/2], s_w f32 [N]) on the weight's device.
 
-        `linear.weight` must already hold round(W/s)*s (RTN gptq_utils.py:296-304 or GPTQ); per-channel
-        scales are taken from `weight_scales` or recovered as max|row|/7 (codes never exceed +-7)."""
+        `linear.weight` must already hold round(W/s)*s (RTN gptq_utils.py:296-304 or GPTQ); see _grid_scales for where
+        the per-channel scales come from.  Codes outside [-8, 7] are rejected, never clamped."""
         w = self.linear.weight.data
         key = (w.data_ptr(), w._version, tuple(w.shape))
         if self._packed is not None and self._packed[0] == key and weight_scales is None:
             return self._packed[1], self._packed[2]
         wf = w.float()
-        if weight_scales is None:
-            s = (wf.abs().amax(1, keepdim=True) / 7).clamp(min=1e-10)
-        else:
-            s = weight_scales.reshape(-1, 1).to(wf)
+        if weight_scales is not None:
+            self.set_weight_scales(weight_scales)
+        s = self._grid_scales(wf)
         codes = torch.round(wf / s)
-        if not torch.allclose(codes * s, wf, rtol=2e-3, atol=0) or codes.abs().max() > 8:
+        if not torch.allclose(codes * s, wf, rtol=2e-3, atol=0) or codes.max() > 7 or codes.min() < -8:
             raise RuntimeError("FlatQuantizedLinear: linear.weight is not on a per-channel INT4 grid; run RTN/GPTQ "
                                "weight quantisation (w_bits=4) before W4A4 inference")
-        codes = codes.clamp(-8, 7).to(torch.int8)
+        codes = codes.to(torch.int8)
         packed = ops.pack_i4(codes.contiguous()) if codes.is_cuda else _pack_cpu(codes)
         self._packed = (key, packed, s.reshape(-1).contiguous())
         return self._packed[1], self._packed[2]

@@ -145,13 +145,16 @@ class WeightQuantizer(torch.nn.Module):
             hi = torch.where(dead, torch.ones_like(hi), hi)
         return lo, hi
 
-    def _scale_zero(self, lo, hi, p=1.0):
+    def _scale_zero(self, lo, hi, p=None):
+        """p=None: the initial parameters (quant_utils.py:166-173, asym range clamped to 1e-5 BEFORE the division);
+        p given: one step of the MSE grid (quant_utils.py:178-188, no clamp -- including its first step p == 1)."""
         if self.sym:
-            s = p * hi / self.maxq
+            s = (hi if p is None else p * hi) / self.maxq
             return s, torch.zeros_like(s)
+        if p is None:
+            s = (hi - lo).clamp(min=1e-5) / self.maxq
+            return s, torch.round(-lo / s)
         s = (p * hi - p * lo) / self.maxq
-        if p == 1.0:
-            s = s.clamp(min=1e-5)
         return s, torch.round(-p * lo / s)
 
     def find_params(self, x):

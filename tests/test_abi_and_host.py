@@ -240,3 +240,40 @@ def test_documents_name_files_that_exist():
             if not os.path.exists(os.path.join(ROOT, m)):
                 missing.append((doc, m))
     assert not missing, missing
+
+
+def test_pack_weights_recovers_gptq_grids_and_rejects_out_of_range_codes():
+    """rows whose extreme code is -8 or below 7 (GPTQ) are valid W4 grids; amax/7 is only one candidate.
+    Scales handed over by the caller are used as they are; a +8 code is rejected, not clamped."""
+    from flatquant_b200.flat_linear import FlatQuantizedLinear
+    from oracle import flatq_oracle as O
+    args = types.SimpleNamespace(w_bits=4, a_bits=4, w_asym=False, a_asym=False, lac=True, lwc=True, a_groupsize=-1)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(64, 16, bias=False)
+    s = torch.rand(16, 1) * 0.1 + 0.01
+    codes = torch.randint(-8, 8, (16, 64)).float()
+    codes[0] = codes[0].clamp(-5, 5); codes[0, 0] = 5      # noqa: E702  largest code 5
+    codes[1] = codes[1].clamp(-8, 6); codes[1, 3] = -8     # noqa: E702  hits -8
+    codes[2] = codes[2].clamp(-7, 7); codes[2, 1] = 7      # noqa: E702  the RTN case
+    lin.weight.data = codes * s
+    packed, sw = FlatQuantizedLinear(args, lin).pack_weights()
+    rec = torch.from_numpy(O.unpack_i4(packed.numpy())).float() * sw[:, None]
+    assert torch.allclose(rec, lin.weight.data, rtol=2e-3, atol=1e-7)
+    packed2, sw2 = FlatQuantizedLinear(args, lin).pack_weights(weight_scales=s)
+    assert torch.equal(torch.from_numpy(O.unpack_i4(packed2.numpy())).float(), codes) and torch.allclose(sw2, s.reshape(-1))
+    bad = codes.clone(); bad[5, 5] = 8                      # noqa: E702
+    lin.weight.data = bad * s
+    with pytest.raises(RuntimeError, match="INT4 grid"):
+        FlatQuantizedLinear(args, lin).pack_weights(weight_scales=s)
+
+
+def test_weight_quantizer_asym_clamps_the_range_before_dividing():
+    """ADVICE r1 / quant_utils.py:172-173,186-187: near-constant channels in w_asym mode."""
+    from flatquant_b200.quant_utils import WeightQuantizer
+    w = torch.tensor([[0.0, 1e-6, 2e-6, 3e-6], [-1.0, 0.5, 0.25, 1.0], [0.0, 0.0, 0.0, 0.0]])
+    q = WeightQuantizer()
+    q.configure(4, perchannel=True, sym=False, mse=False)
+    q.find_params(w)
+    lo, hi = torch.tensor([0.0, -1.0, -1.0]), torch.tensor([3e-6, 1.0, 1.0])
+    want = (hi - lo).clamp(min=1e-5) / 15
+    assert torch.equal(q.scale.reshape(-1), want) and torch.equal(q.zero.reshape(-1), torch.round(-lo / want))
