@@ -296,18 +296,48 @@ def test_deploy_api_chain(dev):
     ot.right_matrix.data = (torch.randn(64, 64) / 8).half().to(dev)
     x = torch.rand(bsz, seq, k).half()
     y = mod(x.to(dev))
-    assert y.shape == (bsz * seq, n) and y.dtype == torch.float16
+    assert y.shape == (bsz, seq, n) and y.dtype == torch.float16   # leading dims kept, as deploy.matmul / sym_dequant do
+    y = y.reshape(bsz * seq, n)
     packed = ot(x.to(dev))
-    assert isinstance(packed, deploy.PackedQuantizedTensor) and packed.quantized_x.shape == (bsz * seq, k // 2)
-    codes = O.unpack_i4(packed.quantized_x.cpu().numpy())
+    # deploy/functional/online_trans.py:121-122: quantized_x [bsz, seq, K/2], scales_x [bsz, 1, seq]
+    assert isinstance(packed, deploy.PackedQuantizedTensor) and packed.quantized_x.shape == (bsz, seq, k // 2)
+    assert packed.scales_x.shape == (bsz, 1, seq)
+    codes = O.unpack_i4(packed.quantized_x.reshape(bsz * seq, -1).cpu().numpy())
     acc = O.gemm_i4(codes, base.weight.data.float().numpy())
     ref = O.sym_dequant(acc, packed.scales_x.float().cpu().numpy().reshape(-1), np.ones(n, np.float32)).astype(np.float16)
     assert np.array_equal(y.cpu().numpy(), ref)
     # int-only chain of the reference API
     acc_gpu = deploy.matmul(packed.quantized_x, mod[2].weight)
-    assert np.array_equal(acc_gpu.cpu().numpy(), acc)
+    assert acc_gpu.shape == (bsz, seq, n) and np.array_equal(acc_gpu.reshape(-1, n).cpu().numpy(), acc)
     y2 = deploy.sym_dequant(acc_gpu, packed.scales_x, mod[2].weight_scales)
-    assert np.array_equal(y2.cpu().numpy(), ref)
+    assert np.array_equal(y2.reshape(-1, n).cpu().numpy(), ref)
+
+
+def test_online_trans_single_matrix_is_the_reference_block_path(dev):
+    """OnlineTrans(decompose=False) -- the o_proj transform over the heads axis -- takes the reference's 4-D
+    [bsz, seq, head_dim, heads] input (modeling_llama.py:146: o_proj_trans(attn.transpose(-1, -2))): ONE scale per token
+    over the whole block, codes of (b_t @ inv) packed in the transposed (heads-major) order, quantized_x reshaped to
+    (bsz, seq, -1, heads), scales_x to (bsz, 1, seq)  (deploy/functional/online_trans.py:124-139, block_matmul.py:29-104)."""
+    from flatquant_b200 import deploy
+    from flatquant_b200.deploy.nn import OnlineTrans
+    torch.manual_seed(5)
+    bsz, seq, heads, hd = 2, 9, 32, 128
+    ot = OnlineTrans(heads, trans="matmul", decompose=False).to(dev)
+    inv = (torch.eye(heads) * 0.8 + torch.randn(heads, heads) / 16).half()
+    ot.right_matrix.data = inv.to(dev)
+    attn = torch.randn(bsz, seq, heads, hd).half()
+    packed = ot(attn.transpose(-1, -2).contiguous().to(dev))
+    assert isinstance(packed, deploy.PackedQuantizedTensor)
+    assert packed.quantized_x.shape == (bsz, seq, hd * heads // 2 // heads, heads) and packed.scales_x.shape == (bsz, 1, seq)
+    # oracle: z_t = b_t @ inv with b_t [head_dim, heads]; per-token scale over the whole block; codes of z_t^T row-major
+    z = attn.transpose(-1, -2).float() @ inv.float()                     # [bsz, seq, hd, heads]
+    zt = z.transpose(-1, -2).reshape(bsz * seq, heads * hd)               # heads-major
+    s = O.act_scale(zt, 1.0, 1.0)                                          # sigmoid(1.0) clip factors (kron_matmul.py:86-92)
+    codes = O.sym_codes(zt, s).numpy()
+    got = O.unpack_i4(packed.quantized_x.reshape(bsz * seq, -1).cpu().numpy())
+    flips = (got != codes)
+    assert flips.mean() <= 0.006 and np.abs(got.astype(np.int32) - codes).max() <= 1
+    assert torch.allclose(packed.scales_x.reshape(-1).float().cpu(), s.reshape(-1), rtol=2e-3)
 
 
 def test_error_behaviour(ops, dev):

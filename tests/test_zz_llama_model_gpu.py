@@ -87,7 +87,10 @@ def test_decode_attention_over_paged_int4_cache(model, g, dev):
     at = model.model.layers[1].self_attn
     gq, gk, gv = (torch.from_numpy(g[f"prefill_l1_{n}"]).reshape(b, s, -1, hd).half().float()
                   for n in ("q_proj", "k_proj", "v_proj"))
-    rope = lambda t: ML.apply_rope(t.half(), cos_c.half(), sin_c.half()).float()  # noqa: E731  (the model's fp16 RoPE)
+    def rope(t):   # HF's fp16 rotate_half expression (what the fused glue kernel reproduces bit for bit), on the CPU
+        t, c, s_ = t.half(), cos_c.half(), sin_c.half()
+        h = t.shape[-1] // 2
+        return (t * c + torch.cat((-t[..., h:], t[..., :h]), dim=-1) * s_).float()
     k_t = (rope(gk) @ at.trans_matrix_k.float().cpu().half().float()).half()
     q_t = (rope(gq)[:, -1] @ at.trans_matrix_k_inv_t.float().cpu().half().float()).half().float()
     kp, ks, kz = O.kv_asym_quant(k_t)

@@ -17,7 +17,7 @@ __device__ __forceinline__ void mma_f8_ts(uint32_t d, uint32_t a, uint64_t b, ui
 }
 
 // mode: 0 i8 TS, 1 i8 SS, 2 f8 SS, 3 f8 TS, 4 f16 SS
-__global__ void __launch_bounds__(128, 1) rate_kernel(int mode, int n, int reps, long long* out) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int mode, int n, int reps, long long* out, int nacc = 1) {
     extern __shared__ uint8_t raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t bar;
@@ -40,11 +40,13 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int mode, int n, int reps,
         const long long t0 = clock64();
         for (int r = 0; r < reps; ++r) {
             const uint32_t koff = (r & 3) * 2;  // advance K inside the atom like a real loop
-            if (mode == 0) mma_i8_ts(tmem, tmem + 256 + (r & 7) * 8, bdesc + koff, idesc, r != 0);
-            else if (mode == 1) mma_i8_ss(tmem, adesc + koff, bdesc + koff, idesc, r != 0);
-            else if (mode == 2) mma_f8_ss(tmem, adesc + koff, bdesc + koff, idesc, r != 0);
-            else if (mode == 3) mma_f8_ts(tmem, tmem + 256 + (r & 7) * 8, bdesc + koff, idesc, r != 0);
-            else mma_f16_ss(tmem, adesc + koff, bdesc + koff, idesc, r != 0);
+            const uint32_t d = tmem + (uint32_t)(r % nacc) * (uint32_t)n;   // nacc > 1: independent accumulators, round robin
+            const uint32_t a_t = tmem + (nacc > 1 ? 448 : 256) + (r & 7) * 8;
+            if (mode == 0) mma_i8_ts(d, a_t, bdesc + koff, idesc, r >= nacc);
+            else if (mode == 1) mma_i8_ss(d, adesc + koff, bdesc + koff, idesc, r >= nacc);
+            else if (mode == 2) mma_f8_ss(d, adesc + koff, bdesc + koff, idesc, r >= nacc);
+            else if (mode == 3) mma_f8_ts(d, a_t, bdesc + koff, idesc, r >= nacc);
+            else mma_f16_ss(d, adesc + koff, bdesc + koff, idesc, r >= nacc);
         }
         const long long t1 = clock64();
         tc_commit(&bar);
@@ -182,6 +184,20 @@ int main() {
                        kper[mode], grid, (double)h[0] / reps, cyc, 128.0 * n * kper[mode] / cyc, e == cudaSuccess ? "" : cudaGetErrorString(e));
             }
         }
+    // round 2: is the ~128-cycle cost of a small-N MMA an issue floor, or the latency of accumulating into the SAME
+    // accumulator?  Same loop, `nacc` independent accumulators (n columns each) round robin.
+    for (int mode : {0, 1, 4})
+        for (int n : {16, 32, 64, 128})
+            for (int nacc : {1, 2, 4}) {
+                if (n * nacc > 448) continue;
+                rate_kernel<<<148, 128, 60 * 1024>>>(mode, n, reps, out, nacc);
+                cudaError_t e = cudaDeviceSynchronize();
+                long long h[2];
+                cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
+                const double cyc = (double)h[1] / reps;
+                printf("%s M128 N%3d K%d nacc %d: issue %.1f cyc/mma, complete %.1f cyc/mma -> %.0f MAC/cyc/SM %s\n", names[mode], n,
+                       kper[mode], nacc, (double)h[0] / reps, cyc, 128.0 * n * kper[mode] / cyc, e == cudaSuccess ? "" : cudaGetErrorString(e));
+            }
     cudaFuncSetAttribute(pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024);
     for (int per : {4, 8, 16, 4096})
         for (int do_wait : {0, 1})
