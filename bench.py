@@ -44,6 +44,17 @@ def peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed summary of this round's
+    `ncu --set full` capture (profiles/ncu_traffic.json: {kernel: {"bytes_per_launch": ..., "source": ...}}); None when
+    the kernel has not been captured."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return d[kernel]["bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -183,20 +194,14 @@ class Runner:
 H70, I70, KV70, L70 = 8192, 28672, 1024, 80
 
 
-def run_tp70(args, rank, world, local):
-    """Llama-3-70B FlatLinears sharded row/column parallel over `world` GPUs (flatquant_b200/tp.py): per layer
-    qkv (column), o (row + all-reduce), gate_up (column), down (row + all-reduce); seq 2048.  Strong scaling."""
-    import torch.distributed as dist
+def measure_tp70(args, rank, world, dev, dist, barrier, steps, n_layers=None):
+    """BASELINE configs[3]: Llama-3-70B FlatLinears sharded row/column parallel over `world` GPUs (flatquant_b200/tp.py):
+    per layer qkv (column), o (row + all-reduce), gate_up (column), down (row + all-reduce); seq 2048; strong scaling.
+    Timed three ways in the same process group: the full step, the same step with the reductions left out (compute
+    only), and the reductions alone (bus bandwidth) -> the exposed-communication share of the step."""
     from flatquant_b200 import ops, tp as TP
-    dev = torch.device(f"cuda:{local}")
-    torch.cuda.set_device(dev)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout, where only the JSON line belongs
-        dist.init_process_group("nccl", device_id=dev)
-    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
     gen = torch.Generator(device=dev).manual_seed(77 + rank)
-    n_layers = args.layers if args.layers != N_LAYERS else L70
+    n_layers = n_layers or L70
     cm = float(torch.sigmoid(torch.tensor(4.0)))
     specs = [("qkv", "col", H70, H70 + 2 * KV70), ("o", "row", H70, H70), ("gate_up", "col", H70, 2 * I70), ("down", "row", I70, H70)]
     layers = []
@@ -216,156 +221,237 @@ def run_tp70(args, rank, world, local):
     xq = {kk: (torch.empty(SEQ, kk, dtype=torch.int8, device=dev), torch.empty(SEQ, dtype=torch.float32, device=dev)) for kk in xs}
     ys = {i: torch.empty(SEQ, l["nn"], dtype=torch.float16, device=dev) for i, l in enumerate(layers[0])}
     launches = [0]
+    reducer = TP.make_reducer(world, rank, dev, (SEQ, H70), torch.float16) if world > 1 else None
+    how = reducer.name if reducer is not None else "none (tp1)"
 
-    def step():
+    def step(comm=True):
         for layer in layers:
             for i, l in enumerate(layer):
+                row = l["kind"] == "row" and world > 1
                 ops.act_quant(xs[l["kk"]], l["left"], l["right"], l["n1"], l["n2"], cm, cm, out=xq[l["kk"]])
-                ops.gemm_w4a8(xq[l["kk"]][0], xq[l["kk"]][1], l["w"], l["s_w"], out=ys[i])
+                out = reducer.partial_buffer() if (row and comm) else ys[i]
+                ops.gemm_w4a8(xq[l["kk"]][0], xq[l["kk"]][1], l["w"], l["s_w"], out=out)
                 launches[0] += 2
-                if l["kind"] == "row" and world > 1:
-                    dist.all_reduce(ys[i])
-    for _ in range(max(3, args.warmup)):
+                if row and comm:
+                    reducer.all_reduce(out)
+
+    def comm_only():
+        for layer in layers:
+            for i, l in enumerate(layer):
+                if l["kind"] == "row":
+                    reducer.all_reduce(reducer.partial_buffer())
+    for _ in range(3):
         step()
     torch.cuda.synchronize()
     launches[0] = 0
-    ms = timed(step, args.steps, barrier)
+    ms = timed(step, steps, barrier)
+    n_launch = launches[0]
+    ms_nocomm = timed(lambda: step(False), steps, barrier) if world > 1 else ms
+    ms_comm = timed(comm_only, steps, barrier) if world > 1 else 0.0
     if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_nocomm, ms_comm], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
+        ms, ms_nocomm, ms_comm = t.tolist()
+    scale = L70 / n_layers
+    ops_layer = sum(2 * K * N for _, _, K, N in specs) * SEQ
+    ar_bytes = SEQ * H70 * 2
+    n_ar = 2 * n_layers * steps
+    res = {"tokens_per_s": SEQ * steps / (ms * 1e-3) / scale, "ms_per_step": ms / steps * scale,
+           "ms_per_step_compute_only": ms_nocomm / steps * scale, "exposed_comm_share": max(0.0, 1.0 - ms_nocomm / ms),
+           "tops_gemm_per_gpu": ops_layer * n_layers * steps / world / (ms * 1e-3) / 1e12,
+           "parallelism": f"tp{world}", "layers_timed": n_layers, "gpu_launches": n_launch, "reduction": how,
+           "allreduce_bytes": ar_bytes, "allreduces_per_step": 2 * L70}
+    if world > 1:
+        us_ar = ms_comm * 1e3 / n_ar
+        res.update({"allreduce_us_alone": us_ar, "allreduce_bus_GBps": 2 * (world - 1) / world * ar_bytes / us_ar / 1e3,
+                    "limiter": "all-reduce" if ms - ms_nocomm > 0.5 * ms_nocomm else "FlatLinear GEMMs (per-launch fixed cost at the sharded shapes)"})
+    if n_layers != L70:
+        res["note"] = f"{n_layers} of 80 identical layers timed, scaled"
+    del layers
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_tp70(args, rank, world, local):
+    """`--workload llama70b-tp`: configs[3] as its own bench line."""
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    dist, barrier = _init_dist(world, dev)
+    r = measure_tp70(args, rank, world, dev, dist, barrier, args.steps, args.layers if args.layers != N_LAYERS else L70)
     if rank == 0:
-        scale = L70 / n_layers
-        ops_layer = sum(2 * K * N for _, _, K, N in specs) * SEQ
         line = {"metric": "Llama-3-70B W4A4 tensor-parallel prefill tokens/sec (FlatLinear path, 80 layers, seq 2048)",
-                "value": SEQ * args.steps / (ms * 1e-3) / scale, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps * scale, "higher_is_better": True,
+                "value": r["tokens_per_s"], "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+                "warmup": 3, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "s4 x s4 -> s32, f16 in/out", "data": "synthetic",
-                "config": {"workload": "llama3-70b FlatLinear prefill, row/column parallel, 2 NCCL all-reduces of [2048, 8192] f16 per layer",
-                           "parallelism": f"tp{world}", "layers": n_layers},
-                "tops_gemm_per_gpu": ops_layer * n_layers * args.steps / world / (ms * 1e-3) / 1e12,
-                "gpu_launches": launches[0]}
-        if n_layers != L70:
-            line["note"] = f"{n_layers} of 80 identical layers timed, scaled"
+                "config": {"workload": "llama3-70b FlatLinear prefill, row/column parallel, 2 all-reduces of [2048, 8192] f16 per layer",
+                           "parallelism": f"tp{world}", "layers": r["layers_timed"]},
+                "gpu_launches": r["gpu_launches"], "tp70b": r}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------- configs[2]: Llama-3-8B end to end (model stack)
-def run_model(args, rank, world, local):
+def _init_dist(world, dev):
+    if world <= 1:
+        return None, (lambda: None)
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout, where only the JSON line belongs
+        dist.init_process_group("nccl", device_id=dev)
+    return dist, (lambda: dist.barrier())
+
+
+def _count_ops(ops, names, counted):
+    """Wrap the named flatquant_b200.ops entry points with a launch counter; returns the undo function."""
+    saved = {n: getattr(ops, n) for n in names}
+    for name, fn in saved.items():
+        def wrap(f):
+            def inner(*a, **k):
+                counted["n"] += 1
+                return f(*a, **k)
+            return inner
+        setattr(ops, name, wrap(fn))
+
+    def undo():
+        for n, f in saved.items():
+            setattr(ops, n, f)
+    return undo
+
+
+def measure_model(args, rank, world, dev, dist, barrier, steps, sample_clocks=True):
     """BASELINE configs[2]: the whole random-init Llama-3-8B W4A4 model (flatquant_b200.deploy.transformers) -- embedding,
     32 decoder layers (FlatLinears + RoPE + KV transform/quantise + attention), final norm, fp16 lm_head -- prefill at
-    seq 2048 and CUDA-event-timed decode steps at bsz 1 and 16 over the paged INT4 cache
-    (benchmarks/benchmark_model.py:264-305 protocol).  Data-parallel replicas for N > 1."""
+    seq 2048 and CUDA-event-timed decode steps at bsz 1 and 16 over the paged INT4 cache, eager and replayed from one
+    CUDA graph (benchmarks/benchmark_model.py:264-305 protocol).  Returns the measurements as a dict."""
     from flatquant_b200 import ops
     from flatquant_b200.deploy.transformers import FlatQuantLlamaConfig, FlatQuantLlamaForCausalLM
-    dev = torch.device(f"cuda:{local}")
-    torch.cuda.set_device(dev)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
-    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
     cfg = FlatQuantLlamaConfig(num_hidden_layers=args.layers)  # defaults = Llama-3-8B
     model = FlatQuantLlamaForCausalLM.random_init(cfg, dev, seed=1234 + rank)
     counted = {"n": 0}
-    for name in ("act_quant", "gemm_w4a8", "kron_transform", "kv_quant", "kv_decode_i4", "hadamard"):
-        def wrap(fn):
-            def inner(*a, **k):
-                counted["n"] += 1
-                return fn(*a, **k)
-            return inner
-        setattr(ops, name, wrap(getattr(ops, name)))
-    gen = torch.Generator().manual_seed(rank)
-    ids_host = torch.randint(100, 200, (1, SEQ), generator=gen).pin_memory()  # benchmark_model.py:281
-    ids = ids_host.to(dev)
-    decode_len = 64
-    cache = model.build_cache(1, page_size=2048, max_length=SEQ + decode_len)
-    out_host = torch.empty(1, cfg.vocab_size, dtype=torch.float16).pin_memory()
+    undo = _count_ops(ops, ("act_quant", "gemm_w4a8", "kron_transform", "kv_quant", "kv_decode_i4", "hadamard", "rmsnorm",
+                            "rope_", "silu_mul"), counted)
+    try:
+        gen = torch.Generator().manual_seed(rank)
+        ids_host = torch.randint(100, 200, (1, SEQ), generator=gen).pin_memory()  # benchmark_model.py:281
+        ids = ids_host.to(dev)
+        decode_len = 64
+        cache = model.build_cache(1, page_size=2048, max_length=SEQ + decode_len)
+        out_host = torch.empty(1, cfg.vocab_size, dtype=torch.float16).pin_memory()
 
-    def prefill():
-        cache.reset()
-        with torch.no_grad():
-            return model(ids, past_key_values=cache)[0]
+        def prefill():
+            cache.reset()
+            with torch.no_grad():
+                return model(ids, past_key_values=cache)[0]
 
-    def prefill_e2e():
-        cache.reset()
-        with torch.no_grad():
-            logits = model(ids_host.to(dev, non_blocking=True), past_key_values=cache)[0]
-        out_host.copy_(logits[:, -1], non_blocking=True)
+        def prefill_e2e():
+            cache.reset()
+            with torch.no_grad():
+                logits = model(ids_host.to(dev, non_blocking=True), past_key_values=cache)[0]
+            out_host.copy_(logits[:, -1], non_blocking=True)
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    for _ in range(max(3, args.warmup)):
-        prefill()
-    torch.cuda.synchronize()
-    if rank == 0:
-        sampler.wait_first()
-    counted["n"] = 0
-    t0 = sampler.mark()
-    ms = timed(prefill, args.steps, barrier)
-    t1 = sampler.mark()
-    launches = counted["n"]
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
-    ms_e2e = timed(prefill_e2e, args.steps, barrier)
+        sampler = ClockSampler(dev.index or 0)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+        for _ in range(3):
+            prefill()
+        torch.cuda.synchronize()
+        if rank == 0 and sample_clocks:
+            sampler.wait_first()
+        counted["n"] = 0
+        t0 = sampler.mark()
+        ms = timed(prefill, steps, barrier)
+        t1 = sampler.mark()
+        launches = counted["n"]
+        clocks = sampler.stop(t0, t1) if (rank == 0 and sample_clocks) else None
+        ms_e2e = timed(prefill_e2e, steps, barrier)
 
-    def decode_ms(bsz):
-        c = model.build_cache(bsz, page_size=2048, max_length=SEQ + decode_len)
-        tok = torch.randint(100, 200, (bsz, 1), device=dev)
-        with torch.no_grad():
-            model(ids.expand(bsz, SEQ).contiguous(), past_key_values=c, logits_to_keep=1)
-            for _ in range(4):
-                model(tok, past_key_values=c)
-
-            def steps():
-                for _ in range(decode_len - 8):
+        def decode_ms(bsz):
+            c = model.build_cache(bsz, page_size=2048, max_length=SEQ + decode_len)
+            tok = torch.randint(100, 200, (bsz, 1), device=dev)
+            with torch.no_grad():
+                model(ids.expand(bsz, SEQ).contiguous(), past_key_values=c, logits_to_keep=1)
+                for _ in range(4):
                     model(tok, past_key_values=c)
-            return timed(steps, 1, barrier) / (decode_len - 8)
-    dec = {f"bsz{b}_ms_per_token": decode_ms(b) for b in (1, 16)}
 
-    def decode_graph_ms(bsz):
-        """The same steps replayed from one CUDA graph (position on the device, graphs.GraphedDecoder)."""
-        from flatquant_b200.deploy.transformers.graphs import GraphedDecoder
-        c = model.build_cache(bsz, page_size=SEQ + decode_len, max_length=SEQ + decode_len)
-        tok = torch.randint(100, 200, (bsz, 1), device=dev)
-        with torch.no_grad():
-            model(ids.expand(bsz, SEQ).contiguous(), past_key_values=c, logits_to_keep=1)
-        g = GraphedDecoder(model, c)
-        for _ in range(4):
-            g.step(tok)
+                def run_steps():
+                    for _ in range(decode_len - 8):
+                        model(tok, past_key_values=c)
+                return timed(run_steps, 1, barrier) / (decode_len - 8)
+        dec = {}
+        for b in (1, 16):
+            try:
+                dec[f"bsz{b}_ms_per_token"] = decode_ms(b)
+            except Exception as e:  # noqa: BLE001
+                dec[f"bsz{b}_error"] = f"{type(e).__name__}: {e}"[:200]
 
-        def steps():
-            for _ in range(decode_len - 8):
+        def decode_graph_ms(bsz):
+            """The same steps replayed from one CUDA graph (position on the device, graphs.GraphedDecoder)."""
+            from flatquant_b200.deploy.transformers.graphs import GraphedDecoder
+            c = model.build_cache(bsz, page_size=SEQ + decode_len, max_length=SEQ + decode_len)
+            tok = torch.randint(100, 200, (bsz, 1), device=dev)
+            with torch.no_grad():
+                model(ids.expand(bsz, SEQ).contiguous(), past_key_values=c, logits_to_keep=1)
+            g = GraphedDecoder(model, c)
+            for _ in range(4):
                 g.step(tok)
-        return timed(steps, 1, barrier) / (decode_len - 8)
-    for b in (1, 16):
-        try:
-            dec[f"bsz{b}_graph_ms_per_token"] = decode_graph_ms(b)
-        except Exception as e:  # a capture problem must not lose the eager numbers of the same run
-            dec[f"bsz{b}_graph_error"] = f"{type(e).__name__}: {e}"[:200]
 
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
+            def run_steps():
+                for _ in range(decode_len - 8):
+                    g.step(tok)
+            return timed(run_steps, 1, barrier) / (decode_len - 8)
+        for b in (1, 16):
+            try:
+                dec[f"bsz{b}_graph_ms_per_token"] = decode_graph_ms(b)
+            except Exception as e:  # a capture problem must not lose the eager numbers of the same run
+                dec[f"bsz{b}_graph_error"] = f"{type(e).__name__}: {e}"[:200]
+        # HBM floor of one decode step: every packed weight + the fp16 lm_head streamed once (bsz-independent), plus the
+        # INT4 KV cache of the attended 2048 tokens
+        w_bytes = args.layers * sum(k * n // 2 for _, k, n, _ in LINEARS) + cfg.vocab_size * HIDDEN * 2
+        hbm = peaks()[0]
+        for b in (1, 16):
+            kv_bytes = args.layers * b * cfg.num_key_value_heads * SEQ * 2 * (64 + 4)
+            floor_ms = (w_bytes + kv_bytes) / (hbm * 1e9) * 1e3
+            dec[f"bsz{b}_hbm_floor_ms"] = floor_ms
+            best = min([v for k_, v in dec.items() if k_.startswith(f"bsz{b}_") and k_.endswith("ms_per_token")], default=None)
+            if best:
+                dec[f"bsz{b}_frac_of_hbm_floor"] = floor_ms / best
+        if world > 1:
+            t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, ms_e2e = t.tolist()
+        return {"prefill_tokens_per_s": world * SEQ * steps / (ms * 1e-3), "prefill_ms": ms / steps,
+                "e2e_prefill_tokens_per_s": world * SEQ * steps / (ms_e2e * 1e-3),
+                "h2d_bytes_per_step": ids_host.numel() * 8, "d2h_bytes_per_step": out_host.numel() * 2,
+                "gpu_launches": launches, "clocks": clocks, "decode": dec, "steps": steps, "layers": args.layers,
+                "decode_protocol": "prefill 2048 then 56 timed single-token steps (benchmarks/benchmark_model.py:285-297); "
+                                   "graph = the whole step replayed from one CUDA graph"}
+    finally:
+        undo()
+        del model
+        torch.cuda.empty_cache()
+
+
+def run_model(args, rank, world, local):
+    """`--workload llama8b-model`: configs[2] as its own bench line.  Data-parallel replicas for N > 1."""
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    dist, barrier = _init_dist(world, dev)
+    r = measure_model(args, rank, world, dev, dist, barrier, args.steps)
     if rank == 0:
-        scale = N_LAYERS / args.layers
         line = {"metric": "Llama-3-8B W4A4 end-to-end prefill tokens/sec/GPU (whole model, seq 2048, bsz 1)",
-                "value": world * SEQ * args.steps / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "value": r["prefill_tokens_per_s"], "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+                "warmup": 3, "ms_per_step": r["prefill_ms"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "s4 x s4 -> s32 linears, f16 attention / lm_head", "data": "synthetic",
                 "config": {"workload": "llama3-8b whole-model prefill seq 2048 + decode bsz 1/16, random-init weights",
                            "l2": "inputs larger than L2: 3.5 GB of packed weights + 1 GB lm_head per step",
                            "parallelism": f"dp{world} (independent replicas)", "layers": args.layers},
-                "clocks": clocks, "gpu_launches": launches,
-                "e2e": {"value": world * SEQ * args.steps / (ms_e2e * 1e-3), "unit": "tokens/s",
-                        "h2d_bytes_per_step": ids_host.numel() * 8, "d2h_bytes_per_step": out_host.numel() * 2},
-                "decode": dec}
-        if scale != 1:
+                "clocks": r["clocks"], "gpu_launches": r["gpu_launches"],
+                "e2e": {"value": r["e2e_prefill_tokens_per_s"], "unit": "tokens/s",
+                        "h2d_bytes_per_step": r["h2d_bytes_per_step"], "d2h_bytes_per_step": r["d2h_bytes_per_step"]},
+                "decode": r["decode"]}
+        if args.layers != N_LAYERS:
             line["INVALID"] = "debug run with fewer layers"
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -373,82 +459,175 @@ def run_model(args, rank, world, local):
 
 
 # ---------------------------------------------------------------- configs[4]: DeepSeek-V3 single block
-def run_deepseek(args, rank, world, local):
+def measure_deepseek(args, rank, world, dev, dist, barrier, steps, sample_clocks=True):
     """BASELINE configs[4]: one random-init DeepSeek-V3 MoE block at the public V3 shape (dim 7168, 128 heads, MLA
     ranks 1536 / 512, 256 routed experts top-8 + 1 shared, moe_inter 2048; 5.8 GB of packed expert weights), prefill of
-    2048 tokens.  Data-parallel replicas for N > 1."""
+    2048 tokens.  Returns the measurements as a dict."""
     from types import SimpleNamespace
 
     from flatquant_b200 import ops
     from flatquant_b200.deploy.transformers import modeling_deepseek as MD
-    dev = torch.device(f"cuda:{local}")
-    torch.cuda.set_device(dev)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
-    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
     a = SimpleNamespace(**MD.V3_ARGS)
     block = MD.FlatQuantDeepSeekBlock(a, MD.random_block_params(a, dev, seed=99 + rank), dev)
     counted = {"n": 0}
-    for name in ("act_quant", "gemm_w4a8"):
-        def wrap(fn):
-            def inner(*aa, **k):
-                counted["n"] += 1
-                return fn(*aa, **k)
-            return inner
-        setattr(ops, name, wrap(getattr(ops, name)))
-    x_host = torch.randn(1, SEQ, a.dim, generator=torch.Generator().manual_seed(rank)).half().pin_memory()
-    x = x_host.to(dev)
-    y_host = torch.empty(1, SEQ, a.dim, dtype=torch.float16).pin_memory()
-    cos, sin = MD.precompute_freqs(a, SEQ, dev)
+    undo = _count_ops(ops, ("act_quant", "gemm_w4a8", "gemm_w4a8_grouped"), counted)
+    try:
+        x_host = torch.randn(1, SEQ, a.dim, generator=torch.Generator().manual_seed(rank)).half().pin_memory()
+        x = x_host.to(dev)
+        y_host = torch.empty(1, SEQ, a.dim, dtype=torch.float16).pin_memory()
+        cos, sin = MD.precompute_freqs(a, SEQ, dev)
 
-    def step():
-        with torch.no_grad():
-            return block(x, 0, cos, sin)
+        def step():
+            with torch.no_grad():
+                return block(x, 0, cos, sin)
 
-    def step_e2e():
-        with torch.no_grad():
-            y_host.copy_(block(x_host.to(dev, non_blocking=True), 0, cos, sin), non_blocking=True)
+        def step_e2e():
+            with torch.no_grad():
+                y_host.copy_(block(x_host.to(dev, non_blocking=True), 0, cos, sin), non_blocking=True)
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    for _ in range(max(3, args.warmup)):
-        step()
-    torch.cuda.synchronize()
-    if rank == 0:
-        sampler.wait_first()
-    counted["n"] = 0
-    t0 = sampler.mark()
-    ms = timed(step, args.steps, barrier)
-    t1 = sampler.mark()
-    launches = counted["n"]
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
-    ms_e2e = timed(step_e2e, args.steps, barrier)
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
-    if rank == 0:
+        sampler = ClockSampler(dev.index or 0)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        if rank == 0 and sample_clocks:
+            sampler.wait_first()
+        counted["n"] = 0
+        t0 = sampler.mark()
+        ms = timed(step, steps, barrier)
+        t1 = sampler.mark()
+        launches = counted["n"]
+        clocks = sampler.stop(t0, t1) if (rank == 0 and sample_clocks) else None
+        ms_e2e = timed(step_e2e, steps, barrier)
+        if world > 1:
+            t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, ms_e2e = t.tolist()
         qk = a.qk_nope_head_dim + a.qk_rope_head_dim
         ops_tok = 2 * (a.dim * (a.q_lora_rank + a.kv_lora_rank + a.qk_rope_head_dim) + a.q_lora_rank * a.n_heads * qk +
                        a.n_heads * a.v_head_dim * a.dim + 3 * a.dim * a.moe_inter_dim * (a.n_activated_experts + a.n_shared_experts))
+        return {"tokens_per_s": world * SEQ * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+                "e2e_tokens_per_s": world * SEQ * steps / (ms_e2e * 1e-3),
+                "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": y_host.numel() * 2,
+                "tops_flatlinear": ops_tok * SEQ * steps / (ms * 1e-3) / 1e12, "gpu_launches": launches, "clocks": clocks,
+                "steps": steps,
+                "workload": "deepseek-v3 MoE block (public 671B shape), MLA + 256 routed experts top-8 (grouped GEMM) + shared, seq 2048"}
+    finally:
+        undo()
+        del block
+        torch.cuda.empty_cache()
+
+
+def run_deepseek(args, rank, world, local):
+    """`--workload deepseek-block`: configs[4] as its own bench line.  Data-parallel replicas for N > 1."""
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    dist, barrier = _init_dist(world, dev)
+    r = measure_deepseek(args, rank, world, dev, dist, barrier, args.steps)
+    if rank == 0:
         line = {"metric": "DeepSeek-V3 single MoE block W4A4 prefill tokens/sec/GPU (seq 2048)",
-                "value": world * SEQ * args.steps / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "value": r["tokens_per_s"], "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+                "warmup": 3, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "s4 x s4 -> s32 FlatLinears, f16 attention / gate", "data": "synthetic",
-                "config": {"workload": "deepseek-v3 MoE block (public 671B shape), MLA + 256 routed experts top-8 + shared, seq 2048",
-                           "l2": "inputs larger than L2: 5.8 GB of packed expert weights",
+                "config": {"workload": r["workload"], "l2": "inputs larger than L2: 5.8 GB of packed expert weights",
                            "parallelism": f"dp{world} (independent replicas)"},
-                "tops_flatlinear": ops_tok * SEQ * args.steps / (ms * 1e-3) / 1e12, "clocks": clocks, "gpu_launches": launches,
-                "e2e": {"value": world * SEQ * args.steps / (ms_e2e * 1e-3), "unit": "tokens/s",
-                        "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": y_host.numel() * 2}}
+                "tops_flatlinear": r["tops_flatlinear"], "clocks": r["clocks"], "gpu_launches": r["gpu_launches"],
+                "e2e": {"value": r["e2e_tokens_per_s"], "unit": "tokens/s",
+                        "h2d_bytes_per_step": r["h2d_bytes_per_step"], "d2h_bytes_per_step": r["d2h_bytes_per_step"]}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------- decode and qattention rooflines (HBM-bound side kernels)
+def measure_decode_linears(dev, barrier):
+    """Decode-shaped FlatLinears (1 and 16 tokens): GPU time of one fused FlatLinear (transform + quantise + weight-stream
+    GEMM + dequant through ops.linear_fused) per Llama-3-8B shape, replayed from a CUDA graph over 16 distinct weights
+    (every launch streams its packed weight from HBM).  Bound: HBM; algorithmic bytes per launch = K*N/2 (the 4-bit
+    weight stream) -- activations, scales and outputs are < 1 % at these shapes."""
+    from flatquant_b200 import ops
+    hbm = peaks()[0]
+    cm = float(torch.sigmoid(torch.tensor(4.0)))
+    out = {}
+    for m in (1, 16):
+        for name, k, n, (n1, n2) in LINEARS:
+            x = torch.randn(m, k, device=dev).half()
+            left = (torch.randn(n1, n1, device=dev) / n1 ** 0.5).half()
+            right = (torch.randn(n2, n2, device=dev) / n2 ** 0.5).half()
+            ws = [torch.randint(0, 256, (n, k // 2), dtype=torch.uint8, device=dev) for _ in range(16)]
+            sw = torch.rand(n, device=dev) * 0.01 + 0.005
+
+            def run(i):
+                return ops.linear_fused(x, left, right, n1, n2, cm, cm, ws[i % 16], sw)
+            for i in range(3):
+                run(i)
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                run(0)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    for i in range(16):
+                        run(i)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g.replay()
+            us = timed(g.replay, 5, barrier) * 1e3 / (5 * 16)
+            gbs = (k * n / 2) / us / 1e3
+            out[f"m{m} {name} {k}->{n}"] = {"us": us, "weight_stream_GBps": gbs, "frac_of_hbm": gbs / hbm}
+            del ws, g
+    return out
+
+
+def measure_qattention(dev, barrier):
+    """The qattention side path (shapes of benchmarks/qattention_benchmark.py:10-14: heads in
+    {32, 40, 64} x 128, seq 2048): online Hadamard (bytes = 4 * rows * n), KV quantise + pack + page scatter (256 B in,
+    64 + 4 B out per (token, head) row) and single-query attention over the packed INT4 cache (2 * bsz * kv_heads * T *
+    (64 + 4) bytes).  CUDA events over 20 launches each; bound: HBM."""
+    from flatquant_b200 import ops
+    hbm = peaks()[0]
+    D = 128
+    out = {}
+
+    def t_us(fn, reps=20):
+        for _ in range(3):
+            fn()
+        return timed(lambda: [fn() for _ in range(reps)], 1, barrier) * 1e3 / reps
+    for n in (128, 4096, 14336):   # K/Q head transform; hidden; Llama-3-8B down_proj input (28 x 512, fused K x 2^m kernel)
+        rows = 2048 * 32 if n == 128 else 2048
+        x = torch.randn(rows, n, device=dev).half()
+        if n & (n - 1) == 0:
+            us = t_us(lambda: ops.hadamard(x, 1.0 / n ** 0.5))
+        else:
+            from flatquant_b200.deploy.functional.hadamard import get_hadK
+            hk, k = get_hadK(n)
+            hk = hk.to(dev).half()
+            us = t_us(lambda: ops.hadamard_kn(x, hk, k, 1.0 / n ** 0.5))
+        gbs = 4.0 * rows * n / us / 1e3
+        out[f"hadamard rows={rows} n={n}"] = {"us": us, "GBps": gbs, "frac_of_hbm": gbs / hbm}
+    for heads in (32, 40, 64):
+        kvh = 8 if heads in (32, 64) else heads   # Llama-3 GQA (8 kv heads); llama-13b is MHA
+        for bsz in (1, 16):
+            T = SEQ
+            pages = torch.zeros(bsz, 1, 2, kvh, T, D // 2, dtype=torch.uint8, device=dev)
+            params = torch.zeros(bsz, 1, 2, kvh, T, 2, dtype=torch.float16, device=dev)
+            slot = (torch.arange(bsz, device=dev)[:, None] * T + torch.arange(T, device=dev)[None]).reshape(-1).int()
+            kx = torch.randn(bsz * T, kvh, D, device=dev).half()
+            us_q = t_us(lambda: ops.kv_quant(kx, pages, params, slot, 0, 0))
+            ops.kv_quant(kx, pages, params, slot, 0, 1)
+            gbs_q = bsz * T * kvh * (256 + 68) / us_q / 1e3
+            ip = torch.arange(bsz + 1, dtype=torch.int32, device=dev)
+            ix = torch.arange(bsz, dtype=torch.int32, device=dev)
+            lp = torch.full((bsz,), T, dtype=torch.int32, device=dev)
+            q = torch.randn(bsz, heads, D, device=dev).half()
+            us_d = t_us(lambda: ops.kv_decode_i4(q, pages, params, ip, ix, lp, layer=0, max_tokens_hint=T))
+            gbs_d = 2.0 * bsz * kvh * T * 68 / us_d / 1e3
+            out[f"heads={heads} kv_heads={kvh} bsz={bsz}"] = {
+                "kv_quant_us": us_q, "kv_quant_GBps": gbs_q, "kv_quant_frac_of_hbm": gbs_q / hbm,
+                "decode_attn_us": us_d, "decode_attn_GBps": gbs_d, "decode_attn_frac_of_hbm": gbs_d / hbm}
+            del pages, params, kx
+    return out
 
 
 def timed(fn, steps, dist_barrier):
@@ -464,30 +643,38 @@ def timed(fn, steps, dist_barrier):
     return e0.elapsed_time(e1)  # ms on the launching (current) stream
 
 
-def cpu_reference_pass(n_layers_sample, threads, reps, warm):
-    """The oracle's fake-quant path (the reference's own CPU arithmetic: trans -> fake-quant -> F.linear),
-    fp32, on the host cores.  Sample = `n_layers_sample` full decoder layers at seq 2048."""
+CPU_SAMPLE_TOKENS = 256
+
+
+def cpu_reference_pass(threads, reps, warm, tokens=CPU_SAMPLE_TOKENS, n_layers=None):
+    """The oracle's fake-quant path (the reference's own CPU arithmetic: trans -> fake-quant -> F.linear), fp32, on the
+    host cores.  One step = `tokens` tokens (a bounded sample of the 2048-token batch; tokens are independent on this
+    path) through ALL 224 linears -- 32 passes over one layer's weights (same shapes; 872 MB of fp32 weights per layer is
+    far beyond any last-level cache, so every pass streams them from DRAM).  Nothing is extrapolated: tokens/s =
+    tokens / measured step time.  Returns (tokens/s, seconds per step)."""
     from oracle import flatq_oracle as O
     torch.set_num_threads(threads)
+    n_layers = n_layers or N_LAYERS
     g = torch.Generator().manual_seed(0)
     lin = []
     for name, k, n, (n1, n2) in LINEARS:
         codes = torch.randint(-8, 8, (n, k), generator=g).float()
-        lin.append((torch.randn(SEQ, k, generator=g), torch.randn(n1, n1, generator=g) / n1 ** 0.5,
+        lin.append((torch.randn(tokens, k, generator=g), torch.randn(n1, n1, generator=g) / n1 ** 0.5,
                     torch.randn(n2, n2, generator=g) / n2 ** 0.5, codes * 0.01))
-    def one():
-        for x, L, R, w in lin:
-            O.flat_linear_fake(x, L, R, 4.0, 4.0, w)
+
+    def one_step():
+        for _ in range(n_layers):
+            for x, L, R, w in lin:
+                O.flat_linear_fake(x, L, R, 4.0, 4.0, w)
     for _ in range(warm):
-        one()
+        one_step()
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        for _ in range(n_layers_sample):
-            one()
-        times.append((time.perf_counter() - t0) / n_layers_sample)
-    t_layer = statistics.mean(times)
-    return SEQ / (t_layer * N_LAYERS), t_layer
+        one_step()
+        times.append(time.perf_counter() - t0)
+    t_step = statistics.mean(times)
+    return tokens / t_step, t_step
 
 
 def reference_gpu_kernels(device_index):
@@ -512,6 +699,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=N_LAYERS, help="debug only: fewer layers => INVALID as a bench value")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="default arm only: skip the extra sub-measurements (model_e2e, deepseek_block, roofline_decode, "
+                         "roofline_qattention at N = 1; tp70b at N > 1)")
     ap.add_argument("--workload", default="llama8b", choices=["llama8b", "llama70b-tp", "llama8b-model", "deepseek-block"],
                     help="llama8b = BASELINE configs[1] (default, data-parallel replicas); llama70b-tp = configs[3]; "
                          "llama8b-model = configs[2] (whole model: prefill + decode); deepseek-block = configs[4]")
@@ -527,14 +717,20 @@ def main():
         # fake-quant code; /root/reference is not on the GPU box) on all host threads.  Rank 0 only.
         if rank != 0:
             return
-        tok_s, t_layer = cpu_reference_pass(1, threads, max(1, args.steps), max(1, min(args.warmup, 1)))
+        # every step = CPU_SAMPLE_TOKENS tokens through all 224 linears (nothing extrapolated); the step count is bounded
+        # so that the whole arm ends within a few minutes whatever --steps the driver passes
+        steps_run = max(1, min(args.steps, 8))
+        warm_run = max(1, min(args.warmup, 2))
+        tok_s, t_step = cpu_reference_pass(threads, steps_run, warm_run)
+        sample = (f"{CPU_SAMPLE_TOKENS} of the 2048 tokens per step through all 32 layers x 7 linears (oracle port of the "
+                  f"reference's CPU fake-quant path, fp32, {threads} threads); {warm_run} warm-up + {steps_run} timed steps")
         line = {"impl": "reference", "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_layer * N_LAYERS * 1e3,
+                "steps": steps_run, "warmup": warm_run, "ms_per_step": t_step * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": {"workload": "llama3-8b FlatLinear prefill, seq 2048, 224 linears",
-                                                "note": "each step times 1 of 32 identical-shape layers and scales by 32"},
-                "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": threads, "kind": "port",
-                                 "sample": "1 decoder layer (7 linears) at seq 2048 per step, x32"},
+                "data": "synthetic", "config": {"workload": "llama3-8b FlatLinear prefill: 32 layers x (qkv, o, gate_up, down) W4A4, seq 2048, bsz 1",
+                                                "sample": sample,
+                                                "n_gpus_note": "one CPU process on rank 0 whatever N: compare at N = 1"},
+                "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
                 "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         # extra, GPU boxes only: the reference's own native GEMM + dequant kernels on this GPU (compare with the other
         # arm's roofline.avg_launch_us x launches / steps, i.e. its GEMM-only pass)
@@ -685,11 +881,12 @@ def main():
                          "achieved": achieved, "peak": peak_i8, "unit": "TOP/s", "frac": achieved / peak_i8,
                          "peak_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({src})",
                          "avg_launch_us": ms_gemm * 1e3 / n_gemm, "launches": n_gemm,
-                         # dram__bytes_read+write per GEMM launch, mean over the 4 shapes of a layer, from the ncu --set full
-                         # capture summarised in profiles/r01_ncu_full_final.md (algorithmic bytes: 85.0 MB per launch; the
-                         # difference is output that is still dirty in the 126 MB L2 when the kernel ends)
-                         "traffic": 62.9e6, "traffic_unit": "bytes/launch", "algorithmic_bytes_per_launch": 85.0e6,
-                         "issue_peak_note": "tcgen05 kind::i8 issue peak measured by tools/mma_rate.cu: 8185 MAC/cycle/SM"},
+                         # dram__bytes_read+write per GEMM launch, mean over the 4 shapes of a layer, from this round's
+                         # ncu --set full capture (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the
+                         # .ncu-rep; algorithmic bytes 85.0 MB per launch -- the difference is output still dirty in L2)
+                         "traffic": ncu_traffic("gemm_w4a8_2sm_kernel"), "traffic_unit": "bytes/launch",
+                         "algorithmic_bytes_per_launch": 85.0e6,
+                         "issue_peak_note": "tcgen05 kind::i8 issue peak measured by tools/mma_rate2.cu: 8189 MAC/cycle/SM"},
         }
         if ms_tr:
             # HBM-bound companion kernel: algorithmic bytes = fp16 activations in (2 B) + int8 codes out (1 B) + fp32 scale
@@ -711,11 +908,39 @@ def main():
             line["roofline"]["peak_sustained"] = 2 * sus
             line["roofline"]["frac_of_sustained"] = achieved / (2 * sus)
         if not args.no_cpu_baseline and world == 1:
-            v, t_layer = cpu_reference_pass(1, threads, 2, 1)
+            v, t_step = cpu_reference_pass(threads, 3, 1)
             line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
-                                    "sample": "oracle fake-quant path, 1 of 32 decoder layers (7 linears) at seq 2048, x32; 1 warm-up + 2 timed"}
+                                    "sample": f"oracle fake-quant path, {CPU_SAMPLE_TOKENS} of the 2048 tokens through all 32 layers x 7 "
+                                              f"linears per step ({t_step:.2f} s/step), 1 warm-up + 3 timed steps, nothing extrapolated"}
         if args.layers != N_LAYERS:
             line["INVALID"] = "debug run with fewer layers"
+    else:
+        line = None
+
+    # ---- extra sub-measurements in the same line: the other BASELINE configs and the HBM-bound side
+    # kernels.  Each is optional evidence: a failure is recorded under its key and never costs the headline.
+    if not args.no_extras:
+        del run, layers
+        torch.cuda.empty_cache()
+        extras = {}
+
+        def attempt(key, fn):
+            try:
+                extras[key] = fn()
+            except Exception as e:  # noqa: BLE001
+                extras[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
+        sub_steps = max(2, min(args.steps, 5))
+        if world == 1:
+            attempt("model_e2e", lambda: measure_model(args, rank, world, dev, dist, barrier, sub_steps, sample_clocks=False))
+            attempt("deepseek_block", lambda: measure_deepseek(args, rank, world, dev, dist, barrier, sub_steps, sample_clocks=False))
+            attempt("roofline_decode", lambda: measure_decode_linears(dev, barrier))
+            attempt("roofline_qattention", lambda: measure_qattention(dev, barrier))
+        else:
+            attempt("tp70b", lambda: measure_tp70(args, rank, world, dev, dist, barrier, sub_steps))
+        if line is not None:
+            line.update(extras)
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

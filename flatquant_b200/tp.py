@@ -99,3 +99,39 @@ class RowParallelFlatLinear:
 def split_packed_rows(w_packed: torch.Tensor, shard: Shard) -> torch.Tensor:
     """This rank's slice of a packed [N, K/2] weight (rows for column-parallel, byte columns for row-parallel)."""
     return w_packed[shard.n0:shard.n1, shard.k0 // 2:shard.k1 // 2].contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reduction behind a row-parallel linear.  `make_reducer` picks the implementation once per (shape, group):
+#   * PeerReducer  (flatquant_b200/peer_reduce.py): symmetric-memory buffers, the GEMM writes its partial product into
+#     the local one and ONE kernel of this library reduces through the NVSwitch multicast mapping and broadcasts the sum
+#     to every rank (multimem.ld_reduce / multimem.st over NVLink; csrc/peer_reduce.cuh);
+#   * NcclReducer: dist.all_reduce -- the baseline form, and what the gloo CPU tests exercise.
+class NcclReducer:
+    name = "torch.distributed all_reduce (NCCL ring / NVLS, separate launch)"
+
+    def __init__(self, shape, dtype, dev, group=None):
+        self.buf = torch.empty(shape, dtype=dtype, device=dev)
+        self.group = group
+
+    def partial_buffer(self):
+        return self.buf
+
+    def all_reduce(self, partial, out=None):
+        dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.group)
+        if out is not None and out.data_ptr() != partial.data_ptr():
+            out.copy_(partial)
+            return out
+        return partial
+
+
+def make_reducer(world, rank, dev, shape, dtype, group=None, prefer_peer=True):
+    import os
+    if prefer_peer and dev.type == "cuda" and os.environ.get("FLATQ_TP_NCCL") is None:
+        try:
+            from .peer_reduce import PeerReducer
+            return PeerReducer(world, rank, dev, shape, dtype, group)
+        except Exception as e:  # noqa: BLE001 -- no symmetric memory / multicast on this box: say so, use NCCL
+            import warnings
+            warnings.warn(f"flatquant_b200.tp: peer-memory reduction unavailable ({type(e).__name__}: {e}); using NCCL")
+    return NcclReducer(shape, dtype, dev, group)

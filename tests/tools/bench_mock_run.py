@@ -38,5 +38,5 @@ bench.LINEARS = [("qkv", 256, 384, (16, 16)), ("o", 256, 256, (16, 16)), ("gate_
 bench.HIDDEN, bench.INTER, bench.N_LAYERS = 256, 512, 2
 bench.OPS_PER_TOKEN_LAYER = sum(2*k*n for _,k,n,_ in bench.LINEARS)
 bench.cpu_reference_pass = lambda *a, **k: (1.0, 1.0)
-sys.argv = ["bench.py", "--steps", "2", "--warmup", "1", "--layers", "2"]
+sys.argv = ["bench.py", "--steps", "2", "--warmup", "1", "--layers", "2", "--no-extras"]
 bench.main()
