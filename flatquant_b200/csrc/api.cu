@@ -20,6 +20,7 @@
 #include "glue.cuh"
 #include "kron_quant.cuh"
 #include "kron_quant_tc.cuh"
+#include "kron_quant_ts.cuh"
 #include "qattention.cuh"
 
 using namespace flatq;
@@ -381,10 +382,55 @@ int launch_kron_tc_o(const KronParams& p, cudaStream_t st) {
     return p.xq8 ? launch_kron_tc_t<N2, N1P, T, true, false>(p, st) : launch_kron_tc_t<N2, N1P, T, false, false>(p, st);
 }
 
+// ---- second tcgen05 design (kron_quant_ts.cuh): intermediate in TMEM, several token groups in flight per CTA
+template <int N1, int N2, int T, bool OUT8>
+int launch_kron_ts_t(const KronParams& p, cudaStream_t st) {
+    using C = KronTs<N1, N2, T>;
+    auto kern = kron_quant_ts_kernel<N1, N2, T, OUT8>;
+    static PerDeviceOnce attr;
+    if (attr.first_time()) FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    CUtensorMap tx, tr;  // x as a 2-D byte tensor [tokens * n1 rows][n2 * 2 bytes]; R row-major, 64-column panels
+    int rc = make_map_u8(&tx, p.x, (uint64_t)p.tokens * N1, (uint64_t)N2 * 2, (uint64_t)N2 * 2, 128, C::kK1, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_u8(&tr, p.right, N2, (uint64_t)N2 * 2, (uint64_t)N2 * 2, 128, N2, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    const int groups = (p.tokens + T - 1) / T;
+    const int grid = groups < num_sms() ? groups : num_sms();
+    FLATQ_CUDA(launch_pdl(kern, dim3(grid), dim3(C::kThreads), (size_t)C::kSmemBytes, st, tx, tr, p));
+    return FLATQ_OK;
+}
+
+template <int N1, int N2, int T>
+int launch_kron_ts_o(const KronParams& p, cudaStream_t st) {
+    return p.xq8 ? launch_kron_ts_t<N1, N2, T, true>(p, st) : launch_kron_ts_t<N1, N2, T, false>(p, st);
+}
+
+// returns 1 if the request is not one of the instantiated (n1, n2) pairs
+int launch_kron_ts(const KronParams& p, cudaStream_t st) {
+    if (!p.left || !p.right || !aligned16(p.left) || !aligned16(p.right)) return 1;
+    if (p.n2 == 64) {
+        if (p.n1 == 64) return launch_kron_ts_o<64, 64, 2>(p, st);     // 4096 (Llama-3-8B hidden)
+        if (p.n1 == 56) return launch_kron_ts_o<56, 64, 2>(p, st);     // 3584 (70B down_proj at tp 8)
+        if (p.n1 == 32) return launch_kron_ts_o<32, 64, 4>(p, st);     // 2048
+    } else if (p.n2 == 128) {
+        if (p.n1 == 64) return launch_kron_ts_o<64, 128, 2>(p, st);    // 8192 (70B hidden)
+        if (p.n1 == 112) return launch_kron_ts_o<112, 128, 1>(p, st);  // 14336 (Llama-3-8B intermediate)
+        if (p.n1 == 128) return launch_kron_ts_o<128, 128, 1>(p, st);  // 16384 (DeepSeek-V3 wo)
+    }
+    return 1;
+}
+
 // returns 1 if no tcgen05 instantiation covers the request (caller falls back to the HMMA kernel)
 int launch_kron_tc(const KronParams& p, cudaStream_t st) {
     if (!p.do_quant || p.z_out || p.tokens <= 0 || (p.n1 * p.n2) % 32 != 0) return 1;
     if ((p.xq8 != nullptr) == (p.xq4 != nullptr)) return 1;  // exactly one code format per launch
+    {
+        static const bool v1 = getenv("FLATQ_KRON_TC1") != nullptr;   // A/B aid: force the first tcgen05 design
+        if (!v1) {
+            const int rc = launch_kron_ts(p, st);
+            if (rc != 1) return rc;
+        }
+    }
     if (p.n2 == 64) {
         if (p.n1 == 64) return launch_kron_tc_o<64, 64, 2>(p, st);
         if (p.n1 > 32 && p.n1 < 64) return launch_kron_tc_o<64, 64, 1>(p, st);
