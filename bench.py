@@ -160,7 +160,10 @@ class Runner:
         """BASELINE's second metric ("FlatLinear INT4 TFLOPS vs B200 peak", qlinear_benchmark.py protocol: one shape at a
         time): GPU time of ONE fused FlatLinear -- transform + quantise + W4A4 GEMM + dequant through ops.linear_fused --
         per Llama-3-8B shape at 2048 tokens, cycling over the layers' distinct weights.  The 4096 -> 4096 row is the
-        shape the north star quotes its 70 % target on."""
+        shape the north star quotes its 70 % target on.  Timed as a kernel "timed alone" (the burst peak's definition in
+        MEASURED_PEAKS.json): the pass over the 32 layers' weights is replayed from a CUDA graph after a short idle gap,
+        so neither the host's per-call cost (ctypes + tensor-map encoding, ~10-20 us) nor the power state left behind
+        by the preceding sustained passes is in the number; `us_host_loop` is the same pass issued call by call."""
         out = {}
         for name, k, n, (n1, n2) in LINEARS:
             ps = [layer[name] for layer in self.layers]
@@ -169,10 +172,27 @@ class Runner:
                 for p in ps:
                     self.ops.linear_fused(self.x[k], p["left"], p["right"], n1, n2, self.cm, self.cm, p["w"], p["s_w"])
             one_pass()
-            ms = timed(one_pass, reps, barrier)
-            us = ms * 1e3 / (reps * len(ps))
+            ms_loop = timed(one_pass, reps, barrier)
+            row = {"us_host_loop": ms_loop * 1e3 / (reps * len(ps))}
+            try:
+                side = torch.cuda.Stream(device=self.dev)
+                side.wait_stream(torch.cuda.current_stream(self.dev))
+                with torch.cuda.stream(side):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        one_pass()
+                torch.cuda.current_stream(self.dev).wait_stream(side)
+                g.replay()
+                torch.cuda.synchronize()
+                time.sleep(0.25)
+                us = timed(g.replay, reps, barrier) * 1e3 / (reps * len(ps))
+                del g
+            except Exception as e:  # noqa: BLE001 -- no graph support (the CPU mock run): keep the host-loop figure
+                row["graph_error"] = f"{type(e).__name__}: {e}"[:120]
+                us = row["us_host_loop"]
             tops = 2.0 * SEQ * k * n / us / 1e6
-            out[f"{name} {k}->{n}"] = {"us": us, "tops": tops, "frac_of_peak": tops / peak_tops}
+            row.update({"us": us, "tops": tops, "frac_of_peak": tops / peak_tops})
+            out[f"{name} {k}->{n}"] = row
         return out
 
     def transform_only(self):

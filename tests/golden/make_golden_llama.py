@@ -27,6 +27,13 @@ Shims (this image has transformers 5.5, the reference was written against 4.3x; 
 Outputs:
   tests/golden/llama_ckpt/{model.safetensors, quantization_config.json, flat_matrices.pth, config.json}
   tests/golden/llama_model.npz   input ids, per-stage expected activations and the final logits
+
+`--full-width` writes the same for ONE decoder layer at the Llama-3-8B widths (hidden 4096 -> (64,64), intermediate
+14336 -> (112,128), 32 heads / 8 kv heads x 128; 1 x 16 tokens):
+  tests/golden/llama_fullwidth_ckpt/   (110 MB of packed weights: git-ignored, travels to the GPU box with the working
+                                        tree like the built libraries; __graft_entry__.build() regenerates it when absent)
+  tests/golden/llama_fullwidth.npz     (committed, 3 MB: ids + per-stage expected activations in fp32 -- they are also the
+                                        teacher-forced INPUTS of the later stages, where an fp16 rounding would flip codes)
 """
 import importlib.util
 import json
@@ -80,6 +87,12 @@ ARGS = dict(w_bits=4, a_bits=4, q_bits=16, k_bits=4, v_bits=4, w_asym=False, a_a
             v_asym=True, lac=True, lwc=True, a_groupsize=-1, w_groupsize=-1, direct_inv=False, add_diag=True,
             separate_vtrans=False, diag_init=None, gptq_mse=False, model="tiny-llama-flatquant-fixture")
 BSZ, SEQ = 2, 16
+FULL = "--full-width" in sys.argv
+if FULL:
+    CFG.update(hidden_size=4096, intermediate_size=14336, num_attention_heads=32, num_key_value_heads=8, num_hidden_layers=1)
+    ARGS.update(model="llama3-8b-width-one-layer-fixture")
+    CKPT = os.path.join(OUT, "llama_fullwidth_ckpt")
+    BSZ = 1
 
 
 class Rotary:
@@ -201,7 +214,7 @@ def main():
 
     run("prefill", kv_quant=False)   # = the deployed prefill: attention on the transformed, unquantised K/V
     run("kvq", kv_quant=True)        # fake-quantised (LAC, asymmetric INT4) K/V in the attention
-    np.savez_compressed(os.path.join(OUT, "llama_model.npz"), ids=ids.numpy(), **rec)
+    np.savez_compressed(os.path.join(OUT, "llama_fullwidth.npz" if FULL else "llama_model.npz"), ids=ids.numpy(), **rec)
     print("files:", {f: os.path.getsize(os.path.join(CKPT, f)) for f in sorted(os.listdir(CKPT))})
 
 

@@ -147,7 +147,7 @@ def test_transform_quant_codes(ops, dev, n1, n2):
     #     core differs, which can move an fp16 rounding (and hence a code) in rare cases.
     q_em, s_em = _emulated_codes(x, L, R, cmax, cmin, "xr" if tc and (n1, n2) not in TS_SHAPES else "lx")
     d = np.abs(codes - q_em)
-    assert d.max() <= 1 and (d != 0).mean() < 2e-3
+    assert d.max() <= 1 and (d != 0).mean() < 2e-4   # measured on the B200: <= 3e-5 (128,128), 0 on most shapes
     assert torch.allclose(s32.cpu(), s_em, rtol=1e-3)
     if not tc:
         # HMMA kernel: the quantiser is bit exact given the kernel's own fp16 transform output
@@ -166,8 +166,11 @@ def test_transform_quant_codes(ops, dev, n1, n2):
     so = torch.where(m == 0, torch.ones_like(m), m / 7)
     qo = torch.clamp(torch.round(z32 / so[:, None]), -8, 7).numpy().astype(np.int32)
     diff = np.abs(codes - qo)
+    print(f"({n1},{n2}): flips vs fp32 oracle {(diff != 0).mean():.5f}, vs rounding-point model {(d != 0).mean():.5f}")
     assert diff.max() <= 1
-    assert (diff != 0).mean() < 0.02
+    # measured on the B200: 0.04-0.06 % on the Llama shapes, 0.11 % at (8,16); bound = 2x the worst (SURVEY 8c proposed
+    # >= 99.9 % identical for the deployed shapes: met)
+    assert (diff != 0).mean() < (0.0025 if n1 * n2 < 1024 else 0.0012)
     assert torch.allclose(s32.cpu(), so, rtol=2e-3)
     # (3) the GEMM operand format (int8, K-permuted) carries the same codes
     xq8, sx = ops.act_quant(x.to(dev), L.to(dev), R.to(dev), n1, n2, cmax, cmin)
@@ -176,7 +179,7 @@ def test_transform_quant_codes(ops, dev, n1, n2):
     restored = np.empty_like(unperm)
     restored[:, :, perm] = unperm
     d8 = np.abs(restored.reshape(tokens, k).astype(np.int32) - codes)
-    assert d8.max() <= (1 if tc else 0) and (d8 != 0).mean() < 2e-3
+    assert d8.max() <= (1 if tc else 0) and (d8 != 0).mean() < 2e-4
     assert torch.allclose(sx.cpu(), s32.cpu(), rtol=1e-3)
 
 
@@ -204,10 +207,12 @@ def test_fused_linear_golden(ops, dev, golden, case):
                          T(g["s_w"]).reshape(-1).float().to(dev), bias).float().cpu().numpy()
     y_ref = g["y"].reshape(y.shape)  # the reference's fake-quant output (fp32 CPU)
     # fp16 tolerance (north star): inputs/factors rounded to fp16 and an fp16 transform move a few codes by one
-    # step; each flip changes y by <= s_x*s_w*|w|.  Stated bound: 3% of max|y| worst case, 0.5% on average.
+    # step; each flip changes y by <= s_x*s_w*|w|.  Stated bound: 3% of max|y| worst case, 0.45% on average (measured on
+    # the B200: max 2.3-2.8 %, mean 0.19-0.35 %; the fixtures' x is fp32 and is rounded to fp16 here).
     err = np.abs(y - y_ref)
+    print(f"{case}: max err {err.max() / np.abs(y_ref).max():.5f}, mean err {err.mean() / np.abs(y_ref).max():.6f} of max|y|")
     assert err.max() <= 0.03 * np.abs(y_ref).max()
-    assert err.mean() <= 0.005 * np.abs(y_ref).max()
+    assert err.mean() <= 0.0045 * np.abs(y_ref).max()
     # tight check: oracle evaluated on the same fp16-rounded inputs with the kernel's own codes is exact to fp16
     xq, _, s32 = ops.transform_quant(x.to(dev), L.to(dev), R.to(dev), n1, n2, cmax, cmin)
     acc = O.gemm_i4(O.unpack_i4(xq.cpu().numpy()), g["w_codes"])

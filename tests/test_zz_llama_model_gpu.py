@@ -60,10 +60,10 @@ def test_prefill_then_decode_end_to_end(model, g, dev):
     ref = torch.from_numpy(g["prefill_logits"]).to(dev)
     cos = torch.nn.functional.cosine_similarity(full.float().flatten(), ref.flatten(), dim=0)
     print("prefill logits cosine vs reference fake-quant", float(cos))
-    assert cos > 0.9
+    assert cos > 0.94   # measured 0.964 (two layers, 14 chained W4A4 stages in fp16 vs the fp32 reference)
     cos_d = torch.nn.functional.cosine_similarity(step[:, 0].float(), full[:, -1].float(), dim=-1)
     print("decode vs prefill last-position cosine", cos_d.tolist())
-    assert cos_d.min() > 0.85
+    assert cos_d.min() > 0.92   # measured 0.950 / 0.971
 
 
 def test_decode_attention_over_paged_int4_cache(model, g, dev):
