@@ -4,23 +4,43 @@ import torch
 from . import ops
 
 _KERNEL_MAX = 256
+_F16_MAX = 65504.0
 
 
-def _kernel_ok(x, n1, n2):
-    return (x.is_cuda and x.dtype == torch.float16 and n2 % 16 == 0 and n1 <= _KERNEL_MAX and n2 <= _KERNEL_MAX
-            and (n1 + 15) // 16 * 32 <= (512 if n2 <= 128 else 256) and not torch.is_grad_enabled())
+def _shape_ok(n1, n2):
+    return (n2 % 16 == 0 and n1 <= _KERNEL_MAX and n2 <= _KERNEL_MAX
+            and (n1 + 15) // 16 * 32 <= (512 if n2 <= 128 else 256))
+
+
+def _inference_act(x):
+    """CUDA, 16-bit, no autograd: an inference activation -- the sm_100a kernel's job, never a silent cuBLAS call."""
+    return x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and not torch.is_grad_enabled()
+
+
+def as_kernel_f16(x):
+    """fp16 view of a 16-bit activation for the kernels.  bf16 -> fp16 is exact (8 -> 11 mantissa bits) for finite values
+    up to 65504; larger magnitudes saturate there instead of becoming inf."""
+    if x.dtype == torch.float16:
+        return x.contiguous()
+    return x.clamp(-_F16_MAX, _F16_MAX).to(torch.float16).contiguous()
 
 
 def kronecker_matmul(x, hadL, hadR):
     """x @ kron(hadL, hadR), evaluated per token as hadL^T . reshape(x, n1, n2) . hadR.
 
-    Inference activations (CUDA, fp16, no grad) run on the sm_100a kernel (flatq_kron_transform).
-    Everything else -- the offline fp64 weight reparameterisation and calibration-time autograd,
-    which are not on the inference hot path -- is expressed with torch.matmul as in the reference."""
+    Inference activations (CUDA, fp16 or bf16, no grad) run on the sm_100a kernel (flatq_kron_transform; bf16 is
+    converted exactly to fp16 on the way in, the factors are rounded to the activation dtype like the reference's
+    `.to(inp)`, the result is rounded back to bf16) and RAISE when the factor sizes have no kernel -- they are never
+    routed to cuBLAS behind the caller's back.  What remains on torch.matmul, as in the reference, is not the inference
+    path: the offline fp64 weight reparameterisation, calibration-time autograd, fp32 evaluation and CPU tensors."""
     n1, n2 = hadL.shape[0], hadR.shape[0]
-    if _kernel_ok(x, n1, n2):
-        xc = x.contiguous()
-        return ops.kron_transform(xc, hadL.to(xc).contiguous(), hadR.to(xc).contiguous(), n1, n2).view(x.shape)
+    if _inference_act(x):
+        if not _shape_ok(n1, n2):
+            raise RuntimeError(f"kronecker_matmul: no sm_100a kernel for factor sizes ({n1}, {n2}) (need n2 % 16 == 0, "
+                               "n1, n2 <= 256); fp32 activations take the reference's torch path")
+        xc = as_kernel_f16(x)
+        z = ops.kron_transform(xc, hadL.to(x).to(xc).contiguous(), hadR.to(x).to(xc).contiguous(), n1, n2)
+        return z.view(x.shape).to(x.dtype)
     lead = x.shape
     t = x.reshape(-1, n1, n2)
     return (hadL.transpose(0, 1) @ (t @ hadR)).reshape(lead)

@@ -27,11 +27,17 @@ def _usv(u, diag, v, inverse=False):
 
 
 def _matmul_last(inp, mat):
-    """[..., n] @ mat for a single (non-decomposed) transform."""
+    """[..., n] @ mat for a single (non-decomposed) transform.  16-bit inference activations on CUDA with n <= 256 (head
+    and head-count sized transforms: o_trans, the K / V cache transforms) run on the sm_100a kernel; a larger single
+    matrix is a plain dense GEMM, which is what a library GEMM is for; fp32 / autograd / CPU follow the reference."""
+    from .flat_utils import _inference_act, as_kernel_f16
     n = mat.shape[0]
-    if inp.is_cuda and inp.dtype == torch.float16 and not torch.is_grad_enabled() and n % 16 == 0 and n <= 256:
-        flat = inp.reshape(-1, n).contiguous()
-        return ops.kron_transform(flat, None, mat.to(flat).contiguous(), 1, n).view(inp.shape)
+    if _inference_act(inp) and n <= 256:
+        if n % 16:
+            raise RuntimeError(f"single transform of size {n}: no sm_100a kernel (n % 16 != 0); use fp32 activations for the "
+                               "reference's torch path")
+        flat = as_kernel_f16(inp.reshape(-1, n))
+        return ops.kron_transform(flat, None, mat.to(inp).to(flat).contiguous(), 1, n).view(inp.shape).to(inp.dtype)
     return inp.reshape(-1, n).matmul(mat).reshape(inp.shape)
 
 

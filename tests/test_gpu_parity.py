@@ -290,6 +290,38 @@ def test_flat_quantized_linear_dropin(dev, golden):
         fl(T(g["x"]).half())  # CPU activations: no fallback
 
 
+def test_operator_api_bf16_activations_and_no_silent_library_fallback(ops, dev):
+    """the operator-level transforms (flat_utils.kronecker_matmul, *TransMatrix.forward) take bf16
+    inference activations on the sm_100a kernel (exact bf16 -> fp16 conversion on the way in, result rounded to bf16),
+    and refuse 16-bit activations whose factor sizes have no kernel instead of quietly calling cuBLAS."""
+    from flatquant_b200 import flat_utils as FU
+    from flatquant_b200.trans_utils import _matmul_last
+    torch.manual_seed(11)
+    n1, n2 = 64, 64
+    x = torch.randn(3, 7, n1 * n2).to(torch.bfloat16)
+    L = torch.randn(n1, n1) / n1 ** 0.5
+    R = torch.randn(n2, n2) / n2 ** 0.5
+    calls = []
+    real = ops.kron_transform
+    try:
+        ops.kron_transform = lambda *a, **k: (calls.append(1), real(*a, **k))[1]
+        with torch.no_grad():
+            z = FU.kronecker_matmul(x.to(dev), L.to(dev), R.to(dev))
+            w = _matmul_last(x.to(dev).reshape(3, 7, 32, 128), R.new_tensor(torch.randn(128, 128) / 128 ** 0.5).to(dev))
+    finally:
+        ops.kron_transform = real
+    assert len(calls) == 2 and z.dtype == torch.bfloat16 and z.shape == x.shape and w.dtype == torch.bfloat16
+    ref = O.kronecker_matmul(x.float(), L.to(torch.bfloat16).float(), R.to(torch.bfloat16).float())
+    err = (z.float().cpu() - ref).abs().max() / ref.abs().max()
+    assert err < 2.0 ** -7, err   # one bf16 rounding of the output (2^-9 relative) + the fp16 intermediate
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no sm_100a kernel"):
+        FU.kronecker_matmul(torch.randn(2, 14 * 15, device=dev).half(), torch.eye(14, device=dev), torch.eye(15, device=dev))
+    # fp32 activations are the reference's own torch path (calibration precision), untouched
+    with torch.no_grad():
+        z32 = FU.kronecker_matmul(x.float().to(dev), L.to(dev), R.to(dev))
+    assert z32.dtype == torch.float32
+
+
 def test_deploy_api_chain(dev):
     """benchmarks/qlinear_benchmark.py:70-74: Sequential(OnlineTrans('matmul'), Quantizer, Linear4bit)."""
     from flatquant_b200 import deploy
