@@ -243,23 +243,29 @@ def measure_tp70(args, rank, world, dev, dist, barrier, steps, n_layers=None):
     launches = [0]
     reducer = TP.make_reducer(world, rank, dev, (SEQ, H70), torch.float16) if world > 1 else None
     how = reducer.name if reducer is not None else "none (tp1)"
+    # what the reductions alone cost, for the bus-bandwidth figure: the in-switch all-reduce kernel of the same library
+    # when the box has multicast, else NCCL
+    comm_reducer = reducer
+    if reducer is not None and getattr(reducer, "fused", False) and not getattr(reducer, "par_mc", 0):
+        comm_reducer = TP.NcclReducer((SEQ, H70), torch.float16, dev)
 
     def step(comm=True):
         for layer in layers:
             for i, l in enumerate(layer):
                 row = l["kind"] == "row" and world > 1
                 ops.act_quant(xs[l["kk"]], l["left"], l["right"], l["n1"], l["n2"], cm, cm, out=xq[l["kk"]])
-                out = reducer.partial_buffer() if (row and comm) else ys[i]
-                ops.gemm_w4a8(xq[l["kk"]][0], xq[l["kk"]][1], l["w"], l["s_w"], out=out)
-                launches[0] += 2
-                if row and comm:
-                    reducer.all_reduce(out)
+                if row and comm:   # GEMM + reduction: one call into the reducer (fused epilogue reduce-scatter, or NCCL)
+                    reducer.rowparallel_gemm(xq[l["kk"]][0], xq[l["kk"]][1], l["w"], l["s_w"])
+                    launches[0] += 3
+                else:
+                    ops.gemm_w4a8(xq[l["kk"]][0], xq[l["kk"]][1], l["w"], l["s_w"], out=ys[i])
+                    launches[0] += 2
 
-    def comm_only():
+    def comm_only():   # the same number of all-reduces of the same [2048, 8192] fp16 payload, nothing else
         for layer in layers:
             for i, l in enumerate(layer):
                 if l["kind"] == "row":
-                    reducer.all_reduce(reducer.partial_buffer())
+                    comm_reducer.all_reduce(comm_reducer.partial_buffer())
     for _ in range(3):
         step()
     torch.cuda.synchronize()

@@ -42,6 +42,9 @@ SIGNATURES = {
     "flatq_gemm_w4a8_grouped": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
                                         c_int64, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "flatq_hadamard": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
+    "flatq_kv_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                               c_int, c_int, c_void_p]),
     "flatq_hadamard_kn": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_void_p]),
     "flatq_kv_quant": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                c_int, c_int, c_int, c_void_p]),

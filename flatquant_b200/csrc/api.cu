@@ -22,6 +22,8 @@
 #include "kron_quant_tc.cuh"
 #include "kron_quant_ts.cuh"
 #include "qattention.cuh"
+#include "kv_fused.cuh"
+#include "peer_reduce.cuh"
 
 using namespace flatq;
 
@@ -240,7 +242,7 @@ int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, i
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = acc_shift;
     p.out = out; p.s_x = sx; p.s_w = sw; p.bias = bias; p.prof = nullptr; p.dbg = 0; p.k_splits = k_splits;
     p.streamk = 0; p.sk_part = nullptr; p.sk_flags = nullptr; p.epoch = 0;
-    p.grp_off = nullptr; p.grp_tile = nullptr; p.n_groups = 0; p.t_upper = 0;
+    p.grp_off = nullptr; p.grp_tile = nullptr; p.n_groups = 0; p.t_upper = 0; p.rows_per_owner = 0; p.tp_rank = 0;
     {
         // Stream-K on the partial last wave: worth it when the tail's K stages, dealt to all SMs, finish at least two
         // stages earlier than whole tiles would, and every part is long enough to amortise its fix-up.
@@ -739,8 +741,85 @@ int flatq_gemm_w4a8_grouped(const int8_t* xq8, const float* s_x, const uint8_t* 
     p.out = y; p.s_x = s_x; p.s_w = s_w; p.bias = bias; p.prof = nullptr; p.dbg = 0; p.k_splits = 1;
     p.streamk = 0; p.sk_part = nullptr; p.sk_flags = nullptr; p.epoch = 0;
     p.grp_off = group_offsets; p.grp_tile = tile_prefix; p.n_groups = n_groups; p.t_upper = (int)t_upper;
+    p.rows_per_owner = 0; p.tp_rank = 0;
     return out_dtype == FLATQ_F16 ? launch_gemm_grouped_m<kEpiF16>(tn, tw, tx, p, st)
                                   : launch_gemm_grouped_m<kEpiBF16>(tn, tw, tx, p, st);
+}
+
+// ---- tensor-parallel row-parallel linears over NVLink peer memory (csrc/peer_reduce.cuh)
+static int peer_ctx(const flatq_tp_ctx* tp, PeerCtx* c) {
+    FLATQ_CHECK(tp && tp->world >= 2 && tp->world <= kPeerMaxWorld && tp->rank >= 0 && tp->rank < tp->world, FLATQ_ERR_INVALID,
+                "tp: world must be 2..%d and 0 <= rank < world", kPeerMaxWorld);
+    c->rank = tp->rank; c->world = tp->world;
+    for (int r = 0; r < tp->world; ++r) {
+        FLATQ_CHECK(tp->signal_pads[r], FLATQ_ERR_INVALID, "tp: null signal pad for rank %d", r);
+        c->signal_pads[r] = reinterpret_cast<uint32_t*>(tp->signal_pads[r]);
+    }
+    return FLATQ_OK;
+}
+
+static int peer_grid(const flatq_tp_ctx* tp, long long vecs) {
+    long long g = (vecs + kPeerThreads * 4 - 1) / (kPeerThreads * 4);
+    const long long cap = tp->signal_pad_bytes / (2ull * tp->world * sizeof(uint32_t));   // two flag sets of grid x world words
+    const long long lim = cap < 96 ? cap : 96;
+    if (g > lim) g = lim;
+    return (int)(g < 1 ? 1 : g);
+}
+
+int flatq_gemm_w4a8_rowparallel(const int8_t* xq8, const float* s_x, const uint8_t* w_packed, const float* s_w, int64_t M,
+                                int64_t N, int64_t K, const flatq_tp_ctx* tp, void* const* peer_staging, flatq_stream_t stream) {
+    FLATQ_CHECK(xq8 && s_x && w_packed && s_w && tp && peer_staging, FLATQ_ERR_INVALID, "gemm_w4a8_rowparallel: null pointer");
+    FLATQ_CHECK(tp->world >= 2 && tp->world <= kPeerMaxWorld, FLATQ_ERR_INVALID, "gemm_w4a8_rowparallel: world");
+    FLATQ_CHECK(M % (256ll * tp->world) == 0, FLATQ_ERR_UNSUPPORTED,
+                "gemm_w4a8_rowparallel: M=%lld must be a multiple of 256 x world (use flatq_gemm_w4a8 + flatq_peer_allreduce)", (long long)M);
+    FLATQ_CHECK(K % 32 == 0 && N % 8 == 0 && (M + 256) * N < (1ll << 32), FLATQ_ERR_INVALID, "gemm_w4a8_rowparallel: shape");
+    CUtensorMap tw, tx;
+    int rc = make_map_u8(&tw, w_packed, N, K / 2, K / 2, kGemmBlockK / 2, kGemmBlockW, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_u8(&tx, xq8, M, K, K, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    GemmParams p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = 4;
+    p.out = nullptr; p.s_x = s_x; p.s_w = s_w; p.bias = nullptr; p.prof = nullptr; p.dbg = 0; p.k_splits = 1;
+    p.streamk = 0; p.sk_part = nullptr; p.sk_flags = nullptr; p.epoch = 0;
+    p.grp_off = nullptr; p.grp_tile = nullptr; p.n_groups = 0; p.t_upper = 0;
+    p.rows_per_owner = (int)(M / tp->world); p.tp_rank = tp->rank;
+    for (int r = 0; r < 8; ++r) p.peer_out[r] = r < tp->world ? peer_staging[r] : nullptr;
+    for (int r = 0; r < tp->world; ++r) FLATQ_CHECK(p.peer_out[r], FLATQ_ERR_INVALID, "gemm_w4a8_rowparallel: null staging pointer");
+    return launch_gemm_2sm<kEpiF16>(tw, tx, p, (cudaStream_t)stream);
+}
+
+int flatq_peer_reduce_bcast(const flatq_tp_ctx* tp, const void* staging, void* out_mc, void* const* out_peers, const void* bias,
+                            int64_t M, int64_t N, flatq_stream_t stream) {
+    PeerCtx c;
+    int rc = peer_ctx(tp, &c);
+    if (rc) return rc;
+    FLATQ_CHECK(staging && (out_mc || out_peers), FLATQ_ERR_INVALID, "peer_reduce_bcast: null pointer");
+    FLATQ_CHECK(M % tp->world == 0 && N % 8 == 0 && aligned16(staging) && (!bias || aligned16(bias)), FLATQ_ERR_INVALID, "peer_reduce_bcast: shape / alignment");
+    PeerBcastDst dst;
+    for (int r = 0; r < kPeerMaxWorld; ++r) dst.peers[r] = (out_peers && r < tp->world) ? reinterpret_cast<__half*>(out_peers[r]) : nullptr;
+    const int rpo = (int)(M / tp->world);
+    const int grid = peer_grid(tp, (long long)rpo * N / 8);
+    peer_reduce_bcast_kernel<<<grid, kPeerThreads, 0, (cudaStream_t)stream>>>(c, reinterpret_cast<const __half*>(staging),
+                                                                             reinterpret_cast<__half*>(out_mc), dst,
+                                                                             reinterpret_cast<const __half*>(bias), rpo, (int)N);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+int flatq_peer_allreduce(const flatq_tp_ctx* tp, const void* src_mc, void* dst_mc, const void* bias, int64_t rows, int64_t N,
+                         flatq_stream_t stream) {
+    PeerCtx c;
+    int rc = peer_ctx(tp, &c);
+    if (rc) return rc;
+    FLATQ_CHECK(src_mc && dst_mc, FLATQ_ERR_INVALID, "peer_allreduce: needs the multicast mapping of both buffers");
+    FLATQ_CHECK(rows > 0 && N % 8 == 0 && aligned16(src_mc) && aligned16(dst_mc), FLATQ_ERR_INVALID, "peer_allreduce: shape / alignment");
+    const int grid = peer_grid(tp, rows * N / 8 / tp->world);
+    peer_allreduce_nvls_kernel<<<grid, kPeerThreads, 0, (cudaStream_t)stream>>>(c, reinterpret_cast<const __half*>(src_mc),
+                                                                               reinterpret_cast<__half*>(dst_mc),
+                                                                               reinterpret_cast<const __half*>(bias), rows, (int)N);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
 }
 
 int flatq_linear_fused(const void* x, const void* left, const void* right, int n1, int n2, float clip_max,
@@ -819,6 +898,37 @@ int flatq_kv_quant(const void* x, int64_t tokens, int heads, int head_dim, uint8
     p.layer = layer; p.n_layers = n_layers; p.kv_select = kv_select; p.page_size = page_size;
     kv_quant_kernel<<<grid_for((size_t)tokens * heads * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(p);
     FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+int flatq_kv_fused(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t tokens,
+                   int q_heads, int kv_heads, int head_dim, const void* cos_t, const void* sin_t, const int32_t* pos,
+                   const void* t_q, const void* t_k, void* q_out, void* k_out, uint8_t* kv_data, void* kv_param,
+                   const int32_t* slot, int layer, int n_layers, int page_size, flatq_stream_t stream) {
+    FLATQ_CHECK(q && k && v && q_out && kv_data && kv_param && slot, FLATQ_ERR_INVALID, "kv_fused: null pointer");
+    FLATQ_CHECK(head_dim == 128, FLATQ_ERR_UNSUPPORTED, "kv_fused: head_dim=%d (only 128, as in the reference bindings.cpp:148)", head_dim);
+    FLATQ_CHECK(tokens > 0 && q_heads > 0 && kv_heads > 0 && tokens * q_heads < (1ll << 31), FLATQ_ERR_INVALID, "kv_fused: tokens / heads");
+    FLATQ_CHECK((cos_t == nullptr) == (sin_t == nullptr) && (!cos_t || pos), FLATQ_ERR_INVALID, "kv_fused: RoPE needs cos, sin and pos");
+    FLATQ_CHECK(page_size > 0 && n_layers > 0 && layer >= 0 && layer < n_layers, FLATQ_ERR_INVALID, "kv_fused: paged-cache arguments");
+    FLATQ_CHECK(ld_q % 4 == 0 && ld_k % 4 == 0 && ld_v % 4 == 0 && ld_q >= (int64_t)q_heads * 128 && ld_k >= (int64_t)kv_heads * 128 &&
+                ld_v >= (int64_t)kv_heads * 128, FLATQ_ERR_INVALID, "kv_fused: row strides");
+    auto al8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };
+    FLATQ_CHECK(al8(q) && al8(k) && al8(v) && aligned16(q_out) && (!k_out || aligned16(k_out)) && (!cos_t || (al8(cos_t) && al8(sin_t))) &&
+                (!t_q || aligned16(t_q)) && (!t_k || aligned16(t_k)), FLATQ_ERR_INVALID, "kv_fused: alignment");
+    KvFusedParams p;
+    p.q = reinterpret_cast<const __half*>(q); p.k = reinterpret_cast<const __half*>(k); p.v = reinterpret_cast<const __half*>(v);
+    p.ld_q = ld_q; p.ld_k = ld_k; p.ld_v = ld_v;
+    p.tokens = (int)tokens; p.q_heads = q_heads; p.kv_heads = kv_heads;
+    p.cos_t = reinterpret_cast<const __half*>(cos_t); p.sin_t = reinterpret_cast<const __half*>(sin_t); p.pos = pos;
+    p.t_q = reinterpret_cast<const __half*>(t_q); p.t_k = reinterpret_cast<const __half*>(t_k);
+    p.q_out = reinterpret_cast<__half*>(q_out); p.k_out = reinterpret_cast<__half*>(k_out);
+    p.kv_data = kv_data; p.kv_param = reinterpret_cast<__half*>(kv_param); p.slot = slot;
+    p.layer = layer; p.n_layers = n_layers; p.page_size = page_size;
+    p.q_blocks = (int)((tokens * q_heads + kKvfRows - 1) / kKvfRows);
+    p.k_blocks = (int)((tokens * kv_heads + kKvfRows - 1) / kKvfRows);
+    static PerDeviceOnce attr;
+    if (attr.first_time()) FLATQ_CUDA(cudaFuncSetAttribute(kv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvfSmem));
+    FLATQ_CUDA(launch_pdl(kv_fused_kernel, dim3(p.q_blocks + 2 * p.k_blocks), dim3(kKvfThreads), (size_t)kKvfSmem, (cudaStream_t)stream, p));
     return FLATQ_OK;
 }
 
@@ -942,7 +1052,7 @@ int flatq_debug_gemm_profile(const int8_t* xq8, const float* s_x, const uint8_t*
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = 4;
     p.out = y; p.s_x = s_x; p.s_w = s_w; p.bias = nullptr; p.prof = prof; p.dbg = dbg; p.k_splits = 1;
     p.streamk = 0; p.sk_part = nullptr; p.sk_flags = nullptr; p.epoch = 0;
-    p.grp_off = nullptr; p.grp_tile = nullptr; p.n_groups = 0; p.t_upper = 0;
+    p.grp_off = nullptr; p.grp_tile = nullptr; p.n_groups = 0; p.t_upper = 0; p.rows_per_owner = 0; p.tp_rank = 0;
     auto kern = gemm_w4a8_kernel<256, kEpiF16, true>;
     constexpr int smem = GemmSmem<256>::kBytes;
     FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -104,6 +104,12 @@ struct GemmParams {
     const int* grp_tile;  // [n_groups + 1] tile prefix (device; grouped_prefix_kernel, same stream, just before)
     int n_groups;
     int t_upper;          // host-side bound on the number of tiles: nb_w * (ceil(M / TN) + n_groups)
+    // row-parallel (tensor-parallel) launch of the CTA-pair kernel: the epilogue IS the reduce-scatter.  Token rows
+    // [o rows_per_owner, (o + 1) rows_per_owner) belong to rank o; every tile is stored through the mapped peer pointer
+    // into slot `tp_rank` of its owner's staging buffer [tp slots][rows_per_owner][N] (csrc/peer_reduce.cuh).
+    // rows_per_owner == 0: plain launch (out).  rows_per_owner % 256 == 0: a 256-token tile never straddles two owners.
+    int rows_per_owner, tp_rank;
+    void* peer_out[8];
 };
 
 // ---- work schedule: every warp role walks the same list of units of its CTA

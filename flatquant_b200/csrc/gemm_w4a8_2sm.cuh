@@ -238,8 +238,13 @@ gemm_w4a8_2sm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
                 }
             } else {
                 const bool has_bias = p.bias != nullptr;
-                uint16_t* const out16 = reinterpret_cast<uint16_t*>(p.out);
+                uint16_t* out16 = reinterpret_cast<uint16_t*>(p.out);
                 uint32_t idx = (uint32_t)(m0 + c0) * (uint32_t)p.N + (uint32_t)n;
+                if (p.rows_per_owner > 0) {   // reduce-scatter in the epilogue: this tile goes to its owner's staging slot
+                    const int owner = m0 / p.rows_per_owner;
+                    out16 = reinterpret_cast<uint16_t*>(p.peer_out[owner]);
+                    idx = (uint32_t)(p.tp_rank * p.rows_per_owner + (m0 - owner * p.rows_per_owner) + c0) * (uint32_t)p.N + (uint32_t)n;
+                }
                 const int j_end = n_ok ? p.M - (m0 + c0) : 0;
                 auto finish = [&](auto fold_c) {
                     constexpr bool FOLD = decltype(fold_c)::value;

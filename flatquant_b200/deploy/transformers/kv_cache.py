@@ -156,6 +156,56 @@ class MultiLayerPagedKVCache4Bit:
         return functools.partial(self._decode, num_kv_heads=heads, attention_kwargs=self._static_attn,
                                  layer_idx=layer_idx, k_inv_t=k_inv_t if self.trans.startswith("matmul") else None)
 
+    def fused_ok(self, q):
+        """Can this step go through ops.kv_fused (one launch for RoPE, K / Q transform, KV quantise, page scatter)?"""
+        return (ops.FUSED_KV and self.org_head_dim == 128 and q.dtype == torch.float16 and q.shape[-1] == 128
+                and (self.trans == "none" or self.trans.startswith("matmul")))
+
+    def fused_update(self, query_states, key_states, value_states, layer_idx, rope, cache_kwargs=None):
+        """`update` for the fused path: takes the PRE-RoPE q / k / v (views of the qkv GEMM output are read in place) and
+        the RoPE context `rope` = (cos table [P, 128], sin table, pos int32 [tokens]); returns
+        prefill: (q_t, k_t, v) -- the transformed fp16 states the causal attention runs on;
+        decode:  the attention output [b, 1, Hq, 128] over the packed INT4 cache (the closure of `update`, applied)."""
+        cache_kwargs = cache_kwargs or {}
+        matmul = self.trans.startswith("matmul")
+        t_k = cache_kwargs.get("trans_matrix_k") if matmul else None
+        t_q = cache_kwargs.get("trans_matrix_k_inv_t") if matmul else None
+        b, added, heads, d = key_states.shape
+        assert b == self.batch_size
+        cos_t, sin_t, pos = rope
+        static = getattr(self, "_static_mode", False)
+        if static:
+            assert added == 1
+            if layer_idx == 0:
+                self._static_slots.copy_(self._page_base * self.page_size + self.pos_dev)
+                self._static_attn["last_page_len"].copy_((self.pos_dev + 1).expand(b))
+            slots, prefill = self._static_slots, False
+        else:
+            if layer_idx == 0:
+                self._ensure_page_cnt_per_batch(self.page_cnt_from_length(self.length + added))
+                self._start = self.length
+                self.length += added
+            key = (self._start, added, self.max_page_cnt)
+            if getattr(self, "_step_key", None) != key:
+                self._step_key, self._step_slots, self._step_attn = key, self._slots(self._start, added), None
+            slots = self._step_slots
+            prefill = self._needs_init[layer_idx]
+            self._needs_init[layer_idx] = False
+        q_t, k_t = ops.kv_fused(query_states, key_states, value_states, cos_t, sin_t, pos, t_q, t_k, self.pages, self.scales,
+                                slots, layer_idx, want_k=prefill)
+        hq = query_states.shape[-2]
+        if prefill:
+            return q_t.view(b, added, hq, d), k_t.view(b, added, heads, d), value_states
+        assert added == 1
+        if static:
+            kw, bound = self._static_attn, self.max_seq_len
+        else:
+            if self._step_attn is None:
+                self._step_attn = self._attention_kwargs()
+            kw, bound = self._step_attn, self.length
+        o = ops.kv_decode_i4(q_t, self.pages, self.scales, layer=layer_idx, max_tokens_hint=bound, **kw)
+        return o.unsqueeze(1)
+
     def update(self, key_states, value_states, layer_idx, cache_kwargs=None):
         cache_kwargs = cache_kwargs or {}
         if getattr(self, "_static_mode", False):

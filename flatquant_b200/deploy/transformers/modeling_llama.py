@@ -354,10 +354,22 @@ class FlatQuantLlamaAttention(torch.nn.Module):
                 qkv["k"].reshape(b, s, self.num_key_value_heads, self.head_dim),
                 qkv["v"].reshape(b, s, self.num_key_value_heads, self.head_dim))
 
-    def attend(self, q, k, v, cos, sin, past_key_value):
-        """Stage 2: RoPE, K/Q cache transform, KV quantise + append, attention -> [b, s, H*d]."""
+    def attend(self, q, k, v, cos, sin, past_key_value, rope=None):
+        """Stage 2: RoPE, K/Q cache transform, KV quantise + append, attention -> [b, s, H*d].  With a RoPE context
+        `rope` = (cos table, sin table, positions) and a cache that supports it, everything up to the attention is ONE
+        launch on the strided q / k / v views (ops.kv_fused); same bits as the launches below."""
         b, s = q.shape[:2]
         rt = self._runtime(q.device)
+        if rope is not None and hasattr(past_key_value, "fused_ok") and past_key_value.fused_ok(q):
+            out = past_key_value.fused_update(q, k, v, self.layer_idx, rope, rt.cache_kwargs)
+            if isinstance(out, tuple):
+                q_t, k_t, v_t = out
+                attn = F.scaled_dot_product_attention(q_t.transpose(1, 2), k_t.transpose(1, 2), v_t.transpose(1, 2),
+                                                      is_causal=True, enable_gqa=self.num_heads != self.num_key_value_heads)
+                attn = attn.transpose(1, 2)
+            else:
+                attn = out
+            return attn.reshape(b, s, self.num_heads * self.head_dim)
         q, k = apply_rope(q, cos, sin), apply_rope(k, cos, sin)
         cache_out = past_key_value.update(k.contiguous(), v.contiguous(), self.layer_idx, rt.cache_kwargs)
         if isinstance(cache_out, tuple):  # prefill: causal attention over the transformed fp16 states
@@ -378,10 +390,10 @@ class FlatQuantLlamaAttention(torch.nn.Module):
         y = _flat_linears(a2, rt.o_left, rt.o_right, self.num_heads, self.head_dim, rt.o, self.isFlatQ)["o"]
         return self.tp.all_reduce(y).reshape(b, s, self.hidden_size)
 
-    def forward(self, hidden_states, cos, sin, past_key_value):
+    def forward(self, hidden_states, cos, sin, past_key_value, rope=None):
         """hidden_states [b, s, hidden] (already normalised) -> [b, s, hidden]."""
         q, k, v = self.qkv(hidden_states)
-        return self.project_out(self.attend(q, k, v, cos, sin, past_key_value))
+        return self.project_out(self.attend(q, k, v, cos, sin, past_key_value, rope))
 
 
 class FlatQuantLlamaMLP(torch.nn.Module):
@@ -472,8 +484,8 @@ class FlatQuantLlamaDecoderLayer(torch.nn.Module):
         self.mlp = FlatQuantLlamaMLP(options, config, tp)
         self.input_layernorm, self.post_attention_layernorm = norm(), norm()
 
-    def forward(self, h, cos, sin, past_key_value):
-        h = h + self.self_attn(self.input_layernorm(h), cos, sin, past_key_value)
+    def forward(self, h, cos, sin, past_key_value, rope=None):
+        h = h + self.self_attn(self.input_layernorm(h), cos, sin, past_key_value, rope)
         return h + self.mlp(self.post_attention_layernorm(h))
 
 
@@ -527,8 +539,14 @@ class FlatQuantLlamaForCausalLM(torch.nn.Module):
         pos = torch.arange(start, start + s, device=dev)[None].expand(b, s)
         h = self.model.embed_tokens(input_ids)
         cos, sin = rope_cos_sin(self._inv_freq, pos, h.dtype)
+        rope = None
+        if ops.FUSED_KV and ACT_DTYPE == torch.float16:
+            # RoPE context of the fused KV launch: rows of cos / sin per token instead of a table + positions -- the
+            # tensors above ARE a table for positions start .. start + s - 1
+            rope = (cos[0, :, 0].contiguous(), sin[0, :, 0].contiguous(),
+                    torch.arange(s, dtype=torch.int32, device=dev).repeat(b))
         for layer in self.model.layers:
-            h = layer(h, cos, sin, past_key_values)
+            h = layer(h, cos, sin, past_key_values, rope)
         if logits_to_keep:
             h = h[:, -logits_to_keep:]
         return self.lm_head(self.model.norm(h)), past_key_values
@@ -592,9 +610,15 @@ class FlatQuantLlamaForCausalLM(torch.nn.Module):
             self._rope_table = table = rope_cos_sin(self._inv_freq, pos, ACT_DTYPE)  # [1, L, 1, d] each
         row = cache.pos_dev.long()
         cos, sin = table[0].index_select(1, row), table[1].index_select(1, row)
+        rope = None
+        if ops.FUSED_KV and ACT_DTYPE == torch.float16:   # the table itself + the device-side position of every sequence
+            if getattr(cache, "_static_pos", None) is None or cache._static_pos.numel() != input_ids.shape[0]:
+                cache._static_pos = torch.empty(input_ids.shape[0], dtype=torch.int32, device=dev)
+            cache._static_pos.copy_(cache.pos_dev.expand(input_ids.shape[0]))
+            rope = (table[0][0, :, 0], table[1][0, :, 0], cache._static_pos)
         h = self.model.embed_tokens(input_ids)
         for layer in self.model.layers:
-            h = layer(h, cos, sin, cache)
+            h = layer(h, cos, sin, cache, rope)
         cache.pos_dev.add_(1)
         return self.lm_head(self.model.norm(h))
 

@@ -336,6 +336,45 @@ def hadamard_kn(x: torch.Tensor, hadK: torch.Tensor, K: int, scale: float) -> to
     return out
 
 
+FUSED_KV = os.environ.get("FLATQ_FUSED_KV", "1") != "0"   # the model stack's RoPE -> transform -> KV quantise -> scatter in one launch
+
+
+def _rows_view(t: torch.Tensor, heads: int):
+    """t [tokens, heads, 128] or [b, s, heads, 128] whose (head, dim) block is dense and whose tokens are evenly strided
+    (a column slice of the fused qkv GEMM output) -> (t, token stride in elements); anything else is copied."""
+    d = t.shape[-1]
+    if t.stride(-1) == 1 and t.stride(-2) == d and t.dim() in (3, 4):
+        ld = t.stride(-3)
+        if ld % 4 == 0 and ld >= heads * d and (t.dim() == 3 or t.shape[0] == 1 or t.stride(0) == t.shape[1] * ld):
+            return t, ld
+    return t.reshape(-1, heads, d).contiguous(), heads * d
+
+
+def kv_fused(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cos_t, sin_t, pos, t_q, t_k, kv_data, kv_param, slot,
+             layer: int, want_k: bool = False):
+    """RoPE -> K / Q transform -> asymmetric 4-bit KV quantise -> page scatter in one launch (flatq_kv_fused).
+
+    q [..., Hq, 128], k / v [..., Hkv, 128] fp16, possibly strided views of the fused qkv GEMM output (read in place);
+    cos_t / sin_t fp16 [positions, 128] tables and pos int32 [tokens] (None: no RoPE); t_q / t_k fp16 [128, 128] or None.
+    Returns (q_t [tokens, Hq, 128], k_t [tokens, Hkv, 128] or None)."""
+    dev = _need_cuda(cos_t, sin_t, pos, t_q, t_k, kv_data, kv_param, slot)
+    for t in (q, k, v):
+        if not t.is_cuda or t.dtype != torch.float16:
+            raise RuntimeError("kv_fused: q, k, v must be float16 CUDA tensors")
+    hq, hkv, d = q.shape[-2], k.shape[-2], q.shape[-1]
+    q, ld_q = _rows_view(q, hq)
+    k, ld_k = _rows_view(k, hkv)
+    v, ld_v = _rows_view(v, hkv)
+    tokens = q.numel() // (hq * d)
+    q_out = torch.empty((tokens, hq, d), dtype=torch.float16, device=dev)
+    k_out = torch.empty((tokens, hkv, d), dtype=torch.float16, device=dev) if want_k else None
+    n_layers, page_size = kv_data.shape[1], kv_data.shape[4]
+    _lib.check(_lib.load().flatq_kv_fused(_ptr(q), _ptr(k), _ptr(v), ld_q, ld_k, ld_v, tokens, hq, hkv, d, _ptr(cos_t), _ptr(sin_t),
+                                          _ptr(pos), _ptr(t_q), _ptr(t_k), _ptr(q_out), _ptr(k_out), _ptr(kv_data), _ptr(kv_param),
+                                          _ptr(slot), int(layer), n_layers, page_size, _stream()), "kv_fused")
+    return q_out, k_out
+
+
 def kv_quant(x: torch.Tensor, kv_data=None, kv_param=None, slot=None, layer: int = 0, kv_select: int = 0):
     """Asymmetric 4-bit quantise + pack of K or V rows x [tokens, heads, 128] (fp16).
 

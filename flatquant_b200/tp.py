@@ -124,6 +124,12 @@ class NcclReducer:
             return out
         return partial
 
+    def rowparallel_gemm(self, xq8, s_x, w_packed, s_w, bias=None):
+        from . import ops
+        y = ops.gemm_w4a8(xq8, s_x, w_packed, s_w, None, torch.float16, out=self.buf)
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
+        return y if bias is None else y + bias.to(y.dtype)
+
 
 def make_reducer(world, rank, dev, shape, dtype, group=None, prefer_peer=True):
     import os

@@ -146,6 +146,34 @@ int flatq_gemm_w4a8_grouped(const int8_t* xq8, const float* s_x, const uint8_t* 
                             int rows_per_group_hint, void* y, int out_dtype, void* workspace, size_t workspace_bytes,
                             flatq_stream_t stream);
 
+/* ---- (e) tensor parallel: row-parallel linears with the reduction done by THIS library over NVLink peer memory ----------
+ * The reference sums the ranks' partial products with dist.all_reduce after F.linear (flatquant/model_tools/
+ * deepseekv3_utils.py:98-105; vllm_custom/.../llama_flatquant.py:117-126,261-289).  Here the caller hands over mapped peer
+ * memory -- from NCCL's window registration (ncclCommWindowRegister + ncclGetLsaPointer / the multimem pointer of an
+ * ncclComm_t), cuMemMap of fabric handles, or torch.distributed._symmetric_memory as flatquant_b200/peer_reduce.py does --
+ * and the kernels move the bytes: see csrc/peer_reduce.cuh.
+ *   flatq_tp_ctx: rank / world (2..8), signal_pads[r] = rank r's flag area (zero-initialised symmetric memory of
+ *     signal_pad_bytes >= 2 * 96 * world * 4; used only by these calls).
+ *   flatq_gemm_w4a8_rowparallel: the prefill GEMM whose epilogue IS the reduce-scatter: rank `rank` stores every 256-token
+ *     output tile into slot `rank` of the staging buffer [world][M / world][N] fp16 of the tile's owner
+ *     (peer_staging[owner]; rows [o M/world, (o+1) M/world) belong to rank o).  M % (256 world) == 0.
+ *   flatq_peer_reduce_bcast: owner-side sum of the world slots in fp32 (+ bias), rounded to fp16, written to rows
+ *     [rank M/world, ...) of EVERY rank's [M, N] output: through the multicast mapping out_mc (multimem.st) or, when the
+ *     box has none (out_mc == NULL), through out_peers[r].  Begins and ends with a barrier over the signal pads.
+ *   flatq_peer_allreduce: in-switch all-reduce (multimem.ld_reduce / multimem.st) of a symmetric fp16 [rows, N] buffer, for
+ *     the shapes the fused path does not take (decode sizes); src_mc / dst_mc are multicast addresses (may be equal). */
+typedef struct flatq_tp_ctx {
+    int rank, world;
+    void* signal_pads[8];
+    size_t signal_pad_bytes;
+} flatq_tp_ctx;
+int flatq_gemm_w4a8_rowparallel(const int8_t* xq8, const float* s_x, const uint8_t* w_packed, const float* s_w, int64_t M,
+                                int64_t N, int64_t K, const flatq_tp_ctx* tp, void* const* peer_staging, flatq_stream_t stream);
+int flatq_peer_reduce_bcast(const flatq_tp_ctx* tp, const void* staging, void* out_mc, void* const* out_peers, const void* bias_f16,
+                            int64_t M, int64_t N, flatq_stream_t stream);
+int flatq_peer_allreduce(const flatq_tp_ctx* tp, const void* src_mc, void* dst_mc, const void* bias_f16, int64_t rows, int64_t N,
+                         flatq_stream_t stream);
+
 /* ---- a14: qattention side path ------------------------------------------------------------------
  * flatq_hadamard: out = scale * x . H_n per row, n a power of two in [8, 32768], fp16 in/out, fp32 butterflies.
  *   Replaces fast_hadamard_transform.hadamard_transform (third-party/fast-hadamard-transform/csrc/
@@ -172,6 +200,20 @@ int flatq_kv_decode_i4(const void* q_f16, void* o_f16, const uint8_t* kv_data, c
                        const int32_t* kv_indptr, const int32_t* kv_indices, const int32_t* last_page_len, int batch,
                        int q_heads, int kv_heads, int head_dim, int page_size, int layer, int n_layers, float sm_scale,
                        flatq_stream_t stream);
+
+/* flatq_kv_fused: everything between the q/k/v FlatLinears and the attention in ONE launch, reading
+ *   the rows (token, head) of the fused qkv GEMM output in place (row of X at X + token * ld_X + head * 128 halves):
+ *     q: RoPE -> . t_q (T_k^-T) -> q_out [tokens, q_heads, 128];   k: RoPE -> . t_k -> (k_out) -> asym 4-bit -> page scatter;
+ *     v: asym 4-bit -> page scatter.
+ *   Replaces apply_rotary_pos_emb (deploy/transformers/modeling_llama.py:125-137), the K / Q transform, asym_quantize_and_
+ *   pack_i4 and init_kv_i4 / append_kv_i4 (deploy/transformers/kv_cache.py:11-51,263-353; deploy/kernels/bindings.cpp:
+ *   171-245).  cos/sin: fp16 tables [positions, 128] (NULL: no RoPE), pos[token] the row to use; t_q / t_k: fp16 [128, 128]
+ *   row-major or NULL (identity); k_out: NULL at decode.  Same bits as flatq_rope + flatq_kron_transform + flatq_kv_quant. */
+int flatq_kv_fused(const void* q_f16, const void* k_f16, const void* v_f16, int64_t ld_q, int64_t ld_k, int64_t ld_v,
+                   int64_t tokens, int q_heads, int kv_heads, int head_dim, const void* cos_f16, const void* sin_f16,
+                   const int32_t* pos, const void* t_q_f16, const void* t_k_f16, void* q_out_f16, void* k_out_f16,
+                   uint8_t* kv_data, void* kv_param_f16, const int32_t* slot, int layer, int n_layers, int page_size,
+                   flatq_stream_t stream);
 
 /* flatq_kv_decode_i4_split: the same attention with the sequence split over CTAs (flash-decoding) and one CTA per kv head
  *   serving up to four of its query heads (grouped-query attention reads each K/V row once per group): fills the chip at

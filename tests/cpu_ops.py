@@ -108,12 +108,20 @@ def _h(t):
     return t.half().float() if EMULATE_FP16 else t.float()
 
 
-def _transform(x2, left, right, n1, n2):
+# the factor pairs served by the second tcgen05 design (csrc/kron_quant_ts.cuh, launch_kron_ts of api.cu)
+TS_SHAPES = {(64, 64), (56, 64), (32, 64), (64, 128), (112, 128), (128, 128)}
+
+
+def _transform(x2, left, right, n1, n2, right_first=False):
+    """The kernels' rounding points: one fp16 rounding after each factor.  Left factor first -- (L^T X) R, the order of
+    the deployed reference (kron_matmul.py:62-76), of kron_quant_ts.cuh and of the legacy-MMA kernel kron_quant.cuh --
+    except on the first tcgen05 design (kron_quant_tc.cuh: L^T (X R)), which still serves a few padded shapes."""
     xm = _h(x2).reshape(-1, n1, n2)
-    if right is not None:
-        xm = _h(torch.matmul(xm, _h(right)))
-    if left is not None:
-        xm = _h(torch.matmul(_h(left).t(), xm))
+    steps = [("r", right), ("l", left)] if right_first else [("l", left), ("r", right)]
+    for kind, m in steps:
+        if m is None:
+            continue
+        xm = _h(torch.matmul(xm, _h(m))) if kind == "r" else _h(torch.matmul(_h(m).t(), xm))
     return xm.reshape(x2.shape[0], n1 * n2)
 
 
@@ -145,17 +153,20 @@ def act_quant(x, left, right, n1, n2, clip_max=1.0, clip_min=1.0, out=None):
     _contig(x=x, left=left, right=right)
     _req(k % 32 == 0, f"act_quant: K={k} must be a multiple of 32")
     m = x.numel() // k
+    kernel = None
     if left is None and right is None:
         _check_rowquant(x, m, k)
         CALLS.append(("act_quant", ("rowquant", k)))
     else:
-        CALLS.append(("act_quant", (_check_kron(m, n1, n2, left, right, True, False, x, True), n1, n2,
-                                    left is not None, right is not None)))
+        kernel = _check_kron(m, n1, n2, left, right, True, False, x, True)
+        CALLS.append(("act_quant", (kernel, n1, n2, left is not None, right is not None)))
     if out is not None:
         _contig(xq8=out[0], s_x=out[1])
         _dtype(out[0], torch.int8, "act_quant out codes"), _dtype(out[1], torch.float32, "act_quant out scales")
         _al16(out[0], 1, "act_quant xq8")
-    z = _transform(x.reshape(-1, k), left, right, n1, n2)
+    first_design = (left is not None or right is not None) and kernel == "tcgen05" and not (
+        (n1, n2) in TS_SHAPES and left is not None and right is not None)
+    z = _transform(x.reshape(-1, k), left, right, n1, n2, right_first=first_design)
     q, s = _scale_codes(z, clip_max, clip_min)
     if out is not None:
         out[0].copy_(q)
@@ -285,6 +296,24 @@ def hadamard_kn(x, hadK, K, scale):
     return torch.from_numpy(y).to(x.dtype)
 
 
+def kv_fused(q, k, v, cos_t, sin_t, pos, t_q, t_k, kv_data, kv_param, slot, layer, want_k=False):
+    """Stand-in of flatq_kv_fused built from the stand-ins of the launches it replaces (same bits by construction)."""
+    hq, hkv, d = q.shape[-2], k.shape[-2], q.shape[-1]
+    _req(d == 128, "kv_fused: head_dim"), _act_dtype(q, "kv_fused q")
+    tokens = q.numel() // (hq * d)
+    q2, k2, v2 = q.reshape(tokens, hq, d).contiguous(), k.reshape(tokens, hkv, d).contiguous(), v.reshape(tokens, hkv, d).contiguous()
+    if cos_t is not None:
+        c, s_ = cos_t[pos.long()].contiguous(), sin_t[pos.long()].contiguous()
+        q2, k2 = rope_(q2.clone(), c, s_), rope_(k2.clone(), c, s_)
+    if t_q is not None:
+        q2 = kron_transform(q2.reshape(-1, d).contiguous(), None, t_q, 1, d).view(tokens, hq, d)
+    if t_k is not None:
+        k2 = kron_transform(k2.reshape(-1, d).contiguous(), None, t_k, 1, d).view(tokens, hkv, d)
+    kv_quant(k2.contiguous(), kv_data, kv_param, slot, layer, 0)
+    kv_quant(v2, kv_data, kv_param, slot, layer, 1)
+    return q2, (k2 if want_k else None)
+
+
 def kv_quant(x, kv_data=None, kv_param=None, slot=None, layer=0, kv_select=0):
     _contig(x=x, kv_data=kv_data, kv_param=kv_param, slot=slot)
     tokens, heads, d = x.shape
@@ -345,7 +374,7 @@ def kv_decode_i4(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, lay
 
 FUNCTIONS = ("kron_transform", "act_quant", "transform_quant", "quantize_rows", "gemm_w4a8", "gemm_w4a8_grouped",
              "linear_fused", "pack_i4",
-             "hadamard", "hadamard_kn", "kv_quant", "kv_decode_i4", "rmsnorm", "rope_", "silu_mul")
+             "hadamard", "hadamard_kn", "kv_fused", "kv_quant", "kv_decode_i4", "rmsnorm", "rope_", "silu_mul")
 
 
 def install(monkeypatch):
