@@ -8,15 +8,14 @@
 //     into the OWNER's staging buffer, slot `rank` (st.global through the mapped peer pointer, 64 contiguous bytes per
 //     warp store): the reduce-scatter traffic leaves the SM tile by tile while the tensor pipe works on the next tile.
 //   * peer_reduce_bcast_kernel: barrier; the owner adds the tp slots of its rows in fp32 (local HBM reads), adds the
-//     bias once, rounds to fp16 and writes the result to EVERY rank with one multimem.st per 16 bytes (the switch
-//     replicates); barrier.  NVLink bytes per rank and linear: (tp-1)/tp S out during the GEMM, S/tp out +
-//     (tp-1)/tp S in during the broadcast (S = M N 2 bytes), against 2 (tp-1)/tp S each way for a ring all-reduce.
+//     bias once, rounds to fp16 and stores the result into EVERY rank's output through the peer pointers; barrier.
+//     NVLink bytes per rank and linear: (tp-1)/tp S out during the GEMM (hidden under the MMAs), (tp-1)/tp S out and
+//     in during the broadcast (S = M N 2 bytes) -- half of the exposed traffic of an all-reduce after the GEMM.
 // Any other shape (decode sizes, ragged M) -- peer_allreduce_nvls_kernel on the GEMM's local output:
 //   barrier; rank r pulls ITS 1/tp of the elements already summed by the switch (multimem.ld_reduce.add, fp32
 //   accumulation), adds the bias, multimem.st to every rank; barrier.
 //
-// Barriers: one 32-bit flag per (CTA, peer) in each rank's signal pad; a CTA of rank r raises flag [blk][r] on every
-// peer (release, system scope) and waits for [blk][p] of all peers p on its own pad (acquire), then clears them.
+// Barriers: epoch flags in each rank's signal pad, posted with st.release.sys and awaited on local memory (peer_barrier).
 #pragma once
 #include "ptx.cuh"
 
@@ -27,29 +26,35 @@ constexpr int kPeerThreads = 512;
 
 struct PeerCtx {
     int rank, world;
-    uint32_t* signal_pads[kPeerMaxWorld];   // each rank's signal pad (symmetric memory), >= 2 * grid * world words
+    uint32_t* signal_pads[kPeerMaxWorld];   // each rank's signal pad (zero-initialised symmetric memory), >= 2 * grid * (world + 1) words
 };
 
-__device__ __forceinline__ void peer_put_flag(uint32_t* addr) {
-    uint32_t old;
-    do {
-        asm volatile("atom.global.release.sys.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(addr) : "memory");
-    } while (old != 0);
-}
-__device__ __forceinline__ void peer_wait_flag(uint32_t* addr) {
-    uint32_t old;
-    do {
-        asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], 1, 0;" : "=r"(old) : "l"(addr) : "memory");
-    } while (old != 1);
-}
-// all CTAs with the same blockIdx on every rank meet here; `phase` selects one of two flag sets so that back-to-back
-// barriers of one kernel cannot overtake each other
+// Barrier over the ranks, one per CTA index: flags are EPOCH counters, never reset.  Every CTA keeps the number of
+// barriers it has passed in its own (local) counter word; a barrier bumps it to e, posts e into slot [blk][rank] of
+// every peer's pad with one st.release.sys (a posted write: no NVLink round trip), and spins on its OWN pad (local L2)
+// until every peer's slot has reached e.  All ranks issue the same sequence of launches, so the counters stay in step;
+// nothing is baked into launch arguments, so a CUDA graph can replay the launch.  Pad layout per rank (u32 words):
+//   [2 phases][grid][world] flags, then [2 phases][grid] local counters.
 __device__ __forceinline__ void peer_barrier(const PeerCtx& c, int phase) {
+    __shared__ uint32_t epoch_s;
     __syncthreads();
+    uint32_t* pad = c.signal_pads[c.rank];
+    const size_t slot = ((size_t)phase * gridDim.x + blockIdx.x) * c.world;
+    if (threadIdx.x == 0) {
+        uint32_t* ctr = pad + (size_t)2 * gridDim.x * c.world + (size_t)phase * gridDim.x + blockIdx.x;
+        epoch_s = *ctr + 1;
+        *ctr = epoch_s;
+    }
+    __syncthreads();
+    const uint32_t e = epoch_s;
     if ((int)threadIdx.x < c.world) {
-        const size_t slot = ((size_t)phase * gridDim.x + blockIdx.x) * c.world;
-        peer_put_flag(c.signal_pads[threadIdx.x] + slot + c.rank);
-        peer_wait_flag(c.signal_pads[c.rank] + slot + threadIdx.x);
+        uint32_t* remote = c.signal_pads[threadIdx.x] + slot + c.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(e) : "memory");
+        const uint32_t* mine = pad + slot + threadIdx.x;
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        } while ((int32_t)(v - e) < 0);
     }
     __syncthreads();
 }
@@ -114,36 +119,57 @@ peer_reduce_bcast_kernel(const PeerCtx c, const __half* staging, __half* dst_mc,
     const long long vec_rows = (long long)rows_per_owner * N / 8;
     const size_t slot_elems = (size_t)rows_per_owner * N;
     const size_t out0 = (size_t)c.rank * slot_elems;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < vec_rows; i += (long long)gridDim.x * blockDim.x) {
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int s = 0; s < c.world; ++s) {
-            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(staging + s * slot_elems + i * 8));   // written by peers: L2, never a stale L1 line
-            const __half2* h = reinterpret_cast<const __half2*>(&v);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < vec_rows; i0 += 2 * stride) {
+        // two 16-byte columns per thread, all `world` slot loads of both in flight before the first add
+        uint4 v[2][kPeerMaxWorld];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h[j]);
-                acc[2 * j] += f.x;
-                acc[2 * j + 1] += f.y;
-            }
+        for (int u = 0; u < 2; ++u) {
+            const long long i = i0 + u * stride;
+#pragma unroll
+            for (int s = 0; s < kPeerMaxWorld; ++s)
+                if (s < c.world && i < vec_rows) v[u][s] = __ldcg(reinterpret_cast<const uint4*>(staging + s * slot_elems + i * 8));   // written by peers: L2, never a stale L1 line
         }
-        if (bias) {
-            const uint4 b = *reinterpret_cast<const uint4*>(bias + (size_t)((i * 8) % N));
-            const __half2* bh = reinterpret_cast<const __half2*>(&b);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(bh[j]);
-                acc[2 * j] += f.x;
-                acc[2 * j + 1] += f.y;
+        for (int u = 0; u < 2; ++u) {
+            const long long i = i0 + u * stride;
+            if (i >= vec_rows) break;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int s = 0; s < kPeerMaxWorld; ++s) {
+                if (s >= c.world) break;
+                const __half2* h = reinterpret_cast<const __half2*>(&v[u][s]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h[j]);
+                    acc[2 * j] += f.x;
+                    acc[2 * j + 1] += f.y;
+                }
             }
-        }
-        uint4 o;
-        __half2* oh = reinterpret_cast<__half2*>(&o);
+            if (bias) {
+                const uint4 bv = *reinterpret_cast<const uint4*>(bias + (size_t)((i * 8) % N));
+                const __half2* bh = reinterpret_cast<const __half2*>(&bv);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
-        if (dst_mc) {
-            multimem_st_v4(dst_mc + out0 + i * 8, o);
-        } else {
-            for (int r = 0; r < c.world; ++r) *reinterpret_cast<uint4*>(dst.peers[r] + out0 + i * 8) = o;
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(bh[j]);
+                    acc[2 * j] += f.x;
+                    acc[2 * j + 1] += f.y;
+                }
+            }
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+            // Unicast peer stores (own copy: a local store).  A multimem.st would cut the bytes LEAVING this GPU to S/world,
+            // but the switch also returns this rank's own copy, so every rank RECEIVES S bytes instead of (world-1)/world S
+            // -- and the receive side is what bounds an all-gather (measured at world 2: 71 us multicast for 16 MiB).
+            if (dst.peers[0]) {
+#pragma unroll
+                for (int r = 0; r < kPeerMaxWorld; ++r)
+                    if (r < c.world) *reinterpret_cast<uint4*>(dst.peers[r] + out0 + i * 8) = o;
+            } else {
+                multimem_st_v4(dst_mc + out0 + i * 8, o);
+            }
         }
     }
     __threadfence_system();

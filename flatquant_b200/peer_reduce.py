@@ -57,7 +57,7 @@ class PeerReducer:
             return t, symm_mem.rendezvous(t, self.group)
         self.out, h_out = shared(self.M * self.N, torch.float16)
         self.partial, h_par = shared(self.M * self.N, torch.float16)   # staging slots (fused) or the local partial product
-        self.flags, h_flg = shared(2 * _FLAG_CTAS * world, torch.int32)
+        self.flags, h_flg = shared(2 * _FLAG_CTAS * (world + 1), torch.int32)   # epoch flags + per-CTA counters, zeroed once
         self.out, self.partial = self.out.view(self.M, self.N), self.partial.view(self.M, self.N)
         torch.cuda.synchronize(dev)
         dist.barrier(group=self.group)
@@ -75,7 +75,7 @@ class PeerReducer:
         if not self.fused and not self.out_mc:
             raise RuntimeError("PeerReducer: this shape needs the in-switch all-reduce and the box has no multicast support")
         self.name = ("GEMM epilogue peer stores (reduce-scatter) + owner sum + " +
-                     ("multimem.st broadcast" if self.out_mc else "peer-store broadcast")) if self.fused else \
+                     "peer-store broadcast") if self.fused else \
             "in-switch all-reduce (multimem.ld_reduce / multimem.st)"
 
     # ---- the fused prefill path

@@ -153,13 +153,14 @@ int flatq_gemm_w4a8_grouped(const int8_t* xq8, const float* s_x, const uint8_t* 
  * ncclComm_t), cuMemMap of fabric handles, or torch.distributed._symmetric_memory as flatquant_b200/peer_reduce.py does --
  * and the kernels move the bytes: see csrc/peer_reduce.cuh.
  *   flatq_tp_ctx: rank / world (2..8), signal_pads[r] = rank r's flag area (zero-initialised symmetric memory of
- *     signal_pad_bytes >= 2 * 96 * world * 4; used only by these calls).
+ *     signal_pad_bytes >= 2 * 96 * (world + 1) * 4; used only by these calls, never reset).
  *   flatq_gemm_w4a8_rowparallel: the prefill GEMM whose epilogue IS the reduce-scatter: rank `rank` stores every 256-token
  *     output tile into slot `rank` of the staging buffer [world][M / world][N] fp16 of the tile's owner
  *     (peer_staging[owner]; rows [o M/world, (o+1) M/world) belong to rank o).  M % (256 world) == 0.
  *   flatq_peer_reduce_bcast: owner-side sum of the world slots in fp32 (+ bias), rounded to fp16, written to rows
- *     [rank M/world, ...) of EVERY rank's [M, N] output: through the multicast mapping out_mc (multimem.st) or, when the
- *     box has none (out_mc == NULL), through out_peers[r].  Begins and ends with a barrier over the signal pads.
+ *     [rank M/world, ...) of EVERY rank's [M, N] output through out_peers[r] (unicast peer stores: the receive side bounds
+ *     an all-gather and a multicast store would also send this rank's copy back to it); out_mc (multimem.st) is used
+ *     only when out_peers == NULL.  Begins and ends with a barrier over the signal pads.
  *   flatq_peer_allreduce: in-switch all-reduce (multimem.ld_reduce / multimem.st) of a symmetric fp16 [rows, N] buffer, for
  *     the shapes the fused path does not take (decode sizes); src_mc / dst_mc are multicast addresses (may be equal). */
 typedef struct flatq_tp_ctx {

@@ -33,6 +33,19 @@ def timed(fn, reps):
     return float(t)
 
 
+def nvlink_kib(index):
+    """Sum of the NVLink data counters of one GPU (nvidia-smi nvlink -gt d): (tx KiB, rx KiB), or None."""
+    import re
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+        tx = sum(int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out))
+        rx = sum(int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out))
+        return (tx, rx) if (tx or rx) else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device(f"cuda:{local}")
@@ -66,14 +79,34 @@ def main():
         identical = bool(torch.equal(same, y_peer))
         flags = torch.tensor([int(identical), int(err_peer < 2e-3)], device=dev)
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        torch.cuda.synchronize()
+        dist.barrier()
+        nv0 = nvlink_kib(local)
         us_peer = timed(lambda: red.rowparallel_gemm(xq, sx, w, sw), 20)
+        nv1 = nvlink_kib(local)
+        nvlink = None
+        if nv0 and nv1:   # measured NVLink payload per linear on this GPU vs the design's (world-1)/world * M*N*2 bytes out, twice
+            nvlink = {"tx_MiB_per_linear": (nv1[0] - nv0[0]) / 1024 / 20, "rx_MiB_per_linear": (nv1[1] - nv0[1]) / 1024 / 20,
+                      "design_MiB_each_way": 2 * (world - 1) / world * M * N * 2 / 2 ** 20 if red.fused else None}
         us_nccl = timed(lambda: nccl.rowparallel_gemm(xq, sx, w, sw), 20)
         us_gemm = timed(lambda: ops.gemm_w4a8(xq, sx, w, sw, None, torch.float16, out=nccl.buf), 20)
+        parts = {}
+        if red.fused:   # the two halves of the fused path on their own
+            import ctypes
+            from flatquant_b200 import _lib
+            st = torch.cuda.current_stream().cuda_stream
+            parts["gemm_with_peer_stores"] = timed(lambda: _lib.check(red.lib.flatq_gemm_w4a8_rowparallel(
+                xq.data_ptr(), sx.data_ptr(), w.data_ptr(), sw.data_ptr(), M, N, kk, ctypes.addressof(red.ctx), red.par_peers, st), "g"), 20)
+            parts["owner_sum_broadcast"] = timed(lambda: _lib.check(red.lib.flatq_peer_reduce_bcast(
+                ctypes.addressof(red.ctx), red.partial.data_ptr(), red.out_mc or None, red.out_peers, None, M, N, st), "b"), 20)
+        if red.par_mc:
+            parts["in_switch_allreduce_alone"] = timed(lambda: red.all_reduce(), 20)
+        parts["nccl_allreduce_alone"] = timed(lambda: dist.all_reduce(nccl.buf), 20)
         if rank == 0:
             print(json.dumps({"M": M, "N": N, "K_per_rank": kk, "world": world, "path": red.name, "multicast": bool(red.out_mc),
                               "max_rel_err_vs_fp32_sum": {"peer": err_peer, "nccl": err_nccl},
                               "identical_on_all_ranks": bool(flags[0]), "within_tol_on_all_ranks": bool(flags[1]),
-                              "us": {"gemm_alone": us_gemm, "gemm+peer_reduce": us_peer, "gemm+nccl_allreduce": us_nccl}}), flush=True)
+                              "nvlink_counters": nvlink, "us": {"gemm_alone": us_gemm, "gemm+peer_reduce": us_peer, "gemm+nccl_allreduce": us_nccl, **parts}}), flush=True)
         ok &= bool(flags[0]) and bool(flags[1])
         del red
     dist.barrier()
