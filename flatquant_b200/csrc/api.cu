@@ -407,15 +407,35 @@ int launch_kron_ts_o(const KronParams& p, cudaStream_t st) {
     return p.xq8 ? launch_kron_ts_t<N1, N2, T, true>(p, st) : launch_kron_ts_t<N1, N2, T, false>(p, st);
 }
 
+// 128 x 128 fp16 identity for left-only requests (the o_proj transform over the heads axis, Z = O^T . A with A [heads, 128]):
+// they run on the two-factor kernel with R = I, which is exact (every product is x * 1 or x * 0) and three times faster
+// than the legacy-MMA kernel that served them in round 1.
+__device__ __half g_eye128[128 * 128];
+__global__ void eye128_init_kernel() {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 128 * 128) g_eye128[i] = __float2half((i >> 7) == (i & 127) ? 1.f : 0.f);
+}
+static const __half* eye128(cudaStream_t st) {
+    static PerDeviceOnce once;
+    if (once.first_time()) eye128_init_kernel<<<64, 256, 0, st>>>();   // same stream as its first consumer
+    void* ptr = nullptr;
+    if (cudaGetSymbolAddress(&ptr, g_eye128) != cudaSuccess) return nullptr;
+    return reinterpret_cast<const __half*>(ptr);
+}
+
 // returns 1 if the request is not one of the instantiated (n1, n2) pairs
-int launch_kron_ts(const KronParams& p, cudaStream_t st) {
+int launch_kron_ts(const KronParams& p_in, cudaStream_t st) {
+    KronParams p = p_in;
+    if (p.left && !p.right && p.n2 == 128 && (p.n1 == 64 || p.n1 == 32 || p.n1 == 16)) p.right = eye128(st);
     if (!p.left || !p.right || !aligned16(p.left) || !aligned16(p.right)) return 1;
     if (p.n2 == 64) {
         if (p.n1 == 64) return launch_kron_ts_o<64, 64, 2>(p, st);     // 4096 (Llama-3-8B hidden)
         if (p.n1 == 56) return launch_kron_ts_o<56, 64, 2>(p, st);     // 3584 (70B down_proj at tp 8)
         if (p.n1 == 32) return launch_kron_ts_o<32, 64, 4>(p, st);     // 2048
     } else if (p.n2 == 128) {
-        if (p.n1 == 64) return launch_kron_ts_o<64, 128, 2>(p, st);    // 8192 (70B hidden)
+        if (p.n1 == 64) return launch_kron_ts_o<64, 128, 2>(p, st);    // 8192 (70B hidden; left-only: 64 heads)
+        if (p.n1 == 32) return launch_kron_ts_o<32, 128, 4>(p, st);    // left-only: o_proj over 32 heads x 128 (Llama-3-8B)
+        if (p.n1 == 16) return launch_kron_ts_o<16, 128, 4>(p, st);    // left-only: 16 heads per rank (tp 2 / 70B tp 4)
         if (p.n1 == 112) return launch_kron_ts_o<112, 128, 1>(p, st);  // 14336 (Llama-3-8B intermediate)
         if (p.n1 == 128) return launch_kron_ts_o<128, 128, 1>(p, st);  // 16384 (DeepSeek-V3 wo)
     }
@@ -1009,6 +1029,22 @@ int flatq_rmsnorm(const void* x, const void* weight, int64_t rows, int64_t K, fl
     rmsnorm_f16_kernel<<<(int)(rows < cap ? rows : cap), kNormThreads, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(weight), reinterpret_cast<__half*>(y), (int)rows,
         (int)K, mean_dim, eps);
+    FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+int flatq_add_rmsnorm(const void* h, const void* y_add, const void* weight, int64_t rows, int64_t K, float mean_dim, float eps,
+                      void* h_out, void* normed, flatq_stream_t stream) {
+    FLATQ_CHECK(h && y_add && h_out && normed, FLATQ_ERR_INVALID, "add_rmsnorm: null pointer");
+    FLATQ_CHECK(rows > 0 && K > 0 && K % 8 == 0 && rows < (1ll << 31) && K < (1ll << 31), FLATQ_ERR_INVALID,
+                "add_rmsnorm: rows=%lld, K=%lld (K must be a multiple of 8)", (long long)rows, (long long)K);
+    FLATQ_CHECK(mean_dim > 0.f, FLATQ_ERR_INVALID, "add_rmsnorm: mean_dim");
+    FLATQ_CHECK(aligned16(h) && aligned16(y_add) && aligned16(h_out) && aligned16(normed) && (!weight || aligned16(weight)),
+                FLATQ_ERR_INVALID, "add_rmsnorm: alignment");
+    const int64_t cap = (int64_t)num_sms() * 8;
+    rmsnorm_f16_kernel<<<(int)(rows < cap ? rows : cap), kNormThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(h), reinterpret_cast<const __half*>(weight), reinterpret_cast<__half*>(normed), (int)rows,
+        (int)K, mean_dim, eps, reinterpret_cast<const __half*>(y_add), reinterpret_cast<__half*>(h_out));
     FLATQ_CUDA(cudaGetLastError());
     return FLATQ_OK;
 }

@@ -30,14 +30,31 @@ __device__ __forceinline__ float block_sum_256(float v, float* s_red) {
     return t;
 }
 
-// weight may be null (the weight-less norm of deploy/nn/normalization.py: the scale is folded into the next transform)
+// weight may be null (the weight-less norm of deploy/nn/normalization.py: the scale is folded into the next transform).
+// res != null: the residual add of the decoder layer in the same pass -- h = x + res rounded to fp16 (torch's `h + y`),
+// written to h_out, and the norm is taken of that h (saves one elementwise launch and one 4 B/element HBM round trip
+// per sub-layer).
 __global__ void __launch_bounds__(kNormThreads)
 rmsnorm_f16_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __half* __restrict__ y, int rows, int K,
-                   float mean_dim, float eps) {
+                   float mean_dim, float eps, const __half* __restrict__ res = nullptr, __half* __restrict__ h_out = nullptr) {
     __shared__ float s_red[kNormThreads / 32];
     const int nvec = K / 8;   // uint4 vectors per row
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
         const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)row * K);
+        const uint4* rsrc = res ? reinterpret_cast<const uint4*>(res + (size_t)row * K) : nullptr;
+        uint4* hdst = h_out ? reinterpret_cast<uint4*>(h_out + (size_t)row * K) : nullptr;
+        auto fetch = [&](int idx) {   // x (+ res, rounded to fp16 like torch's add; stored back as the new residual stream)
+            uint4 a = src[idx];
+            if (rsrc) {
+                const uint4 b = rsrc[idx];
+                __half2* ah = reinterpret_cast<__half2*>(&a);
+                const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ah[j] = __hadd2_rn(ah[j], bh[j]);
+                if (hdst) hdst[idx] = a;
+            }
+            return a;
+        };
         uint4 v[kNormVecMax];
         float ss = 0.f;
 #pragma unroll
@@ -45,7 +62,7 @@ rmsnorm_f16_kernel(const __half* __restrict__ x, const __half* __restrict__ w, _
             const int idx = threadIdx.x + i * kNormThreads;
             v[i] = make_uint4(0, 0, 0, 0);
             if (idx < nvec) {
-                v[i] = src[idx];
+                v[i] = fetch(idx);
                 const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -56,7 +73,7 @@ rmsnorm_f16_kernel(const __half* __restrict__ x, const __half* __restrict__ w, _
             }
         }
         for (int idx = threadIdx.x + kNormVecMax * kNormThreads; idx < nvec; idx += kNormThreads) {   // K > 8192: re-read later
-            const uint4 t = src[idx];
+            const uint4 t = fetch(idx);
             const __half2* h = reinterpret_cast<const __half2*>(&t);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -88,7 +105,8 @@ rmsnorm_f16_kernel(const __half* __restrict__ x, const __half* __restrict__ w, _
             const int idx = threadIdx.x + i * kNormThreads;
             if (idx < nvec) emit(idx, v[i]);
         }
-        for (int idx = threadIdx.x + kNormVecMax * kNormThreads; idx < nvec; idx += kNormThreads) emit(idx, src[idx]);
+        // K > 8192: the tail is re-read -- from h_out when the residual was added (it already holds x + res)
+        for (int idx = threadIdx.x + kNormVecMax * kNormThreads; idx < nvec; idx += kNormThreads) emit(idx, (rsrc && hdst) ? hdst[idx] : (rsrc ? fetch(idx) : src[idx]));
     }
 }
 

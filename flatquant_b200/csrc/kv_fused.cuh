@@ -38,33 +38,54 @@ struct KvFusedParams {
 constexpr int kKvfRows = 128, kKvfThreads = 256, kKvfLd = 128 + 8;   // smem row stride in halves (ldmatrix bank spread)
 constexpr int kKvfSmem = (128 * kKvfLd + 8 * 16 * kKvfLd) * 2;   // T + per-warp A tiles
 
-// the reference's per-row asymmetric quantiser on 4 consecutive values per lane (kv_quant_kernel, bit-exact)
-__device__ __forceinline__ void kvf_quant_row_warp(const __half (&xv)[4], int lane, __half& scale, __half& zero, uint16_t& packed) {
-    __half2 h0 = __halves2half2(xv[0], xv[1]), h1 = __halves2half2(xv[2], xv[3]);
-    __half2 mx = __hmax2(h0, h1), mn = __hmin2(h0, h1);
+// The reference's per-row asymmetric quantiser (kv_quant_kernel of qattention.cuh, bit-exact: fp16 op-by-op rounding) for
+// FOUR rows of a warp at once, 4 consecutive values per lane and row: the four max / min butterflies are independent, so
+// their shuffles overlap; rows are packed two per half2 register for the butterfly.
+__device__ __forceinline__ void kvf_quant_rows4(const uint2 (&raw)[4], __half (&scale)[4], __half (&zero)[4], uint16_t (&packed)[4]) {
+    __half mxs[4], mns[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const __half2 h0 = *reinterpret_cast<const __half2*>(&raw[r].x), h1 = *reinterpret_cast<const __half2*>(&raw[r].y);
+        const __half2 a = __hmax2(h0, h1), b = __hmin2(h0, h1);
+        mxs[r] = __hmax(__low2half(a), __high2half(a));
+        mns[r] = __hmin(__low2half(b), __high2half(b));
+    }
+    __half2 mx[2] = {__halves2half2(mxs[0], mxs[1]), __halves2half2(mxs[2], mxs[3])};
+    __half2 mn[2] = {__halves2half2(mns[0], mns[1]), __halves2half2(mns[2], mns[3])};
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        uint32_t a = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(&mx), o);
-        uint32_t b = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(&mn), o);
-        mx = __hmax2(mx, *reinterpret_cast<__half2*>(&a));
-        mn = __hmin2(mn, *reinterpret_cast<__half2*>(&b));
-    }
-    const __half xmax = __hmax(__low2half(mx), __high2half(mx)), xmin = __hmin(__low2half(mn), __high2half(mn));
-    __half range = __hsub(xmax, xmin);
-    const __half eps = __float2half_rn(1e-5f);
-    if (__hlt(range, eps)) range = eps;
-    scale = __float2half_rn(__half2float(range) / 15.0f);
-    zero = __hneg(xmin);
-    const float fs = __half2float(scale);
-    uint32_t qv[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const __half t = __hadd(xv[j], zero);
-        const __half u = __float2half_rn(__fdiv_rn(__half2float(t), fs));
-        qv[j] = (uint32_t)max(0, min(15, __half2int_rn(u)));
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t a = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(&mx[i]), o);
+            const uint32_t b = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(&mn[i]), o);
+            mx[i] = __hmax2(mx[i], *reinterpret_cast<const __half2*>(&a));
+            mn[i] = __hmin2(mn[i], *reinterpret_cast<const __half2*>(&b));
+        }
     }
-    packed = (uint16_t)(qv[0] | (qv[1] << 4) | (qv[2] << 8) | (qv[3] << 12));
-    (void)lane;
+    const __half eps = __float2half_rn(1e-5f);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const __half xmax = (r & 1) ? __high2half(mx[r >> 1]) : __low2half(mx[r >> 1]);
+        const __half xmin = (r & 1) ? __high2half(mn[r >> 1]) : __low2half(mn[r >> 1]);
+        __half range = __hsub(xmax, xmin);
+        if (__hlt(range, eps)) range = eps;
+        scale[r] = __float2half_rn(__half2float(range) / 15.0f);
+        zero[r] = __hneg(xmin);
+        const float fs = __half2float(scale[r]), inv = __frcp_rn(fs);
+        const __half xv[4] = {__ushort_as_half((uint16_t)(raw[r].x & 0xFFFF)), __ushort_as_half((uint16_t)(raw[r].x >> 16)),
+                              __ushort_as_half((uint16_t)(raw[r].y & 0xFFFF)), __ushort_as_half((uint16_t)(raw[r].y >> 16))};
+        uint32_t qv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float t = __half2float(__hadd(xv[j], zero[r]));
+            // t / fs, correctly rounded (residual-corrected reciprocal: the recurrence the division routine itself uses;
+            // operands are normal fp16 values, no over/underflow) at 3 FMA-pipe instructions instead of a division call
+            const float q0 = t * inv;
+            const __half u = __float2half_rn(fmaf(fmaf(-fs, q0, t), inv, q0));
+            qv[j] = (uint32_t)max(0, min(15, __half2int_rn(u)));
+        }
+        packed[r] = (uint16_t)(qv[0] | (qv[1] << 4) | (qv[2] << 8) | (qv[3] << 12));
+    }
 }
 
 __global__ void __launch_bounds__(kKvfThreads)
@@ -76,76 +97,77 @@ kv_fused_kernel(const KvFusedParams p) {
     const int kind = (int)blockIdx.x < p.q_blocks ? 0 : ((int)blockIdx.x < p.q_blocks + p.k_blocks ? 1 : 2);
     const int blk = kind == 0 ? blockIdx.x : (kind == 1 ? blockIdx.x - p.q_blocks : blockIdx.x - p.q_blocks - p.k_blocks);
     const int heads = kind == 0 ? p.q_heads : p.kv_heads;
-    const long long n_rows = (long long)p.tokens * heads;
+    const int n_rows = p.tokens * heads;   // < 2^31 (checked on the host)
     const __half* src = kind == 0 ? p.q : (kind == 1 ? p.k : p.v);
     const long long ld = kind == 0 ? p.ld_q : (kind == 1 ? p.ld_k : p.ld_v);
     const __half* T = kind == 0 ? p.t_q : (kind == 1 ? p.t_k : nullptr);
 
-    if (T) {   // static weights: before the dependency wait
-        for (int i = threadIdx.x; i < 128 * 16; i += kKvfThreads) {
-            const int r = i >> 4, c = (i & 15) * 8;
-            *reinterpret_cast<uint4*>(Ts + r * kKvfLd + c) = __ldg(reinterpret_cast<const uint4*>(T + r * 128 + c));
+    if (T) {   // static weights: before the dependency wait; the thread's 8 loads are issued before the first store
+        uint4 tv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) tv[u] = __ldg(reinterpret_cast<const uint4*>(T) + threadIdx.x + u * kKvfThreads);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = threadIdx.x + u * kKvfThreads, r = i >> 4, c = (i & 15) * 8;
+            *reinterpret_cast<uint4*>(Ts + r * kKvfLd + c) = tv[u];
         }
     }
     grid_dep_launch();
     grid_dep_wait();
     __syncthreads();
 
-    const long long row0 = (long long)blk * kKvfRows + warp * 16;
+    // The warp's 16 rows are walked in groups of four (loads of a group in flight together, shuffle chains of its rows
+    // overlapping); the loops over the groups are NOT unrolled: the first version of this kernel was 11 k straight-line
+    // instructions and was bound by instruction fetch (ncu: 32 % of the stalls "no instruction").
+    const int row0 = blk * kKvfRows + warp * 16;
     __half* Aw = As + warp * 16 * kKvfLd;
-    if (kind == 2) {
-        // ---- V rows: quantise as they are (one row per iteration, 4 values per lane), scatter
-        for (int r = 0; r < 16; ++r) {
-            const long long row = row0 + r;
-            if (row >= n_rows) break;
-            const int token = (int)(row / heads), head = (int)(row % heads);
-            const uint2 raw = *reinterpret_cast<const uint2*>(src + token * ld + head * 128 + lane * 4);
-            const __half xv[4] = {__ushort_as_half((uint16_t)(raw.x & 0xFFFF)), __ushort_as_half((uint16_t)(raw.x >> 16)),
-                                  __ushort_as_half((uint16_t)(raw.y & 0xFFFF)), __ushort_as_half((uint16_t)(raw.y >> 16))};
-            __half scale, zero;
-            uint16_t packed;
-            kvf_quant_row_warp(xv, lane, scale, zero, packed);
-            const int s = p.slot[token], page = s / p.page_size, off = s % p.page_size;
-            const size_t idx = ((((size_t)page * p.n_layers + p.layer) * 2 + 1) * p.kv_heads + head) * p.page_size + off;
-            reinterpret_cast<uint16_t*>(p.kv_data + idx * 64)[lane] = packed;
-            if (lane == 0) reinterpret_cast<__half2*>(p.kv_param)[idx] = __halves2half2(scale, zero);
-        }
-        return;
-    }
+    const int t_first = row0 / heads, h_first = row0 - t_first * heads;   // (token, head) advance by increment
 
-    // ---- q / k rows: RoPE into the warp's A tile
-    for (int r = 0; r < 16; ++r) {
-        const long long row = row0 + r;
-        uint2 out = make_uint2(0, 0);
-        if (row < n_rows) {
-            const int token = (int)(row / heads), head = (int)(row % heads);
-            const uint2 raw = *reinterpret_cast<const uint2*>(src + token * ld + head * 128 + lane * 4);
-            out = raw;
-            if (p.cos_t) {
-                const int ps = p.pos[token];
-                const uint2 c = __ldg(reinterpret_cast<const uint2*>(p.cos_t + (size_t)ps * 128 + lane * 4));
-                const uint2 s = __ldg(reinterpret_cast<const uint2*>(p.sin_t + (size_t)ps * 128 + lane * 4));
-                // rotate_half: lanes 0-15 hold dims [0, 64) and pair with lane + 16 (dims + 64): rot = -x_hi ; lanes 16-31: rot = x_lo
-                uint2 other;
-                other.x = __shfl_xor_sync(0xffffffffu, raw.x, 16);
-                other.y = __shfl_xor_sync(0xffffffffu, raw.y, 16);
-                const __half2* xh = reinterpret_cast<const __half2*>(&raw);
-                const __half2* oh = reinterpret_cast<const __half2*>(&other);
-                const __half2* ch = reinterpret_cast<const __half2*>(&c);
-                const __half2* sh = reinterpret_cast<const __half2*>(&s);
-                __half2* rh = reinterpret_cast<__half2*>(&out);
+    // ---- phase 1: rows -> (RoPE) -> the warp's tile in shared memory
+    {
+        int t = t_first, h = h_first;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 16; r0 += 4) {
+            uint2 raw[4], cs[4], sn[4];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const __half2 rot = lane < 16 ? __hneg2(oh[j]) : oh[j];
-                    rh[j] = __hadd2_rn(__hmul2_rn(xh[j], ch[j]), __hmul2_rn(rot, sh[j]));   // _rn: never contracted into HFMA2
+            for (int u = 0; u < 4; ++u) {
+                raw[u] = cs[u] = sn[u] = make_uint2(0, 0);
+                if (row0 + r0 + u < n_rows) {
+                    raw[u] = *reinterpret_cast<const uint2*>(src + t * ld + h * 128 + lane * 4);
+                    if (kind != 2 && p.cos_t) {
+                        const int ps = p.pos[t];
+                        cs[u] = __ldg(reinterpret_cast<const uint2*>(p.cos_t + (size_t)ps * 128 + lane * 4));
+                        sn[u] = __ldg(reinterpret_cast<const uint2*>(p.sin_t + (size_t)ps * 128 + lane * 4));
+                    }
                 }
+                if (++h == heads) { h = 0; ++t; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint2 out = raw[u];
+                if (kind != 2 && p.cos_t) {
+                    // rotate_half: lanes 0-15 hold dims [0, 64) and pair with lane + 16 (dims + 64): rot = -x_hi ; lanes 16-31: rot = x_lo
+                    uint2 other;
+                    other.x = __shfl_xor_sync(0xffffffffu, raw[u].x, 16);
+                    other.y = __shfl_xor_sync(0xffffffffu, raw[u].y, 16);
+                    const __half2* xh = reinterpret_cast<const __half2*>(&raw[u]);
+                    const __half2* oh = reinterpret_cast<const __half2*>(&other);
+                    const __half2* ch = reinterpret_cast<const __half2*>(&cs[u]);
+                    const __half2* sh = reinterpret_cast<const __half2*>(&sn[u]);
+                    __half2* rh = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const __half2 rot = lane < 16 ? __hneg2(oh[j]) : oh[j];
+                        rh[j] = __hadd2_rn(__hmul2_rn(xh[j], ch[j]), __hmul2_rn(rot, sh[j]));   // _rn: never contracted into HFMA2
+                    }
+                }
+                *reinterpret_cast<uint2*>(Aw + (r0 + u) * kKvfLd + lane * 4) = out;
             }
         }
-        *reinterpret_cast<uint2*>(Aw + r * kKvfLd + lane * 4) = out;
     }
     __syncwarp();
 
-    // ---- Z[16 x 128] = A . T  (mma.sync m16n8k16, fp32 accumulate, one fp16 rounding); T == null: Z = A
+    // ---- phase 2: Z[16 x 128] = A . T  (mma.sync m16n8k16, fp32 accumulate, one fp16 rounding); T == null: Z = A
     const int g = lane >> 2, tig = lane & 3, mi = lane >> 3, r8 = lane & 7;
     if (T) {
         uint32_t afrag[8][4];
@@ -153,7 +175,7 @@ kv_fused_kernel(const KvFusedParams p) {
         for (int kt = 0; kt < 8; ++kt)
             ldsm_x4(smem_u32(Aw + (size_t)((mi & 1) * 8 + r8) * kKvfLd + kt * 16 + (mi >> 1) * 8), afrag[kt]);
         __syncwarp();   // every lane has its A fragments: the tile may be overwritten with the results
-#pragma unroll
+#pragma unroll 2
         for (int nt2 = 0; nt2 < 8; ++nt2) {
             float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -172,26 +194,34 @@ kv_fused_kernel(const KvFusedParams p) {
         __syncwarp();
     }
 
-    // ---- rows back out: 4 values per lane per row (coalesced 256-byte rows)
-    for (int r = 0; r < 16; ++r) {
-        const long long row = row0 + r;
-        if (row >= n_rows) break;
-        const int token = (int)(row / heads), head = (int)(row % heads);
-        const uint2 val = *reinterpret_cast<const uint2*>(Aw + r * kKvfLd + lane * 4);
-        if (kind == 0) {
-            *reinterpret_cast<uint2*>(p.q_out + (size_t)row * 128 + lane * 4) = val;
-            continue;
+    // ---- phase 3: rows back out, 4 values per lane per row (coalesced 256-byte rows); k / v: quantise + page scatter
+    {
+        int t = t_first, h = h_first;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 16; r0 += 4) {
+            uint2 val[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) val[u] = *reinterpret_cast<const uint2*>(Aw + (r0 + u) * kKvfLd + lane * 4);
+            __half scale[4], zero[4];
+            uint16_t packed[4];
+            if (kind != 0) kvf_quant_rows4(val, scale, zero, packed);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int row = row0 + r0 + u;
+                if (row < n_rows) {
+                    if (kind == 0) {
+                        *reinterpret_cast<uint2*>(p.q_out + (size_t)row * 128 + lane * 4) = val[u];
+                    } else {
+                        if (kind == 1 && p.k_out) *reinterpret_cast<uint2*>(p.k_out + (size_t)row * 128 + lane * 4) = val[u];
+                        const int s = p.slot[t], page = s / p.page_size, off = s - page * p.page_size;
+                        const size_t idx = ((((size_t)page * p.n_layers + p.layer) * 2 + (kind - 1)) * p.kv_heads + h) * p.page_size + off;
+                        reinterpret_cast<uint16_t*>(p.kv_data + idx * 64)[lane] = packed[u];
+                        if (lane == 0) reinterpret_cast<__half2*>(p.kv_param)[idx] = __halves2half2(scale[u], zero[u]);
+                    }
+                }
+                if (++h == heads) { h = 0; ++t; }
+            }
         }
-        if (p.k_out) *reinterpret_cast<uint2*>(p.k_out + (size_t)row * 128 + lane * 4) = val;
-        const __half xv[4] = {__ushort_as_half((uint16_t)(val.x & 0xFFFF)), __ushort_as_half((uint16_t)(val.x >> 16)),
-                              __ushort_as_half((uint16_t)(val.y & 0xFFFF)), __ushort_as_half((uint16_t)(val.y >> 16))};
-        __half scale, zero;
-        uint16_t packed;
-        kvf_quant_row_warp(xv, lane, scale, zero, packed);
-        const int s = p.slot[token], page = s / p.page_size, off = s % p.page_size;
-        const size_t idx = ((((size_t)page * p.n_layers + p.layer) * 2 + 0) * p.kv_heads + head) * p.page_size + off;
-        reinterpret_cast<uint16_t*>(p.kv_data + idx * 64)[lane] = packed;
-        if (lane == 0) reinterpret_cast<__half2*>(p.kv_param)[idx] = __halves2half2(scale, zero);
     }
 }
 

@@ -131,10 +131,18 @@ class LlamaRMSNorm(torch.nn.Module):
 
     def forward(self, x):
         if ops.FUSED_GLUE and x.dtype == torch.float16 and self.weight.dtype == torch.float16:
-            return ops.rmsnorm(x.contiguous(), self.weight, self.variance_epsilon)   # one pass (csrc/glue.cuh), opt-in
+            return ops.rmsnorm(x.contiguous(), self.weight, self.variance_epsilon)   # one pass (csrc/glue.cuh)
         xf = x.float()
         xf = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + self.variance_epsilon)
         return self.weight * xf.to(x.dtype)
+
+    def add_forward(self, h, y):
+        """(h + y, norm(h + y)): the residual add of the decoder layer fused into this norm (ops.add_rmsnorm); same
+        bits as `h = h + y; x = self(h)`."""
+        if ops.FUSED_GLUE and h.dtype == torch.float16 and y.dtype == torch.float16 and self.weight.dtype == torch.float16:
+            return ops.add_rmsnorm(h.contiguous(), y.contiguous(), self.weight, self.variance_epsilon)
+        h = h + y
+        return h, self(h)
 
 
 def rope_inv_freq(config, device=None):
@@ -488,6 +496,26 @@ class FlatQuantLlamaDecoderLayer(torch.nn.Module):
         h = h + self.self_attn(self.input_layernorm(h), cos, sin, past_key_value, rope)
         return h + self.mlp(self.post_attention_layernorm(h))
 
+    def forward_deferred(self, h, pending, cos, sin, past_key_value, rope=None):
+        """The same layer with the residual adds folded into the norms that follow them: `pending` is the previous
+        layer's MLP output, not yet added to the residual stream `h` (None for the first layer).  Returns (h, pending)."""
+        norm = self.input_layernorm
+        if pending is None:
+            x = norm(h)
+        elif hasattr(norm, "add_forward"):
+            h, x = norm.add_forward(h, pending)
+        else:
+            h = h + pending
+            x = norm(h)
+        a = self.self_attn(x, cos, sin, past_key_value, rope)
+        norm2 = self.post_attention_layernorm
+        if hasattr(norm2, "add_forward"):
+            h, x2 = norm2.add_forward(h, a)
+        else:
+            h = h + a
+            x2 = norm2(h)
+        return h, self.mlp(x2)
+
 
 class FlatQuantLlamaModel(torch.nn.Module):
     def __init__(self, options, config, tp=None):
@@ -545,11 +573,21 @@ class FlatQuantLlamaForCausalLM(torch.nn.Module):
             # tensors above ARE a table for positions start .. start + s - 1
             rope = (cos[0, :, 0].contiguous(), sin[0, :, 0].contiguous(),
                     torch.arange(s, dtype=torch.int32, device=dev).repeat(b))
+        h = self._run_layers(h, cos, sin, past_key_values, rope, logits_to_keep)
+        return self.lm_head(h), past_key_values
+
+    def _run_layers(self, h, cos, sin, cache, rope, logits_to_keep):
+        """All decoder layers + the final norm.  Every residual add is folded into the norm that follows it
+        (forward_deferred / add_forward): one launch instead of two per sub-layer, same bits."""
+        pending = None
         for layer in self.model.layers:
-            h = layer(h, cos, sin, past_key_values, rope)
+            h, pending = layer.forward_deferred(h, pending, cos, sin, cache, rope)
         if logits_to_keep:
-            h = h[:, -logits_to_keep:]
-        return self.lm_head(self.model.norm(h)), past_key_values
+            h, pending = h[:, -logits_to_keep:], pending[:, -logits_to_keep:]
+        norm = self.model.norm
+        if hasattr(norm, "add_forward"):
+            return norm.add_forward(h, pending)[1]
+        return norm(h + pending)
 
     @classmethod
     def random_init(cls, config, device, seed=0, weight_scale=0.002, tp=None):
@@ -617,10 +655,9 @@ class FlatQuantLlamaForCausalLM(torch.nn.Module):
             cache._static_pos.copy_(cache.pos_dev.expand(input_ids.shape[0]))
             rope = (table[0][0, :, 0], table[1][0, :, 0], cache._static_pos)
         h = self.model.embed_tokens(input_ids)
-        for layer in self.model.layers:
-            h = layer(h, cos, sin, cache, rope)
+        h = self._run_layers(h, cos, sin, cache, rope, 0)
         cache.pos_dev.add_(1)
-        return self.lm_head(self.model.norm(h))
+        return self.lm_head(h)
 
     # ------------------------------------------------------------------------------------------ checkpoint ingest
     @classmethod

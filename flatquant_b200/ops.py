@@ -287,6 +287,20 @@ def rmsnorm(x: torch.Tensor, weight=None, eps: float = 1e-5, mean_dim=None) -> t
     return y
 
 
+def add_rmsnorm(h: torch.Tensor, y: torch.Tensor, weight=None, eps: float = 1e-5):
+    """(h + y rounded to fp16, rmsnorm of that) in one pass: the residual add fused into the following norm."""
+    dev = _need_cuda(h, y, weight)
+    if h.dtype != torch.float16 or y.dtype != torch.float16 or (weight is not None and weight.dtype != torch.float16):
+        raise RuntimeError("add_rmsnorm: float16 activations and weight")
+    if h.shape != y.shape:
+        raise RuntimeError("add_rmsnorm: shapes")
+    k = h.shape[-1]
+    h_out, normed = torch.empty_like(h), torch.empty_like(h)
+    _lib.check(_lib.load().flatq_add_rmsnorm(_ptr(h), _ptr(y), _ptr(weight), h.numel() // k, k, float(k), float(eps), _ptr(h_out),
+                                             _ptr(normed), _stream()), "add_rmsnorm")
+    return h_out, normed
+
+
 def rope_(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
     """In-place HF rotary embedding: x [..., tokens, heads, 128] contiguous fp16, cos / sin with tokens * 128 elements."""
     _need_cuda(x, cos, sin)

@@ -240,6 +240,11 @@ int flatq_kv_decode_i4_split(const void* q_f16, void* o_f16, const uint8_t* kv_d
  *                 half(silu_f32(gate)) * up (LlamaMLP.forward: act_fn(gate_proj(x)) * up_proj(x)). */
 int flatq_rmsnorm(const void* x_f16, const void* weight_f16, int64_t rows, int64_t K, float mean_dim, float eps,
                   void* y_f16, flatq_stream_t stream);
+/* flatq_add_rmsnorm: the residual add of a decoder layer fused into the norm that follows it: h_out = half(h + y_add)
+ * (torch's fp16 add), normed = flatq_rmsnorm(h_out).  h_out may alias h.  Replaces `h = h + sublayer(...)` followed by
+ * LlamaRMSNorm.forward (HF modeling_llama.py; called from deploy/transformers/modeling_llama.py's decoder layer). */
+int flatq_add_rmsnorm(const void* h_f16, const void* y_add_f16, const void* weight_f16, int64_t rows, int64_t K, float mean_dim,
+                      float eps, void* h_out_f16, void* normed_f16, flatq_stream_t stream);
 int flatq_rope(void* x_f16, const void* cos_f16, const void* sin_f16, int64_t tokens, int heads, int head_dim,
                flatq_stream_t stream);
 int flatq_silu_mul(const void* gu_f16, int64_t rows, int64_t inter, void* out_f16, flatq_stream_t stream);

@@ -65,6 +65,8 @@ def _check_kron(tokens, n1, n2, left, right, quant, z_out, x, out8):
     if right is not None:
         _req(tuple(right.shape) == (n2, n2), f"right factor {tuple(right.shape)} != ({n2}, {n2})")
     if quant and not z_out and (n1 * n2) % 32 == 0:
+        if left is not None and right is None and n2 == 128 and n1 in (16, 32, 64):
+            return "tcgen05"   # launch_kron_ts: left-only over the heads axis runs with R = I (exact)
         if (n2 == 64 and (32 <= n1 <= 64)) or (n2 == 128 and 32 < n1 <= 128):
             return "tcgen05"
     _req(1 <= n1 <= 256 and 16 <= n2 <= 256 and n2 % 16 == 0,
@@ -255,6 +257,13 @@ def rmsnorm(x, weight=None, eps=1e-5, mean_dim=None):
     return n if weight is None else weight * n
 
 
+def add_rmsnorm(h, y, weight=None, eps=1e-5):
+    """torch's `h = h + y` (rounded to the activation dtype) followed by the norm"""
+    _contig(h=h, y=y)
+    hn = h + y
+    return hn, rmsnorm(hn, weight, eps)
+
+
 def rope_(x, cos, sin):
     """in place; the torch expression flatq_rope replaces (apply_rotary_pos_emb, every op rounded to x.dtype)"""
     _contig(x=x, cos=cos, sin=sin), _al16(x, 2, "rope x"), _al16(cos, 2, "rope cos"), _al16(sin, 2, "rope sin")
@@ -374,7 +383,7 @@ def kv_decode_i4(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, lay
 
 FUNCTIONS = ("kron_transform", "act_quant", "transform_quant", "quantize_rows", "gemm_w4a8", "gemm_w4a8_grouped",
              "linear_fused", "pack_i4",
-             "hadamard", "hadamard_kn", "kv_fused", "kv_quant", "kv_decode_i4", "rmsnorm", "rope_", "silu_mul")
+             "hadamard", "hadamard_kn", "kv_fused", "kv_quant", "kv_decode_i4", "rmsnorm", "add_rmsnorm", "rope_", "silu_mul")
 
 
 def install(monkeypatch):

@@ -183,6 +183,35 @@ def test_transform_quant_codes(ops, dev, n1, n2):
     assert torch.allclose(sx.cpu(), s32.cpu(), rtol=1e-3)
 
 
+@pytest.mark.parametrize("heads", [16, 32, 64])
+def test_left_only_transform_on_the_tcgen05_kernel(ops, dev, heads):
+    """o_proj's online transform Z = O^T . A over the heads axis (A = attention output [heads, 128] per token): served by
+    the two-factor tcgen05 kernel with an identity right factor since round 2 -- exact, so the codes must equal the
+    left-only rounding model (one fp16 rounding after O^T . A) up to tensor-core summation order, and the legacy-MMA
+    kernel's codes (FLATQ_KRON_HMMA semantics) on the same input."""
+    torch.manual_seed(heads)
+    tokens, d = 77, 128
+    x = torch.randn(tokens, heads * d).half()
+    L = (torch.eye(heads) * 0.8 + torch.randn(heads, heads) / heads ** 0.5 * 0.5).half()
+    cmax, cmin = 0.982, 0.95
+    xq, s16, s32 = ops.transform_quant(x.to(dev), L.to(dev), None, heads, d, cmax, cmin)
+    codes = O.unpack_i4(xq.cpu().numpy())
+    z = torch.matmul(L.float().t(), x.float().reshape(tokens, heads, d)).half().float().reshape(tokens, -1)
+    hi, lo = z.amax(1).clamp(min=0) * torch.tensor(cmax), z.amin(1).clamp(max=0) * torch.tensor(cmin)
+    m = torch.maximum(lo.abs(), hi)
+    s = torch.where(m == 0, torch.ones_like(m), m / 7)
+    q = torch.clamp(torch.round(z / s[:, None]), -8, 7).numpy().astype(np.int32)
+    d_ = np.abs(codes - q)
+    assert d_.max() <= 1 and (d_ != 0).mean() < 2e-4
+    assert torch.allclose(s32.cpu(), s, rtol=1e-3)
+    xq8, sx = ops.act_quant(x.to(dev), L.to(dev), None, heads, d, cmax, cmin)
+    perm = np.array([0, 2, 4, 6, 1, 3, 5, 7])
+    un = xq8.cpu().numpy().reshape(tokens, heads * d // 8, 8)
+    rest = np.empty_like(un)
+    rest[:, :, perm] = un
+    assert np.array_equal(rest.reshape(tokens, -1).astype(np.int32), codes)
+
+
 def test_quantize_rows_deploy_semantics(ops, dev):
     """deploy.nn.Quantizer: fp16 scale = max|x|/7, codes = sym_quant(x, scale)."""
     torch.manual_seed(3)

@@ -13,9 +13,10 @@ from conftest import GOLDEN
 # kernel class -> the `-m gpu` test that runs it on the B200 against the oracle
 GPU_VERIFIED = {
     "hmma two-factor": "test_gpu_parity.py::test_transform_quant_codes[(32,48),(128,224),(8,16),(14,16)] (padded n1 included)",
-    "hmma left-only": "test_gpu_parity.py::test_kernel_level_api (block_matmul, 32 heads x 128)",
+    "hmma left-only": "test_gpu_parity.py::test_kernel_level_api (block_matmul; head counts other than 16 / 32 / 64)",
     "hmma right-only": "test_zz_llama_model_gpu.py::test_right_only_transform_and_matmul_kv_cache (hardware-verified round 2; the K / Q cache transform)",
-    "tcgen05": "test_gpu_parity.py::test_transform_quant_codes[(64,64),(112,128),(86,128),(56,64),(32,64),(64,128)]",
+    "tcgen05": "test_gpu_parity.py::test_transform_quant_codes[(64,64),(112,128),(86,128),(56,64),(32,64),(64,128),(128,128),(48,64)], "
+               "test_left_only_transform_on_the_tcgen05_kernel (o_proj over 16 / 32 / 64 heads x 128)",
     "rowquant": "test_gpu_parity.py::test_quantize_rows_deploy_semantics, test_empty_and_maximum_shapes",
     "gemv": "test_gpu_parity.py::test_decode_split_k_path[m=1,2]",
     "split-k": "test_gpu_parity.py::test_decode_split_k_path[m=5..64]",
@@ -77,8 +78,9 @@ def test_llama8b_shape_kernel_configurations(monkeypatch):
         _, cache = model(ids, max_length=8)
         model(ids[:, -1:], past_key_values=cache)
     configs = {cfg for op, cfg in cpu_ops.CALLS if op == "act_quant"}
-    # hidden 4096 -> (64,64) and inter 14336 -> (112,128) on the tcgen05 kernel; o_proj = left-only 32 heads x 128
-    assert configs == {("tcgen05", 64, 64, True, True), ("tcgen05", 112, 128, True, True), ("hmma", 32, 128, True, False)}, configs
+    # hidden 4096 -> (64,64) and inter 14336 -> (112,128) on the tcgen05 kernel; o_proj = left-only 32 heads x 128, also
+    # on the tcgen05 kernel (identity right factor) since round 2
+    assert configs == {("tcgen05", 64, 64, True, True), ("tcgen05", 112, 128, True, True), ("tcgen05", 32, 128, True, False)}, configs
     assert _classes(cpu_ops.CALLS) <= set(GPU_VERIFIED)
 
 

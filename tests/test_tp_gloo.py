@@ -96,3 +96,43 @@ def test_row_and_column_parallel_world2():
     Lf, Rf = facs["full"][0]
     full = O.flat_linear_int(x, Lf, Rf, 4.0, 4.0, w.numpy(), s_w.numpy(), bias.numpy())["y"]
     assert np.array_equal(ret["col"], full)
+
+
+def _reducer_worker(rank, world, port, ret):
+    """The reducer interface bench.py and the model stack use (tp.make_reducer): on CPU / gloo it is the NCCL-style
+    reducer (the peer-memory one needs CUDA symmetric memory), driving the oracle-backed GEMM stand-in."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    import cpu_ops
+    from flatquant_b200 import ops
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        for name in cpu_ops.FUNCTIONS:
+            setattr(ops, name, getattr(cpu_ops, name))
+        M, N, K = 8, 32, 128
+        g = torch.Generator().manual_seed(10 + rank)
+        xq = torch.randint(-8, 8, (M, K), generator=g, dtype=torch.int8)
+        sx = torch.rand(M, generator=g) + 0.5
+        codes = torch.randint(-8, 8, (N, K), generator=g, dtype=torch.int8)
+        w = torch.from_numpy(O.pack_i4(codes.numpy()))
+        sw = torch.rand(N, generator=g) * 0.01
+        bias = torch.arange(N).half()
+        red = TP.make_reducer(world, rank, torch.device("cpu"), (M, N), torch.float16)
+        assert isinstance(red, TP.NcclReducer) and red.partial_buffer().shape == (M, N)
+        y = red.rowparallel_gemm(xq, sx, w, sw, bias)
+        part = torch.from_numpy(O.sym_dequant(O.gemm_i4(xq.numpy(), codes.numpy()), sx.numpy(), sw.numpy())).half()
+        ret[rank] = (y.float().numpy(), part.float().numpy())
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_reducer_interface_world2():
+    world = 2
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    mp.spawn(_reducer_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    want = (torch.from_numpy(ret[0][1]).half() + torch.from_numpy(ret[1][1]).half()) + torch.arange(32).half()
+    for r in range(world):
+        assert np.array_equal(ret[r][0], want.float().numpy()), r   # same sum, bias once, on every rank

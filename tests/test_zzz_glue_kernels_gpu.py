@@ -31,6 +31,20 @@ def test_rmsnorm_matches_hf_expression(dev, rows, k):
     assert float((d / bare.float().abs().clamp(min=1e-3)).max()) < 2.0 ** -9
 
 
+@pytest.mark.parametrize("rows,k", [(1, 4096), (2048, 4096), (16, 4096), (5, 14336)])
+def test_add_rmsnorm_equals_add_then_rmsnorm(dev, rows, k):
+    """The residual add folded into the norm: h_out is bit-identical to torch's fp16 `h + y`, and the normalised output
+    is bit-identical to flatq_rmsnorm of that sum (same kernel body, same summation order)."""
+    from flatquant_b200 import ops
+    torch.manual_seed(rows * 7 + k)
+    h = (torch.randn(rows, k, device=dev) * 2).half()
+    y = torch.randn(rows, k, device=dev).half()
+    w = (torch.rand(k, device=dev) + 0.5).half()
+    h_out, normed = ops.add_rmsnorm(h, y, w, 1e-5)
+    assert torch.equal(h_out, h + y)
+    assert torch.equal(normed, ops.rmsnorm(h + y, w, 1e-5))
+
+
 @pytest.mark.parametrize("b,s,h", [(1, 7, 4), (2, 2048, 32), (16, 1, 8)])
 def test_rope_is_bit_identical_to_the_torch_expression(dev, b, s, h):
     from flatquant_b200 import ops

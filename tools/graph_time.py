@@ -60,3 +60,54 @@ if "fused" in which:
         us_g = graph_us(lambda i: ops.gemm_w4a8(xq[0], xq[1], ws[i % 16], sw, out=y))
         tops = 2 * m * n * k / us / 1e6
         print(f"fused linear 2048 x {k}->{n}: {us:7.1f} us (GEMM alone {us_g:6.1f})  {tops:7.0f} TOP/s = {100 * tops / peak:4.1f}% of measured burst peak ({peak:.0f})", flush=True)
+if "side" in which:
+    # the launches between the FlatLinears of one decoder layer, replayed from a graph (decode bsz 1 / 16 and prefill 2048)
+    D, HQ, HKV, L = 128, 32, 8, 1
+    for tokens, seq in ((1, 2048), (16, 2048), (2048, 0)):
+        b = tokens if seq else 1
+        s = 1 if seq else tokens
+        qkv = torch.randn(tokens, (HQ + 2 * HKV) * D, device=dev).half()
+        q, k, v = (t.reshape(b, s, -1, D) for t in torch.split(qkv.view(b, s, -1), [HQ * D, HKV * D, HKV * D], dim=-1))
+        P = 4096
+        ang = torch.arange(P, device=dev)[:, None].float() * (1.0 / 500000.0 ** (torch.arange(0, D, 2, device=dev).float() / D))[None]
+        emb = torch.cat((ang, ang), -1)
+        cos_t, sin_t = emb.cos().half(), emb.sin().half()
+        pos = (torch.arange(s, device=dev) + (seq or 0)).repeat(b).int()
+        t_k = (torch.eye(D, device=dev) * 0.75 + torch.randn(D, D, device=dev) * (0.5 / D ** 0.5)).half()
+        t_q = torch.linalg.inv(t_k.double()).t().float().half().contiguous()
+        ps = 2048 + 64
+        pages = torch.zeros(b, L, 2, HKV, ps, D // 2, dtype=torch.uint8, device=dev)
+        params = torch.zeros(b, L, 2, HKV, ps, 2, dtype=torch.float16, device=dev)
+        slot = (torch.arange(b, device=dev)[:, None] * ps + (torch.arange(s, device=dev) + (seq or 0))[None]).reshape(-1).int()
+        us = graph_us(lambda i: ops.kv_fused(q, k, v, cos_t, sin_t, pos, t_q, t_k, pages, params, slot, 0, want_k=not seq))
+        print(f"kv_fused tokens={tokens}: {us:7.2f} us", flush=True)
+        h = torch.randn(tokens, 4096, device=dev).half()
+        w = torch.rand(4096, device=dev).half()
+        us = graph_us(lambda i: ops.add_rmsnorm(h, h, w, 1e-5))
+        print(f"add_rmsnorm tokens={tokens}: {us:7.2f} us", flush=True)
+        gu = torch.randn(tokens, 2 * 14336, device=dev).half()
+        us = graph_us(lambda i: ops.silu_mul(gu))
+        print(f"silu_mul tokens={tokens}: {us:7.2f} us", flush=True)
+        if seq:
+            kx = torch.randn(b * seq, HKV, D, device=dev).half()
+            sl = (torch.arange(b, device=dev)[:, None] * ps + torch.arange(seq, device=dev)[None]).reshape(-1).int()
+            ops.kv_quant(kx, pages, params, sl, 0, 0)
+            ops.kv_quant(kx, pages, params, sl, 0, 1)
+            ip = torch.arange(b + 1, dtype=torch.int32, device=dev)
+            ix = torch.arange(b, dtype=torch.int32, device=dev)
+            lp = torch.full((b,), seq + 1, dtype=torch.int32, device=dev)
+            qq = torch.randn(b, HQ, D, device=dev).half()
+            us = graph_us(lambda i: ops.kv_decode_i4(qq, pages, params, ip, ix, lp, layer=0, max_tokens_hint=ps))
+            kvb = 2.0 * b * HKV * (seq + 1) * 68
+            print(f"decode attention (split + merge) bsz={b} seq={seq}: {us:7.2f} us  {kvb / us / 1e3:6.0f} GB/s", flush=True)
+            for (kk, nn, n1, n2, left_only) in ((4096, 6144, 64, 64, False), (4096, 4096, 32, 128, True), (4096, 28672, 64, 64, False), (14336, 4096, 112, 128, False)):
+                x = torch.randn(tokens, kk, device=dev).half()
+                Lm = (torch.randn(n1, n1, device=dev) / n1 ** 0.5).half()
+                Rm = None if left_only else (torch.randn(n2, n2, device=dev) / n2 ** 0.5).half()
+                ws = [torch.randint(0, 256, (nn, kk // 2), dtype=torch.uint8, device=dev) for _ in range(16)]
+                sw = torch.rand(nn, device=dev) * 0.01
+                out = (torch.empty(tokens, kk, dtype=torch.int8, device=dev), torch.empty(tokens, dtype=torch.float32, device=dev))
+                y = torch.empty(tokens, nn, dtype=torch.float16, device=dev)
+                us_t = graph_us(lambda i: ops.act_quant(x, Lm, Rm, n1, n2, 0.98, 0.98, out=out))
+                us_g = graph_us(lambda i: ops.gemm_w4a8(out[0], out[1], ws[i % 16], sw, out=y))
+                print(f"  M={tokens} {kk}->{nn}: transform {us_t:6.2f} us, GEMV/GEMM {us_g:6.2f} us (weight stream floor {kk * nn / 2 / 6.544e6:5.2f} us)", flush=True)
