@@ -319,6 +319,39 @@ def test_flat_quantized_linear_dropin(dev, golden):
         fl(T(g["x"]).half())  # CPU activations: no fallback
 
 
+@pytest.mark.parametrize("case", ["flatlinear_256_svd", "flatlinear_224_inv_bias", "flatlinear_4096_svd"])
+def test_offline_weight_preparation_on_the_gpu(ops, dev, golden, case):
+    """reparameterize (fp64 Kronecker on the weight + LWC clip) -> RTN -> 4-bit pack, with the module and
+    its weight RESIDENT ON THE GPU (the path a 70B / V3-scale model takes), against the reference-generated fixture:
+    the re-parameterised weight to 1e-6, the RTN scales bit for bit, the codes and the packed bytes exactly."""
+    from flatquant_b200.flat_linear import FlatQuantizedLinear
+    from flatquant_b200.quant_utils import WeightQuantizer
+    g = golden(case)
+    n1, n2 = g["left"].shape[0], g["right"].shape[0]
+    n = g["w0"].shape[0]
+    has_bias = g["bias"].size > 0
+    lin = torch.nn.Linear(n1 * n2, n, bias=has_bias)
+    lin.weight.data = T(g["w0"]).clone()
+    if has_bias:
+        lin.bias.data = T(g["bias"]).clone()
+    fl = FlatQuantizedLinear(_args(), lin).to(dev)
+    with torch.no_grad():
+        fl.clip_factor_w_max.copy_(T(g["cw_max"]).to(dev))
+        fl.clip_factor_w_min.copy_(T(g["cw_min"]).to(dev))
+        fl.reparameterize(qa_trans=[T(g["left_inv"]).to(dev), T(g["right_inv"]).to(dev)])
+        assert fl.linear.weight.is_cuda
+        assert torch.allclose(fl.linear.weight.data.cpu(), T(g["w_rep"]), atol=1e-6)
+        wq = WeightQuantizer()
+        wq.configure(4, perchannel=True, sym=True, mse=False)
+        wq.find_params(fl.linear.weight.data)
+        fl.linear.weight.data = wq.quantize(fl.linear.weight.data)
+        assert torch.equal(wq.scale.reshape(-1, 1).cpu(), T(g["s_w"]))
+        packed, s_w = fl.pack_weights(weight_scales=wq.scale)        # flatq_pack_i4 on the device
+    assert packed.is_cuda and np.array_equal(packed.cpu().numpy(), g["w_packed"])
+    assert np.array_equal(O.unpack_i4(packed.cpu().numpy()), g["w_codes"])
+    assert torch.equal(s_w.cpu().reshape(-1, 1), T(g["s_w"]))
+
+
 def test_operator_api_bf16_activations_and_no_silent_library_fallback(ops, dev):
     """the operator-level transforms (flat_utils.kronecker_matmul, *TransMatrix.forward) take bf16
     inference activations on the sm_100a kernel (exact bf16 -> fp16 conversion on the way in, result rounded to bf16),
