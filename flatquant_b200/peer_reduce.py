@@ -43,12 +43,6 @@ class PeerReducer:
         self.M, self.N = int(shape[0]), int(shape[1])
         self.fused = self.M % (256 * world) == 0
         lib = _lib.load()
-        for name, res, args in (
-                ("flatq_gemm_w4a8_rowparallel", ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int64] * 3 + [ctypes.c_void_p] * 3),
-                ("flatq_peer_reduce_bcast", ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int64] * 2 + [ctypes.c_void_p]),
-                ("flatq_peer_allreduce", ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int64] * 2 + [ctypes.c_void_p])):
-            fn = getattr(lib, name)
-            fn.restype, fn.argtypes = res, args
         self.lib = lib
 
         def shared(numel, dt):
