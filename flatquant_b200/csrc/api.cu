@@ -866,14 +866,19 @@ int flatq_hadamard(const void* x, void* out, int64_t rows, int n, float scale, f
     FLATQ_CHECK(rows > 0 && aligned16(x) && aligned16(out), FLATQ_ERR_INVALID, "hadamard: rows / alignment");
     int log_n = 0;
     while ((1 << log_n) < n) ++log_n;
-    int threads = n / 8 < 32 ? 32 : (n / 8 > 1024 ? 1024 : n / 8);
-    const size_t smem = (size_t)(n + n / 32 + 1) * sizeof(float);
+    // threads per row: one per 8 elements (at least 8); short rows share a CTA of 256 threads
+    const int tpr = n / 8 < 8 ? 8 : (n / 8 > 1024 ? 1024 : n / 8);
+    int rpc = tpr >= 256 ? 1 : 256 / tpr;
+    if (rows < rpc) rpc = (int)rows;
+    const int threads = tpr * rpc;
+    const size_t smem = (size_t)rpc * (n + n / 32 + 1) * sizeof(float);
     static PerDeviceMax attr;
     if (smem > 48 * 1024 && attr.grows(smem))
         FLATQ_CUDA(cudaFuncSetAttribute(fht_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ctas = (rows + rpc - 1) / rpc;
     const int64_t cap = (int64_t)num_sms() * (n <= 1024 ? 8 : 2);
-    fht_kernel<<<(int)(rows < cap ? rows : cap), threads, smem, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), (int)rows, n, log_n, scale);
+    fht_kernel<<<(int)(ctas < cap ? ctas : cap), threads, smem, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), (int)rows, n, log_n, scale, tpr);
     FLATQ_CUDA(cudaGetLastError());
     return FLATQ_OK;
 }

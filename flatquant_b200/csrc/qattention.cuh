@@ -47,20 +47,27 @@ __device__ __forceinline__ void fht_pass(float* s, int n, int shift, int tid, in
     }
 }
 
+// `tpr` threads per row, blockDim / tpr rows per CTA (short rows -- the 128-wide K / Q head transform -- would otherwise
+// leave a CTA with one warp and a serial walk over its rows: 290 us for 65536 rows in round 2's first measurement).
 __global__ void __launch_bounds__(1024) fht_kernel(const __half* __restrict__ x, __half* __restrict__ out, int rows, int n,
-                                                  int log_n, float scale) {
-    extern __shared__ float fht_s[];
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+                                                  int log_n, float scale, int tpr) {
+    extern __shared__ float fht_all[];
+    const int rpc = blockDim.x / tpr, sub = threadIdx.x / tpr, tid = threadIdx.x % tpr, nt = tpr;
+    float* fht_s = fht_all + (size_t)sub * (n + n / 32 + 1);
+    for (int row0 = blockIdx.x * rpc; row0 < rows; row0 += gridDim.x * rpc) {   // uniform trip count: barriers are CTA-wide
+        const int row = row0 + sub;
+        const bool ok = row < rows;
         const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)row * n);
-        for (int i = tid; i < n / 8; i += nt) {
-            const uint4 v = src[i];
-            const __half2* h = reinterpret_cast<const __half2*>(&v);
+        if (ok) {
+            for (int i = tid; i < n / 8; i += nt) {
+                const uint4 v = src[i];
+                const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h[j]);
-                fht_s[fht_pad(i * 8 + 2 * j)] = f.x;
-                fht_s[fht_pad(i * 8 + 2 * j + 1)] = f.y;
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h[j]);
+                    fht_s[fht_pad(i * 8 + 2 * j)] = f.x;
+                    fht_s[fht_pad(i * 8 + 2 * j + 1)] = f.y;
+                }
             }
         }
         __syncthreads();
@@ -68,14 +75,16 @@ __global__ void __launch_bounds__(1024) fht_kernel(const __half* __restrict__ x,
         for (; shift + 3 <= log_n; shift += 3) { fht_pass<3>(fht_s, n, shift, tid, nt); __syncthreads(); }
         if (log_n - shift == 2) { fht_pass<2>(fht_s, n, shift, tid, nt); __syncthreads(); }
         if (log_n - shift == 1) { fht_pass<1>(fht_s, n, shift, tid, nt); __syncthreads(); }
-        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * n);
-        for (int i = tid; i < n / 8; i += nt) {
-            uint4 v;
-            __half2* h = reinterpret_cast<__half2*>(&v);
+        if (ok) {
+            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * n);
+            for (int i = tid; i < n / 8; i += nt) {
+                uint4 v;
+                __half2* h = reinterpret_cast<__half2*>(&v);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                h[j] = __floats2half2_rn(fht_s[fht_pad(i * 8 + 2 * j)] * scale, fht_s[fht_pad(i * 8 + 2 * j + 1)] * scale);
-            dst[i] = v;
+                for (int j = 0; j < 4; ++j)
+                    h[j] = __floats2half2_rn(fht_s[fht_pad(i * 8 + 2 * j)] * scale, fht_s[fht_pad(i * 8 + 2 * j + 1)] * scale);
+                dst[i] = v;
+            }
         }
         __syncthreads();
     }
