@@ -22,6 +22,7 @@
 #include "kron_quant_tc.cuh"
 #include "kron_quant_ts.cuh"
 #include "qattention.cuh"
+#include "decode_attn_mma.cuh"
 #include "kv_fused.cuh"
 #include "peer_reduce.cuh"
 
@@ -242,7 +243,7 @@ int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, i
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = acc_shift;
     p.out = out; p.s_x = sx; p.s_w = sw; p.bias = bias; p.prof = nullptr; p.dbg = 0; p.k_splits = k_splits;
     p.streamk = 0; p.sk_part = nullptr; p.sk_flags = nullptr; p.epoch = 0;
-    p.grp_off = nullptr; p.grp_tile = nullptr; p.n_groups = 0; p.t_upper = 0; p.rows_per_owner = 0; p.tp_rank = 0;
+    p.grp_off = nullptr; p.grp_tile = nullptr; p.n_groups = 0; p.t_upper = 0; p.rows_per_owner = 0; p.tp_rank = 0; p.silu_pairs = 0;
     {
         // Stream-K on the partial last wave: worth it when the tail's K stages, dealt to all SMs, finish at least two
         // stages earlier than whole tiles would, and every part is long enough to amortise its fix-up.
@@ -761,7 +762,7 @@ int flatq_gemm_w4a8_grouped(const int8_t* xq8, const float* s_x, const uint8_t* 
     p.out = y; p.s_x = s_x; p.s_w = s_w; p.bias = bias; p.prof = nullptr; p.dbg = 0; p.k_splits = 1;
     p.streamk = 0; p.sk_part = nullptr; p.sk_flags = nullptr; p.epoch = 0;
     p.grp_off = group_offsets; p.grp_tile = tile_prefix; p.n_groups = n_groups; p.t_upper = (int)t_upper;
-    p.rows_per_owner = 0; p.tp_rank = 0;
+    p.rows_per_owner = 0; p.tp_rank = 0; p.silu_pairs = 0;
     return out_dtype == FLATQ_F16 ? launch_gemm_grouped_m<kEpiF16>(tn, tw, tx, p, st)
                                   : launch_gemm_grouped_m<kEpiBF16>(tn, tw, tx, p, st);
 }
@@ -803,7 +804,7 @@ int flatq_gemm_w4a8_rowparallel(const int8_t* xq8, const float* s_x, const uint8
     p.out = nullptr; p.s_x = s_x; p.s_w = s_w; p.bias = nullptr; p.prof = nullptr; p.dbg = 0; p.k_splits = 1;
     p.streamk = 0; p.sk_part = nullptr; p.sk_flags = nullptr; p.epoch = 0;
     p.grp_off = nullptr; p.grp_tile = nullptr; p.n_groups = 0; p.t_upper = 0;
-    p.rows_per_owner = (int)(M / tp->world); p.tp_rank = tp->rank;
+    p.rows_per_owner = (int)(M / tp->world); p.tp_rank = tp->rank; p.silu_pairs = 0;
     for (int r = 0; r < 8; ++r) p.peer_out[r] = r < tp->world ? peer_staging[r] : nullptr;
     for (int r = 0; r < tp->world; ++r) FLATQ_CHECK(p.peer_out[r], FLATQ_ERR_INVALID, "gemm_w4a8_rowparallel: null staging pointer");
     return launch_gemm_2sm<kEpiF16>(tw, tx, p, (cudaStream_t)stream);
@@ -995,6 +996,37 @@ int flatq_kv_decode_i4_split(const void* q, void* o, const uint8_t* kv_data, con
     FLATQ_CHECK(ws_bytes >= flatq_kv_decode_i4_split_workspace_bytes(batch, q_heads), FLATQ_ERR_WORKSPACE,
                 "kv_decode_split: workspace too small");
     const int G = q_heads / kv_heads;
+    DecodeParams p;
+    p.q = reinterpret_cast<const __half*>(q); p.o = reinterpret_cast<__half*>(o);
+    p.kv_data = kv_data; p.kv_param = reinterpret_cast<const __half*>(kv_param);
+    p.kv_indptr = kv_indptr; p.kv_indices = kv_indices; p.last_page_len = last_page_len;
+    p.batch = batch; p.q_heads = q_heads; p.kv_heads = kv_heads; p.D = head_dim; p.page_size = page_size;
+    p.layer = layer; p.n_layers = n_layers; p.sm_scale = sm_scale;
+    float* part = reinterpret_cast<float*>(ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        // tensor-core variant (decode_attn_mma.cuh): the query heads of a kv head are the rows of an m16n8k16 tile
+        static const bool simt = getenv("FLATQ_DECODE_SIMT") != nullptr;   // A/B aid: the scalar online-softmax kernel
+        if (!simt && G <= 16) {
+            const int64_t base = (int64_t)batch * kv_heads;
+            int64_t splits = (2 * (int64_t)num_sms() + base - 1) / base;
+            if (max_tokens_hint > 0) {   // no split shorter than one 32-token tile per warp
+                const int64_t by_len = ((int64_t)max_tokens_hint + kDmWarps * kDmTile - 1) / (kDmWarps * kDmTile);
+                if (splits > by_len) splits = by_len;
+            }
+            if (splits > kDecMaxSplits) splits = kDecMaxSplits;
+            if (splits < 1) splits = 1;
+            static PerDeviceOnce attr;
+            if (attr.first_time())
+                FLATQ_CUDA(cudaFuncSetAttribute(decode_attn_i4_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDmSmem));
+            const dim3 grid((unsigned)splits, (unsigned)kv_heads, (unsigned)batch);
+            decode_attn_i4_mma_kernel<<<grid, kDmThreads, kDmSmem, st>>>(p, (int)splits, part);
+            FLATQ_CUDA(cudaGetLastError());
+            decode_attn_merge_kernel<<<batch * q_heads, 128, 0, st>>>(part, (int)splits, reinterpret_cast<__half*>(o));
+            FLATQ_CUDA(cudaGetLastError());
+            return FLATQ_OK;
+        }
+    }
     const int gh = G % 4 == 0 ? 4 : G % 2 == 0 ? 2 : 1;
     const int64_t base = (int64_t)batch * kv_heads * (G / gh);
     // enough CTAs for two per SM, but no split shorter than 64 tokens (4 chunks of 16) when the caller bounds the length
@@ -1005,15 +1037,7 @@ int flatq_kv_decode_i4_split(const void* q, void* o, const uint8_t* kv_data, con
     }
     if (splits > kDecMaxSplits) splits = kDecMaxSplits;
     if (splits < 1) splits = 1;
-    DecodeParams p;
-    p.q = reinterpret_cast<const __half*>(q); p.o = reinterpret_cast<__half*>(o);
-    p.kv_data = kv_data; p.kv_param = reinterpret_cast<const __half*>(kv_param);
-    p.kv_indptr = kv_indptr; p.kv_indices = kv_indices; p.last_page_len = last_page_len;
-    p.batch = batch; p.q_heads = q_heads; p.kv_heads = kv_heads; p.D = head_dim; p.page_size = page_size;
-    p.layer = layer; p.n_layers = n_layers; p.sm_scale = sm_scale;
-    float* part = reinterpret_cast<float*>(ws);
     const dim3 grid((unsigned)splits, (unsigned)(kv_heads * (G / gh)), (unsigned)batch);
-    cudaStream_t st = (cudaStream_t)stream;
     if (gh == 4) decode_attn_i4_split_kernel<4><<<grid, kDecSplitThreads, 0, st>>>(p, (int)splits, part);
     else if (gh == 2) decode_attn_i4_split_kernel<2><<<grid, kDecSplitThreads, 0, st>>>(p, (int)splits, part);
     else decode_attn_i4_split_kernel<1><<<grid, kDecSplitThreads, 0, st>>>(p, (int)splits, part);
@@ -1093,7 +1117,7 @@ int flatq_debug_gemm_profile(const int8_t* xq8, const float* s_x, const uint8_t*
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.acc_shift = 4;
     p.out = y; p.s_x = s_x; p.s_w = s_w; p.bias = nullptr; p.prof = prof; p.dbg = dbg; p.k_splits = 1;
     p.streamk = 0; p.sk_part = nullptr; p.sk_flags = nullptr; p.epoch = 0;
-    p.grp_off = nullptr; p.grp_tile = nullptr; p.n_groups = 0; p.t_upper = 0; p.rows_per_owner = 0; p.tp_rank = 0;
+    p.grp_off = nullptr; p.grp_tile = nullptr; p.n_groups = 0; p.t_upper = 0; p.rows_per_owner = 0; p.tp_rank = 0; p.silu_pairs = 0;
     auto kern = gemm_w4a8_kernel<256, kEpiF16, true>;
     constexpr int smem = GemmSmem<256>::kBytes;
     FLATQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

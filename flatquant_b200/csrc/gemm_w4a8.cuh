@@ -110,6 +110,11 @@ struct GemmParams {
     // rows_per_owner == 0: plain launch (out).  rows_per_owner % 256 == 0: a 256-token tile never straddles two owners.
     int rows_per_owner, tp_rank;
     void* peer_out[8];
+    // SiLU(gate) * up in the epilogue of the fused [gate; up] GEMM (CTA-pair kernel, 16-bit outputs): the weight rows are
+    // interleaved offline (row 2j = gate_j, row 2j + 1 = up_j), so a lane pair holds (gate_j, up_j) of a token; the even
+    // lane rounds both to the output type (what the unfused GEMM would have stored), applies HF's act_fn(gate) * up with
+    // the rounding points of silu_mul_f16_kernel (glue.cuh) and stores column j of an [M, N / 2] output.
+    int silu_pairs;
 };
 
 // ---- work schedule: every warp role walks the same list of units of its CTA

@@ -240,6 +240,7 @@ gemm_w4a8_2sm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
                 const bool has_bias = p.bias != nullptr;
                 uint16_t* out16 = reinterpret_cast<uint16_t*>(p.out);
                 uint32_t idx = (uint32_t)(m0 + c0) * (uint32_t)p.N + (uint32_t)n;
+                if (p.silu_pairs) idx = (uint32_t)(m0 + c0) * (uint32_t)(p.N >> 1) + (uint32_t)(n >> 1);
                 if (p.rows_per_owner > 0) {   // reduce-scatter in the epilogue: this tile goes to its owner's staging slot
                     const int owner = m0 / p.rows_per_owner;
                     out16 = reinterpret_cast<uint16_t*>(p.peer_out[owner]);
@@ -261,6 +262,15 @@ gemm_w4a8_2sm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
                             uint16_t h;
                             if (MODE == kEpiF16) h = __half_as_ushort(__float2half_rn(y));
                             else h = __bfloat16_as_ushort(__float2bfloat16_rn(y));
+                            if (MODE == kEpiF16 && p.silu_pairs) {   // warp-uniform; every lane takes part in the exchange
+                                const uint32_t up = __shfl_xor_sync(0xffffffffu, (uint32_t)h, 1);
+                                const float gf = __half2float(__ushort_as_half(h));
+                                const __half s = __float2half_rn(gf / (1.f + expf(-gf)));          // F.silu: fp32 math, fp16 result
+                                h = __half_as_ushort(__hmul(s, __ushort_as_half((uint16_t)up)));    // * up, rounded to fp16
+                                if (j + i < j_end && !(lane & 1)) out16[idx] = h;
+                                idx += (uint32_t)(p.N >> 1);
+                                continue;
+                            }
                             if (j + i < j_end) out16[idx] = h;
                             idx += (uint32_t)p.N;
                         }
