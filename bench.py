@@ -353,7 +353,7 @@ def measure_model(args, rank, world, dev, dist, barrier, steps, sample_clocks=Tr
     CUDA graph (benchmarks/benchmark_model.py:264-305 protocol).  Returns the measurements as a dict."""
     from flatquant_b200 import ops
     from flatquant_b200.deploy.transformers import FlatQuantLlamaConfig, FlatQuantLlamaForCausalLM
-    cfg = FlatQuantLlamaConfig(num_hidden_layers=args.layers)  # defaults = Llama-3-8B
+    cfg = FlatQuantLlamaConfig.llama3_8b(num_hidden_layers=args.layers)
     model = FlatQuantLlamaForCausalLM.random_init(cfg, dev, seed=1234 + rank)
     counted = {"n": 0}
     undo = _count_ops(ops, ("act_quant", "gemm_w4a8", "kron_transform", "kv_quant", "kv_decode_i4", "hadamard", "rmsnorm",

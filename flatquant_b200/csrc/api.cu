@@ -223,7 +223,7 @@ static unsigned long long next_epoch() {
 
 int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, int64_t K, int acc_shift, void* out,
                 int mode, const float* sx, const float* sw, const void* bias, cudaStream_t st, int k_splits = 1,
-                void* sk_ws = nullptr, size_t sk_ws_bytes = 0) {
+                void* sk_ws = nullptr, size_t sk_ws_bytes = 0, bool silu_pairs = false) {
     FLATQ_CHECK(M > 0 && N > 0 && K > 0, FLATQ_ERR_INVALID, "empty GEMM %lldx%lldx%lld", (long long)M, (long long)N,
                 (long long)K);
     FLATQ_CHECK(K % 32 == 0, FLATQ_ERR_INVALID, "K=%lld must be a multiple of 32", (long long)K);
@@ -259,6 +259,8 @@ int launch_gemm(const uint8_t* w_packed, const void* x8, int64_t M, int64_t N, i
             p.epoch = next_epoch();
         }
     }
+    FLATQ_CHECK(!silu_pairs || (pair && mode == kEpiF16), FLATQ_ERR_UNSUPPORTED, "SiLU epilogue outside the CTA-pair fp16 kernel");
+    p.silu_pairs = silu_pairs ? 1 : 0;
     if (pair) {
         switch (mode) {
             case kEpiI32: return launch_gemm_2sm<kEpiI32>(tw, tx, p, st);
@@ -465,6 +467,17 @@ int launch_kron_tc(const KronParams& p, cudaStream_t st) {
         if (p.n1 > 112 && p.n1 <= 128) return launch_kron_tc_o<128, 128, 1>(p, st);
     }
     return 1;
+}
+
+template <int MT, int CPL, int R>
+cudaError_t launch_gemv_pre(dim3 grid, size_t smem, cudaStream_t st, const GemvParams& g) {
+    auto kern = gemv_w4a8_pre_kernel<MT, CPL, R>;
+    static PerDeviceOnce attr;
+    if (attr.first_time()) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    return launch_pdl(kern, grid, dim3(kGemvWarps * 32), smem, st, g);
 }
 
 int launch_rowquant(const void* x, int64_t tokens, int64_t K, float cmax, float cmin, int half_math, uint8_t* xq4,
@@ -696,6 +709,22 @@ int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed
             FLATQ_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             FLATQ_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         }
+        static const bool generic = getenv("FLATQ_GEMV_GENERIC") != nullptr;   // A/B aid
+        if (K % 1024 == 0 && !generic) {   // weight rows in registers, first rows requested before the PDL wait
+            const dim3 grid2((unsigned)(2 * num_sms() < ctas ? 2 * num_sms() : ctas));
+            switch ((int)(K / 1024) * 10 + (int)M) {
+#define FLATQ_GEMV_PRE(CPL, R1, R2) /* rows in flight per warp for one / two tokens: <= 128 registers, no spills */    \
+    case CPL * 10 + 1: FLATQ_CUDA((launch_gemv_pre<1, CPL, R1>(grid2, smem, st, g))); return FLATQ_OK;                  \
+    case CPL * 10 + 2: FLATQ_CUDA((launch_gemv_pre<2, CPL, R2>(grid2, smem, st, g))); return FLATQ_OK;
+                FLATQ_GEMV_PRE(4, 4, 2)     // K = 4096
+                FLATQ_GEMV_PRE(5, 3, 1)     // 5120
+                FLATQ_GEMV_PRE(7, 2, 1)     // 7168
+                FLATQ_GEMV_PRE(8, 1, 1)     // 8192
+                FLATQ_GEMV_PRE(14, 1, 1)    // 14336
+#undef FLATQ_GEMV_PRE
+                default: break;
+            }
+        }
         FLATQ_CUDA(M == 1 ? launch_pdl(k1, grid, block, smem, st, g) : launch_pdl(k2, grid, block, smem, st, g));
         return FLATQ_OK;
     }
@@ -717,6 +746,35 @@ int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed
                                                                  reinterpret_cast<const __nv_bfloat16*>(bias),
                                                                  reinterpret_cast<__nv_bfloat16*>(y), (int)M, (int)N);
     FLATQ_CUDA(cudaGetLastError());
+    return FLATQ_OK;
+}
+
+// ---- fused [gate; up] GEMM + SiLU(gate) * up (row-interleaved weight)
+static bool silu_in_epilogue(int64_t M) { return M > 128 && !opt_gemm_1sm(); }
+
+size_t flatq_gemm_w4a8_silu_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    if (silu_in_epilogue(M)) return 0;
+    return align_up((size_t)M * N * 2, 256) + flatq_gemm_w4a8_workspace_bytes(M, N, K);
+}
+
+int flatq_gemm_w4a8_silu(const int8_t* xq8, const float* s_x, const uint8_t* w_packed, const float* s_w, int64_t M,
+                         int64_t N, int64_t K, void* out_f16, void* ws, size_t ws_bytes, flatq_stream_t stream) {
+    FLATQ_CHECK(xq8 && s_x && w_packed && s_w && out_f16, FLATQ_ERR_INVALID, "gemm_w4a8_silu: null pointer");
+    FLATQ_CHECK(N > 0 && N % 16 == 0, FLATQ_ERR_INVALID, "gemm_w4a8_silu: N=%lld (2 x intermediate size) must be a multiple of 16", (long long)N);
+    FLATQ_CHECK(K % 32 == 0, FLATQ_ERR_INVALID, "gemm_w4a8_silu: K=%lld must be a multiple of 32", (long long)K);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (silu_in_epilogue(M))
+        return launch_gemm(w_packed, xq8, M, N, K, 4, out_f16, kEpiF16, s_x, s_w, nullptr, st, 1, nullptr, 0, true);
+    FLATQ_CHECK(ws && aligned16(ws) && ws_bytes >= flatq_gemm_w4a8_silu_workspace_bytes(M, N, K), FLATQ_ERR_WORKSPACE,
+                "gemm_w4a8_silu: workspace too small or misaligned");
+    FLATQ_CHECK(aligned16(out_f16), FLATQ_ERR_INVALID, "gemm_w4a8_silu: output alignment");
+    const size_t off = align_up((size_t)M * N * 2, 256);
+    int rc = flatq_gemm_w4a8(xq8, s_x, w_packed, s_w, nullptr, M, N, K, ws, FLATQ_F16, reinterpret_cast<uint8_t*>(ws) + off,
+                             ws_bytes - off, stream);
+    if (rc) return rc;
+    const size_t total_vec = (size_t)M * N / 16;
+    FLATQ_CUDA(launch_pdl(silu_mul_il_f16_kernel, dim3(grid_for(total_vec, 256, 4)), dim3(256), 0, st,
+                          reinterpret_cast<const __half*>(ws), reinterpret_cast<__half*>(out_f16), total_vec));
     return FLATQ_OK;
 }
 
@@ -1007,7 +1065,7 @@ int flatq_kv_decode_i4_split(const void* q, void* o, const uint8_t* kv_data, con
     {
         // tensor-core variant (decode_attn_mma.cuh): the query heads of a kv head are the rows of an m16n8k16 tile
         static const bool simt = getenv("FLATQ_DECODE_SIMT") != nullptr;   // A/B aid: the scalar online-softmax kernel
-        if (!simt && G <= 16) {
+        if (!simt && G >= 2 && G <= 16) {   // G = 1 (no grouped queries): 15 of the tile's 16 rows would be padding; the scalar kernel wins
             const int64_t base = (int64_t)batch * kv_heads;
             int64_t splits = (2 * (int64_t)num_sms() + base - 1) / base;
             if (max_tokens_hint > 0) {   // no split shorter than one 32-token tile per warp
@@ -1020,10 +1078,9 @@ int flatq_kv_decode_i4_split(const void* q, void* o, const uint8_t* kv_data, con
             if (attr.first_time())
                 FLATQ_CUDA(cudaFuncSetAttribute(decode_attn_i4_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDmSmem));
             const dim3 grid((unsigned)splits, (unsigned)kv_heads, (unsigned)batch);
-            decode_attn_i4_mma_kernel<<<grid, kDmThreads, kDmSmem, st>>>(p, (int)splits, part);
-            FLATQ_CUDA(cudaGetLastError());
-            decode_attn_merge_kernel<<<batch * q_heads, 128, 0, st>>>(part, (int)splits, reinterpret_cast<__half*>(o));
-            FLATQ_CUDA(cudaGetLastError());
+            FLATQ_CUDA(launch_pdl(decode_attn_i4_mma_kernel, grid, dim3(kDmThreads), (size_t)kDmSmem, st, p, (int)splits, part));
+            FLATQ_CUDA(launch_pdl(decode_attn_merge_kernel, dim3(batch * q_heads), dim3(128), 0, st, (const float*)part, (int)splits,
+                                  reinterpret_cast<__half*>(o)));
             return FLATQ_OK;
         }
     }
@@ -1038,12 +1095,11 @@ int flatq_kv_decode_i4_split(const void* q, void* o, const uint8_t* kv_data, con
     if (splits > kDecMaxSplits) splits = kDecMaxSplits;
     if (splits < 1) splits = 1;
     const dim3 grid((unsigned)splits, (unsigned)(kv_heads * (G / gh)), (unsigned)batch);
-    if (gh == 4) decode_attn_i4_split_kernel<4><<<grid, kDecSplitThreads, 0, st>>>(p, (int)splits, part);
-    else if (gh == 2) decode_attn_i4_split_kernel<2><<<grid, kDecSplitThreads, 0, st>>>(p, (int)splits, part);
-    else decode_attn_i4_split_kernel<1><<<grid, kDecSplitThreads, 0, st>>>(p, (int)splits, part);
-    FLATQ_CUDA(cudaGetLastError());
-    decode_attn_merge_kernel<<<batch * q_heads, 128, 0, st>>>(part, (int)splits, reinterpret_cast<__half*>(o));
-    FLATQ_CUDA(cudaGetLastError());
+    if (gh == 4) FLATQ_CUDA(launch_pdl(decode_attn_i4_split_kernel<4>, grid, dim3(kDecSplitThreads), 0, st, p, (int)splits, part));
+    else if (gh == 2) FLATQ_CUDA(launch_pdl(decode_attn_i4_split_kernel<2>, grid, dim3(kDecSplitThreads), 0, st, p, (int)splits, part));
+    else FLATQ_CUDA(launch_pdl(decode_attn_i4_split_kernel<1>, grid, dim3(kDecSplitThreads), 0, st, p, (int)splits, part));
+    FLATQ_CUDA(launch_pdl(decode_attn_merge_kernel, dim3(batch * q_heads), dim3(128), 0, st, (const float*)part, (int)splits,
+                          reinterpret_cast<__half*>(o)));
     return FLATQ_OK;
 }
 
@@ -1055,10 +1111,9 @@ int flatq_rmsnorm(const void* x, const void* weight, int64_t rows, int64_t K, fl
     FLATQ_CHECK(mean_dim > 0.f, FLATQ_ERR_INVALID, "rmsnorm: mean_dim");
     FLATQ_CHECK(aligned16(x) && aligned16(y) && (!weight || aligned16(weight)), FLATQ_ERR_INVALID, "rmsnorm: alignment");
     const int64_t cap = (int64_t)num_sms() * 8;
-    rmsnorm_f16_kernel<<<(int)(rows < cap ? rows : cap), kNormThreads, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(weight), reinterpret_cast<__half*>(y), (int)rows,
-        (int)K, mean_dim, eps);
-    FLATQ_CUDA(cudaGetLastError());
+    FLATQ_CUDA(launch_pdl(rmsnorm_f16_kernel, dim3((unsigned)(rows < cap ? rows : cap)), dim3(kNormThreads), 0, (cudaStream_t)stream,
+                          reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(weight), reinterpret_cast<__half*>(y),
+                          (int)rows, (int)K, mean_dim, eps, (const __half*)nullptr, (__half*)nullptr));
     return FLATQ_OK;
 }
 
@@ -1071,10 +1126,9 @@ int flatq_add_rmsnorm(const void* h, const void* y_add, const void* weight, int6
     FLATQ_CHECK(aligned16(h) && aligned16(y_add) && aligned16(h_out) && aligned16(normed) && (!weight || aligned16(weight)),
                 FLATQ_ERR_INVALID, "add_rmsnorm: alignment");
     const int64_t cap = (int64_t)num_sms() * 8;
-    rmsnorm_f16_kernel<<<(int)(rows < cap ? rows : cap), kNormThreads, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __half*>(h), reinterpret_cast<const __half*>(weight), reinterpret_cast<__half*>(normed), (int)rows,
-        (int)K, mean_dim, eps, reinterpret_cast<const __half*>(y_add), reinterpret_cast<__half*>(h_out));
-    FLATQ_CUDA(cudaGetLastError());
+    FLATQ_CUDA(launch_pdl(rmsnorm_f16_kernel, dim3((unsigned)(rows < cap ? rows : cap)), dim3(kNormThreads), 0, (cudaStream_t)stream,
+                          reinterpret_cast<const __half*>(h), reinterpret_cast<const __half*>(weight), reinterpret_cast<__half*>(normed),
+                          (int)rows, (int)K, mean_dim, eps, reinterpret_cast<const __half*>(y_add), reinterpret_cast<__half*>(h_out)));
     return FLATQ_OK;
 }
 
@@ -1083,10 +1137,9 @@ int flatq_rope(void* x, const void* cos_t, const void* sin_t, int64_t tokens, in
     FLATQ_CHECK(head_dim == 128, FLATQ_ERR_UNSUPPORTED, "rope: head_dim=%d (only 128)", head_dim);
     FLATQ_CHECK(tokens > 0 && heads > 0 && tokens * heads < (1ll << 31), FLATQ_ERR_INVALID, "rope: tokens / heads");
     FLATQ_CHECK(aligned16(x) && aligned16(cos_t) && aligned16(sin_t), FLATQ_ERR_INVALID, "rope: alignment");
-    rope_f16_kernel<<<grid_for((size_t)tokens * heads * 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<__half*>(x), reinterpret_cast<const __half*>(cos_t), reinterpret_cast<const __half*>(sin_t),
-        (int)tokens, heads);
-    FLATQ_CUDA(cudaGetLastError());
+    FLATQ_CUDA(launch_pdl(rope_f16_kernel, dim3(grid_for((size_t)tokens * heads * 8, 256, 8)), dim3(256), 0, (cudaStream_t)stream,
+                          reinterpret_cast<__half*>(x), reinterpret_cast<const __half*>(cos_t), reinterpret_cast<const __half*>(sin_t),
+                          (int)tokens, heads));
     return FLATQ_OK;
 }
 
@@ -1095,9 +1148,8 @@ int flatq_silu_mul(const void* gu, int64_t rows, int64_t inter, void* out, flatq
     FLATQ_CHECK(rows > 0 && inter > 0 && inter % 8 == 0 && rows < (1ll << 31) && inter < (1ll << 30), FLATQ_ERR_INVALID,
                 "silu_mul: rows=%lld, inter=%lld (inter must be a multiple of 8)", (long long)rows, (long long)inter);
     FLATQ_CHECK(aligned16(gu) && aligned16(out), FLATQ_ERR_INVALID, "silu_mul: alignment");
-    silu_mul_f16_kernel<<<grid_for((size_t)rows * (inter / 8), 256, 8), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __half*>(gu), reinterpret_cast<__half*>(out), (int)rows, (int)inter);
-    FLATQ_CUDA(cudaGetLastError());
+    FLATQ_CUDA(launch_pdl(silu_mul_f16_kernel, dim3(grid_for((size_t)rows * (inter / 8), 256, 8)), dim3(256), 0, (cudaStream_t)stream,
+                          reinterpret_cast<const __half*>(gu), reinterpret_cast<__half*>(out), (int)rows, (int)inter));
     return FLATQ_OK;
 }
 

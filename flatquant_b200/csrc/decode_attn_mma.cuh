@@ -46,6 +46,8 @@ __host__ __device__ constexpr int dm_perm(int d) { return (d & ~7) + ((d & 1) <<
 __global__ void __launch_bounds__(kDmThreads)
 decode_attn_i4_mma_kernel(const DecodeParams p, int splits, float* __restrict__ part) {
     extern __shared__ __align__(16) uint8_t dm_smem[];
+    grid_dep_launch();   // PDL: the merge kernel becomes resident under this one
+    grid_dep_wait();     // q and this step's cache rows come from the kernel in front (kv_fused)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
     const int G = p.q_heads / p.kv_heads, hq0 = hk * G;       // G <= 16 (host)

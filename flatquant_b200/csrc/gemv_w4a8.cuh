@@ -92,4 +92,84 @@ __global__ void __launch_bounds__(kGemvWarps * 32) gemv_w4a8_kernel(const GemvPa
     }
 }
 
+// The same GEMV with the weight stream started BEFORE the dependency wait.  In a decode step the kernel in front of a
+// GEMV is the one-CTA transform + quantise kernel (6-10 us on one SM); launched with PDL, this kernel is resident on the
+// other SMs meanwhile, and its weights are static.  A warp owns R rows at a time and keeps all R x CPL 16-byte chunks of
+// them in registers (CPL = K / 1024 chunks per lane and row); the first R rows are requested before griddepcontrol.wait,
+// so that once the activation codes exist only the dp4a pass is left.  R x CPL = 14..16 loads in flight per lane also
+// lifts the steady-state stream of the longer GEMVs (gate/up) over the 4 in flight of the generic kernel.
+// Same arithmetic, same operand order: bit-identical to gemv_w4a8_kernel.
+template <int MT, int CPL, int R>
+__global__ void __launch_bounds__(kGemvWarps * 32, 2) gemv_w4a8_pre_kernel(const GemvParams p) {
+    extern __shared__ __align__(16) uint8_t xs[];  // [MT][K] int8
+    grid_dep_launch();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * kGemvWarps + warp, nw = gridDim.x * kGemvWarps;
+    const size_t row_bytes = (size_t)p.K / 2;
+    uint4 wb[R][CPL];
+    auto load_rows = [&](int n0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int n = n0 + r * nw;
+            if (n < p.N) {
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) wb[r][j] = ldg_nc_v4(p.w + (size_t)n * row_bytes + (size_t)(lane + 32 * j) * 16);
+            }
+        }
+    };
+    load_rows(gw);
+    grid_dep_wait();
+    for (int i = threadIdx.x; i < MT * p.K / 16; i += blockDim.x) {
+        const int m = i / (p.K / 16);
+        reinterpret_cast<uint4*>(xs)[i] = m < p.M ? reinterpret_cast<const uint4*>(p.x)[i] : make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    for (int n0 = gw; n0 < p.N; n0 += R * nw) {
+        if (n0 != gw) load_rows(n0);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int n = n0 + r * nw;
+            if (n >= p.N) break;
+            int32_t acc[MT];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) acc[m] = 0;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const uint32_t pw[4] = {wb[r][j].x, wb[r][j].y, wb[r][j].z, wb[r][j].w};
+                const int c = lane + 32 * j;
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    const uint4 x0 = *reinterpret_cast<const uint4*>(xs + (size_t)m * p.K + (size_t)c * 32);
+                    const uint4 x1 = *reinterpret_cast<const uint4*>(xs + (size_t)m * p.K + (size_t)c * 32 + 16);
+                    const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                    int32_t a = acc[m];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        a = __dp4a((int)((pw[q] << 4) & 0xF0F0F0F0u), (int)xw[2 * q], a);
+                        a = __dp4a((int)(pw[q] & 0xF0F0F0F0u), (int)xw[2 * q + 1], a);
+                    }
+                    acc[m] = a;
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+            }
+            if (lane < MT && lane < p.M) {
+                int32_t s = acc[0];
+#pragma unroll
+                for (int m = 1; m < MT; ++m) if (lane == m) s = acc[m];
+                float y = __fmul_rn(__fmul_rn((float)(s >> 4), p.s_x[lane]), p.s_w[n]);
+                if (p.bias) {
+                    y = __fadd_rn(y, p.bf16_out ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n])
+                                                : __half2float(reinterpret_cast<const __half*>(p.bias)[n]));
+                }
+                if (p.bf16_out) reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)lane * p.N + n] = __float2bfloat16_rn(y);
+                else reinterpret_cast<__half*>(p.out)[(size_t)lane * p.N + n] = __float2half_rn(y);
+            }
+        }
+    }
+}
+
 }  // namespace flatq

@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(kNormThreads)
 rmsnorm_f16_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __half* __restrict__ y, int rows, int K,
                    float mean_dim, float eps, const __half* __restrict__ res = nullptr, __half* __restrict__ h_out = nullptr) {
     __shared__ float s_red[kNormThreads / 32];
+    grid_dep_launch();   // PDL: the next kernel of a decode step becomes resident while this one runs
+    grid_dep_wait();
     const int nvec = K / 8;   // uint4 vectors per row
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
         const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)row * K);
@@ -114,6 +116,8 @@ rmsnorm_f16_kernel(const __half* __restrict__ x, const __half* __restrict__ w, _
 // 8 threads per (token, head) row: thread i owns dims [8i, 8i+8) of the first half and the same dims + 64.
 __global__ void __launch_bounds__(256)
 rope_f16_kernel(__half* __restrict__ x, const __half* __restrict__ cos_t, const __half* __restrict__ sin_t, int tokens, int heads) {
+    grid_dep_launch();
+    grid_dep_wait();
     const size_t n_units = (size_t)tokens * heads * 8;
     for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < n_units; u += (size_t)gridDim.x * blockDim.x) {
         const int i = (int)(u & 7);
@@ -146,6 +150,8 @@ rope_f16_kernel(__half* __restrict__ x, const __half* __restrict__ cos_t, const 
 // ---- SiLU(gate) * up over the fused [gate; up] GEMM output: gu [rows, 2 * inter] -> out [rows, inter]
 __global__ void __launch_bounds__(256)
 silu_mul_f16_kernel(const __half* __restrict__ gu, __half* __restrict__ out, int rows, int inter) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int nvec = inter / 8;
     const size_t total = (size_t)rows * nvec;
     for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < total; u += (size_t)gridDim.x * blockDim.x) {
@@ -164,6 +170,29 @@ silu_mul_f16_kernel(const __half* __restrict__ gu, __half* __restrict__ out, int
             oh[j] = __hmul2(s, vh[j]);
         }
         reinterpret_cast<uint4*>(out + row * inter)[c] = o;
+    }
+}
+
+// The same over the row-INTERLEAVED layout gu [rows, 2 * inter] = [g0, u0, g1, u1, ...] (the weight layout
+// flatq_gemm_w4a8_silu takes; this kernel is its small-M leg, where the GEMM runs split-K or as a GEMV).
+__global__ void __launch_bounds__(256)
+silu_mul_il_f16_kernel(const __half* __restrict__ gu, __half* __restrict__ out, size_t total_vec) {
+    grid_dep_launch();
+    grid_dep_wait();
+    for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < total_vec; u += (size_t)gridDim.x * blockDim.x) {
+        const uint4 a = reinterpret_cast<const uint4*>(gu)[2 * u], b = reinterpret_cast<const uint4*>(gu)[2 * u + 1];
+        const __half2 p[8] = {*reinterpret_cast<const __half2*>(&a.x), *reinterpret_cast<const __half2*>(&a.y),
+                              *reinterpret_cast<const __half2*>(&a.z), *reinterpret_cast<const __half2*>(&a.w),
+                              *reinterpret_cast<const __half2*>(&b.x), *reinterpret_cast<const __half2*>(&b.y),
+                              *reinterpret_cast<const __half2*>(&b.z), *reinterpret_cast<const __half2*>(&b.w)};
+        uint4 o;
+        __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float g = __low2float(p[j]);
+            oh[j] = __hmul(__float2half_rn(g / (1.f + expf(-g))), __high2half(p[j]));
+        }
+        reinterpret_cast<uint4*>(out)[u] = o;
     }
 }
 

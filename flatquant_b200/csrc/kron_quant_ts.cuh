@@ -79,6 +79,10 @@ kron_quant_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int groups = (p.tokens + T - 1) / T;
+    // PDL trigger first: at decode sizes this kernel is one CTA, and the GEMV that follows uses the time to become
+    // resident and pull its (static) weight rows into registers (gemv_w4a8.cuh); a prefill-sized dependent cannot become
+    // resident before this grid's CTAs retire (shared memory), so the early trigger costs nothing there.
+    grid_dep_launch();
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < XS; ++i) { mbar_init(&full_x[i], 1); mbar_init(&empty_x[i], 1); }
@@ -111,7 +115,6 @@ kron_quant_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    grid_dep_launch();
     grid_dep_wait();
 
     if (warp == 0) {

@@ -102,6 +102,7 @@ kv_fused_kernel(const KvFusedParams p) {
     const long long ld = kind == 0 ? p.ld_q : (kind == 1 ? p.ld_k : p.ld_v);
     const __half* T = kind == 0 ? p.t_q : (kind == 1 ? p.t_k : nullptr);
 
+    grid_dep_launch();   // PDL trigger first: the attention kernel behind this one becomes resident early
     if (T) {   // static weights: before the dependency wait; the thread's 8 loads are issued before the first store
         uint4 tv[8];
 #pragma unroll
@@ -112,7 +113,6 @@ kv_fused_kernel(const KvFusedParams p) {
             *reinterpret_cast<uint4*>(Ts + r * kKvfLd + c) = tv[u];
         }
     }
-    grid_dep_launch();
     grid_dep_wait();
     __syncthreads();
 

@@ -341,6 +341,8 @@ __device__ __forceinline__ void dec_dequant16(const uint2 raw, const float2 par,
 template <int GH>  // query heads of one kv head handled by a CTA (1, 2 or 4)
 __global__ void __launch_bounds__(kDecSplitThreads)
 decode_attn_i4_split_kernel(const DecodeParams p, int splits, float* __restrict__ part) {
+    grid_dep_launch();   // PDL: the merge kernel becomes resident under this one
+    grid_dep_wait();
     const int split = blockIdx.x, b = blockIdx.z;
     const int G = p.q_heads / p.kv_heads, head_groups = G / GH;
     const int hk = blockIdx.y / head_groups, hq0 = hk * G + (blockIdx.y % head_groups) * GH;
@@ -446,6 +448,8 @@ decode_attn_i4_split_kernel(const DecodeParams p, int splits, float* __restrict_
 
 // grid = batch * q_heads, 128 threads (thread j = output dim j): combine the splits' partial softmax states
 __global__ void __launch_bounds__(128) decode_attn_merge_kernel(const float* __restrict__ part, int splits, __half* __restrict__ o) {
+    grid_dep_launch();
+    grid_dep_wait();
     const float* src = part + (size_t)blockIdx.x * splits * kDecPartStride;
     const int j = threadIdx.x;
     float mm = -INFINITY;

@@ -26,7 +26,7 @@ class Linear4bit(torch.nn.Module):
         lead = q.shape[:-1]
         q2 = q.reshape(-1, q.shape[-1]).contiguous()
         out_dtype = self.weight_scales.dtype if self.weight_scales.dtype in (torch.float16, torch.bfloat16) else torch.float16
-        y = ops.linear4bit(q2, s.reshape(-1).to(torch.float16).contiguous(), self.weight,
+        y = ops.linear4bit(q2, s.reshape(-1).to(torch.float16).contiguous(), self.weight.contiguous(),
                            self.weight_scales.reshape(-1).to(torch.float16).contiguous(),
                            None if self.bias is None else self.bias.to(out_dtype).contiguous(), out_dtype)
         return y.view(*lead, -1)

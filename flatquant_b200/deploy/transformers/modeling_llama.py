@@ -111,6 +111,14 @@ class FlatQuantLlamaConfig:
         with open(os.path.join(path, "config.json")) as f:
             return cls(**json.load(f))
 
+    @classmethod
+    def llama3_8b(cls, **overrides):
+        """meta-llama/Meta-Llama-3-8B's config.json (the model BASELINE.json's configs are quoted on): grouped-query
+        attention with 8 kv heads -- `num_key_value_heads=None` would mean 32 (HF's rule), a different, heavier model."""
+        return cls(**dict(dict(hidden_size=4096, intermediate_size=14336, num_attention_heads=32, num_key_value_heads=8,
+                               num_hidden_layers=32, vocab_size=128256, rms_norm_eps=1e-5, rope_theta=500000.0,
+                               max_position_embeddings=8192), **overrides))
+
 
 def options_from_config(config) -> SimpleNamespace:
     """The `args` object of the reference (modeling_llama.py:371-379)."""
@@ -235,28 +243,38 @@ def _pre_hadamard(module, x2):
 class _QuantGroup:
     """Projections that share one quantised activation (equal clip factors): one act_quant + one GEMM."""
 
-    def __init__(self, clip, names, linears):
+    def __init__(self, clip, names, linears, interleave=False):
         self.clip, self.names = clip, names
-        self.w = torch.cat([l.weight for l in linears], 0).contiguous()
-        self.s_w = torch.cat([l.weight_scales.reshape(-1).float() for l in linears], 0).contiguous()
         self.sizes = [l.weight.shape[0] for l in linears]
-        row = 0
-        for l, n in zip(linears, self.sizes):  # the modules keep their buffers as views: no second copy of the weights
-            l.weight = self.w[row:row + n]
-            row += n
         biases = [l.bias for l in linears]
+        # interleave: rows alternate between the two projections (row 2j = first, 2j + 1 = second) -- the layout
+        # ops.gemm_w4a8_silu takes for [gate; up], so that a lane pair of the GEMM epilogue holds (gate_j, up_j)
+        self.interleaved = bool(interleave) and len(linears) == 2 and self.sizes[0] == self.sizes[1] and \
+            self.sizes[0] % 8 == 0 and all(b is None for b in biases)
+        if self.interleaved:
+            self.w = torch.stack([l.weight for l in linears], 1).reshape(2 * self.sizes[0], -1).contiguous()
+            self.s_w = torch.stack([l.weight_scales.reshape(-1).float() for l in linears], 1).reshape(-1).contiguous()
+            for i, l in enumerate(linears):  # strided views of the one copy
+                l.weight = self.w[i::2]
+        else:
+            self.w = torch.cat([l.weight for l in linears], 0).contiguous()
+            self.s_w = torch.cat([l.weight_scales.reshape(-1).float() for l in linears], 0).contiguous()
+            row = 0
+            for l, n in zip(linears, self.sizes):  # the modules keep their buffers as views: no second copy of the weights
+                l.weight = self.w[row:row + n]
+                row += n
         self.bias = None if all(b is None for b in biases) else torch.cat(
             [torch.zeros(l.weight.shape[0], dtype=ACT_DTYPE, device=l.weight.device) if b is None else b.to(ACT_DTYPE)
              for l, b in zip(linears, biases)]).contiguous()
 
 
-def _group_by_clip(names, linears, clips):
+def _group_by_clip(names, linears, clips, interleave=False):
     groups = {}
     for name, lin, clip in zip(names, linears, clips):
         groups.setdefault(clip, ([], []))
         groups[clip][0].append(name)
         groups[clip][1].append(lin)
-    return [_QuantGroup(clip, n, l) for clip, (n, l) in groups.items()]
+    return [_QuantGroup(clip, n, l, interleave) for clip, (n, l) in groups.items()]
 
 
 def _flat_linears(x2, left, right, n1, n2, groups, lac, raw=False):
@@ -269,6 +287,9 @@ def _flat_linears(x2, left, right, n1, n2, groups, lac, raw=False):
         y = ops.gemm_w4a8(xq8, s_x, g.w, g.s_w, g.bias, out_dtype=ACT_DTYPE)
         if raw:
             out[tuple(g.names)] = y
+            continue
+        if g.interleaved:
+            out[g.names[0]], out[g.names[1]] = y[..., 0::2], y[..., 1::2]
             continue
         for name, part in zip(g.names, torch.split(y, g.sizes, dim=-1)):
             out[name] = part
@@ -441,7 +462,8 @@ class FlatQuantLlamaMLP(torch.nn.Module):
             rt.n1, rt.n2 = 1, self.hidden_size
             c = (float(self.quantizer_g.clip_factor_a_max), float(self.quantizer_g.clip_factor_a_min))
             clips = [c, c]
-        rt.gate_up = _group_by_clip(("gate", "up"), (self.gate_proj, self.up_proj), clips)
+        rt.gate_up = _group_by_clip(("gate", "up"), (self.gate_proj, self.up_proj), clips,
+                                    interleave=ops.FUSED_GLUE and ACT_DTYPE == torch.float16)
         first = self.down_proj[0]
         if isinstance(first, OnlineTrans) and first.trans == "matmul":
             rt.d_left, rt.d_right = _f16(first.left_matrix), _f16(first.right_matrix)
@@ -461,7 +483,7 @@ class FlatQuantLlamaMLP(torch.nn.Module):
         rt = self._runtime(x.device)
         x2 = x.reshape(b * s, self.hidden_size).to(ACT_DTYPE).contiguous()
         x2 = _pre_hadamard(getattr(self, "inp_trans_g", None), x2)
-        if fused:
+        if fused:   # layout of the undivided output: [gate | up], or [g0, u0, g1, u1, ...] for an interleaved group
             gu = _flat_linears(x2, rt.left, rt.right, rt.n1, rt.n2, rt.gate_up, self.isFlatQ, True)
             return gu[("gate", "up")].reshape(b, s, -1)
         gu = _flat_linears(x2, rt.left, rt.right, rt.n1, rt.n2, rt.gate_up, self.isFlatQ)
@@ -476,8 +498,23 @@ class FlatQuantLlamaMLP(torch.nn.Module):
         y = _flat_linears(a2, rt.d_left, rt.d_right, rt.d_n1, rt.d_n2, rt.down, self.isFlatQ)["down"]
         return self.tp.all_reduce(y).reshape(b, s, self.hidden_size)
 
+    def act(self, x):
+        """Stage 1 + activation, act_fn(gate) * up [b, s, inter], in one call when gate and up share their quantised input:
+        the GEMM over the interleaved [gate; up] rows applies SiLU * up in its epilogue (ops.gemm_w4a8_silu)."""
+        b, s, _ = x.shape
+        rt = self._runtime(x.device)
+        g = rt.gate_up[0]
+        x2 = x.reshape(b * s, self.hidden_size).to(ACT_DTYPE).contiguous()
+        x2 = _pre_hadamard(getattr(self, "inp_trans_g", None), x2)
+        cmax, cmin = (_sig(g.clip[0]), _sig(g.clip[1])) if self.isFlatQ else (1.0, 1.0)
+        xq8, s_x = ops.act_quant(x2, rt.left, rt.right, rt.n1, rt.n2, cmax, cmin)
+        return ops.gemm_w4a8_silu(xq8, s_x, g.w, g.s_w).view(b, s, -1)
+
     def forward(self, x):
-        if ops.FUSED_GLUE and ACT_DTYPE == torch.float16 and len(self._runtime(x.device).gate_up) == 1:
+        rt = self._runtime(x.device)
+        if len(rt.gate_up) == 1 and rt.gate_up[0].interleaved:
+            return self.down(self.act(x))
+        if ops.FUSED_GLUE and ACT_DTYPE == torch.float16 and len(rt.gate_up) == 1:
             return self.down(ops.silu_mul(self.gate_up(x, fused=True)))   # SiLU * up in one pass over the GEMM output
         gate, up = self.gate_up(x)
         return self.down(F.silu(gate) * up)

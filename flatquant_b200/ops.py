@@ -245,6 +245,22 @@ def gemm_w4a8(xq8: torch.Tensor, s_x: torch.Tensor, w_packed: torch.Tensor, s_w:
     return y
 
 
+def gemm_w4a8_silu(xq8: torch.Tensor, s_x: torch.Tensor, w_packed_il: torch.Tensor, s_w_il: torch.Tensor, out=None) -> torch.Tensor:
+    """act_fn(gate_proj(x)) * up_proj(x) in one call: `w_packed_il` [2 * inter, K/2] / `s_w_il` hold gate and up rows
+    interleaved (row 2j = gate j, row 2j + 1 = up j).  Returns [M, inter] fp16, bit-identical to gemm_w4a8 + silu_mul;
+    for M > 128 the activation runs in the GEMM epilogue."""
+    dev = _need_cuda(xq8, s_x, w_packed_il, s_w_il)
+    m, k = xq8.shape
+    n = w_packed_il.shape[0]
+    y = out if out is not None else torch.empty((m, n // 2), dtype=torch.float16, device=dev)
+    lib = _lib.load()
+    nb = lib.flatq_gemm_w4a8_silu_workspace_bytes(m, n, k)
+    ws = _ws2.get(dev, nb) if nb else None
+    _lib.check(lib.flatq_gemm_w4a8_silu(_ptr(xq8), _ptr(s_x), _ptr(w_packed_il), _ptr(s_w_il), m, n, k, _ptr(y), _ptr(ws),
+                                        ws.numel() if ws is not None else 0, _stream()), "gemm_w4a8_silu")
+    return y
+
+
 def gemm_w4a8_grouped(xq8: torch.Tensor, s_x: torch.Tensor, w_packed: torch.Tensor, s_w: torch.Tensor,
                       group_offsets: torch.Tensor, bias=None, out_dtype=torch.float16, out=None,
                       rows_per_group_hint: int = 0) -> torch.Tensor:

@@ -131,6 +131,20 @@ int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed
                     int64_t M, int64_t N, int64_t K, void* y, int out_dtype, void* workspace, size_t workspace_bytes,
                     flatq_stream_t stream);
 
+/* ---- a6 + the MLP activation: the fused [gate; up] FlatLinear followed by act_fn(gate) * up
+ *      (transformers' LlamaMLP.forward under flatquant/model_tools/llama_utils.py:16-54: down_proj(act_fn(gate_proj(x))
+ *      * up_proj(x)); the reference runs two F.linear calls, F.silu and a multiply).
+ *      w_packed [N, K/2] / s_w [N] hold the two projections ROW-INTERLEAVED: row 2j = gate_proj row j, row 2j + 1 =
+ *      up_proj row j (N = 2 * intermediate_size, N % 16 == 0; no bias: Llama's MLP has none).
+ *      out [M, N/2] fp16 = half(silu_f32(g)) * u with g, u the fp16-rounded GEMM outputs -- bit-identical to
+ *      flatq_gemm_w4a8 into [M, N] followed by flatq_silu_mul on the de-interleaved columns.  For M > 128 the
+ *      activation runs in the GEMM epilogue (the [M, N] pre-activation never reaches HBM) and no workspace is needed;
+ *      smaller M use the workspace (flatq_gemm_w4a8_silu_workspace_bytes) for the pre-activation + split-K. */
+size_t flatq_gemm_w4a8_silu_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int flatq_gemm_w4a8_silu(const int8_t* xq8, const float* s_x, const uint8_t* w_packed_il, const float* s_w_il, int64_t M,
+                         int64_t N, int64_t K, void* out_f16, void* workspace, size_t workspace_bytes,
+                         flatq_stream_t stream);
+
 /* ---- a6 for mixture-of-experts layers: the routed-expert FlatLinears of the DeepSeek block (BASELINE configs[4];
  *      deepseek_v3/model.py:677-683 -- a Python loop over experts, each `expert(x[idx])` -- under
  *      flatquant/model_tools/deepseekv3_utils.py:413-470).  ONE launch for all experts of a stage:

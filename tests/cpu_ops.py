@@ -207,6 +207,18 @@ def gemm_w4a8(xq8, s_x, w_packed, s_w, bias=None, out_dtype=torch.float16, out=N
     return y
 
 
+def gemm_w4a8_silu(xq8, s_x, w_packed_il, s_w_il, out=None):
+    n = w_packed_il.shape[0]
+    _req(n % 16 == 0, f"gemm_w4a8_silu: N={n} must be a multiple of 16")
+    gu = gemm_w4a8(xq8, s_x, w_packed_il, s_w_il)
+    CALLS[-1] = ("gemm_w4a8_silu", CALLS[-1][1])
+    y = torch.nn.functional.silu(gu[:, 0::2]) * gu[:, 1::2]
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
 def gemm_w4a8_grouped(xq8, s_x, w_packed, s_w, group_offsets, bias=None, out_dtype=torch.float16, out=None,
                       rows_per_group_hint=0):
     _contig(xq8=xq8, s_x=s_x, w_packed=w_packed, s_w=s_w, group_offsets=group_offsets, bias=bias)
@@ -381,7 +393,7 @@ def kv_decode_i4(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, lay
     return torch.cat(outs).to(q.dtype)
 
 
-FUNCTIONS = ("kron_transform", "act_quant", "transform_quant", "quantize_rows", "gemm_w4a8", "gemm_w4a8_grouped",
+FUNCTIONS = ("kron_transform", "act_quant", "transform_quant", "quantize_rows", "gemm_w4a8", "gemm_w4a8_silu", "gemm_w4a8_grouped",
              "linear_fused", "pack_i4",
              "hadamard", "hadamard_kn", "kv_fused", "kv_quant", "kv_decode_i4", "rmsnorm", "add_rmsnorm", "rope_", "silu_mul")
 

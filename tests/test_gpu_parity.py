@@ -776,3 +776,27 @@ def test_empty_and_maximum_shapes(ops, dev):
     ref = O.sym_dequant(acc, s32.cpu().numpy(), s_w.cpu().numpy()).astype(np.float16)
     assert np.array_equal(y.cpu().numpy(), ref)
     assert np.abs(acc).max() < 2 ** 24  # the folded-shift fast path of the epilogue is exact only below this
+
+
+@pytest.mark.parametrize("k", [2048, 4096, 5120, 7168, 8192, 14336])
+@pytest.mark.parametrize("m", [1, 2])
+def test_decode_gemv_register_resident_rows_bit_exact(ops, dev, m, k):
+    """The one / two token GEMV (csrc/gemv_w4a8.cuh): the register-resident variant that requests its first weight rows
+    before the PDL wait (K a multiple of 1024 among the instantiated widths) and the generic one (K = 2048) against the
+    integer arithmetic of the path, bit for bit; N ragged against the grid (rows per warp not uniform), with bias."""
+    torch.manual_seed(m * 100003 + k)
+    n = 4100 if k != 4096 else 28672 + 8
+    xq8 = torch.randint(-8, 8, (m, k), dtype=torch.int8, device=dev)
+    sx = torch.rand(m, device=dev) * 0.05 + 0.01
+    wq = torch.randint(-8, 8, (n, k), dtype=torch.int8, device=dev)
+    wp = ops.pack_i4(wq)
+    sw = torch.rand(n, device=dev) * 0.02 + 0.01
+    bias = torch.randn(n, device=dev).half()
+    y = ops.gemm_w4a8(xq8, sx, wp, sw, bias, torch.float16)
+    y2 = ops.gemm_w4a8(xq8, sx, wp, sw, bias, torch.float16)
+    perm = torch.tensor([0, 2, 4, 6, 1, 3, 5, 7], device=dev)
+    codes = torch.empty_like(xq8).view(m, k // 8, 8)
+    codes[:, :, perm] = xq8.view(m, k // 8, 8)          # the operand is stored K-permuted (DESIGN.md section 2)
+    acc = codes.view(m, k).float() @ wq.float().t()      # exact in fp32: |sum| <= 64 K < 2^24
+    ref = ((acc * sx[:, None]) * sw[None, :] + bias.float()[None, :]).half()
+    assert torch.equal(y, ref) and torch.equal(y, y2)

@@ -71,7 +71,7 @@ def test_llama8b_shape_kernel_configurations(monkeypatch):
     from flatquant_b200.deploy.transformers import FlatQuantLlamaConfig, FlatQuantLlamaForCausalLM
     cpu_ops.install(monkeypatch)
     monkeypatch.setattr(cpu_ops, "CALLS", [])
-    cfg = FlatQuantLlamaConfig(num_hidden_layers=1, vocab_size=32)
+    cfg = FlatQuantLlamaConfig.llama3_8b(num_hidden_layers=1, vocab_size=32)
     model = FlatQuantLlamaForCausalLM.random_init(cfg, torch.device("cpu"), seed=0)
     ids = torch.randint(0, 32, (1, 6), generator=torch.Generator().manual_seed(0))
     with torch.no_grad():

@@ -426,3 +426,7 @@ def test_fused_glue_wiring_is_a_no_op_on_results(monkeypatch):
         assert torch.equal(a, b)
     # layer 0 has one shared gate/up quantisation (fused SiLU path), layer 1 two (torch path): both were exercised
     assert len(model.model.layers[0].mlp._rt.gate_up) == 1 and len(model.model.layers[1].mlp._rt.gate_up) == 2
+    # ... and layer 0's shared quantisation feeds the GEMM with the SiLU * up epilogue over row-interleaved [gate; up]
+    assert model.model.layers[0].mlp._rt.gate_up[0].interleaved and any(op == "gemm_w4a8_silu" for op, _ in cpu_ops.CALLS)
+    gp = model.model.layers[0].mlp.gate_proj.weight
+    assert not gp.is_contiguous() and gp.data_ptr() == model.model.layers[0].mlp._rt.gate_up[0].w.data_ptr()

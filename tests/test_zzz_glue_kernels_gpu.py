@@ -71,3 +71,26 @@ def test_silu_mul_matches_the_torch_expression(dev, rows, inter):
     d = (got.float() - ref.float()).abs()
     # torch's silu kernel and expf may differ in the last fp32 bit before the fp16 rounding: at most one fp16 ulp, rarely
     assert float((d / ref.float().abs().clamp(min=1e-3)).max()) < 2.0 ** -9 and float((d > 0).float().mean()) < 1e-3
+
+
+@pytest.mark.parametrize("m,inter,k", [(1, 512, 512), (16, 1032, 512), (100, 1024, 1024), (129, 1032, 512), (300, 520, 2048),
+                                       (2048, 14336, 4096)])
+def test_gate_up_gemm_with_silu_epilogue_is_bit_identical_to_gemm_then_silu_mul(dev, m, inter, k):
+    """flatq_gemm_w4a8_silu on row-interleaved [gate; up] weights == flatq_gemm_w4a8 on the concatenated weights followed
+    by flatq_silu_mul, bit for bit (same fp16 rounding of the GEMM output, same fp32 SiLU, same fp16 product): the
+    epilogue-fused leg (M > 128, CTA-pair kernel, ragged last tiles included) and the workspace leg (GEMV / split-K)."""
+    from flatquant_b200 import ops
+    torch.manual_seed(m + inter + k)
+    xq8 = torch.randint(-8, 8, (m, k), dtype=torch.int8, device=dev)
+    sx = torch.rand(m, device=dev) * 0.05 + 0.02
+    wg, wu = (torch.randint(-8, 8, (inter, k), dtype=torch.int8, device=dev) for _ in range(2))
+    sg, su = (torch.rand(inter, device=dev) * 0.05 + 0.02 for _ in range(2))
+    w_cat, s_cat = ops.pack_i4(torch.cat([wg, wu], 0)), torch.cat([sg, su]).contiguous()
+    w_il = ops.pack_i4(torch.stack([wg, wu], 1).reshape(2 * inter, k).contiguous())
+    s_il = torch.stack([sg, su], 1).reshape(-1).contiguous()
+    ref = ops.silu_mul(ops.gemm_w4a8(xq8, sx, w_cat, s_cat, None, torch.float16))
+    got = ops.gemm_w4a8_silu(xq8, sx, w_il, s_il)
+    got2 = ops.gemm_w4a8_silu(xq8, sx, w_il, s_il)
+    torch.cuda.synchronize()
+    assert got.shape == (m, inter) and torch.equal(got, ref) and torch.equal(got, got2)
+    assert float(ref.float().abs().mean()) > 1e-3   # not a comparison of zeros

@@ -11,7 +11,7 @@ from flatquant_b200.deploy.transformers.graphs import GraphedDecoder
 layers = int(os.environ.get("PROBE_LAYERS", "4"))
 bsz = int(os.environ.get("PROBE_BSZ", "1"))
 dev = torch.device("cuda:0")
-cfg = FlatQuantLlamaConfig(num_hidden_layers=layers)
+cfg = FlatQuantLlamaConfig.llama3_8b(num_hidden_layers=layers)
 model = FlatQuantLlamaForCausalLM.random_init(cfg, dev, seed=1)
 ids = torch.randint(100, 200, (bsz, 2048), device=dev)
 cache = model.build_cache(bsz, page_size=2048 + 64, max_length=2048 + 64)
