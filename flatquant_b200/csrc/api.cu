@@ -17,6 +17,7 @@
 #include "gemm_w4a8.cuh"
 #include "gemm_w4a8_2sm.cuh"
 #include "gemv_w4a8.cuh"
+#include "gemm_w4a8_skinny.cuh"
 #include "glue.cuh"
 #include "kron_quant.cuh"
 #include "kron_quant_tc.cuh"
@@ -469,15 +470,30 @@ int launch_kron_tc(const KronParams& p, cudaStream_t st) {
     return 1;
 }
 
-template <int MT, int CPL, int R>
-cudaError_t launch_gemv_pre(dim3 grid, size_t smem, cudaStream_t st, const GemvParams& g) {
-    auto kern = gemv_w4a8_pre_kernel<MT, CPL, R>;
+// decode batches (3..32 tokens): the weight-streaming mma.sync kernel of gemm_w4a8_skinny.cuh
+static bool skinny_ok(int64_t M, int64_t N, int64_t K, const void* x, const void* w) {
+    static const bool off = getenv("FLATQ_NO_SKINNY") != nullptr;   // A/B aid: back to the tcgen05 split-K route
+    return !off && M >= 1 && M <= 32 && K % 128 == 0 && N >= 1 && aligned16(x) && aligned16(w);
+}
+
+template <bool SILU>
+cudaError_t launch_skinny(const GemvParams& g, cudaStream_t st) {
+    const dim3 grid((unsigned)((g.N + kSkinnyRows - 1) / kSkinnyRows)), block(kSkinnyWarps * 32);
+    if (g.M <= 8) return launch_pdl(gemm_w4a8_skinny_kernel<1, SILU>, grid, block, 0, st, g);
+    if (g.M <= 16) return launch_pdl(gemm_w4a8_skinny_kernel<2, SILU>, grid, block, 0, st, g);
+    return launch_pdl(gemm_w4a8_skinny_kernel<4, SILU>, grid, block, 0, st, g);
+}
+
+template <int MT, int CPL, int R, int MINB, bool SILU = false>
+cudaError_t launch_gemv_pre(int64_t ctas, size_t smem, cudaStream_t st, const GemvParams& g) {
+    auto kern = gemv_w4a8_pre_kernel<MT, CPL, R, MINB, SILU>;
     static PerDeviceOnce attr;
     if (attr.first_time()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         if (e != cudaSuccess) return e;
     }
-    return launch_pdl(kern, grid, dim3(kGemvWarps * 32), smem, st, g);
+    const int64_t cap = (int64_t)MINB * num_sms();   // one wave of resident CTAs
+    return launch_pdl(kern, dim3((unsigned)(cap < ctas ? cap : ctas)), dim3(kGemvWarps * 32), smem, st, g);
 }
 
 int launch_rowquant(const void* x, int64_t tokens, int64_t K, float cmax, float cmin, int half_math, uint8_t* xq4,
@@ -711,21 +727,27 @@ int flatq_gemm_w4a8(const int8_t* xq8, const float* s_x, const uint8_t* w_packed
         }
         static const bool generic = getenv("FLATQ_GEMV_GENERIC") != nullptr;   // A/B aid
         if (K % 1024 == 0 && !generic) {   // weight rows in registers, first rows requested before the PDL wait
-            const dim3 grid2((unsigned)(2 * num_sms() < ctas ? 2 * num_sms() : ctas));
             switch ((int)(K / 1024) * 10 + (int)M) {
-#define FLATQ_GEMV_PRE(CPL, R1, R2) /* rows in flight per warp for one / two tokens: <= 128 registers, no spills */    \
-    case CPL * 10 + 1: FLATQ_CUDA((launch_gemv_pre<1, CPL, R1>(grid2, smem, st, g))); return FLATQ_OK;                  \
-    case CPL * 10 + 2: FLATQ_CUDA((launch_gemv_pre<2, CPL, R2>(grid2, smem, st, g))); return FLATQ_OK;
-                FLATQ_GEMV_PRE(4, 4, 2)     // K = 4096
-                FLATQ_GEMV_PRE(5, 3, 1)     // 5120
-                FLATQ_GEMV_PRE(7, 2, 1)     // 7168
-                FLATQ_GEMV_PRE(8, 1, 1)     // 8192
-                FLATQ_GEMV_PRE(14, 1, 1)    // 14336
+#define FLATQ_GEMV_PRE(CPL, R, MINB) /* R rows of CPL 16-byte chunks per lane in registers, MINB CTAs per SM */           \
+    case CPL * 10 + 1: FLATQ_CUDA((launch_gemv_pre<1, CPL, R, MINB>(ctas, smem, st, g))); return FLATQ_OK;              \
+    case CPL * 10 + 2: FLATQ_CUDA((launch_gemv_pre<2, CPL, R, MINB>(ctas, smem, st, g))); return FLATQ_OK;
+                FLATQ_GEMV_PRE(4, 1, 5)     // K = 4096: short rows, many CTAs (as the generic kernel), first row before the wait
+                FLATQ_GEMV_PRE(5, 1, 4)     // 5120
+                FLATQ_GEMV_PRE(7, 1, 4)     // 7168
+                FLATQ_GEMV_PRE(8, 1, 4)     // 8192
+                FLATQ_GEMV_PRE(14, 1, 2)    // 14336: a row is 56 registers per lane
 #undef FLATQ_GEMV_PRE
                 default: break;
             }
         }
         FLATQ_CUDA(M == 1 ? launch_pdl(k1, grid, block, smem, st, g) : launch_pdl(k2, grid, block, smem, st, g));
+        return FLATQ_OK;
+    }
+    if (skinny_ok(M, N, K, xq8, w_packed)) {
+        GemvParams g;
+        g.w = w_packed; g.x = xq8; g.s_x = s_x; g.s_w = s_w; g.bias = bias; g.out = y;
+        g.M = (int)M; g.N = (int)N; g.K = (int)K; g.bf16_out = out_dtype == FLATQ_BF16;
+        FLATQ_CUDA(launch_skinny<false>(g, st));
         return FLATQ_OK;
     }
     const int splits = (ws && ws_bytes >= flatq_gemm_w4a8_workspace_bytes(M, N, K)) ? decode_splits(M, N, K) : 1;
@@ -765,6 +787,31 @@ int flatq_gemm_w4a8_silu(const int8_t* xq8, const float* s_x, const uint8_t* w_p
     cudaStream_t st = (cudaStream_t)stream;
     if (silu_in_epilogue(M))
         return launch_gemm(w_packed, xq8, M, N, K, 4, out_f16, kEpiF16, s_x, s_w, nullptr, st, 1, nullptr, 0, true);
+    if (M <= 2 && (size_t)M * K <= 96 * 1024 && K % 1024 == 0 && aligned16(xq8) && aligned16(w_packed)) {
+        // decode: the GEMV's warps own (gate, up) row pairs and apply the activation themselves -- one launch
+        GemvParams g;
+        g.w = w_packed; g.x = xq8; g.s_x = s_x; g.s_w = s_w; g.bias = nullptr; g.out = out_f16;
+        g.M = (int)M; g.N = (int)N; g.K = (int)K; g.bf16_out = 0;
+        const int64_t ctas = (N / 2 + kGemvWarps - 1) / kGemvWarps;
+        const size_t smem = (size_t)(M == 1 ? 1 : 2) * K;
+        switch ((int)(K / 1024) * 10 + (int)M) {
+#define FLATQ_GEMV_SILU(CPL, MINB)                                                                                      \
+    case CPL * 10 + 1: FLATQ_CUDA((launch_gemv_pre<1, CPL, 2, MINB, true>(ctas, smem, st, g))); return FLATQ_OK;        \
+    case CPL * 10 + 2: FLATQ_CUDA((launch_gemv_pre<2, CPL, 2, MINB, true>(ctas, smem, st, g))); return FLATQ_OK;
+            FLATQ_GEMV_SILU(4, 4)    // hidden 4096
+            FLATQ_GEMV_SILU(5, 3)    // 5120
+            FLATQ_GEMV_SILU(8, 2)    // 8192
+#undef FLATQ_GEMV_SILU
+            default: break;
+        }
+    }
+    if (skinny_ok(M, N, K, xq8, w_packed)) {   // decode batches: the activation in the streaming kernel's epilogue
+        GemvParams g;
+        g.w = w_packed; g.x = xq8; g.s_x = s_x; g.s_w = s_w; g.bias = nullptr; g.out = out_f16;
+        g.M = (int)M; g.N = (int)N; g.K = (int)K; g.bf16_out = 0;
+        FLATQ_CUDA(launch_skinny<true>(g, st));
+        return FLATQ_OK;
+    }
     FLATQ_CHECK(ws && aligned16(ws) && ws_bytes >= flatq_gemm_w4a8_silu_workspace_bytes(M, N, K), FLATQ_ERR_WORKSPACE,
                 "gemm_w4a8_silu: workspace too small or misaligned");
     FLATQ_CHECK(aligned16(out_f16), FLATQ_ERR_INVALID, "gemm_w4a8_silu: output alignment");

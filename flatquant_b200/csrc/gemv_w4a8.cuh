@@ -99,36 +99,44 @@ __global__ void __launch_bounds__(kGemvWarps * 32) gemv_w4a8_kernel(const GemvPa
 // so that once the activation codes exist only the dp4a pass is left.  R x CPL = 14..16 loads in flight per lane also
 // lifts the steady-state stream of the longer GEMVs (gate/up) over the 4 in flight of the generic kernel.
 // Same arithmetic, same operand order: bit-identical to gemv_w4a8_kernel.
-template <int MT, int CPL, int R>
-__global__ void __launch_bounds__(kGemvWarps * 32, 2) gemv_w4a8_pre_kernel(const GemvParams p) {
+// SILU (R == 2, fp16, no bias): the weight rows are interleaved [gate_0, up_0, gate_1, ...] (flatq_gemm_w4a8_silu); a warp
+// owns the PAIR (2u, 2u + 1) and stores half(silu_f32(half(g))) * half(u) into column u of an [M, N / 2] output -- the
+// rounding points of the GEMM followed by silu_mul_il_f16_kernel, without the launch.
+template <int MT, int CPL, int R, int MINB, bool SILU>
+__global__ void __launch_bounds__(kGemvWarps * 32, MINB) gemv_w4a8_pre_kernel(const GemvParams p) {
+    static_assert(!SILU || R == 2, "SiLU pairs: two rows per warp and pass");
     extern __shared__ __align__(16) uint8_t xs[];  // [MT][K] int8
     grid_dep_launch();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * kGemvWarps + warp, nw = gridDim.x * kGemvWarps;
     const size_t row_bytes = (size_t)p.K / 2;
+    const int units = SILU ? p.N / 2 : p.N;              // what a warp strides over: row pairs or rows
+    auto row_of = [&](int u0, int r) { return SILU ? 2 * u0 + r : u0 + r * nw; };
     uint4 wb[R][CPL];
-    auto load_rows = [&](int n0) {
+    auto load_rows = [&](int u0) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int n = n0 + r * nw;
+            const int n = row_of(u0, r);
             if (n < p.N) {
 #pragma unroll
                 for (int j = 0; j < CPL; ++j) wb[r][j] = ldg_nc_v4(p.w + (size_t)n * row_bytes + (size_t)(lane + 32 * j) * 16);
             }
         }
     };
-    load_rows(gw);
+    if (gw < units) load_rows(gw);
     grid_dep_wait();
     for (int i = threadIdx.x; i < MT * p.K / 16; i += blockDim.x) {
         const int m = i / (p.K / 16);
         reinterpret_cast<uint4*>(xs)[i] = m < p.M ? reinterpret_cast<const uint4*>(p.x)[i] : make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-    for (int n0 = gw; n0 < p.N; n0 += R * nw) {
-        if (n0 != gw) load_rows(n0);
+    for (int u0 = gw; u0 < units; u0 += (SILU ? 1 : R) * nw) {
+        if (u0 != gw) load_rows(u0);
+        float yv[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int n = n0 + r * nw;
+            const int n = row_of(u0, r);
+            yv[r] = 0.f;
             if (n >= p.N) break;
             int32_t acc[MT];
 #pragma unroll
@@ -161,13 +169,22 @@ __global__ void __launch_bounds__(kGemvWarps * 32, 2) gemv_w4a8_pre_kernel(const
 #pragma unroll
                 for (int m = 1; m < MT; ++m) if (lane == m) s = acc[m];
                 float y = __fmul_rn(__fmul_rn((float)(s >> 4), p.s_x[lane]), p.s_w[n]);
-                if (p.bias) {
-                    y = __fadd_rn(y, p.bf16_out ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n])
-                                                : __half2float(reinterpret_cast<const __half*>(p.bias)[n]));
+                if (SILU) {
+                    yv[r] = y;
+                } else {
+                    if (p.bias) {
+                        y = __fadd_rn(y, p.bf16_out ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n])
+                                                    : __half2float(reinterpret_cast<const __half*>(p.bias)[n]));
+                    }
+                    if (p.bf16_out) reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)lane * p.N + n] = __float2bfloat16_rn(y);
+                    else reinterpret_cast<__half*>(p.out)[(size_t)lane * p.N + n] = __float2half_rn(y);
                 }
-                if (p.bf16_out) reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)lane * p.N + n] = __float2bfloat16_rn(y);
-                else reinterpret_cast<__half*>(p.out)[(size_t)lane * p.N + n] = __float2half_rn(y);
             }
+        }
+        if (SILU && lane < MT && lane < p.M) {
+            const float g = __half2float(__float2half_rn(yv[0]));
+            const __half act = __float2half_rn(g / (1.f + expf(-g)));
+            reinterpret_cast<__half*>(p.out)[(size_t)lane * (p.N / 2) + u0] = __hmul(act, __float2half_rn(yv[R - 1]));
         }
     }
 }

@@ -195,7 +195,7 @@ def gemm_w4a8(xq8, s_x, w_packed, s_w, bias=None, out_dtype=torch.float16, out=N
     m, k = xq8.shape
     n = w_packed.shape[0]
     _check_gemm(m, n, k, xq8, s_x, w_packed, s_w, bias, out, out_dtype)
-    CALLS.append(("gemm_w4a8", ("gemv" if m <= 2 and m * k <= 96 * 1024 else "split-k" if m <= 64 else
+    CALLS.append(("gemm_w4a8", ("gemv" if m <= 2 and m * k <= 96 * 1024 else "skinny" if m <= 32 and k % 128 == 0 else "split-k" if m <= 64 else
                                 "1sm-128" if m <= 128 else "2sm", m, n, k)))
     wq = O.unpack_i4(w_packed.numpy())
     acc = O.gemm_i4(xq8.numpy(), wq)

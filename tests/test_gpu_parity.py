@@ -652,7 +652,8 @@ def test_kernel_level_api(dev):
                                          (5, 256, 128, 16, 16), (2, 4096, 1000, 64, 64), (2, 14336, 4096, 112, 128), (9, 14336, 4096, 112, 128),
                                          (17, 4096, 4096, 64, 64), (40, 4096, 28672, 64, 64)])
 def test_decode_split_k_path(ops, dev, m, k, n, n1, n2):
-    """Decode shapes: M <= 2 -> dp4a GEMV kernel, M <= 64 -> split-K tensor-core route (int32 atomics + finalize);
+    """Decode shapes: M <= 2 -> dp4a GEMV kernel, M <= 32 -> weight-streaming mma.sync kernel (gemm_w4a8_skinny.cuh),
+    M <= 64 -> split-K tcgen05 route (int32 atomics + finalize);
     results must be identical to the
     oracle arithmetic on the kernel's own codes, and run-to-run deterministic (integer atomics commute)."""
     torch.manual_seed(m + n)
@@ -778,12 +779,14 @@ def test_empty_and_maximum_shapes(ops, dev):
     assert np.abs(acc).max() < 2 ** 24  # the folded-shift fast path of the epilogue is exact only below this
 
 
-@pytest.mark.parametrize("k", [2048, 4096, 5120, 7168, 8192, 14336])
-@pytest.mark.parametrize("m", [1, 2])
-def test_decode_gemv_register_resident_rows_bit_exact(ops, dev, m, k):
-    """The one / two token GEMV (csrc/gemv_w4a8.cuh): the register-resident variant that requests its first weight rows
-    before the PDL wait (K a multiple of 1024 among the instantiated widths) and the generic one (K = 2048) against the
-    integer arithmetic of the path, bit for bit; N ragged against the grid (rows per warp not uniform), with bias."""
+@pytest.mark.parametrize("k", [2048, 2176, 4096, 5120, 7168, 8192, 14336])
+@pytest.mark.parametrize("m", [1, 2, 3, 8, 9, 16, 17, 31, 32])
+def test_decode_gemv_and_skinny_gemm_bit_exact(ops, dev, m, k):
+    """One / two tokens: the GEMV (csrc/gemv_w4a8.cuh) -- the register-resident variant that requests its first weight
+    rows before the PDL wait (K a multiple of 1024 among the instantiated widths) and the generic one (K = 2048, 2176);
+    3..32 tokens: the weight-streaming mma.sync.m16n8k32 kernel (csrc/gemm_w4a8_skinny.cuh; 1, 2 and 4 eight-token
+    blocks, K = 2176 = 17 super-steps leaves its warps uneven).  Against the integer arithmetic of the path, bit for
+    bit; N ragged against the grid / the 16-row tile, with bias."""
     torch.manual_seed(m * 100003 + k)
     n = 4100 if k != 4096 else 28672 + 8
     xq8 = torch.randint(-8, 8, (m, k), dtype=torch.int8, device=dev)

@@ -19,7 +19,8 @@ GPU_VERIFIED = {
                "test_left_only_transform_on_the_tcgen05_kernel (o_proj over 16 / 32 / 64 heads x 128)",
     "rowquant": "test_gpu_parity.py::test_quantize_rows_deploy_semantics, test_empty_and_maximum_shapes",
     "gemv": "test_gpu_parity.py::test_decode_split_k_path[m=1,2]",
-    "split-k": "test_gpu_parity.py::test_decode_split_k_path[m=5..64]",
+    "skinny": "test_gpu_parity.py::test_decode_gemv_and_skinny_gemm_bit_exact[m=3..32], test_decode_split_k_path[m=5..17]",
+    "split-k": "test_gpu_parity.py::test_decode_split_k_path[m=40,64]",
     "1sm-128": "test_gpu_parity.py::test_gemm_i4_exact[(100,200,192),(128,256,4096)], __graft_entry__.smoke (96 tokens)",
     "2sm": "test_gpu_parity.py::test_prefill_gemm_variants_bit_identical, __graft_entry__.smoke (320 tokens)",
     "kv_quant": "test_gpu_parity.py::test_kv_quant_golden_bit_exact, test_paged_kv_append_and_decode",
@@ -58,9 +59,9 @@ def test_llama_stack_kernel_configurations(monkeypatch):
         _, cache = model(ids[:, :-1], max_length=ids.shape[1])
         model(ids[:, -1:], past_key_values=cache)
     used = _classes(cpu_ops.CALLS)
-    # prefill 30 tokens -> split-K GEMM route, decode 2 tokens -> GEMV; (16,32) / (32,32) / padded (4,128)+identity
+    # prefill 30 tokens -> weight-streaming mma.sync GEMM (gemm_w4a8_skinny.cuh), decode 2 tokens -> GEMV; (16,32) / (32,32) / padded (4,128)+identity
     # Kronecker pairs on the HMMA kernel; K.T_k and Q.T_k^-T as right-only 128x128 transforms; paged INT4 KV
-    assert used == {"hmma two-factor", "hmma right-only", "split-k", "gemv", "kv_quant", "kv_decode_i4"}, used
+    assert used == {"hmma two-factor", "hmma right-only", "skinny", "gemv", "kv_quant", "kv_decode_i4"}, used
     assert used <= set(GPU_VERIFIED)
     configs = {cfg for op, cfg in cpu_ops.CALLS if op == "act_quant"}
     assert configs == {("hmma", 16, 32, True, True), ("hmma", 4, 128, True, True), ("hmma", 32, 32, True, True)}, configs
@@ -97,6 +98,6 @@ def test_deepseek_block_kernel_configurations(monkeypatch):
         block(x[:, :-1], 0, cos[:-1], sin[:-1])
         block(x[:, -1:], x.shape[1] - 1, cos[-1:], sin[-1:])
     used = _classes(cpu_ops.CALLS)
-    assert used == {"hmma two-factor", "split-k", "gemv"}, used
+    assert used == {"hmma two-factor", "skinny", "gemv"}, used
     configs = {cfg[1:3] for op, cfg in cpu_ops.CALLS if op == "act_quant"}
     assert configs == {(16, 16), (8, 16)}, configs  # dim 256; q_lora / wo / moe_inter 128
