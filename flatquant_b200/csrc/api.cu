@@ -476,12 +476,37 @@ static bool skinny_ok(int64_t M, int64_t N, int64_t K, const void* x, const void
     return !off && M >= 1 && M <= 32 && K % 128 == 0 && N >= 1 && aligned16(x) && aligned16(w);
 }
 
+template <int NB, bool SILU, bool XS>
+cudaError_t launch_skinny_nb(const GemvParams& g, cudaStream_t st) {
+    auto kern = gemm_w4a8_skinny_kernel<NB, SILU, XS>;
+    const size_t smem = (size_t)skinny_red_bytes<NB>() + (XS ? (size_t)NB * 8 * (g.K + 16) : 0);
+    static PerDeviceOnce attr;
+    if (attr.first_time()) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    int per_sm = 0;   // resident CTAs per SM (registers and this call's shared memory decide): the grid is one wave
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSkinnyWarps * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t tiles = (g.N + kSkinnyRows - 1) / kSkinnyRows, cap = (int64_t)per_sm * num_sms();
+    return launch_pdl(kern, dim3((unsigned)(tiles < cap ? tiles : cap)), dim3(kSkinnyWarps * 32), smem, st, g);
+}
+
+template <int NB, bool SILU>
+cudaError_t launch_skinny_xs(const GemvParams& g, cudaStream_t st) {
+    // staging the codes costs every CTA one pass over them: worth it from ~3 row tiles per CTA on (gate/up: 1792 tiles on
+    // 296 CTAs, 21.5 -> 15.8 us at 16 tokens; qkv / o with 384 / 256 tiles lose 0.7-1.4 us to it)
+    const int64_t tiles = (g.N + kSkinnyRows - 1) / kSkinnyRows;
+    const bool xs = (size_t)skinny_red_bytes<NB>() + (size_t)NB * 8 * (g.K + 16) <= 200 * 1024 && tiles >= 6 * (int64_t)num_sms();
+    return xs ? launch_skinny_nb<NB, SILU, true>(g, st) : launch_skinny_nb<NB, SILU, false>(g, st);
+}
+
 template <bool SILU>
 cudaError_t launch_skinny(const GemvParams& g, cudaStream_t st) {
-    const dim3 grid((unsigned)((g.N + kSkinnyRows - 1) / kSkinnyRows)), block(kSkinnyWarps * 32);
-    if (g.M <= 8) return launch_pdl(gemm_w4a8_skinny_kernel<1, SILU>, grid, block, 0, st, g);
-    if (g.M <= 16) return launch_pdl(gemm_w4a8_skinny_kernel<2, SILU>, grid, block, 0, st, g);
-    return launch_pdl(gemm_w4a8_skinny_kernel<4, SILU>, grid, block, 0, st, g);
+    if (g.M <= 8) return launch_skinny_xs<1, SILU>(g, st);
+    if (g.M <= 16) return launch_skinny_xs<2, SILU>(g, st);
+    return launch_skinny_xs<4, SILU>(g, st);
 }
 
 template <int MT, int CPL, int R, int MINB, bool SILU = false>
@@ -798,9 +823,9 @@ int flatq_gemm_w4a8_silu(const int8_t* xq8, const float* s_x, const uint8_t* w_p
 #define FLATQ_GEMV_SILU(CPL, MINB)                                                                                      \
     case CPL * 10 + 1: FLATQ_CUDA((launch_gemv_pre<1, CPL, 2, MINB, true>(ctas, smem, st, g))); return FLATQ_OK;        \
     case CPL * 10 + 2: FLATQ_CUDA((launch_gemv_pre<2, CPL, 2, MINB, true>(ctas, smem, st, g))); return FLATQ_OK;
-            FLATQ_GEMV_SILU(4, 4)    // hidden 4096
-            FLATQ_GEMV_SILU(5, 3)    // 5120
-            FLATQ_GEMV_SILU(8, 2)    // 8192
+            FLATQ_GEMV_SILU(4, 3)    // hidden 4096
+            FLATQ_GEMV_SILU(5, 2)    // 5120
+            FLATQ_GEMV_SILU(8, 1)    // 8192
 #undef FLATQ_GEMV_SILU
             default: break;
         }
@@ -1055,11 +1080,16 @@ int flatq_kv_fused(const void* q, const void* k, const void* v, int64_t ld_q, in
     p.q_out = reinterpret_cast<__half*>(q_out); p.k_out = reinterpret_cast<__half*>(k_out);
     p.kv_data = kv_data; p.kv_param = reinterpret_cast<__half*>(kv_param); p.slot = slot;
     p.layer = layer; p.n_layers = n_layers; p.page_size = page_size;
-    p.q_blocks = (int)((tokens * q_heads + kKvfRows - 1) / kKvfRows);
-    p.k_blocks = (int)((tokens * kv_heads + kKvfRows - 1) / kKvfRows);
+    // a decode step has a few hundred rows: spread them over the chip in 2-warp CTAs instead of stacking 8 latency chains
+    // on each of a handful of SMs (16 tokens of Llama-3-8B: 6 CTAs of 8 warps -> 24 of 2; measured 19 -> see DESIGN.md 6)
+    const int64_t tiles = (tokens * (q_heads + 2 * (int64_t)kv_heads) + 15) / 16;
+    const int warps = tiles <= 2 * num_sms() ? 2 : tiles <= 4 * num_sms() ? 4 : 8;
+    p.rows_per_cta = 16 * warps;
+    p.q_blocks = (int)((tokens * q_heads + p.rows_per_cta - 1) / p.rows_per_cta);
+    p.k_blocks = (int)((tokens * kv_heads + p.rows_per_cta - 1) / p.rows_per_cta);
     static PerDeviceOnce attr;
     if (attr.first_time()) FLATQ_CUDA(cudaFuncSetAttribute(kv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvfSmem));
-    FLATQ_CUDA(launch_pdl(kv_fused_kernel, dim3(p.q_blocks + 2 * p.k_blocks), dim3(kKvfThreads), (size_t)kKvfSmem, (cudaStream_t)stream, p));
+    FLATQ_CUDA(launch_pdl(kv_fused_kernel, dim3(p.q_blocks + 2 * p.k_blocks), dim3(32 * warps), (size_t)kKvfSmem, (cudaStream_t)stream, p));
     return FLATQ_OK;
 }
 
@@ -1113,8 +1143,10 @@ int flatq_kv_decode_i4_split(const void* q, void* o, const uint8_t* kv_data, con
         // tensor-core variant (decode_attn_mma.cuh): the query heads of a kv head are the rows of an m16n8k16 tile
         static const bool simt = getenv("FLATQ_DECODE_SIMT") != nullptr;   // A/B aid: the scalar online-softmax kernel
         if (!simt && G >= 2 && G <= 16) {   // G = 1 (no grouped queries): 15 of the tile's 16 rows would be padding; the scalar kernel wins
+            // splits: fill ONE wave of resident CTAs (2 per SM: registers) -- rounding the split count up would leave a
+            // second, mostly empty wave (16 x 8 heads: 3 splits = 384 CTAs on 296 slots)
             const int64_t base = (int64_t)batch * kv_heads;
-            int64_t splits = (2 * (int64_t)num_sms() + base - 1) / base;
+            int64_t splits = (2 * (int64_t)num_sms()) / base;
             if (max_tokens_hint > 0) {   // no split shorter than one 32-token tile per warp
                 const int64_t by_len = ((int64_t)max_tokens_hint + kDmWarps * kDmTile - 1) / (kDmWarps * kDmTile);
                 if (splits > by_len) splits = by_len;

@@ -130,17 +130,14 @@ __global__ void __launch_bounds__(kGemvWarps * 32, MINB) gemv_w4a8_pre_kernel(co
         reinterpret_cast<uint4*>(xs)[i] = m < p.M ? reinterpret_cast<const uint4*>(p.x)[i] : make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-    for (int u0 = gw; u0 < units; u0 += (SILU ? 1 : R) * nw) {
-        if (u0 != gw) load_rows(u0);
-        float yv[R];
+    const int stride = (SILU ? 1 : R) * nw;
+    for (int u0 = gw; u0 < units; u0 += stride) {
+        int32_t acc[R][MT];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int n = row_of(u0, r);
-            yv[r] = 0.f;
-            if (n >= p.N) break;
-            int32_t acc[MT];
 #pragma unroll
-            for (int m = 0; m < MT; ++m) acc[m] = 0;
+            for (int m = 0; m < MT; ++m) acc[r][m] = 0;
+            if (row_of(u0, r) >= p.N) break;
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
                 const uint32_t pw[4] = {wb[r][j].x, wb[r][j].y, wb[r][j].z, wb[r][j].w};
@@ -150,24 +147,32 @@ __global__ void __launch_bounds__(kGemvWarps * 32, MINB) gemv_w4a8_pre_kernel(co
                     const uint4 x0 = *reinterpret_cast<const uint4*>(xs + (size_t)m * p.K + (size_t)c * 32);
                     const uint4 x1 = *reinterpret_cast<const uint4*>(xs + (size_t)m * p.K + (size_t)c * 32 + 16);
                     const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-                    int32_t a = acc[m];
+                    int32_t a = acc[r][m];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         a = __dp4a((int)((pw[q] << 4) & 0xF0F0F0F0u), (int)xw[2 * q], a);
                         a = __dp4a((int)(pw[q] & 0xF0F0F0F0u), (int)xw[2 * q + 1], a);
                     }
-                    acc[m] = a;
+                    acc[r][m] = a;
                 }
             }
+        }
+        if (u0 + stride < units) load_rows(u0 + stride);   // the next rows are in flight under the reduction and the epilogue
+        float yv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int n = row_of(u0, r);
+            yv[r] = 0.f;
+            if (n >= p.N) break;
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+                for (int o = 16; o > 0; o >>= 1) acc[r][m] += __shfl_xor_sync(0xffffffffu, acc[r][m], o);
             }
             if (lane < MT && lane < p.M) {
-                int32_t s = acc[0];
+                int32_t s = acc[r][0];
 #pragma unroll
-                for (int m = 1; m < MT; ++m) if (lane == m) s = acc[m];
+                for (int m = 1; m < MT; ++m) if (lane == m) s = acc[r][m];
                 float y = __fmul_rn(__fmul_rn((float)(s >> 4), p.s_x[lane]), p.s_w[n]);
                 if (SILU) {
                     yv[r] = y;

@@ -33,6 +33,7 @@ struct KvFusedParams {
     uint8_t* kv_data; __half* kv_param; const int* slot; // paged INT4 cache (qattention.cuh layout), slot[token]
     int layer, n_layers, page_size;
     int q_blocks, k_blocks;                              // CTAs [0, q_blocks): q rows; [q_blocks, q_blocks + k_blocks): k; rest: v
+    int rows_per_cta;                                    // 16 rows per warp x 2 / 4 / 8 warps (decode steps: few rows, many small CTAs)
 };
 
 constexpr int kKvfRows = 128, kKvfThreads = 256, kKvfLd = 128 + 8;   // smem row stride in halves (ldmatrix bank spread)
@@ -104,13 +105,16 @@ kv_fused_kernel(const KvFusedParams p) {
 
     grid_dep_launch();   // PDL trigger first: the attention kernel behind this one becomes resident early
     if (T) {   // static weights: before the dependency wait; the thread's 8 loads are issued before the first store
-        uint4 tv[8];
+#pragma unroll 1
+        for (int i0 = threadIdx.x; i0 < 128 * 16; i0 += 8 * blockDim.x) {   // blockDim = 64 / 128 / 256: whole batches of 8
+            uint4 tv[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) tv[u] = __ldg(reinterpret_cast<const uint4*>(T) + threadIdx.x + u * kKvfThreads);
+            for (int u = 0; u < 8; ++u) tv[u] = __ldg(reinterpret_cast<const uint4*>(T) + i0 + u * blockDim.x);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = threadIdx.x + u * kKvfThreads, r = i >> 4, c = (i & 15) * 8;
-            *reinterpret_cast<uint4*>(Ts + r * kKvfLd + c) = tv[u];
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * blockDim.x, r = i >> 4, c = (i & 15) * 8;
+                *reinterpret_cast<uint4*>(Ts + r * kKvfLd + c) = tv[u];
+            }
         }
     }
     grid_dep_wait();
@@ -119,7 +123,7 @@ kv_fused_kernel(const KvFusedParams p) {
     // The warp's 16 rows are walked in groups of four (loads of a group in flight together, shuffle chains of its rows
     // overlapping); the loops over the groups are NOT unrolled: the first version of this kernel was 11 k straight-line
     // instructions and was bound by instruction fetch (ncu: 32 % of the stalls "no instruction").
-    const int row0 = blk * kKvfRows + warp * 16;
+    const int row0 = blk * p.rows_per_cta + warp * 16;   // rows_per_cta = 16 x the CTA's warps
     __half* Aw = As + warp * 16 * kKvfLd;
     const int t_first = row0 / heads, h_first = row0 - t_first * heads;   // (token, head) advance by increment
 

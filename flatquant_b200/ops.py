@@ -374,8 +374,17 @@ def _rows_view(t: torch.Tensor, heads: int):
     (a column slice of the fused qkv GEMM output) -> (t, token stride in elements); anything else is copied."""
     d = t.shape[-1]
     if t.stride(-1) == 1 and t.stride(-2) == d and t.dim() in (3, 4):
-        ld = t.stride(-3)
-        if ld % 4 == 0 and ld >= heads * d and (t.dim() == 3 or t.shape[0] == 1 or t.stride(0) == t.shape[1] * ld):
+        # the stride of a size-1 dimension is arbitrary ([b, 1, H, 128] decode views of a [b, N] GEMM output carry the
+        # dense value there): take the token stride from the dimension that actually steps
+        if t.dim() == 3 or t.shape[0] == 1:
+            ld, even = t.stride(-3), True
+        elif t.shape[1] == 1:
+            ld, even = t.stride(0), True
+        else:
+            ld, even = t.stride(1), t.stride(0) == t.shape[1] * t.stride(1)
+        if t.numel() // (heads * d) == 1:
+            ld = max(ld, heads * d)
+        if even and ld % 4 == 0 and ld >= heads * d:
             return t, ld
     return t.reshape(-1, heads, d).contiguous(), heads * d
 

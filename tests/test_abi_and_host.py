@@ -277,3 +277,22 @@ def test_weight_quantizer_asym_clamps_the_range_before_dividing():
     lo, hi = torch.tensor([0.0, -1.0, -1.0]), torch.tensor([3e-6, 1.0, 1.0])
     want = (hi - lo).clamp(min=1e-5) / 15
     assert torch.equal(q.scale.reshape(-1), want) and torch.equal(q.zero.reshape(-1), torch.round(-lo / want))
+
+
+def test_kv_fused_reads_decode_views_of_the_qkv_output_in_place():
+    """ops._rows_view: the [b, 1, H, 128] views a batched decode step takes of the fused qkv GEMM output [b, N] must be read
+    in place (the size-1 token dimension carries an arbitrary stride); a copy here was three extra launches per layer."""
+    import torch
+    from flatquant_b200.ops import _rows_view
+    y = torch.zeros(16, 6144, dtype=torch.float16)
+    for t, h in zip(torch.split(y, [4096, 1024, 1024], dim=-1), (32, 8, 8)):
+        r = t.reshape(16, 1, h, 128)
+        got, ld = _rows_view(r, h)
+        assert got.data_ptr() == r.data_ptr() and ld == 6144
+    y = torch.zeros(10, 6144, dtype=torch.float16)
+    q = y[:, :4096].reshape(2, 5, 32, 128)                       # prefill, two sequences: evenly strided tokens
+    got, ld = _rows_view(q, 32)
+    assert got.data_ptr() == q.data_ptr() and ld == 6144
+    odd = torch.zeros(2, 7, 6144, dtype=torch.float16)[:, :5, :4096].reshape(2, 5, 32, 128)   # batch stride != s * token stride
+    got, ld = _rows_view(odd, 32)
+    assert got.is_contiguous() and ld == 4096 and got.data_ptr() != odd.data_ptr()

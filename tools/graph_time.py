@@ -110,4 +110,34 @@ if "side" in which:
                 y = torch.empty(tokens, nn, dtype=torch.float16, device=dev)
                 us_t = graph_us(lambda i: ops.act_quant(x, Lm, Rm, n1, n2, 0.98, 0.98, out=out))
                 us_g = graph_us(lambda i: ops.gemm_w4a8(out[0], out[1], ws[i % 16], sw, out=y))
-                print(f"  M={tokens} {kk}->{nn}: transform {us_t:6.2f} us, GEMV/GEMM {us_g:6.2f} us (weight stream floor {kk * nn / 2 / 6.544e6:5.2f} us)", flush=True)
+                us_c = graph_us(lambda i: ops.gemm_w4a8(*ops.act_quant(x, Lm, Rm, n1, n2, 0.98, 0.98, out=out), ws[i % 16], sw, out=y))
+                extra = ""
+                if nn == 28672:
+                    ya = torch.empty(tokens, nn // 2, dtype=torch.float16, device=dev)
+                    us_s = graph_us(lambda i: ops.gemm_w4a8_silu(out[0], out[1], ws[i % 16], sw, out=ya))
+                    us_m = graph_us(lambda i: ops.silu_mul(y))
+                    extra = f", GEMM+SiLU in one launch {us_s:6.2f} us (separate silu_mul {us_m:5.2f} us)"
+                print(f"  M={tokens} {kk}->{nn}: transform {us_t:6.2f} us, GEMV/GEMM {us_g:6.2f} us, chained (PDL) {us_c:6.2f} us "
+                      f"(weight stream floor {kk * nn / 2 / 6.544e6:5.2f} us){extra}", flush=True)
+
+if "kvf" in which:
+    # kv_fused alone over decode batch sizes, with parts switched off (what scales with the number of tokens?)
+    D, HQ, HKV, L = 128, 32, 8, 1
+    P = 4096
+    ang = torch.arange(P, device=dev)[:, None].float() * (1.0 / 500000.0 ** (torch.arange(0, D, 2, device=dev).float() / D))[None]
+    emb = torch.cat((ang, ang), -1)
+    cos_t, sin_t = emb.cos().half(), emb.sin().half()
+    t_k = (torch.eye(D, device=dev) * 0.75 + torch.randn(D, D, device=dev) * (0.5 / D ** 0.5)).half()
+    t_q = torch.linalg.inv(t_k.double()).t().float().half().contiguous()
+    ps = 2048 + 64
+    for b in (1, 2, 4, 8, 16, 32):
+        qkv = torch.randn(b, (HQ + 2 * HKV) * D, device=dev).half()
+        q, k, v = (t.reshape(b, 1, -1, D) for t in torch.split(qkv.view(b, 1, -1), [HQ * D, HKV * D, HKV * D], dim=-1))
+        pos = torch.full((b,), 2048, device=dev).int()
+        pages = torch.zeros(b, L, 2, HKV, ps, D // 2, dtype=torch.uint8, device=dev)
+        params = torch.zeros(b, L, 2, HKV, ps, 2, dtype=torch.float16, device=dev)
+        slot = (torch.arange(b, device=dev) * ps + 2048).int()
+        full = graph_us(lambda i: ops.kv_fused(q, k, v, cos_t, sin_t, pos, t_q, t_k, pages, params, slot, 0))
+        norope = graph_us(lambda i: ops.kv_fused(q, k, v, None, None, None, t_q, t_k, pages, params, slot, 0))
+        not_ = graph_us(lambda i: ops.kv_fused(q, k, v, cos_t, sin_t, pos, None, None, pages, params, slot, 0))
+        print(f"kv_fused bsz={b}: {full:6.2f} us, without RoPE {norope:6.2f}, without transforms {not_:6.2f}", flush=True)
