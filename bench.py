@@ -356,8 +356,8 @@ def measure_model(args, rank, world, dev, dist, barrier, steps, sample_clocks=Tr
     cfg = FlatQuantLlamaConfig.llama3_8b(num_hidden_layers=args.layers)
     model = FlatQuantLlamaForCausalLM.random_init(cfg, dev, seed=1234 + rank)
     counted = {"n": 0}
-    undo = _count_ops(ops, ("act_quant", "gemm_w4a8", "kron_transform", "kv_quant", "kv_decode_i4", "hadamard", "rmsnorm",
-                            "rope_", "silu_mul"), counted)
+    undo = _count_ops(ops, ("act_quant", "gemm_w4a8", "gemm_w4a8_silu", "kron_transform", "kv_quant", "kv_fused", "kv_decode_i4",
+                            "hadamard", "rmsnorm", "add_rmsnorm", "rope_", "silu_mul"), counted)
     try:
         gen = torch.Generator().manual_seed(rank)
         ids_host = torch.randint(100, 200, (1, SEQ), generator=gen).pin_memory()  # benchmark_model.py:281

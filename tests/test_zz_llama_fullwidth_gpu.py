@@ -26,6 +26,12 @@ FULLWIDTH_STAGE_TOL = (0.042, 0.026)
 # vs that CPU rounding-point model, stage by stage on the same inputs: only the summation order inside the tensor cores
 # differs (measured: max <= 0.9 %, mean <= 0.012 % of max|y| -- a handful of +-1 code flips per stage)
 MODEL_TOL = (0.02, 0.0005)
+# o_proj alone sits behind the causal attention, which is library code on both sides (torch SDPA: a flash kernel on the GPU,
+# the math path on the CPU) and is not modelled rounding point by rounding point: its fp16-ulp differences move a few more
+# activation codes of the o_proj input.  Measured 1.06 % / 0.070 % -- the same figures with the legacy HMMA transform, with
+# PDL off, with the tcgen05 split-K GEMM instead of the weight-streaming one and with the torch glue (FLATQ_KRON_HMMA,
+# FLATQ_NO_PDL, FLATQ_NO_SKINNY, FLATQ_FUSED_GLUE=0), i.e. independent of this repo's kernel variants.
+MODEL_TOL_BEHIND_SDPA = (0.02, 0.0015)
 
 
 @pytest.fixture(scope="module")
@@ -74,7 +80,8 @@ def test_full_width_layer_every_stage_teacher_forced(model, g, dev):
         d = np.abs(got[key] - want[key])
         mx, mean = float(d.max() / np.abs(want[key]).max()), float(d.mean() / np.abs(want[key]).max())
         print(key, f"vs CPU rounding-point model: max {mx:.4f} mean {mean:.6f}")
-        assert mx < MODEL_TOL[0] and mean < MODEL_TOL[1], (key, mx, mean)
+        tol = MODEL_TOL_BEHIND_SDPA if key[1] == "o_proj" else MODEL_TOL
+        assert mx < tol[0] and mean < tol[1], (key, mx, mean)
 
 
 def test_full_width_layer_end_to_end(model, g, dev):

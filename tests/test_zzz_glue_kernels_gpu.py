@@ -75,7 +75,8 @@ def test_silu_mul_matches_the_torch_expression(dev, rows, inter):
 
 @pytest.mark.parametrize("m,inter,k", [(1, 512, 512), (16, 1032, 512), (100, 1024, 1024), (129, 1032, 512), (300, 520, 2048),
                                        (2048, 14336, 4096), (1, 14336, 4096), (2, 1032, 4096), (2, 520, 5120), (1, 1024, 8192),
-                                       (2, 14336, 4096), (1, 72, 7168)])
+                                       (2, 14336, 4096), (1, 72, 7168), (8, 14336, 4096), (16, 14336, 4096), (32, 14336, 4096),
+                                       (16, 14344, 4096)])
 def test_gate_up_gemm_with_silu_epilogue_is_bit_identical_to_gemm_then_silu_mul(dev, m, inter, k):
     """flatq_gemm_w4a8_silu on row-interleaved [gate; up] weights == flatq_gemm_w4a8 on the concatenated weights followed
     by flatq_silu_mul, bit for bit (same fp16 rounding of the GEMM output, same fp32 SiLU, same fp16 product): the
