@@ -617,9 +617,11 @@ def measure_qattention(dev, barrier):
     out = {}
 
     def t_us(fn, reps=20):
+        # best of three timed regions: the first region after an allocation / an idle gap has come out 10-20x slow on some
+        # boxes (clock ramp after idling; seen on whichever sub-measurement ran first), a property of the box, not the kernel
         for _ in range(5):
             fn()
-        return timed(lambda: [fn() for _ in range(reps)], 1, barrier) * 1e3 / reps
+        return min(timed(lambda: [fn() for _ in range(reps)], 1, barrier) for _ in range(3)) * 1e3 / reps
     spin = torch.randn(4096, 4096, device=dev, dtype=torch.float16)   # the sub-benchmarks before this one end with frees and
     for _ in range(50):                                                # idle gaps: bring the clocks back up before timing
         spin = (spin @ spin).clamp_(-1, 1)                             # microsecond-scale kernels

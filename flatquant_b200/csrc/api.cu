@@ -997,6 +997,24 @@ int flatq_hadamard(const void* x, void* out, int64_t rows, int n, float scale, f
     FLATQ_CHECK(rows > 0 && aligned16(x) && aligned16(out), FLATQ_ERR_INVALID, "hadamard: rows / alignment");
     int log_n = 0;
     while ((1 << log_n) < n) ++log_n;
+    if (n <= 256) {   // a row in 1..32 lanes of a warp, no shared memory
+        const int lanes = n / 8;
+        const int64_t warps = (rows + 32 / lanes - 1) / (32 / lanes);
+        const dim3 grid((unsigned)grid_for((size_t)warps * 32, 256, 8)), block(256);
+        const __half* xi = reinterpret_cast<const __half*>(x);
+        __half* oo = reinterpret_cast<__half*>(out);
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (lanes) {
+            case 1: fht_warp_kernel<1><<<grid, block, 0, st>>>(xi, oo, rows, scale); break;
+            case 2: fht_warp_kernel<2><<<grid, block, 0, st>>>(xi, oo, rows, scale); break;
+            case 4: fht_warp_kernel<4><<<grid, block, 0, st>>>(xi, oo, rows, scale); break;
+            case 8: fht_warp_kernel<8><<<grid, block, 0, st>>>(xi, oo, rows, scale); break;
+            case 16: fht_warp_kernel<16><<<grid, block, 0, st>>>(xi, oo, rows, scale); break;
+            default: fht_warp_kernel<32><<<grid, block, 0, st>>>(xi, oo, rows, scale); break;
+        }
+        FLATQ_CUDA(cudaGetLastError());
+        return FLATQ_OK;
+    }
     // threads per row: one per 8 elements (at least 8); short rows share a CTA of 256 threads
     const int tpr = n / 8 < 8 ? 8 : (n / 8 > 1024 ? 1024 : n / 8);
     int rpc = tpr >= 256 ? 1 : 256 / tpr;
@@ -1007,7 +1025,11 @@ int flatq_hadamard(const void* x, void* out, int64_t rows, int n, float scale, f
     if (smem > 48 * 1024 && attr.grows(smem))
         FLATQ_CUDA(cudaFuncSetAttribute(fht_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ctas = (rows + rpc - 1) / rpc;
-    const int64_t cap = (int64_t)num_sms() * (n <= 1024 ? 8 : 2);
+    // one wave of resident CTAs: several rows per SM in flight hide each row's load -> passes -> store chain
+    int64_t per_sm = 2048 / threads;
+    if ((int64_t)(200 * 1024 / (smem + 1024)) < per_sm) per_sm = (int64_t)(200 * 1024 / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t cap = (int64_t)num_sms() * per_sm;
     fht_kernel<<<(int)(ctas < cap ? ctas : cap), threads, smem, (cudaStream_t)stream>>>(
         reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), (int)rows, n, log_n, scale, tpr);
     FLATQ_CUDA(cudaGetLastError());

@@ -253,6 +253,29 @@ gemm_w4a8_2sm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
                     for (int j = 0; j < COLS; j += 4) {
                         const float4 s4 = *reinterpret_cast<const float4*>(&sx_s[c0 + j]);
                         const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+                        if (MODE == kEpiF16 && p.silu_pairs) {
+                            // Lanes (2k, 2k + 1) hold (gate_k, up_k) of every token.  Tokens go two at a time: the even lane
+                            // finishes token j + i (it receives that token's `up`), the odd lane token j + i + 1 (it receives
+                            // that token's `gate`) -- ONE exchange and ONE SiLU per lane and token pair, all lanes busy.
+                            const bool odd = (lane & 1) != 0;
+#pragma unroll
+                            for (int i = 0; i < 4; i += 2) {
+                                uint16_t hh[2];
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const int32_t a = FOLD ? static_cast<int32_t>(r[j + i + e]) : static_cast<int32_t>(r[j + i + e]) >> p.acc_shift;
+                                    hh[e] = __half_as_ushort(__float2half_rn(__fmul_rn(__fmul_rn((float)a, sv[i + e]), sw_n)));
+                                }
+                                const uint32_t recv = __shfl_xor_sync(0xffffffffu, (uint32_t)(odd ? hh[0] : hh[1]), 1);
+                                const uint16_t g16 = odd ? (uint16_t)recv : hh[0], u16 = odd ? hh[1] : (uint16_t)recv;
+                                const float gf = __half2float(__ushort_as_half(g16));
+                                const __half s = __float2half_rn(gf / (1.f + expf(-gf)));            // F.silu: fp32 math, fp16 result
+                                const uint16_t o16 = __half_as_ushort(__hmul(s, __ushort_as_half(u16)));   // * up, rounded to fp16
+                                if (j + i + (odd ? 1 : 0) < j_end) out16[idx + (odd ? (uint32_t)(p.N >> 1) : 0u)] = o16;
+                                idx += (uint32_t)p.N;   // two tokens of N / 2 columns
+                            }
+                            continue;
+                        }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int32_t a = FOLD ? static_cast<int32_t>(r[j + i]) : static_cast<int32_t>(r[j + i]) >> p.acc_shift;
@@ -262,15 +285,6 @@ gemm_w4a8_2sm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
                             uint16_t h;
                             if (MODE == kEpiF16) h = __half_as_ushort(__float2half_rn(y));
                             else h = __bfloat16_as_ushort(__float2bfloat16_rn(y));
-                            if (MODE == kEpiF16 && p.silu_pairs) {   // warp-uniform; every lane takes part in the exchange
-                                const uint32_t up = __shfl_xor_sync(0xffffffffu, (uint32_t)h, 1);
-                                const float gf = __half2float(__ushort_as_half(h));
-                                const __half s = __float2half_rn(gf / (1.f + expf(-gf)));          // F.silu: fp32 math, fp16 result
-                                h = __half_as_ushort(__hmul(s, __ushort_as_half((uint16_t)up)));    // * up, rounded to fp16
-                                if (j + i < j_end && !(lane & 1)) out16[idx] = h;
-                                idx += (uint32_t)(p.N >> 1);
-                                continue;
-                            }
                             if (j + i < j_end) out16[idx] = h;
                             idx += (uint32_t)p.N;
                         }

@@ -90,6 +90,60 @@ __global__ void __launch_bounds__(1024) fht_kernel(const __half* __restrict__ x,
     }
 }
 
+// Short rows (n = 8 LANES <= 256: the 128-wide K / Q head transform of the Hadamard baseline mode): no shared memory and
+// no barrier -- a row lives in LANES lanes of a warp, 8 consecutive elements (one 16-byte access) per lane; butterflies
+// over index bits 0-2 in registers, over the higher bits by shuffles.  Same butterfly order (bit 0 upwards) and the same
+// fp32 operations as fht_kernel: bit-identical results.
+template <int LANES>
+__global__ void __launch_bounds__(256) fht_warp_kernel(const __half* __restrict__ x, __half* __restrict__ out, long long rows, float scale) {
+    constexpr int RPW = 32 / LANES;   // rows per warp
+    const int lane = threadIdx.x & 31, sub = lane / LANES, l = lane % LANES;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r0 = ((((long long)blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * RPW; r0 < rows; r0 += warps * RPW) {   // warp-uniform
+        const long long row = r0 + sub;
+        const bool ok = row < rows;
+        float v[8];
+        {
+            uint4 raw = make_uint4(0, 0, 0, 0);
+            if (ok) raw = reinterpret_cast<const uint4*>(x + row * (8 * LANES))[l];
+            const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h[j]);
+                v[2 * j] = f.x;
+                v[2 * j + 1] = f.y;
+            }
+        }
+#pragma unroll
+        for (int h = 1; h < 8; h <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (!(j & h)) {
+                    const float a = v[j], b = v[j | h];
+                    v[j] = a + b;
+                    v[j | h] = a - b;
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 1; m < LANES; m <<= 1) {
+            const bool upper = (l & m) != 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float o = __shfl_xor_sync(0xffffffffu, v[j], m);
+                v[j] = upper ? o - v[j] : v[j] + o;   // (a + b) in the lower lane, (a - b) in the upper one
+            }
+        }
+        if (ok) {
+            uint4 o;
+            __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j] * scale, v[2 * j + 1] * scale);
+            reinterpret_cast<uint4*>(out + row * (8 * LANES))[l] = o;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ FHT, n = K * 2^m
 // matmul_hadU_cuda for the sizes that are not a power of two (deploy/functional/online_trans.py:144-151; the reference
 // runs hadamard_transform over the 2^m axis and then `hadK @ input`, a cuBLAS batched GEMM with an fp16 round trip

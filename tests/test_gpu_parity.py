@@ -803,3 +803,17 @@ def test_decode_gemv_and_skinny_gemm_bit_exact(ops, dev, m, k):
     acc = codes.view(m, k).float() @ wq.float().t()      # exact in fp32: |sum| <= 64 K < 2^24
     ref = ((acc * sx[:, None]) * sw[None, :] + bias.float()[None, :]).half()
     assert torch.equal(y, ref) and torch.equal(y, y2)
+
+
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256])
+def test_hadamard_short_rows_in_warp_lanes(ops, dev, n):
+    """n <= 256: a row lives in n / 8 lanes of a warp (fht_warp_kernel, no shared memory); ragged row counts (the last
+    warp is partly empty), against the oracle's transform, and an involution: H(H(x)) / n == x."""
+    torch.manual_seed(n)
+    for rows in (1, 37, 4099):
+        x = torch.randn(rows, n).half()
+        y = ops.hadamard(x.to(dev), 1.0 / n ** 0.5)
+        ref = O.hadamard_transform(x.float().numpy(), 1.0 / n ** 0.5)
+        assert np.abs(y.float().cpu().numpy() - ref).max() <= 2 ** -9 * max(1.0, np.abs(ref).max())
+        back = ops.hadamard(y, 1.0 / n ** 0.5).float().cpu()
+        assert float((back - x.float()).abs().max()) <= 2 ** -8 * max(1.0, float(x.float().abs().max()))
