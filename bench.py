@@ -330,12 +330,14 @@ def _init_dist(world, dev):
 
 
 def _count_ops(ops, names, counted):
-    """Wrap the named flatquant_b200.ops entry points with a launch counter; returns the undo function."""
+    """Wrap the named flatquant_b200.ops entry points with a launch counter; returns the undo function.
+    linear_fused / linear_fused_silu are two launches (transform + GEMM) except for the one or two tokens of a decode
+    step with a two-sided or one-sided Kronecker pair, where they are one (csrc/flatlinear_decode.cuh)."""
     saved = {n: getattr(ops, n) for n in names}
     for name, fn in saved.items():
-        def wrap(f):
+        def wrap(f, two=name.startswith("linear_fused")):
             def inner(*a, **k):
-                counted["n"] += 1
+                counted["n"] += 2 if two and a[0].numel() // a[0].shape[-1] > 2 else 1
                 return f(*a, **k)
             return inner
         setattr(ops, name, wrap(fn))
@@ -356,7 +358,8 @@ def measure_model(args, rank, world, dev, dist, barrier, steps, sample_clocks=Tr
     cfg = FlatQuantLlamaConfig.llama3_8b(num_hidden_layers=args.layers)
     model = FlatQuantLlamaForCausalLM.random_init(cfg, dev, seed=1234 + rank)
     counted = {"n": 0}
-    undo = _count_ops(ops, ("act_quant", "gemm_w4a8", "gemm_w4a8_silu", "kron_transform", "kv_quant", "kv_fused", "kv_decode_i4",
+    undo = _count_ops(ops, ("act_quant", "gemm_w4a8", "gemm_w4a8_silu", "linear_fused", "linear_fused_silu", "kron_transform", "kv_quant",
+                            "kv_fused", "kv_decode_i4",
                             "hadamard", "rmsnorm", "add_rmsnorm", "rope_", "silu_mul"), counted)
     try:
         gen = torch.Generator().manual_seed(rank)

@@ -41,6 +41,9 @@ SIGNATURES = {
     "flatq_gemm_w4a8_silu_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "flatq_gemm_w4a8_silu": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                      c_size_t, c_void_p]),
+    "flatq_linear_fused_silu_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "flatq_linear_fused_silu": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
+                                        c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "flatq_gemm_w4a8_grouped_workspace_bytes": (c_size_t, [c_int]),
     "flatq_gemm_w4a8_grouped": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
                                         c_int64, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),

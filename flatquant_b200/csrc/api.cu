@@ -18,6 +18,7 @@
 #include "gemm_w4a8_2sm.cuh"
 #include "gemv_w4a8.cuh"
 #include "gemm_w4a8_skinny.cuh"
+#include "flatlinear_decode.cuh"
 #include "glue.cuh"
 #include "kron_quant.cuh"
 #include "kron_quant_tc.cuh"
@@ -468,6 +469,67 @@ int launch_kron_tc(const KronParams& p, cudaStream_t st) {
         if (p.n1 > 112 && p.n1 <= 128) return launch_kron_tc_o<128, 128, 1>(p, st);
     }
     return 1;
+}
+
+// ---- one-launch decode FlatLinear (flatlinear_decode.cuh): transform + quantise in the GEMV's own prologue
+static int8_t* g_decode_dump_codes = nullptr;   // tests only (flatq_debug_set_decode_dump)
+static float* g_decode_dump_sx = nullptr;
+
+static bool flat_decode_ok(int64_t M, int64_t N, int n1, int n2, const void* x, const void* left, const void* right,
+                           const void* w, bool silu) {
+    static const bool off = getenv("FLATQ_NO_FUSED_DECODE") != nullptr;   // A/B aid: transform kernel + GEMV
+    if (off || M < 1 || M > 2 || (!left && !right) || n1 % 16 || n1 < 16 || n1 > 128 || (n2 != 64 && n2 != 128)) return false;
+    const int64_t K = (int64_t)n1 * n2;
+    if (K % 1024 || !aligned16(x) || !aligned16(w) || (left && !aligned16(left)) || (right && !aligned16(right))) return false;
+    if (silu && N % 2) return false;
+    const int cpl = (int)(K / 1024);
+    if (n2 == 64) return cpl == 2 || cpl == 4;
+    return silu ? cpl == 8 : (cpl == 4 || cpl == 8 || cpl == 14);
+}
+
+template <int MT, int N2, int CPL, int R, int MINB, bool SILU>
+cudaError_t launch_flat_decode_t(const FlatDecodeParams& q, cudaStream_t st) {
+    auto kern = flatlinear_decode_kernel<MT, N2, CPL, R, MINB, SILU>;
+    static PerDeviceOnce attr;
+    if (attr.first_time()) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    const size_t smem = flat_decode_smem_bytes(q.n1, N2, MT);
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGemvWarps * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t units = SILU ? q.g.N / 2 : q.g.N, ctas = (units + kGemvWarps - 1) / kGemvWarps, cap = (int64_t)per_sm * num_sms();
+    return launch_pdl(kern, dim3((unsigned)(cap < ctas ? cap : ctas)), dim3(kGemvWarps * 32), smem, st, q);
+}
+
+template <bool SILU>
+cudaError_t launch_flat_decode(const FlatDecodeParams& q, cudaStream_t st) {
+    const int cpl = q.g.K / 1024, key = (q.n2 == 64 ? 0 : 1000) + cpl * 10 + q.g.M;
+    constexpr int R = SILU ? 2 : 1;
+    switch (key) {
+#define FLATQ_FD(N2, CPL, MINB)                                                                                \
+    case (N2 == 64 ? 0 : 1000) + CPL * 10 + 1: return launch_flat_decode_t<1, N2, CPL, R, MINB, SILU>(q, st);  \
+    case (N2 == 64 ? 0 : 1000) + CPL * 10 + 2: return launch_flat_decode_t<2, N2, CPL, R, MINB, SILU>(q, st);
+        FLATQ_FD(64, 2, 3)      // K = 2048  (32 x 64)
+        FLATQ_FD(64, 4, 2)      // K = 4096  (64 x 64): Llama-3-8B hidden
+        FLATQ_FD(128, 8, 1)     // K = 8192  (64 x 128): Llama-3-70B hidden
+#undef FLATQ_FD
+        default: break;
+    }
+    if (!SILU) {
+        switch (key) {
+#define FLATQ_FD(N2, CPL, MINB)                                                                                 \
+    case 1000 + CPL * 10 + 1: return launch_flat_decode_t<1, N2, CPL, 1, MINB, false>(q, st);                   \
+    case 1000 + CPL * 10 + 2: return launch_flat_decode_t<2, N2, CPL, 1, MINB, false>(q, st);
+            FLATQ_FD(128, 4, 2)     // K = 4096  (32 x 128): o_proj over 32 heads, left factor only
+            FLATQ_FD(128, 14, 1)    // K = 14336 (112 x 128): Llama-3-8B down_proj
+#undef FLATQ_FD
+            default: break;
+        }
+    }
+    return cudaErrorInvalidValue;
 }
 
 // decode batches (3..32 tokens): the weight-streaming mma.sync kernel of gemm_w4a8_skinny.cuh
@@ -978,6 +1040,17 @@ int flatq_linear_fused(const void* x, const void* left, const void* right, int n
                        void* y, int out_dtype, void* ws, size_t ws_bytes, flatq_stream_t stream) {
     FLATQ_CHECK(x && w_packed && s_w && y && ws, FLATQ_ERR_INVALID, "linear_fused: null pointer");
     const int64_t K = (int64_t)n1 * n2;
+    if (N > 0 && N < (1ll << 31) && flat_decode_ok(M, N, n1, n2, x, left, right, w_packed, false)) {   // one launch for 1-2 tokens
+        FLATQ_CHECK(out_dtype == FLATQ_F16 || out_dtype == FLATQ_BF16, FLATQ_ERR_INVALID, "linear_fused: out_dtype");
+        FlatDecodeParams q;
+        q.g.w = w_packed; q.g.x = nullptr; q.g.s_x = nullptr; q.g.s_w = s_w; q.g.bias = bias; q.g.out = y;
+        q.g.M = (int)M; q.g.N = (int)N; q.g.K = (int)K; q.g.bf16_out = out_dtype == FLATQ_BF16;
+        q.x = reinterpret_cast<const __half*>(x); q.left = reinterpret_cast<const __half*>(left);
+        q.right = reinterpret_cast<const __half*>(right); q.n1 = n1; q.n2 = n2; q.c_max = clip_max; q.c_min = clip_min;
+        q.dbg_codes = g_decode_dump_codes; q.dbg_sx = g_decode_dump_sx;
+        FLATQ_CUDA(launch_flat_decode<false>(q, (cudaStream_t)stream));
+        return FLATQ_OK;
+    }
     FLATQ_CHECK(ws_bytes >= flatq_linear_fused_workspace_bytes(M, N, K), FLATQ_ERR_WORKSPACE, "linear_fused: workspace too small");
     FLATQ_CHECK(aligned16(ws), FLATQ_ERR_INVALID, "linear_fused: workspace alignment");
     int8_t* x8 = reinterpret_cast<int8_t*>(ws);
@@ -988,6 +1061,38 @@ int flatq_linear_fused(const void* x, const void* left, const void* right, int n
     if (rc) return rc;
     return flatq_gemm_w4a8(x8, sx, w_packed, s_w, bias, M, N, K, y, out_dtype, acc_ws,
                            flatq_gemm_w4a8_workspace_bytes(M, N, K), stream);
+}
+
+size_t flatq_linear_fused_silu_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    return align_up((size_t)M * K, 256) + align_up((size_t)M * 4, 256) + flatq_gemm_w4a8_silu_workspace_bytes(M, N, K);
+}
+
+int flatq_linear_fused_silu(const void* x, const void* left, const void* right, int n1, int n2, float clip_max, float clip_min,
+                            const uint8_t* w_packed_il, const float* s_w_il, int64_t M, int64_t N, void* out_f16, void* ws,
+                            size_t ws_bytes, flatq_stream_t stream) {
+    FLATQ_CHECK(x && w_packed_il && s_w_il && out_f16, FLATQ_ERR_INVALID, "linear_fused_silu: null pointer");
+    FLATQ_CHECK(N > 0 && N % 16 == 0 && N < (1ll << 31), FLATQ_ERR_INVALID, "linear_fused_silu: N=%lld (2 x intermediate size) must be a multiple of 16", (long long)N);
+    const int64_t K = (int64_t)n1 * n2;
+    if (flat_decode_ok(M, N, n1, n2, x, left, right, w_packed_il, true)) {
+        FlatDecodeParams q;
+        q.g.w = w_packed_il; q.g.x = nullptr; q.g.s_x = nullptr; q.g.s_w = s_w_il; q.g.bias = nullptr; q.g.out = out_f16;
+        q.g.M = (int)M; q.g.N = (int)N; q.g.K = (int)K; q.g.bf16_out = 0;
+        q.x = reinterpret_cast<const __half*>(x); q.left = reinterpret_cast<const __half*>(left);
+        q.right = reinterpret_cast<const __half*>(right); q.n1 = n1; q.n2 = n2; q.c_max = clip_max; q.c_min = clip_min;
+        q.dbg_codes = g_decode_dump_codes; q.dbg_sx = g_decode_dump_sx;
+        FLATQ_CUDA(launch_flat_decode<true>(q, (cudaStream_t)stream));
+        return FLATQ_OK;
+    }
+    FLATQ_CHECK(ws && aligned16(ws) && ws_bytes >= flatq_linear_fused_silu_workspace_bytes(M, N, K), FLATQ_ERR_WORKSPACE,
+                "linear_fused_silu: workspace too small or misaligned");
+    int8_t* x8 = reinterpret_cast<int8_t*>(ws);
+    uint8_t* p = reinterpret_cast<uint8_t*>(ws) + align_up((size_t)M * K, 256);
+    float* sx = reinterpret_cast<float*>(p);
+    uint8_t* rest = p + align_up((size_t)M * 4, 256);
+    int rc = flatq_act_quant(x, left, right, n1, n2, clip_max, clip_min, M, x8, sx, stream);
+    if (rc) return rc;
+    return flatq_gemm_w4a8_silu(x8, sx, w_packed_il, s_w_il, M, N, K, out_f16, rest,
+                                ws_bytes - (size_t)(rest - reinterpret_cast<uint8_t*>(ws)), stream);
 }
 
 int flatq_hadamard(const void* x, void* out, int64_t rows, int n, float scale, flatq_stream_t stream) {
@@ -1255,6 +1360,10 @@ int flatq_silu_mul(const void* gu, int64_t rows, int64_t inter, void* out, flatq
 }
 
 // Debug only (not part of the public header): select the GEMM variants listed at opt_gemm_1sm(); -1 = from the environment
+// Debug only: CTA 0 of the one-launch decode FlatLinear dumps the activation codes [M, K] (int8, GEMM operand order) and
+// scales [M] it computed (tests check the result exactly against the integer arithmetic on those codes); null = off
+void flatq_debug_set_decode_dump(int8_t* codes, float* sx) { g_decode_dump_codes = codes; g_decode_dump_sx = sx; }
+
 void flatq_debug_set_gemm_options(int one_sm, int streamk) { g_gemm_1sm = one_sm; g_streamk = streamk; }
 
 // Debug only (not part of the public header): role-level cycle counters of the GEMM, TN=128 fp16 epilogue.

@@ -283,8 +283,8 @@ def _flat_linears(x2, left, right, n1, n2, groups, lac, raw=False):
     out = {}
     for g in groups:
         cmax, cmin = (_sig(g.clip[0]), _sig(g.clip[1])) if lac else (1.0, 1.0)
-        xq8, s_x = ops.act_quant(x2, left, right, n1, n2, cmax, cmin)
-        y = ops.gemm_w4a8(xq8, s_x, g.w, g.s_w, g.bias, out_dtype=ACT_DTYPE)
+        # transform + quantise + GEMM (+ dequant, bias); one launch for the one or two tokens of a decode step
+        y = ops.linear_fused(x2, left, right, n1, n2, cmax, cmin, g.w, g.s_w, g.bias, out_dtype=ACT_DTYPE)
         if raw:
             out[tuple(g.names)] = y
             continue
@@ -507,8 +507,7 @@ class FlatQuantLlamaMLP(torch.nn.Module):
         x2 = x.reshape(b * s, self.hidden_size).to(ACT_DTYPE).contiguous()
         x2 = _pre_hadamard(getattr(self, "inp_trans_g", None), x2)
         cmax, cmin = (_sig(g.clip[0]), _sig(g.clip[1])) if self.isFlatQ else (1.0, 1.0)
-        xq8, s_x = ops.act_quant(x2, rt.left, rt.right, rt.n1, rt.n2, cmax, cmin)
-        return ops.gemm_w4a8_silu(xq8, s_x, g.w, g.s_w).view(b, s, -1)
+        return ops.linear_fused_silu(x2, rt.left, rt.right, rt.n1, rt.n2, cmax, cmin, g.w, g.s_w).view(b, s, -1)
 
     def forward(self, x):
         rt = self._runtime(x.device)

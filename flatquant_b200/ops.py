@@ -217,6 +217,29 @@ def linear_fused(x: torch.Tensor, left, right, n1: int, n2: int, clip_max: float
     return y
 
 
+def linear_fused_silu(x: torch.Tensor, left, right, n1: int, n2: int, clip_max: float, clip_min: float,
+                      w_packed_il: torch.Tensor, s_w_il: torch.Tensor) -> torch.Tensor:
+    """act_fn(gate_proj(x)) * up_proj(x) from the fp16 activations: transform -> quantise -> GEMM over the row-interleaved
+    [gate; up] weight -> SiLU * up (act_quant + gemm_w4a8_silu; one launch for one or two tokens).  Returns [..., N/2]."""
+    dev = _need_cuda(x, left, right, w_packed_il, s_w_il)
+    k = n1 * n2
+    if x.shape[-1] != k or w_packed_il.shape[1] * 2 != k:
+        raise RuntimeError(f"linear_fused_silu: K mismatch (x {x.shape[-1]}, factors {n1}x{n2}, W {w_packed_il.shape[1] * 2})")
+    if x.dtype != torch.float16 or s_w_il.dtype != torch.float32:
+        raise RuntimeError("linear_fused_silu: float16 activations, float32 weight scales")
+    m = x.numel() // k
+    n = w_packed_il.shape[0]
+    y = torch.empty(x.shape[:-1] + (n // 2,), dtype=torch.float16, device=dev)
+    if m == 0:
+        return y
+    lib = _lib.load()
+    ws = _ws.get(dev, lib.flatq_linear_fused_silu_workspace_bytes(m, n, k))
+    _lib.check(lib.flatq_linear_fused_silu(_ptr(x), _ptr(left), _ptr(right), n1, n2, float(clip_max), float(clip_min),
+                                           _ptr(w_packed_il), _ptr(s_w_il), m, n, _ptr(y), _ptr(ws), ws.numel(), _stream()),
+               "linear_fused_silu")
+    return y
+
+
 def act_quant(x: torch.Tensor, left, right, n1: int, n2: int, clip_max: float = 1.0, clip_min: float = 1.0, out=None):
     """Transform + per-token quantise into the GEMM operand format: (xq8 int8 [M, K] opaque, s_x f32 [M])."""
     dev = _need_cuda(x, left, right)

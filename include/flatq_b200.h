@@ -105,7 +105,10 @@ int flatq_quantize_rows(const void* x_f16, int64_t tokens, int64_t K, float clip
  *      == OnlineTrans -> Quantizer -> Linear4bit of benchmarks/qlinear_benchmark.py:70-74).
  *      x fp16 [M, K=n1*n2]; left/right may be NULL (no transform / single-sided);
  *      w_packed [N, K/2]; s_w fp32 [N]; bias out_dtype [N] or NULL; y [M, N] out_dtype.
- *      workspace >= flatq_linear_fused_workspace_bytes(M, N, K). */
+ *      workspace >= flatq_linear_fused_workspace_bytes(M, N, K).
+ *      One or two tokens (a decode step) with factor sizes n1 % 16 == 0, n2 in {64, 128} run as ONE launch: every CTA of
+ *      the weight-stream GEMV computes the transform + quantisation of the token(s) itself while its first weight rows
+ *      are in flight (csrc/flatlinear_decode.cuh); other shapes are the transform kernel followed by the GEMM. */
 size_t flatq_linear_fused_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int flatq_linear_fused(const void* x_f16, const void* left_f16, const void* right_f16, int n1, int n2,
                        float clip_max, float clip_min, const uint8_t* w_packed, const float* s_w, const void* bias,
@@ -144,6 +147,14 @@ size_t flatq_gemm_w4a8_silu_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int flatq_gemm_w4a8_silu(const int8_t* xq8, const float* s_x, const uint8_t* w_packed_il, const float* s_w_il, int64_t M,
                          int64_t N, int64_t K, void* out_f16, void* workspace, size_t workspace_bytes,
                          flatq_stream_t stream);
+
+/* ---- the whole MLP front half: transform -> quantise -> fused [gate; up] GEMM -> act_fn(gate) * up, i.e.
+ *      flatq_act_quant + flatq_gemm_w4a8_silu (same arguments, same row-interleaved weight); one launch for one or two
+ *      tokens (see flatq_linear_fused).  out [M, N/2] fp16. */
+size_t flatq_linear_fused_silu_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int flatq_linear_fused_silu(const void* x_f16, const void* left_f16, const void* right_f16, int n1, int n2, float clip_max,
+                            float clip_min, const uint8_t* w_packed_il, const float* s_w_il, int64_t M, int64_t N,
+                            void* out_f16, void* workspace, size_t workspace_bytes, flatq_stream_t stream);
 
 /* ---- a6 for mixture-of-experts layers: the routed-expert FlatLinears of the DeepSeek block (BASELINE configs[4];
  *      deepseek_v3/model.py:677-683 -- a Python loop over experts, each `expert(x[idx])` -- under

@@ -250,7 +250,38 @@ def linear_fused(x, left, right, n1, n2, clip_max, clip_min, w_packed, s_w, bias
     if x.numel() == 0:
         return torch.empty(x.shape[:-1] + (w_packed.shape[0],), dtype=out_dtype)
     q, s = act_quant(x.reshape(-1, k), left, right, n1, n2, clip_max, clip_min)
-    return gemm_w4a8(q, s, w_packed, s_w, bias, out_dtype).reshape(x.shape[:-1] + (w_packed.shape[0],))
+    y = gemm_w4a8(q, s, w_packed, s_w, bias, out_dtype).reshape(x.shape[:-1] + (w_packed.shape[0],))
+    _tag_decode(x.numel() // k, w_packed.shape[0], n1, n2, left, right, False)
+    return y
+
+
+def _decode_fused(m, n1, n2, left, right, silu):
+    """mirrors flat_decode_ok of csrc/api.cu: the shapes that run as ONE launch (csrc/flatlinear_decode.cuh)"""
+    k = n1 * n2
+    if not (1 <= m <= 2) or (left is None and right is None) or n1 % 16 or not (16 <= n1 <= 128) or n2 not in (64, 128) or k % 1024:
+        return False
+    cpl = k // 1024
+    return cpl in (2, 4) if n2 == 64 else (cpl == 8 if silu else cpl in (4, 8, 14))
+
+
+def _tag_decode(m, n, n1, n2, left, right, silu):
+    if _decode_fused(m, n1, n2, left, right, silu):   # replace the (act_quant, gemm) pair just recorded
+        del CALLS[-2:]
+        CALLS.append(("linear_fused_decode", (m, n, n1 * n2, n1, n2, silu)))
+
+
+def linear_fused_silu(x, left, right, n1, n2, clip_max, clip_min, w_packed_il, s_w_il):
+    k = n1 * n2
+    _contig(x=x, left=left, right=right, w_packed_il=w_packed_il, s_w_il=s_w_il)
+    _req(x.shape[-1] == k and w_packed_il.shape[1] * 2 == k, "linear_fused_silu: K mismatch")
+    _act_dtype(x, "linear_fused_silu x"), _dtype(s_w_il, torch.float32, "linear_fused_silu s_w")
+    n = w_packed_il.shape[0]
+    if x.numel() == 0:
+        return torch.empty(x.shape[:-1] + (n // 2,), dtype=x.dtype)
+    q, s = act_quant(x.reshape(-1, k), left, right, n1, n2, clip_max, clip_min)
+    y = gemm_w4a8_silu(q, s, w_packed_il, s_w_il).reshape(x.shape[:-1] + (n // 2,))
+    _tag_decode(x.numel() // k, n, n1, n2, left, right, True)
+    return y
 
 
 def pack_i4(q):
@@ -394,7 +425,7 @@ def kv_decode_i4(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, lay
 
 
 FUNCTIONS = ("kron_transform", "act_quant", "transform_quant", "quantize_rows", "gemm_w4a8", "gemm_w4a8_silu", "gemm_w4a8_grouped",
-             "linear_fused", "pack_i4",
+             "linear_fused", "linear_fused_silu", "pack_i4",
              "hadamard", "hadamard_kn", "kv_fused", "kv_quant", "kv_decode_i4", "rmsnorm", "add_rmsnorm", "rope_", "silu_mul")
 
 

@@ -664,8 +664,12 @@ def test_decode_split_k_path(ops, dev, m, k, n, n1, n2):
     wp = ops.pack_i4(wq)
     s_w = torch.rand(n, device=dev) * 0.02 + 0.01
     bias = torch.randn(n, device=dev).half()
-    y = ops.linear_fused(x, L, R, n1, n2, 0.97, 0.99, wp, s_w, bias)
-    y_again = ops.linear_fused(x, L, R, n1, n2, 0.97, 0.99, wp, s_w, bias)
+    if m <= 2:   # linear_fused is the one-launch kernel there (test_one_launch_decode_flatlinear): pin the GEMV by itself
+        fused = lambda: ops.gemm_w4a8(*ops.act_quant(x, L, R, n1, n2, 0.97, 0.99), wp, s_w, bias)   # noqa: E731
+    else:
+        fused = lambda: ops.linear_fused(x, L, R, n1, n2, 0.97, 0.99, wp, s_w, bias)   # noqa: E731
+    y = fused()
+    y_again = fused()
     assert torch.equal(y, y_again)
     xq8, sx = ops.act_quant(x, L, R, n1, n2, 0.97, 0.99)
     perm = np.array([0, 2, 4, 6, 1, 3, 5, 7])
@@ -817,3 +821,97 @@ def test_hadamard_short_rows_in_warp_lanes(ops, dev, n):
         assert np.abs(y.float().cpu().numpy() - ref).max() <= 2 ** -9 * max(1.0, np.abs(ref).max())
         back = ops.hadamard(y, 1.0 / n ** 0.5).float().cpu()
         assert float((back - x.float()).abs().max()) <= 2 ** -8 * max(1.0, float(x.float().abs().max()))
+
+
+@pytest.mark.parametrize("m,n1,n2,n,sides", [(1, 64, 64, 6144, "lr"), (2, 64, 64, 4100, "lr"), (1, 32, 128, 4096, "l"), (2, 32, 128, 4100, "l"),
+                                             (1, 112, 128, 4096, "lr"), (2, 112, 128, 4100, "lr"), (1, 64, 128, 1032, "lr"),
+                                             (2, 32, 64, 520, "lr"), (1, 64, 64, 4096, "r"), (2, 64, 128, 28672, "lr")])
+def test_one_launch_decode_flatlinear(ops, dev, m, n1, n2, n, sides):
+    """csrc/flatlinear_decode.cuh: for one or two tokens flatq_linear_fused is ONE launch -- every CTA of the weight-stream
+    GEMV computes the Kronecker transform and the quantisation of the token(s) itself (mma.sync, the rounding points of the
+    tcgen05 kernel: left factor first, one fp16 rounding per factor).  CTA 0 dumps its codes and scales (debug hook):
+    (1) the output is EXACTLY the integer arithmetic of the path on those codes; (2) the codes equal the CPU model of the
+    rounding points and the two-launch path up to rare +-1 flips (fp32 summation order inside the tensor cores);
+    (3) an all-zero token gives scale 1 and zero codes."""
+    import ctypes
+    from flatquant_b200 import _lib
+    torch.manual_seed(m * 7919 + n1 * 131 + n2 + n)
+    k = n1 * n2
+    x = torch.randn(m, k).half()
+    if m == 2:
+        x[1] = 0
+    L = (torch.randn(n1, n1) / n1 ** 0.5).half() if "l" in sides else None
+    R = (torch.randn(n2, n2) / n2 ** 0.5).half() if "r" in sides else None
+    wq = torch.randint(-8, 8, (n, k), dtype=torch.int8, device=dev)
+    wp = ops.pack_i4(wq)
+    s_w = torch.rand(n, device=dev) * 0.02 + 0.01
+    bias = torch.randn(n, device=dev).half()
+    cmax, cmin = 0.97, 0.99
+    Ld, Rd = (None if L is None else L.to(dev)), (None if R is None else R.to(dev))
+    codes = torch.full((m, k), 99, dtype=torch.int8, device=dev)
+    sx = torch.zeros(m, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    dump = lib.flatq_debug_set_decode_dump
+    dump.restype, dump.argtypes = None, [ctypes.c_void_p, ctypes.c_void_p]
+    try:
+        dump(codes.data_ptr(), sx.data_ptr())
+        y = ops.linear_fused(x.to(dev), Ld, Rd, n1, n2, cmax, cmin, wp, s_w, bias)
+        torch.cuda.synchronize()
+    finally:
+        dump(None, None)
+    assert int(codes.max()) <= 7 and int(codes.min()) >= -8, "the one-launch kernel did not run (codes not dumped)"
+    y_again = ops.linear_fused(x.to(dev), Ld, Rd, n1, n2, cmax, cmin, wp, s_w, bias)
+    assert torch.equal(y, y_again)
+    # (1) exact given the codes: the GEMV on the dumped operand (bit-exact against the integer oracle elsewhere)
+    assert torch.equal(y, ops.gemm_w4a8(codes, sx, wp, s_w, bias, torch.float16))
+    # (2) codes: CPU rounding-point model (left factor first) and the two-launch path
+    perm = torch.tensor([0, 2, 4, 6, 1, 3, 5, 7])
+    logical = torch.empty(m, k // 8, 8, dtype=torch.int8)
+    logical[:, :, perm] = codes.cpu().view(m, k // 8, 8)
+    logical = logical.view(m, k).numpy().astype(np.int32)
+    eye1, eye2 = torch.eye(n1).half(), torch.eye(n2).half()
+    q_em, s_em = _emulated_codes(x, eye1 if L is None else L, eye2 if R is None else R, cmax, cmin, "lx")
+    d = np.abs(logical - q_em)
+    assert d.max() <= 1 and (d != 0).mean() < 1e-3, (d.max(), (d != 0).mean())
+    assert torch.allclose(sx.cpu(), s_em, rtol=1e-3)
+    xq8, sx2 = ops.act_quant(x.to(dev), Ld, Rd, n1, n2, cmax, cmin)
+    d2 = (xq8.int() - codes.int()).abs()
+    assert int(d2.max()) <= 1 and float((d2 != 0).float().mean()) < 1e-3
+    assert torch.allclose(sx, sx2, rtol=1e-3)
+    # (3) the all-zero token
+    if m == 2:
+        assert sx[1].item() == 1.0 and not codes[1].any() and torch.equal(y[1], bias)
+
+
+@pytest.mark.parametrize("m,n1,n2,inter", [(1, 64, 64, 14336), (2, 64, 64, 1032), (1, 64, 128, 520), (2, 32, 64, 264)])
+def test_one_launch_decode_gate_up_silu(ops, dev, m, n1, n2, inter):
+    """flatq_linear_fused_silu at one / two tokens: the same kernel with the (gate, up) pair epilogue; exact given its codes."""
+    import ctypes
+    from flatquant_b200 import _lib
+    torch.manual_seed(m + n1 + n2 + inter)
+    k = n1 * n2
+    x = torch.randn(m, k, device=dev).half()
+    L = (torch.randn(n1, n1, device=dev) / n1 ** 0.5).half()
+    R = (torch.randn(n2, n2, device=dev) / n2 ** 0.5).half()
+    w_il = ops.pack_i4(torch.randint(-8, 8, (2 * inter, k), dtype=torch.int8, device=dev))
+    s_il = torch.rand(2 * inter, device=dev) * 0.05 + 0.02
+    codes = torch.full((m, k), 99, dtype=torch.int8, device=dev)
+    sx = torch.zeros(m, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    dump = lib.flatq_debug_set_decode_dump
+    dump.restype, dump.argtypes = None, [ctypes.c_void_p, ctypes.c_void_p]
+    try:
+        dump(codes.data_ptr(), sx.data_ptr())
+        y = ops.linear_fused_silu(x, L, R, n1, n2, 0.98, 0.96, w_il, s_il)
+        torch.cuda.synchronize()
+    finally:
+        dump(None, None)
+    assert int(codes.max()) <= 7 and int(codes.min()) >= -8, "the one-launch kernel did not run"
+    assert y.shape == (m, inter) and torch.equal(y, ops.gemm_w4a8_silu(codes, sx, w_il, s_il))
+    xq8, sx2 = ops.act_quant(x, L, R, n1, n2, 0.98, 0.96)
+    d2 = (xq8.int() - codes.int()).abs()
+    assert int(d2.max()) <= 1 and float((d2 != 0).float().mean()) < 1e-3 and torch.allclose(sx, sx2, rtol=1e-3)
+    # larger batches take the two-launch route with the same result as its parts
+    x8 = torch.randn(40, k, device=dev).half()
+    q8, s8 = ops.act_quant(x8, L, R, n1, n2, 0.98, 0.96)
+    assert torch.equal(ops.linear_fused_silu(x8, L, R, n1, n2, 0.98, 0.96, w_il, s_il), ops.gemm_w4a8_silu(q8, s8, w_il, s_il))

@@ -21,6 +21,7 @@ GPU_VERIFIED = {
     "gemv": "test_gpu_parity.py::test_decode_split_k_path[m=1,2]",
     "skinny": "test_gpu_parity.py::test_decode_gemv_and_skinny_gemm_bit_exact[m=3..32], test_decode_split_k_path[m=5..17]",
     "split-k": "test_gpu_parity.py::test_decode_split_k_path[m=40,64]",
+    "fused-decode": "test_gpu_parity.py::test_one_launch_decode_flatlinear (transform + quantise in the GEMV's prologue, 1-2 tokens)",
     "1sm-128": "test_gpu_parity.py::test_gemm_i4_exact[(100,200,192),(128,256,4096)], __graft_entry__.smoke (96 tokens)",
     "2sm": "test_gpu_parity.py::test_prefill_gemm_variants_bit_identical, __graft_entry__.smoke (320 tokens)",
     "kv_quant": "test_gpu_parity.py::test_kv_quant_golden_bit_exact, test_paged_kv_append_and_decode",
@@ -29,8 +30,10 @@ GPU_VERIFIED = {
 
 
 def _classify(op, cfg):
-    if op == "gemm_w4a8":
+    if op in ("gemm_w4a8", "gemm_w4a8_silu"):
         return cfg[0]
+    if op == "linear_fused_decode":
+        return "fused-decode"
     if op in ("kv_quant", "kv_decode_i4"):
         return op
     if op == "act_quant" and cfg[0] == "rowquant":
