@@ -484,7 +484,9 @@ static bool flat_decode_ok(int64_t M, int64_t N, int n1, int n2, const void* x, 
     if (silu && N % 2) return false;
     const int cpl = (int)(K / 1024);
     if (n2 == 64) return cpl == 2 || cpl == 4;
-    return silu ? cpl == 8 : (cpl == 4 || cpl == 8 || cpl == 14);
+    // K = 14336 (112 x 128, Llama-3-8B down_proj) stays on the transform kernel + GEMV: 6.9 MFLOP of transform per CTA and
+    // 173 registers made the one-launch form slower there (16.7 vs 12.3 us per fused linear from a graph)
+    return silu ? cpl == 8 : (cpl == 4 || cpl == 8);
 }
 
 template <int MT, int N2, int CPL, int R, int MINB, bool SILU>
@@ -524,7 +526,6 @@ cudaError_t launch_flat_decode(const FlatDecodeParams& q, cudaStream_t st) {
     case 1000 + CPL * 10 + 1: return launch_flat_decode_t<1, N2, CPL, 1, MINB, false>(q, st);                   \
     case 1000 + CPL * 10 + 2: return launch_flat_decode_t<2, N2, CPL, 1, MINB, false>(q, st);
             FLATQ_FD(128, 4, 2)     // K = 4096  (32 x 128): o_proj over 32 heads, left factor only
-            FLATQ_FD(128, 14, 1)    // K = 14336 (112 x 128): Llama-3-8B down_proj
 #undef FLATQ_FD
             default: break;
         }

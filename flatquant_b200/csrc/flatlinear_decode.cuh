@@ -18,7 +18,8 @@
 // The products are the same fp16 -> fp32 sums as the tcgen05 kernel's, in a different order: Z can differ in the last
 // fp16 bit on a few elements, so an activation code differs from the two-launch path about once in 10^3-10^4 (the same
 // class of difference as between that kernel and the oracle); given its codes the result is exact.
-// Redundant work: 2 n1 n2 (n1 + n2) FLOP per CTA (0.5 M at 64 x 64, 6.9 M at 112 x 128) and one L2 read of the factors.
+// Redundant work: 2 n1 n2 (n1 + n2) FLOP per CTA (0.5 M at 64 x 64) and one L2 read of the factors; instantiated for
+// K = 2048 / 4096 / 8192 -- at 112 x 128 (K = 14336: 6.9 MFLOP per CTA) the two-launch path measured faster and is kept.
 #pragma once
 #include "gemv_w4a8.cuh"
 #include "kron_quant_tc.cuh"

@@ -261,7 +261,7 @@ def _decode_fused(m, n1, n2, left, right, silu):
     if not (1 <= m <= 2) or (left is None and right is None) or n1 % 16 or not (16 <= n1 <= 128) or n2 not in (64, 128) or k % 1024:
         return False
     cpl = k // 1024
-    return cpl in (2, 4) if n2 == 64 else (cpl == 8 if silu else cpl in (4, 8, 14))
+    return cpl in (2, 4) if n2 == 64 else (cpl == 8 if silu else cpl in (4, 8))
 
 
 def _tag_decode(m, n, n1, n2, left, right, silu):
