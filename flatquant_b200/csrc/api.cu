@@ -965,6 +965,8 @@ static int peer_ctx(const flatq_tp_ctx* tp, PeerCtx* c) {
     FLATQ_CHECK(tp && tp->world >= 2 && tp->world <= kPeerMaxWorld && tp->rank >= 0 && tp->rank < tp->world, FLATQ_ERR_INVALID,
                 "tp: world must be 2..%d and 0 <= rank < world", kPeerMaxWorld);
     c->rank = tp->rank; c->world = tp->world;
+    c->pad_ctas = (int)(tp->signal_pad_bytes / (2ull * (tp->world + 1) * sizeof(uint32_t)));   // two phases x (world flags + 1 counter) per CTA slot
+    FLATQ_CHECK(c->pad_ctas >= 1, FLATQ_ERR_INVALID, "tp: signal pad too small (%zu bytes)", tp->signal_pad_bytes);
     for (int r = 0; r < tp->world; ++r) {
         FLATQ_CHECK(tp->signal_pads[r], FLATQ_ERR_INVALID, "tp: null signal pad for rank %d", r);
         c->signal_pads[r] = reinterpret_cast<uint32_t*>(tp->signal_pads[r]);

@@ -26,7 +26,8 @@ constexpr int kPeerThreads = 512;
 
 struct PeerCtx {
     int rank, world;
-    uint32_t* signal_pads[kPeerMaxWorld];   // each rank's signal pad (zero-initialised symmetric memory), >= 2 * grid * (world + 1) words
+    int pad_ctas;                           // CTA slots of the signal pad: the layout below does NOT depend on a launch's grid
+    uint32_t* signal_pads[kPeerMaxWorld];   // each rank's signal pad (zero-initialised symmetric memory), >= 2 * pad_ctas * (world + 1) words
 };
 
 // Barrier over the ranks, one per CTA index: flags are EPOCH counters, never reset.  Every CTA keeps the number of
@@ -34,14 +35,16 @@ struct PeerCtx {
 // every peer's pad with one st.release.sys (a posted write: no NVLink round trip), and spins on its OWN pad (local L2)
 // until every peer's slot has reached e.  All ranks issue the same sequence of launches, so the counters stay in step;
 // nothing is baked into launch arguments, so a CUDA graph can replay the launch.  Pad layout per rank (u32 words):
-//   [2 phases][grid][world] flags, then [2 phases][grid] local counters.
+//   [2 phases][pad_ctas][world] flags, then [2 phases][pad_ctas] local counters -- indexed by CTA number with the pad's own
+//   stride, so launches of different grid sizes (a prefill's broadcast, a decode step's all-reduce: one reducer serves
+//   both) share the pad without aliasing each other's slots; every launch uses grid <= pad_ctas.
 __device__ __forceinline__ void peer_barrier(const PeerCtx& c, int phase) {
     __shared__ uint32_t epoch_s;
     __syncthreads();
     uint32_t* pad = c.signal_pads[c.rank];
-    const size_t slot = ((size_t)phase * gridDim.x + blockIdx.x) * c.world;
+    const size_t slot = ((size_t)phase * c.pad_ctas + blockIdx.x) * c.world;
     if (threadIdx.x == 0) {
-        uint32_t* ctr = pad + (size_t)2 * gridDim.x * c.world + (size_t)phase * gridDim.x + blockIdx.x;
+        uint32_t* ctr = pad + (size_t)2 * c.pad_ctas * c.world + (size_t)phase * c.pad_ctas + blockIdx.x;
         epoch_s = *ctr + 1;
         *ctr = epoch_s;
     }

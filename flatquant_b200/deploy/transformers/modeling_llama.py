@@ -195,6 +195,27 @@ class TensorParallel:
 
     def __init__(self, size=1, rank=0, group=None):
         self.size, self.rank, self.group = size, rank, group
+        self._reducers = {}
+        self.fused_reduction = True   # False: plain GEMM + self.all_reduce (what the lock-step serial restatement of the tests overrides)
+
+    def reducer(self, m, n, dev):
+        """The reduction object of the row-parallel linears of width n (flatquant_b200/tp.py make_reducer): peer-memory
+        kernels of this library on NVLink boxes, dist.all_reduce otherwise.  One per width, sized for the largest token
+        count seen so far (creation is a collective: every rank reaches it with the same shapes in the same order)."""
+        r = self._reducers.get(n)
+        if r is None or m > r.partial_buffer().shape[0]:
+            from ...tp import make_reducer
+            cap = max(m, 2048) if r is None else max(m, 2 * r.partial_buffer().shape[0])
+            r = self._reducers[n] = make_reducer(self.size, self.rank, dev, (cap, n), ACT_DTYPE, self.group)
+        return r
+
+    def row_parallel(self, x2, left, right, n1, n2, group, lac):
+        """A row-parallel FlatLinear (o_proj, down_proj): this rank's transform + quantisation of its input shard, then
+        the GEMM whose epilogue is the reduce-scatter + the peer broadcast (or GEMM + in-switch all-reduce at decode
+        sizes) -- SURVEY 8(e); the reference: F.linear + dist.all_reduce (llama_flatquant.py:117-126, 261-289)."""
+        cmax, cmin = (_sig(group.clip[0]), _sig(group.clip[1])) if lac else (1.0, 1.0)
+        xq8, s_x = ops.act_quant(x2, left, right, n1, n2, cmax, cmin)
+        return self.reducer(x2.shape[0], group.w.shape[0], x2.device).rowparallel_gemm(xq8, s_x, group.w, group.s_w, group.bias)
 
     def shard(self, n, what):
         if n % self.size:
@@ -416,6 +437,9 @@ class FlatQuantLlamaAttention(torch.nn.Module):
         b, s, _ = attn.shape
         rt = self._runtime(attn.device)
         a2 = attn.reshape(b * s, self.num_heads * self.head_dim).to(ACT_DTYPE).contiguous()
+        if self.tp.size > 1 and self.tp.fused_reduction and ACT_DTYPE == torch.float16:
+            y = self.tp.row_parallel(a2, rt.o_left, rt.o_right, self.num_heads, self.head_dim, rt.o[0], self.isFlatQ)
+            return y.reshape(b, s, self.hidden_size)
         y = _flat_linears(a2, rt.o_left, rt.o_right, self.num_heads, self.head_dim, rt.o, self.isFlatQ)["o"]
         return self.tp.all_reduce(y).reshape(b, s, self.hidden_size)
 
@@ -495,6 +519,9 @@ class FlatQuantLlamaMLP(torch.nn.Module):
         rt = self._runtime(act.device)
         a2 = act.reshape(b * s, self.intermediate_size).to(ACT_DTYPE).contiguous()
         a2 = _pre_hadamard(self.down_proj[0], a2)
+        if self.tp.size > 1 and self.tp.fused_reduction and ACT_DTYPE == torch.float16:
+            y = self.tp.row_parallel(a2, rt.d_left, rt.d_right, rt.d_n1, rt.d_n2, rt.down[0], self.isFlatQ)
+            return y.reshape(b, s, self.hidden_size)
         y = _flat_linears(a2, rt.d_left, rt.d_right, rt.d_n1, rt.d_n2, rt.down, self.isFlatQ)["down"]
         return self.tp.all_reduce(y).reshape(b, s, self.hidden_size)
 

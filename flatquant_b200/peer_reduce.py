@@ -29,9 +29,10 @@ def _ptr_array(ptrs):
 
 
 class PeerReducer:
-    """One per (shape, group).  `rowparallel_gemm` is the whole row-parallel linear after the activation quantiser:
-    GEMM with the reduce-scatter in its epilogue + owner-side sum + broadcast; `all_reduce` is the in-switch all-reduce
-    for shapes the fused path does not take."""
+    """One per (capacity, width, group): serves every call with m <= capacity rows (the symmetric buffers are flat; a
+    decode step and a prefill of any length share them).  `rowparallel_gemm` is the whole row-parallel linear after the
+    activation quantiser: GEMM with the reduce-scatter in its epilogue + owner-side sum + broadcast (m a multiple of
+    256 x world), else GEMM + the in-switch all-reduce; `all_reduce` is that all-reduce by itself."""
 
     def __init__(self, world, rank, dev, shape, dtype=torch.float16, group=None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -41,7 +42,7 @@ class PeerReducer:
             raise RuntimeError("PeerReducer: 2..8 ranks")
         self.world, self.rank, self.dev, self.group = world, rank, dev, group or dist.group.WORLD
         self.M, self.N = int(shape[0]), int(shape[1])
-        self.fused = self.M % (256 * world) == 0
+        self.fused = self.M % (256 * world) == 0     # of a call with m == capacity (reported by the bench)
         lib = _lib.load()
         self.lib = lib
 
@@ -76,31 +77,33 @@ class PeerReducer:
     def rowparallel_gemm(self, xq8, s_x, w_packed, s_w, bias=None):
         """y [M, N] fp16 = sum over ranks of (xq8 . W^T) s_x s_w (+ bias once): returns this reducer's output buffer."""
         m, k = xq8.shape
-        if (m, w_packed.shape[0]) != (self.M, self.N):
-            raise RuntimeError(f"PeerReducer built for {(self.M, self.N)}, got {(m, w_packed.shape[0])}")
+        if m > self.M or w_packed.shape[0] != self.N:
+            raise RuntimeError(f"PeerReducer built for up to {self.M} x {self.N}, got {(m, w_packed.shape[0])}")
         st = torch.cuda.current_stream().cuda_stream
         b = None if bias is None else bias.to(torch.float16).contiguous()
-        if self.fused:
+        if m % (256 * self.world) == 0:
             _lib.check(self.lib.flatq_gemm_w4a8_rowparallel(xq8.data_ptr(), s_x.data_ptr(), w_packed.data_ptr(), s_w.data_ptr(),
                                                             m, self.N, k, ctypes.addressof(self.ctx), self.par_peers, st),
                        "gemm_w4a8_rowparallel")
             _lib.check(self.lib.flatq_peer_reduce_bcast(ctypes.addressof(self.ctx), self.partial.data_ptr(), self.out_mc or None,
-                                                        self.out_peers, None if b is None else b.data_ptr(), self.M, self.N, st),
+                                                        self.out_peers, None if b is None else b.data_ptr(), m, self.N, st),
                        "peer_reduce_bcast")
-            return self.out
-        ops.gemm_w4a8(xq8, s_x, w_packed, s_w, None, torch.float16, out=self.partial)
-        return self.all_reduce(self.partial, bias=b)
+            return self.out[:m]
+        part = self.partial[:m]
+        ops.gemm_w4a8(xq8, s_x, w_packed, s_w, None, torch.float16, out=part)
+        return self.all_reduce(part, bias=b)
 
     # ---- any shape: in-switch all-reduce of the symmetric partial buffer
     def partial_buffer(self):
         return self.partial
 
     def all_reduce(self, partial=None, bias=None):
+        m = self.M if partial is None else partial.shape[0]
         if partial is not None and partial.data_ptr() != self.partial.data_ptr():
-            self.partial.copy_(partial)
+            self.partial[:m].copy_(partial)
         if not self.par_mc:
             raise RuntimeError("PeerReducer.all_reduce: no multicast support on this box")
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(self.lib.flatq_peer_allreduce(ctypes.addressof(self.ctx), self.par_mc, self.out_mc,
-                                                 None if bias is None else bias.data_ptr(), self.M, self.N, st), "peer_allreduce")
-        return self.out
+                                                 None if bias is None else bias.data_ptr(), m, self.N, st), "peer_allreduce")
+        return self.out[:m]

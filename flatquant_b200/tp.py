@@ -126,7 +126,7 @@ class NcclReducer:
 
     def rowparallel_gemm(self, xq8, s_x, w_packed, s_w, bias=None):
         from . import ops
-        y = ops.gemm_w4a8(xq8, s_x, w_packed, s_w, None, torch.float16, out=self.buf)
+        y = ops.gemm_w4a8(xq8, s_x, w_packed, s_w, None, self.buf.dtype, out=self.buf[:xq8.shape[0]])
         dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
         return y if bias is None else y + bias.to(y.dtype)
 

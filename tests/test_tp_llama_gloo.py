@@ -69,6 +69,7 @@ def test_tp2_stack_equals_lockstep_serial_restatement(monkeypatch):
     for r in range(WORLD):
         tp = ML.TensorParallel(WORLD, r)
         tp.all_reduce = lambda y: y  # partial products are summed by hand below
+        tp.fused_reduction = False   # ... so the row-parallel linears must not reduce through a reducer object either
         models.append(FlatQuantLlamaForCausalLM.random_init(cfg, torch.device("cpu"), seed=SEED, tp=tp))
     m0 = models[0]
     # shapes of the shards (llama_flatquant.py:148-170, 106-112)
