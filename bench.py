@@ -604,7 +604,8 @@ def measure_decode_linears(dev, barrier):
             g.replay()
             us = timed(g.replay, 5, barrier) * 1e3 / (5 * 16)
             gbs = (k * n / 2) / us / 1e3
-            out[f"m{m} {name} {k}->{n}"] = {"us": us, "weight_stream_GBps": gbs, "frac_of_hbm": gbs / hbm}
+            out[f"m{m} {name} {k}->{n}"] = {"us": us, "weight_stream_GBps": gbs, "frac_of_hbm": gbs / hbm,
+                                            "algorithmic_bytes": k * n // 2, "traffic": ncu_traffic(f"decode m{m} {name}")}
             del ws, g
     return out
 
