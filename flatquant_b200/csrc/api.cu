@@ -1285,9 +1285,9 @@ int flatq_kv_decode_i4_split(const void* q, void* o, const uint8_t* kv_data, con
             if (splits < 1) splits = 1;
             static PerDeviceOnce attr;
             if (attr.first_time())
-                FLATQ_CUDA(cudaFuncSetAttribute(decode_attn_i4_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDmSmem));
+                FLATQ_CUDA(cudaFuncSetAttribute(decode_attn_i4_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDmSmem));
             const dim3 grid((unsigned)splits, (unsigned)kv_heads, (unsigned)batch);
-            FLATQ_CUDA(launch_pdl(decode_attn_i4_mma_kernel, grid, dim3(kDmThreads), (size_t)kDmSmem, st, p, (int)splits, part));
+            FLATQ_CUDA(launch_pdl(decode_attn_i4_mma_kernel<false>, grid, dim3(kDmThreads), (size_t)kDmSmem, st, p, DecodeFront{}, (int)splits, part));
             FLATQ_CUDA(launch_pdl(decode_attn_merge_kernel, dim3(batch * q_heads), dim3(128), 0, st, (const float*)part, (int)splits,
                                   reinterpret_cast<__half*>(o)));
             return FLATQ_OK;
@@ -1307,6 +1307,57 @@ int flatq_kv_decode_i4_split(const void* q, void* o, const uint8_t* kv_data, con
     if (gh == 4) FLATQ_CUDA(launch_pdl(decode_attn_i4_split_kernel<4>, grid, dim3(kDecSplitThreads), 0, st, p, (int)splits, part));
     else if (gh == 2) FLATQ_CUDA(launch_pdl(decode_attn_i4_split_kernel<2>, grid, dim3(kDecSplitThreads), 0, st, p, (int)splits, part));
     else FLATQ_CUDA(launch_pdl(decode_attn_i4_split_kernel<1>, grid, dim3(kDecSplitThreads), 0, st, p, (int)splits, part));
+    FLATQ_CUDA(launch_pdl(decode_attn_merge_kernel, dim3(batch * q_heads), dim3(128), 0, st, (const float*)part, (int)splits,
+                          reinterpret_cast<__half*>(o)));
+    return FLATQ_OK;
+}
+
+int flatq_kv_decode_fused(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_k, int64_t ld_v, const void* cos_t,
+                          const void* sin_t, const int32_t* pos, const void* t_q, const void* t_k, const int32_t* slot, void* o,
+                          uint8_t* kv_data, void* kv_param, const int32_t* kv_indptr, const int32_t* kv_indices,
+                          const int32_t* last_page_len, int batch, int q_heads, int kv_heads, int head_dim, int page_size, int layer,
+                          int n_layers, float sm_scale, int max_tokens_hint, void* ws, size_t ws_bytes, flatq_stream_t stream) {
+    FLATQ_CHECK(q && k && v && cos_t && sin_t && pos && t_q && t_k && slot && o && kv_data && kv_param && kv_indptr && kv_indices &&
+                last_page_len && ws, FLATQ_ERR_INVALID, "kv_decode_fused: null pointer");
+    FLATQ_CHECK(head_dim == 128, FLATQ_ERR_UNSUPPORTED, "kv_decode_fused: head_dim=%d (only 128)", head_dim);
+    FLATQ_CHECK(batch > 0 && q_heads > 0 && kv_heads > 0 && q_heads % kv_heads == 0, FLATQ_ERR_INVALID, "kv_decode_fused: heads");
+    const int G = q_heads / kv_heads;
+    FLATQ_CHECK(G >= 2 && G <= 16, FLATQ_ERR_UNSUPPORTED,
+                "kv_decode_fused: %d query heads per kv head (2..16: the grouped-query tensor-core kernel); use flatq_kv_fused + flatq_kv_decode_i4_split", G);
+    FLATQ_CHECK(page_size > 0 && n_layers > 0 && layer >= 0 && layer < n_layers, FLATQ_ERR_INVALID, "kv_decode_fused: cache arguments");
+    FLATQ_CHECK(ld_q % 4 == 0 && ld_k % 4 == 0 && ld_v % 4 == 0 && ld_q >= (int64_t)q_heads * 128 && ld_k >= (int64_t)kv_heads * 128 &&
+                ld_v >= (int64_t)kv_heads * 128, FLATQ_ERR_INVALID, "kv_decode_fused: row strides");
+    auto al8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };
+    FLATQ_CHECK(al8(q) && al8(k) && al8(v) && al8(cos_t) && al8(sin_t) && aligned16(t_q) && aligned16(t_k) && aligned16(kv_data) &&
+                (reinterpret_cast<uintptr_t>(ws) & 15) == 0, FLATQ_ERR_INVALID, "kv_decode_fused: alignment");
+    FLATQ_CHECK(ws_bytes >= flatq_kv_decode_i4_split_workspace_bytes(batch, q_heads), FLATQ_ERR_WORKSPACE, "kv_decode_fused: workspace too small");
+    DecodeParams p;
+    p.q = nullptr; p.o = reinterpret_cast<__half*>(o);
+    p.kv_data = kv_data; p.kv_param = reinterpret_cast<const __half*>(kv_param);
+    p.kv_indptr = kv_indptr; p.kv_indices = kv_indices; p.last_page_len = last_page_len;
+    p.batch = batch; p.q_heads = q_heads; p.kv_heads = kv_heads; p.D = head_dim; p.page_size = page_size;
+    p.layer = layer; p.n_layers = n_layers; p.sm_scale = sm_scale;
+    DecodeFront f;
+    f.q = reinterpret_cast<const __half*>(q); f.k = reinterpret_cast<const __half*>(k); f.v = reinterpret_cast<const __half*>(v);
+    f.ld_q = ld_q; f.ld_k = ld_k; f.ld_v = ld_v;
+    f.cos_t = reinterpret_cast<const __half*>(cos_t); f.sin_t = reinterpret_cast<const __half*>(sin_t); f.pos = pos;
+    f.t_q = reinterpret_cast<const __half*>(t_q); f.t_k = reinterpret_cast<const __half*>(t_k); f.slot = slot;
+    f.kv_data = kv_data; f.kv_param = reinterpret_cast<__half*>(kv_param);
+    float* part = reinterpret_cast<float*>(ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t base = (int64_t)batch * kv_heads;
+    int64_t splits = (2 * (int64_t)num_sms()) / base;   // one wave of resident CTAs (see flatq_kv_decode_i4_split)
+    if (max_tokens_hint > 0) {
+        const int64_t by_len = ((int64_t)max_tokens_hint + kDmWarps * kDmTile - 1) / (kDmWarps * kDmTile);
+        if (splits > by_len) splits = by_len;
+    }
+    if (splits > kDecMaxSplits) splits = kDecMaxSplits;
+    if (splits < 1) splits = 1;
+    static PerDeviceOnce attr;
+    if (attr.first_time())
+        FLATQ_CUDA(cudaFuncSetAttribute(decode_attn_i4_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDmSmem));
+    const dim3 grid((unsigned)splits, (unsigned)kv_heads, (unsigned)batch);
+    FLATQ_CUDA(launch_pdl(decode_attn_i4_mma_kernel<true>, grid, dim3(kDmThreads), (size_t)kDmSmem, st, p, f, (int)splits, part));
     FLATQ_CUDA(launch_pdl(decode_attn_merge_kernel, dim3(batch * q_heads), dim3(128), 0, st, (const float*)part, (int)splits,
                           reinterpret_cast<__half*>(o)));
     return FLATQ_OK;

@@ -16,8 +16,18 @@
 // (inside every 8: 0,2,4,6,1,3,5,7): Q is staged with the same permutation (a dot product does not care) and the output
 // is un-permuted when it is written.  Partial results and the merge over splits are those of the SIMT kernel
 // (part[..][130], decode_attn_merge_kernel).  Same arithmetic up to fp32 summation order and the fp16 rounding of P.
+//
+// FRONT = true (flatq_kv_decode_fused): the kernel in front of the attention in a decode step -- kv_fused_kernel: RoPE ->
+// Q . T_k^-T, K . T_k -> 4-bit quantise -> page scatter of the ONE new token per sequence -- is folded into this kernel's
+// prologue, so that a decode layer has one launch less on its latency chain.  Every CTA rotates and transforms the G query
+// rows of its kv head itself (the same m16n8k16 sequence as kv_fused.cuh: bit-identical q_t; T_k^-T and T_k are static and
+// are copied to shared memory before the dependency wait, aliased onto the K / V tile buffers); the CTA whose split holds
+// the newest token also rotates, transforms, quantises and stores that token's K row and quantises and stores its V row
+// (kvf_quant_rows4: the reference's fp16 op-by-op quantiser) before it enters the token loop, where it reads them back
+// like any other token.
 #pragma once
 #include "kron_quant.cuh"
+#include "kv_fused.cuh"
 #include "qattention.cuh"
 
 namespace flatq {
@@ -43,11 +53,60 @@ __device__ __forceinline__ void dm_nibbles8(uint32_t w, uint32_t (&h)[4]) {
 // position of original dim d (0..127) in the permuted order
 __host__ __device__ constexpr int dm_perm(int d) { return (d & ~7) + ((d & 1) << 2) + ((d & 7) >> 1); }
 
+struct DecodeFront {         // the new token's pre-RoPE rows (strided views of the qkv GEMM output) and what kv_fused needs
+    const __half* q; const __half* k; const __half* v;   // row (sequence b, head h) at X + b * ld_X + h * 128
+    long long ld_q, ld_k, ld_v;
+    const __half* cos_t; const __half* sin_t;            // [positions, 128]
+    const int* pos;                                      // [batch] position of the new token
+    const __half* t_q; const __half* t_k;                // [128, 128] row-major: q_t = q . t_q, k_t = k . t_k
+    const int* slot;                                     // [batch] cache slot (page * page_size + offset) of the new token
+    uint8_t* kv_data; __half* kv_param;                  // the cache, writable
+};
+
+// one row (128 halves, 4 per lane) through HF's rotate_half RoPE -- the arithmetic of kv_fused_kernel, phase 1
+__device__ __forceinline__ uint2 dm_rope_row(uint2 raw, uint2 cs, uint2 sn, int lane) {
+    uint2 other, out;
+    other.x = __shfl_xor_sync(0xffffffffu, raw.x, 16);
+    other.y = __shfl_xor_sync(0xffffffffu, raw.y, 16);
+    const __half2* xh = reinterpret_cast<const __half2*>(&raw);
+    const __half2* oh = reinterpret_cast<const __half2*>(&other);
+    const __half2* ch = reinterpret_cast<const __half2*>(&cs);
+    const __half2* sh = reinterpret_cast<const __half2*>(&sn);
+    __half2* rh = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const __half2 rot = lane < 16 ? __hneg2(oh[j]) : oh[j];
+        rh[j] = __hadd2_rn(__hmul2_rn(xh[j], ch[j]), __hmul2_rn(rot, sh[j]));
+    }
+    return out;
+}
+
+template <bool FRONT>
 __global__ void __launch_bounds__(kDmThreads)
-decode_attn_i4_mma_kernel(const DecodeParams p, int splits, float* __restrict__ part) {
+decode_attn_i4_mma_kernel(const DecodeParams p, const DecodeFront f, int splits, float* __restrict__ part) {
     extern __shared__ __align__(16) uint8_t dm_smem[];
     grid_dep_launch();   // PDL: the merge kernel becomes resident under this one
-    grid_dep_wait();     // q and this step's cache rows come from the kernel in front (kv_fused)
+    if (FRONT) {         // static transform matrices -> shared memory (the tile buffers are not in use yet)
+        static_assert(2 * 128 * kDmLd * 2 <= kDmWarps * kDmWarpBytes, "T_q and T_k alias the K / V tile buffers");
+        __half* Tq = reinterpret_cast<__half*>(dm_smem);
+        __half* Tk = Tq + 128 * kDmLd;
+#pragma unroll 1
+        for (int i0 = threadIdx.x; i0 < 128 * 16; i0 += 8 * kDmThreads) {
+            uint4 a[8], c[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                a[u] = __ldg(reinterpret_cast<const uint4*>(f.t_q) + i0 + u * kDmThreads);
+                c[u] = __ldg(reinterpret_cast<const uint4*>(f.t_k) + i0 + u * kDmThreads);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * kDmThreads, r = i >> 4, col = (i & 15) * 8;
+                *reinterpret_cast<uint4*>(Tq + r * kDmLd + col) = a[u];
+                *reinterpret_cast<uint4*>(Tk + r * kDmLd + col) = c[u];
+            }
+        }
+    }
+    grid_dep_wait();     // q (and, without FRONT, this step's cache rows) come from the kernel in front
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
     const int G = p.q_heads / p.kv_heads, hq0 = hk * G;       // G <= 16 (host)
@@ -58,14 +117,117 @@ decode_attn_i4_mma_kernel(const DecodeParams p, int splits, float* __restrict__ 
     float* qsum = reinterpret_cast<float*>(Qs + 16 * kDmLd);                      // [16] sum over dims of the scaled q row
     float* s_ml = qsum + 16;                                                      // [warps][16][2]
 
-    // ---- Q rows of the group -> shared (fp16, scaled, permuted); rows >= G are zero
-    for (int i = threadIdx.x; i < 16 * 16; i += kDmThreads) {
-        const int r = i >> 4, d0 = (i & 15) * 8;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (r < G) v = *reinterpret_cast<const uint4*>(p.q + ((size_t)b * p.q_heads + hq0 + r) * 128 + d0);
-        const __half* h = reinterpret_cast<const __half*>(&v);
+    const int pg0 = p.kv_indptr[b], pg1 = p.kv_indptr[b + 1];
+    const int n_tok = (pg1 - pg0 - 1) * p.page_size + p.last_page_len[b];
+    const int per = (n_tok + splits - 1) / splits;
+    const int t0 = split * per, t1 = min(n_tok, t0 + per);
+
+    if (FRONT) {
+        const __half* Tq = reinterpret_cast<const __half*>(dm_smem);
+        const __half* Tk = Tq + 128 * kDmLd;
+        const int gq = lane >> 2, tq = lane & 3, mq = lane >> 3, rq = lane & 7;
+        const int ps = f.pos[b];
+        const uint2 cs = __ldg(reinterpret_cast<const uint2*>(f.cos_t + (size_t)ps * 128 + lane * 4));
+        const uint2 sn = __ldg(reinterpret_cast<const uint2*>(f.sin_t + (size_t)ps * 128 + lane * 4));
+        // ---- the group's query rows: RoPE -> Qs (natural dim order; rows >= G zero)
+        for (int r = warp; r < 16; r += kDmWarps) {
+            uint2 out = make_uint2(0, 0);
+            if (r < G) out = dm_rope_row(*reinterpret_cast<const uint2*>(f.q + (size_t)b * f.ld_q + (size_t)(hq0 + r) * 128 + lane * 4), cs, sn, lane);
+            *reinterpret_cast<uint2*>(Qs + r * kDmLd + lane * 4) = out;
+        }
+        __syncthreads();
+        uint32_t af[8][4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) Qs[r * kDmLd + dm_perm(d0 + u)] = __float2half_rn(__half2float(h[u]) * p.sm_scale);
+        for (int kt = 0; kt < 8; ++kt)
+            ldsm_x4(smem_u32(Qs + (size_t)((mq & 1) * 8 + rq) * kDmLd + kt * 16 + (mq >> 1) * 8), af[kt]);
+        __syncthreads();   // every warp holds its A fragments: Qs may be reused
+        // ---- q_t = q . T_q: warp w owns output columns [32 w, 32 w + 32) (k order as kv_fused_kernel: bit-identical)
+        uint32_t qt[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int nt2 = 2 * warp + i;
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int kt = 0; kt < 8; ++kt) {
+                uint32_t bb[4];
+                ldsm_x4_t(smem_u32(Tq + (size_t)(kt * 16 + (mq & 1) * 8 + rq) * kDmLd + nt2 * 16 + (mq >> 1) * 8), bb);
+                hmma16816(c0, af[kt], bb[0], bb[1]);
+                hmma16816(c1, af[kt], bb[2], bb[3]);
+            }
+            qt[i][0] = pack_h2(c0[0], c0[1]); qt[i][1] = pack_h2(c0[2], c0[3]);
+            qt[i][2] = pack_h2(c1[0], c1[1]); qt[i][3] = pack_h2(c1[2], c1[3]);
+        }
+        // ---- the CTA whose split holds the newest token writes that token's K and V rows into the cache
+        if (t0 <= n_tok - 1 && n_tok - 1 < t1) {   // CTA-uniform
+            const int sl = f.slot[b], page = sl / p.page_size, off = sl - page * p.page_size;
+            const size_t kidx = ((((size_t)page * p.n_layers + p.layer) * 2 + 0) * p.kv_heads + hk) * p.page_size + off;
+            const size_t vidx = kidx + (size_t)p.kv_heads * p.page_size;
+            if (warp == 0) {
+                const uint2 kr0 = dm_rope_row(*reinterpret_cast<const uint2*>(f.k + (size_t)b * f.ld_k + (size_t)hk * 128 + lane * 4), cs, sn, lane);
+                *reinterpret_cast<uint2*>(Qs + lane * 4) = kr0;   // row 0 of the A tile; rows 1..15 hold finite leftovers (rows are independent)
+            } else if (warp == 1) {
+                uint2 raw4[4] = {*reinterpret_cast<const uint2*>(f.v + (size_t)b * f.ld_v + (size_t)hk * 128 + lane * 4), make_uint2(0, 0), make_uint2(0, 0), make_uint2(0, 0)};
+                __half sc4[4], ze4[4];
+                uint16_t pk4[4];
+                kvf_quant_rows4(raw4, sc4, ze4, pk4);
+                reinterpret_cast<uint16_t*>(f.kv_data + vidx * 64)[lane] = pk4[0];
+                if (lane == 0) reinterpret_cast<__half2*>(f.kv_param)[vidx] = __halves2half2(sc4[0], ze4[0]);
+            }
+            __syncthreads();
+            uint32_t kf[8][4];
+#pragma unroll
+            for (int kt = 0; kt < 8; ++kt)
+                ldsm_x4(smem_u32(Qs + (size_t)((mq & 1) * 8 + rq) * kDmLd + kt * 16 + (mq >> 1) * 8), kf[kt]);
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int nt2 = 2 * warp + i;
+                float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int kt = 0; kt < 8; ++kt) {
+                    uint32_t bb[4];
+                    ldsm_x4_t(smem_u32(Tk + (size_t)(kt * 16 + (mq & 1) * 8 + rq) * kDmLd + nt2 * 16 + (mq >> 1) * 8), bb);
+                    hmma16816(c0, kf[kt], bb[0], bb[1]);
+                    hmma16816(c1, kf[kt], bb[2], bb[3]);
+                }
+                if (gq == 0) {   // row 0 of the tile = the K row
+                    *reinterpret_cast<uint32_t*>(Qs + nt2 * 16 + 2 * tq) = pack_h2(c0[0], c0[1]);
+                    *reinterpret_cast<uint32_t*>(Qs + nt2 * 16 + 8 + 2 * tq) = pack_h2(c1[0], c1[1]);
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                uint2 raw4[4] = {*reinterpret_cast<const uint2*>(Qs + lane * 4), make_uint2(0, 0), make_uint2(0, 0), make_uint2(0, 0)};
+                __half sc4[4], ze4[4];
+                uint16_t pk4[4];
+                kvf_quant_rows4(raw4, sc4, ze4, pk4);
+                reinterpret_cast<uint16_t*>(f.kv_data + kidx * 64)[lane] = pk4[0];
+                if (lane == 0) reinterpret_cast<__half2*>(f.kv_param)[kidx] = __halves2half2(sc4[0], ze4[0]);
+            }
+            __threadfence();   // the token loop of this CTA reads the two rows back through global memory
+            __syncthreads();
+        }
+        // ---- q_t -> Qs, scaled and in the permuted dim order (what the plain prologue does with the q_t it is handed)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int row = gq + (j & 1) * 8, col = (2 * warp + i) * 16 + (j >> 1) * 8 + 2 * tq;
+                const float2 v2 = __half22float2(*reinterpret_cast<const __half2*>(&qt[i][j]));
+                Qs[row * kDmLd + dm_perm(col)] = __float2half_rn(v2.x * p.sm_scale);
+                Qs[row * kDmLd + dm_perm(col + 1)] = __float2half_rn(v2.y * p.sm_scale);
+            }
+        }
+    } else {
+        // ---- Q rows of the group -> shared (fp16, scaled, permuted); rows >= G are zero
+        for (int i = threadIdx.x; i < 16 * 16; i += kDmThreads) {
+            const int r = i >> 4, d0 = (i & 15) * 8;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (r < G) v = *reinterpret_cast<const uint4*>(p.q + ((size_t)b * p.q_heads + hq0 + r) * 128 + d0);
+            const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) Qs[r * kDmLd + dm_perm(d0 + u)] = __float2half_rn(__half2float(h[u]) * p.sm_scale);
+        }
     }
     __syncthreads();
     for (int r = warp; r < 16; r += kDmWarps) {   // sum of the ROUNDED q values: the same numbers the mma multiplies
@@ -84,11 +246,6 @@ decode_attn_i4_mma_kernel(const DecodeParams p, int splits, float* __restrict__ 
     for (int kt = 0; kt < 8; ++kt)
         ldsm_x4(smem_u32(Qs + (size_t)((mi & 1) * 8 + r8) * kDmLd + kt * 16 + (mi >> 1) * 8), qf[kt]);
     const float qs0 = qsum[g], qs1 = qsum[g + 8];
-
-    const int pg0 = p.kv_indptr[b], pg1 = p.kv_indptr[b + 1];
-    const int n_tok = (pg1 - pg0 - 1) * p.page_size + p.last_page_len[b];
-    const int per = (n_tok + splits - 1) / splits;
-    const int t0 = split * per, t1 = min(n_tok, t0 + per);
 
     float o[16][4];
 #pragma unroll

@@ -191,18 +191,25 @@ class MultiLayerPagedKVCache4Bit:
             slots = self._step_slots
             prefill = self._needs_init[layer_idx]
             self._needs_init[layer_idx] = False
+        hq = query_states.shape[-2]
+        if not prefill:
+            assert added == 1
+            if static:
+                kw, bound = self._static_attn, self.max_seq_len
+            else:
+                if self._step_attn is None:
+                    self._step_attn = self._attention_kwargs()
+                kw, bound = self._step_attn, self.length
+            if ops.kv_decode_fused_ok(query_states, key_states, cos_t, t_q, t_k):
+                # the whole step between the qkv GEMM and o_proj in one kernel (+ the split merge): the attention kernel's
+                # prologue does what kv_fused does for the one new token per sequence
+                o = ops.kv_decode_fused(query_states, key_states, value_states, cos_t, sin_t, pos, t_q, t_k, self.pages,
+                                        self.scales, slots, layer=layer_idx, max_tokens_hint=bound, **kw)
+                return o.unsqueeze(1)
         q_t, k_t = ops.kv_fused(query_states, key_states, value_states, cos_t, sin_t, pos, t_q, t_k, self.pages, self.scales,
                                 slots, layer_idx, want_k=prefill)
-        hq = query_states.shape[-2]
         if prefill:
             return q_t.view(b, added, hq, d), k_t.view(b, added, heads, d), value_states
-        assert added == 1
-        if static:
-            kw, bound = self._static_attn, self.max_seq_len
-        else:
-            if self._step_attn is None:
-                self._step_attn = self._attention_kwargs()
-            kw, bound = self._step_attn, self.length
         o = ops.kv_decode_i4(q_t, self.pages, self.scales, layer=layer_idx, max_tokens_hint=bound, **kw)
         return o.unsqueeze(1)
 

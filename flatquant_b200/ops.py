@@ -454,6 +454,44 @@ def kv_quant(x: torch.Tensor, kv_data=None, kv_param=None, slot=None, layer: int
     return q, par
 
 
+FUSED_DECODE_FRONT = os.environ.get("FLATQ_DECODE_FRONT", "1") != "0"   # decode steps: kv_fused folded into the attention kernel
+
+
+def kv_decode_fused_ok(q, k, cos_t, t_q, t_k) -> bool:
+    """The shapes flatq_kv_decode_fused takes: one token per sequence, 2..16 query heads per kv head, head_dim 128, RoPE
+    tables and both cache transforms present."""
+    hq, hkv = q.shape[-2], k.shape[-2]
+    return (FUSED_DECODE_FRONT and _DECODE_SPLIT and cos_t is not None and t_q is not None and t_k is not None and q.shape[-1] == 128
+            and hq % hkv == 0 and 2 <= hq // hkv <= 16 and q.numel() // (hq * 128) == q.shape[0])
+
+
+def kv_decode_fused(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cos_t, sin_t, pos, t_q, t_k, kv_data, kv_param, slot,
+                    kv_indptr, kv_indices, last_page_len, layer: int, sm_scale=None, max_tokens_hint: int = 0) -> torch.Tensor:
+    """A decode step's kv_fused + kv_decode_i4 in one kernel (+ the split merge): q [b, 1, Hq, 128] / k, v [b, 1, Hkv, 128]
+    pre-RoPE views of the qkv GEMM output, read in place; the new token's K / V rows are quantised into slot[b] by the
+    attention kernel itself.  Returns o [b, Hq, 128]."""
+    dev = _need_cuda(cos_t, sin_t, pos, t_q, t_k, kv_data, kv_param, slot, kv_indptr, kv_indices, last_page_len)
+    for t in (q, k, v):
+        if not t.is_cuda or t.dtype != torch.float16:
+            raise RuntimeError("kv_decode_fused: q, k, v must be float16 CUDA tensors")
+    hq, hkv, d = q.shape[-2], k.shape[-2], q.shape[-1]
+    batch = q.shape[0]
+    q, ld_q = _rows_view(q, hq)
+    k, ld_k = _rows_view(k, hkv)
+    v, ld_v = _rows_view(v, hkv)
+    o = torch.empty((batch, hq, d), dtype=torch.float16, device=dev)
+    if sm_scale is None:
+        sm_scale = d ** -0.5
+    lib = _lib.load()
+    ws = _ws4.get(dev, lib.flatq_kv_decode_i4_split_workspace_bytes(batch, hq))
+    _lib.check(lib.flatq_kv_decode_fused(_ptr(q), _ptr(k), _ptr(v), ld_q, ld_k, ld_v, _ptr(cos_t), _ptr(sin_t), _ptr(pos), _ptr(t_q),
+                                         _ptr(t_k), _ptr(slot), _ptr(o), _ptr(kv_data), _ptr(kv_param), _ptr(kv_indptr),
+                                         _ptr(kv_indices), _ptr(last_page_len), batch, hq, hkv, d, kv_data.shape[4], layer,
+                                         kv_data.shape[1], float(sm_scale), int(max_tokens_hint), _ptr(ws), ws.numel(), _stream()),
+               "kv_decode_fused")
+    return o
+
+
 def kv_decode_i4(q: torch.Tensor, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, layer: int = 0,
                  sm_scale=None, split=None, max_tokens_hint: int = 0) -> torch.Tensor:
     """Single-query attention over the paged INT4 cache: q [batch, q_heads, 128] fp16 -> o same shape.

@@ -241,6 +241,21 @@ int flatq_kv_fused(const void* q_f16, const void* k_f16, const void* v_f16, int6
                    uint8_t* kv_data, void* kv_param_f16, const int32_t* slot, int layer, int n_layers, int page_size,
                    flatq_stream_t stream);
 
+/* flatq_kv_decode_fused: a decode step's flatq_kv_fused + flatq_kv_decode_i4_split in one kernel + the split merge (one
+ *   token per sequence; grouped-query models with 2..16 query heads per kv head, head_dim 128, both transforms and RoPE
+ *   present -- other cases: the two calls).  The attention kernel's prologue rotates and transforms its group's query rows
+ *   and, in the CTA whose split holds the newest token, transforms / quantises / stores that token's K and V rows into the
+ *   cache slot slot[b] before attending over [0, length) (csrc/decode_attn_mma.cuh).  q / k / v: the new token's pre-RoPE rows
+ *   of sequence b at X + b * ld_X + head * 128; pos[b]: RoPE table row; last_page_len[b] already counts the new token.
+ *   Bit-identical (cache contents and q_t; the attention arithmetic is the same kernel) to the two calls.
+ *   workspace >= flatq_kv_decode_i4_split_workspace_bytes(batch, q_heads). */
+int flatq_kv_decode_fused(const void* q_f16, const void* k_f16, const void* v_f16, int64_t ld_q, int64_t ld_k, int64_t ld_v,
+                          const void* cos_f16, const void* sin_f16, const int32_t* pos, const void* t_q_f16, const void* t_k_f16,
+                          const int32_t* slot, void* o_f16, uint8_t* kv_data, void* kv_param_f16, const int32_t* kv_indptr,
+                          const int32_t* kv_indices, const int32_t* last_page_len, int batch, int q_heads, int kv_heads,
+                          int head_dim, int page_size, int layer, int n_layers, float sm_scale, int max_tokens_hint,
+                          void* workspace, size_t workspace_bytes, flatq_stream_t stream);
+
 /* flatq_kv_decode_i4_split: the same attention with the sequence split over CTAs (flash-decoding) and one CTA per kv head
  *   serving up to four of its query heads (grouped-query attention reads each K/V row once per group): fills the chip at
  *   small batch, where flatq_kv_decode_i4 runs batch x q_heads CTAs.  max_tokens_hint (host-side upper bound of the

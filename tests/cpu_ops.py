@@ -392,6 +392,17 @@ def kv_quant(x, kv_data=None, kv_param=None, slot=None, layer=0, kv_select=0):
     return packed, par
 
 
+def kv_decode_fused(q, k, v, cos_t, sin_t, pos, t_q, t_k, kv_data, kv_param, slot, kv_indptr, kv_indices, last_page_len, layer,
+                    sm_scale=None, max_tokens_hint=0):
+    """Stand-in of flatq_kv_decode_fused: the two launches it folds together (same bits by construction)."""
+    hq, hkv = q.shape[-2], k.shape[-2]
+    _req(q.numel() // (hq * 128) == q.shape[0] and 2 <= hq // hkv <= 16, "kv_decode_fused: one token per sequence, 2..16 query heads per kv head")
+    _req(cos_t is not None and t_q is not None and t_k is not None, "kv_decode_fused: RoPE tables and both transforms")
+    q_t, _ = kv_fused(q, k, v, cos_t, sin_t, pos, t_q, t_k, kv_data, kv_param, slot, layer)
+    CALLS.append(("kv_decode_fused", (q.shape[0], hq, hkv)))
+    return kv_decode_i4(q_t, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, layer, sm_scale, None, max_tokens_hint)
+
+
 def kv_decode_i4(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, layer=0, sm_scale=None, split=None,
                  max_tokens_hint=0):
     _contig(q=q, kv_data=kv_data, kv_param=kv_param, kv_indptr=kv_indptr, kv_indices=kv_indices, last_page_len=last_page_len)
@@ -426,7 +437,7 @@ def kv_decode_i4(q, kv_data, kv_param, kv_indptr, kv_indices, last_page_len, lay
 
 FUNCTIONS = ("kron_transform", "act_quant", "transform_quant", "quantize_rows", "gemm_w4a8", "gemm_w4a8_silu", "gemm_w4a8_grouped",
              "linear_fused", "linear_fused_silu", "pack_i4",
-             "hadamard", "hadamard_kn", "kv_fused", "kv_quant", "kv_decode_i4", "rmsnorm", "add_rmsnorm", "rope_", "silu_mul")
+             "hadamard", "hadamard_kn", "kv_fused", "kv_quant", "kv_decode_i4", "kv_decode_fused", "rmsnorm", "add_rmsnorm", "rope_", "silu_mul")
 
 
 def install(monkeypatch):

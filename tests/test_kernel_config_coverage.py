@@ -26,6 +26,7 @@ GPU_VERIFIED = {
     "2sm": "test_gpu_parity.py::test_prefill_gemm_variants_bit_identical, __graft_entry__.smoke (320 tokens)",
     "kv_quant": "test_gpu_parity.py::test_kv_quant_golden_bit_exact, test_paged_kv_append_and_decode",
     "kv_decode_i4": "test_gpu_parity.py::test_paged_kv_append_and_decode, test_kv_cache_module_prefill_then_decode",
+    "kv_decode_fused": "test_zzz_kv_fused_gpu.py::test_decode_step_with_the_kv_front_folded_into_the_attention_kernel",
 }
 
 
@@ -34,7 +35,7 @@ def _classify(op, cfg):
         return cfg[0]
     if op == "linear_fused_decode":
         return "fused-decode"
-    if op in ("kv_quant", "kv_decode_i4"):
+    if op in ("kv_quant", "kv_decode_i4", "kv_decode_fused"):
         return op
     if op == "act_quant" and cfg[0] == "rowquant":
         return "rowquant"
@@ -64,7 +65,7 @@ def test_llama_stack_kernel_configurations(monkeypatch):
     used = _classes(cpu_ops.CALLS)
     # prefill 30 tokens -> weight-streaming mma.sync GEMM (gemm_w4a8_skinny.cuh), decode 2 tokens -> GEMV; (16,32) / (32,32) / padded (4,128)+identity
     # Kronecker pairs on the HMMA kernel; K.T_k and Q.T_k^-T as right-only 128x128 transforms; paged INT4 KV
-    assert used == {"hmma two-factor", "hmma right-only", "skinny", "gemv", "kv_quant", "kv_decode_i4"}, used
+    assert used == {"hmma two-factor", "hmma right-only", "skinny", "gemv", "kv_quant", "kv_decode_i4", "kv_decode_fused"}, used
     assert used <= set(GPU_VERIFIED)
     configs = {cfg for op, cfg in cpu_ops.CALLS if op == "act_quant"}
     assert configs == {("hmma", 16, 32, True, True), ("hmma", 4, 128, True, True), ("hmma", 32, 32, True, True)}, configs

@@ -69,3 +69,42 @@ def test_kv_fused_equals_the_launches_it_replaces(dev, b, s, hq, hkv, fused_view
     assert torch.equal(caches[0][0], caches[1][0]), "packed pages"
     assert torch.equal(caches[0][1], caches[1][1]), "scale / zero params"
     assert caches[1][0][:, 0].count_nonzero() == 0   # the other layer is untouched
+
+
+@pytest.mark.parametrize("bsz,hq,hkv,ctx", [(1, 32, 8, 2048), (16, 32, 8, 700), (3, 64, 8, 129), (2, 16, 8, 5), (4, 28, 4, 1), (1, 40, 8, 4097)])
+def test_decode_step_with_the_kv_front_folded_into_the_attention_kernel(dev, bsz, hq, hkv, ctx):
+    """flatq_kv_decode_fused == flatq_kv_fused followed by flatq_kv_decode_i4_split, bit for bit: the packed pages and the
+    (scale, zero) params of the new token (written by the CTA whose split holds it), and the attention output (q_t is
+    produced by the same mma sequence, the rest is the same kernel).  Contexts shorter than the split count (empty splits),
+    a first token (ctx = 1), strided q / k / v views of a fused qkv output, several sequences with their own positions."""
+    from flatquant_b200 import ops
+    D, L, layer = 128, 2, 1
+    torch.manual_seed(bsz * 1000 + hq + ctx)
+    ps = ctx + 3
+    qkv = torch.randn(bsz, (hq + 2 * hkv) * D, device=dev).half()
+    q, k, v = (t.reshape(bsz, 1, -1, D) for t in torch.split(qkv, [hq * D, hkv * D, hkv * D], dim=-1))
+    P = ctx + 8
+    ang = torch.arange(P, device=dev)[:, None].float() * (1.0 / 500000.0 ** (torch.arange(0, D, 2, device=dev).float() / D))[None]
+    emb = torch.cat((ang, ang), -1)
+    cos_t, sin_t = emb.cos().half(), emb.sin().half()
+    pos = torch.full((bsz,), ctx - 1, device=dev).int()
+    t_k = (torch.eye(D, device=dev) * 0.75 + torch.randn(D, D, device=dev) * (0.5 / D ** 0.5)).half()
+    t_q = torch.linalg.inv(t_k.double()).t().float().half().contiguous()
+    pages0 = torch.randint(0, 256, (bsz, L, 2, hkv, ps, D // 2), dtype=torch.uint8, device=dev)
+    params0 = torch.stack((torch.rand(bsz, L, 2, hkv, ps, device=dev) * 0.2 + 0.05, torch.rand(bsz, L, 2, hkv, ps, device=dev) * 1.5), -1).half()
+    slot = (torch.arange(bsz, device=dev) * ps + (ctx - 1)).int()
+    indptr = torch.arange(bsz + 1, dtype=torch.int32, device=dev)
+    indices = torch.arange(bsz, dtype=torch.int32, device=dev)
+    last = torch.full((bsz,), ctx, dtype=torch.int32, device=dev)
+    assert ops.kv_decode_fused_ok(q, k, cos_t, t_q, t_k)
+    pages_a, params_a = pages0.clone(), params0.clone()
+    q_t, _ = ops.kv_fused(q, k, v, cos_t, sin_t, pos, t_q, t_k, pages_a, params_a, slot, layer)
+    want = ops.kv_decode_i4(q_t, pages_a, params_a, indptr, indices, last, layer=layer, max_tokens_hint=ps)
+    pages_b, params_b = pages0.clone(), params0.clone()
+    got = ops.kv_decode_fused(q, k, v, cos_t, sin_t, pos, t_q, t_k, pages_b, params_b, slot, indptr, indices, last, layer=layer,
+                              max_tokens_hint=ps)
+    torch.cuda.synchronize()
+    assert torch.equal(pages_a, pages_b) and torch.equal(params_a, params_b)
+    assert not torch.equal(pages_b, pages0)          # the new token was written
+    assert torch.equal(got, want)
+    assert bool(torch.isfinite(got.float()).all()) and float(got.float().abs().max()) > 0
