@@ -296,3 +296,45 @@ def test_kv_fused_reads_decode_views_of_the_qkv_output_in_place():
     odd = torch.zeros(2, 7, 6144, dtype=torch.float16)[:, :5, :4096].reshape(2, 5, 32, 128)   # batch stride != s * token stride
     got, ld = _rows_view(odd, 32)
     assert got.is_contiguous() and ld == 4096 and got.data_ptr() != odd.data_ptr()
+
+
+def test_decode_front_eligibility_rule():
+    """ops.kv_decode_fused_ok: what the decode step may hand to flatq_kv_decode_fused (one token per sequence, 2..16 query
+    heads per kv head, head_dim 128, RoPE tables and both cache transforms) -- everything else keeps the two launches."""
+    import torch
+    from flatquant_b200 import ops
+    t = torch.zeros(128, 128, dtype=torch.float16)
+    cos = torch.zeros(16, 128, dtype=torch.float16)
+
+    def ok(b, s, hq, hkv, d=128, cos_t=cos, t_q=t, t_k=t):
+        return ops.kv_decode_fused_ok(torch.zeros(b, s, hq, d, dtype=torch.float16), torch.zeros(b, s, hkv, d, dtype=torch.float16), cos_t, t_q, t_k)
+    assert ok(1, 1, 32, 8) and ok(16, 1, 64, 8) and ok(3, 1, 16, 8) and ok(2, 1, 128, 8)
+    assert not ok(1, 1, 32, 32)          # no grouped queries: the scalar kernel
+    assert not ok(1, 1, 136, 8)          # 17 query heads per kv head
+    assert not ok(1, 5, 32, 8)           # a prefill chunk
+    assert not ok(1, 1, 32, 8, d=64)
+    assert not ok(1, 1, 32, 8, cos_t=None) and not ok(1, 1, 32, 8, t_q=None) and not ok(1, 1, 32, 8, t_k=None)
+
+
+def test_gate_up_group_interleaves_rows_and_keeps_module_views():
+    """_QuantGroup(interleave=True): row 2j = gate_j, row 2j + 1 = up_j (the layout flatq_gemm_w4a8_silu takes), scales
+    interleaved alike, the two Linear4bit buffers strided views of the one copy; anything that cannot be interleaved
+    (unequal sizes, a bias) falls back to concatenation."""
+    import torch
+    from flatquant_b200.deploy.nn import Linear4bit
+    from flatquant_b200.deploy.transformers.modeling_llama import _QuantGroup
+    g, u = Linear4bit(64, 24), Linear4bit(64, 24)
+    g.weight.copy_(torch.randint(0, 256, g.weight.shape, dtype=torch.uint8))
+    u.weight.copy_(torch.randint(0, 256, u.weight.shape, dtype=torch.uint8))
+    g.weight_scales.copy_(torch.rand(24, 1) + 0.5)
+    u.weight_scales.copy_(torch.rand(24, 1) + 0.5)
+    wg, wu, sg, su = g.weight.clone(), u.weight.clone(), g.weight_scales.clone(), u.weight_scales.clone()
+    grp = _QuantGroup((4.0, 4.0), ["gate", "up"], [g, u], interleave=True)
+    assert grp.interleaved and grp.w.shape == (48, 32) and grp.w.is_contiguous()
+    assert torch.equal(grp.w[0::2], wg) and torch.equal(grp.w[1::2], wu)
+    assert torch.equal(grp.s_w[0::2], sg.reshape(-1).float()) and torch.equal(grp.s_w[1::2], su.reshape(-1).float())
+    assert torch.equal(g.weight, wg) and torch.equal(u.weight, wu) and g.weight.data_ptr() == grp.w.data_ptr()
+    a, b = Linear4bit(64, 24), Linear4bit(64, 16)
+    assert not _QuantGroup((4.0, 4.0), ["gate", "up"], [a, b], interleave=True).interleaved
+    c, d = Linear4bit(64, 24, bias=True), Linear4bit(64, 24, bias=True)
+    assert not _QuantGroup((4.0, 4.0), ["gate", "up"], [c, d], interleave=True).interleaved

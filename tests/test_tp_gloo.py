@@ -136,3 +136,40 @@ def test_reducer_interface_world2():
     want = (torch.from_numpy(ret[0][1]).half() + torch.from_numpy(ret[1][1]).half()) + torch.arange(32).half()
     for r in range(world):
         assert np.array_equal(ret[r][0], want.float().numpy()), r   # same sum, bias once, on every rank
+
+
+def _capacity_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from flatquant_b200.deploy.transformers.modeling_llama import TensorParallel
+        tp = TensorParallel(world, rank)
+        dev = torch.device("cpu")
+        r1 = tp.reducer(5, 64, dev)                 # first use: sized for max(m, 2048) rows
+        r2 = tp.reducer(2048, 64, dev)              # fits: the same object
+        r3 = tp.reducer(3000, 64, dev)              # grows (a collective: both ranks get here with the same shapes)
+        r4 = tp.reducer(7, 32, dev)                 # another width: another reducer
+        caps = (r1.partial_buffer().shape[0], r3.partial_buffer().shape[0], r4.partial_buffer().shape[0])
+        # the reducer sums a smaller call's rows only
+        buf = r3.partial_buffer()
+        buf.zero_()
+        part = buf[:4]
+        part.fill_(float(rank + 1))
+        out = r3.all_reduce(part)
+        ret[rank] = (r1 is r2, r3 is not r1, r4 is not r3, caps, out.shape[0], float(out[0, 0]), float(buf[5, 0]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_one_reducer_per_width_serves_every_token_count():
+    """TensorParallel.reducer: one reduction object per output width, sized once and reused for every smaller token count
+    (creating one is a collective), grown when a larger count arrives; a call reduces its own rows only."""
+    import torch.multiprocessing as mp
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    mp.spawn(_capacity_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    for r in (0, 1):
+        same, grown, other, caps, rows, val, untouched = ret[r]
+        assert same and grown and other and caps == (2048, 4096, 2048)
+        assert rows == 4 and val == 3.0 and untouched == 0.0
