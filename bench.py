@@ -662,7 +662,8 @@ def measure_qattention(dev, barrier):
             gbs_d = 2.0 * bsz * kvh * T * 68 / us_d / 1e3
             out[f"heads={heads} kv_heads={kvh} bsz={bsz}"] = {
                 "kv_quant_us": us_q, "kv_quant_GBps": gbs_q, "kv_quant_frac_of_hbm": gbs_q / hbm,
-                "decode_attn_us": us_d, "decode_attn_GBps": gbs_d, "decode_attn_frac_of_hbm": gbs_d / hbm}
+                "decode_attn_us": us_d, "decode_attn_GBps": gbs_d, "decode_attn_frac_of_hbm": gbs_d / hbm,
+                "decode_attn_traffic": ncu_traffic(f"decode_attn heads={heads} kv_heads={kvh} bsz={bsz}")}
             del pages, params, kx
     return out
 
