@@ -945,6 +945,16 @@ def main():
         if sus:
             line["roofline"]["peak_sustained"] = 2 * sus
             line["roofline"]["frac_of_sustained"] = achieved / (2 * sus)
+        try:   # third denominator: the tensor pipe's own issue rate (tools/mma_rate2.cu, profiles/r02_mma_rate2.log) at the clock of this run
+            mhz = float((clocks or {}).get("sm_mhz") or 0)
+            if mhz > 0:
+                sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+                pk = 2 * 8189 * sms * mhz * 1e6 / 1e12
+                line["roofline"]["peak_mma_issue"] = pk
+                line["roofline"]["frac_of_mma_issue"] = achieved / pk
+                line["roofline"]["peak_mma_issue_source"] = "measured kind::i8 issue rate 8189 MAC/cycle/SM x SMs x median SM clock of the timed region"
+        except Exception:  # noqa: BLE001 -- optional evidence only
+            pass
         if not args.no_cpu_baseline and world == 1:
             v, t_step = cpu_reference_pass(threads, 3, 1)
             line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
