@@ -935,9 +935,9 @@ int flatq_gemm_w4a8_grouped(const int8_t* xq8, const float* s_x, const uint8_t* 
                 FLATQ_ERR_WORKSPACE, "gemm_w4a8_grouped: workspace too small or misaligned");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t hint = rows_per_group_hint > 0 ? rows_per_group_hint : (M + n_groups - 1) / n_groups;
-    // Token tile ~ twice the mean group size: a tcgen05.mma costs >= 128 cycles whatever its N, so a
-    // wider tile is free in tensor time and halves the MMA count of every group above the mean (routing is skewed);
-    // 256 (single accumulator buffer, 3 stages) only when the mean itself exceeds 128.
+    // Token tile ~ twice the mean group size: below N = 128 a tcgen05.mma sits on its ~45-cycle issue floor (DESIGN.md
+    // section 2), so a wider tile costs little tensor time and halves the MMA count of every group above the mean
+    // (routing is skewed); 256 (single accumulator buffer, 3 stages) only when the mean itself exceeds 128.
     const int tn = hint <= 8 ? 16 : hint <= 16 ? 32 : hint <= 32 ? 64 : hint <= 128 ? 128 : 256;
     const int64_t nb_w = (N + kGemmBlockW - 1) / kGemmBlockW;
     const int64_t t_upper = nb_w * ((M + tn - 1) / tn + n_groups);  // every group adds at most one partial token block

@@ -16,10 +16,10 @@
 //     ([0,2,4,6,1,3,5,7]); the activation operand is stored with the same permutation, so the
 //     contraction is unchanged.  The factor 16 (or 256 when X is expanded the same way) is
 //     removed exactly by an arithmetic shift of the int32 accumulator.
-//   * Measured on B200 (profiles/r01_mma_rate_microbench.log): one tcgen05.mma costs >= 128 cycles whatever N
-//     is (i8 M128 K32: 127 / 127 / 128 cycles at N = 64 / 128 / 256), so only N = 256 reaches the
-//     8192 MAC/cycle/SM peak; and a tcgen05.commit after every 4 MMAs costs 144-173 cycles/MMA while
-//     >= 8 MMAs per commit run at a flat 128.1.  Prefill tiles are therefore 128 weight rows x 256 tokens
+//   * Measured on B200 (tools/mma_rate2.cu, profiles/r02_mma_rate2.log; round 1's "128 cycles whatever N" was an
+//     artefact of its probe): one tcgen05.mma (i8, M128 K32) costs N/2 cycles down to N = 128 (64 cycles) and hits
+//     an issue floor of ~45 cycles below that, i.e. N >= 128 runs at the 8192 MAC/cycle/SM peak; a tcgen05.commit
+//     after every 4 MMAs costs 144-173 cycles/MMA while >= 8 MMAs per commit stay at the flat rate.  Prefill tiles are therefore 128 weight rows x 256 tokens
 //     (256 TMEM columns of int32 accumulator, single-buffered, + a 3-stage A ring of 64 columns) and
 //     one pipeline stage is 256 K-elements = 8 MMAs behind ONE mbarrier wait and ONE commit.
 //   * Stage contents: packed W tile 128 rows x 128 B (SWIZZLE_128B), int8 X tile = two TMA boxes of

@@ -1,7 +1,7 @@
 // Decode GEMV: y[m, n] = (sum_k W[n,k] * X[m,k]) * s_x[m] * s_w[n] (+bias) for M <= 2 tokens.
 //
 // With one or two tokens the FlatLinear is a pure stream of the packed 4-bit weight (4 op/B), and a
-// tcgen05.mma would spend its >= 128-cycle issue slot on a 128 x 16 tile.  The integer dot-product pipe (dp4a) keeps
+// tcgen05.mma would spend its ~45-cycle issue floor on a 128 x 16 tile.  The integer dot-product pipe (dp4a) keeps
 // up with HBM instead:
 //   * a warp owns one weight row at a time and reads it with fully coalesced 128-bit loads (512 contiguous bytes per
 //     instruction, up to 4 in flight per lane); rows are strided over all warps of a persistent grid;
