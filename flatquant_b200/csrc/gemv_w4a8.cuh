@@ -9,8 +9,8 @@
 //     which is why the activation operand format (K-permuted int8) is shared between the two kernels;
 //   * the M activation rows are staged once per CTA in shared memory; per-lane partial sums are combined with five
 //     shuffles per row; the x16 is removed by an exact arithmetic shift.
-// (A first version with one row per lane was limited to ~1.8 TB/s by uncoalesced L1 tag traffic and lost to the
-//  split-K tensor-core route from M = 4 on; 3 <= M <= 64 therefore stays on that route.)
+// (A first version with one row per lane was limited to ~1.8 TB/s by uncoalesced L1 tag traffic.  3 <= M <= 32 is the
+//  weight-streaming mma.sync kernel of gemm_w4a8_skinny.cuh, 33 <= M <= 64 the split-K tcgen05 route.)
 // Replaces the same reference calls as gemm_w4a8.cuh (deploy/kernels/gemm.cu:7-46 + quant.cu:66-101) at decode shapes.
 #pragma once
 #include "ptx.cuh"

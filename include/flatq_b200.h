@@ -124,7 +124,8 @@ int flatq_linear_fused(const void* x_f16, const void* left_f16, const void* righ
  *      flatq_gemm_w4a8: y[M,N] = (xq8 . W^T) * s_x[m] * s_w[n] (+bias), W packed [N, K/2]; K % 32 == 0. */
 int flatq_act_quant(const void* x_f16, const void* left_f16, const void* right_f16, int n1, int n2, float clip_max,
                     float clip_min, int64_t M, int8_t* xq8, float* s_x, flatq_stream_t stream);
-/*      workspace (may be NULL): with flatq_gemm_w4a8_workspace_bytes(M, N, K) bytes, decode shapes (M <= 64) split K
+/*      M <= 2: dp4a GEMV; 3 <= M <= 32 (K % 128 == 0): the weight-streaming mma.sync kernel -- neither needs a workspace.
+ *      workspace (may be NULL): with flatq_gemm_w4a8_workspace_bytes(M, N, K) bytes, 33 <= M <= 64 split K
  *      across CTAs (int32 atomics + a finalize pass) so that the packed-weight stream uses the whole chip, and
  *      prefill shapes whose last wave of output tiles is partial deal that wave's K ranges to all SMs (stream-K:
  *      raw int32 partials + per-launch epoch flags in the workspace; needs no zeroing, must not be shared by
